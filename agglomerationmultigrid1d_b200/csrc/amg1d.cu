@@ -1,0 +1,1075 @@
+// libamg1d: C ABI (include/amg1d.h) + host-side driver of the B200 V-cycle.
+//
+// The V-cycle structure follows src/solvers.jl:19-50 of the reference; what each kernel computes is
+// documented next to it in kernels_generic.cuh / kernels_fused.cuh.  Nothing here falls back to the
+// CPU: every numerical operation is a kernel launch on the handle's stream.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/amg1d.h"
+#include "kernels_generic.cuh"
+#include "kernels_fused.cuh"
+
+#define AMG1D_VERSION 100
+#define PAD_FRONT 32  // doubles in front of element 0 (ghost element lives in the last m of them)
+#define PAD_BACK 64
+
+namespace {
+
+std::string g_create_error;
+
+struct DVec {
+    double* raw = nullptr;
+    double* p = nullptr;  // element 0
+    int64_t len = 0;      // n * m
+};
+
+struct Level {
+    bool set = false;
+    int64_t n = 0;  // elements (device blocks)
+    int m = 0;
+    int diag = 0;
+    int K = 0;
+    int64_t n_host = 0;  // reference vector length
+    double* mat = nullptr;
+    int64_t* perm = nullptr;  // device, n*m entries, or null
+    DVec x[2], b;
+    int cur = 0;
+    // host copy of the blocks, kept only for small levels (coarsest-level factorisation)
+    std::vector<double> h_lo, h_di, h_up;
+    int64_t mat_bytes = 0;
+};
+
+struct Transfer {
+    bool set = false;
+    int64_t n_fine = 0, n_coarse = 0;
+    int mf = 0, mc = 0;
+    int64_t* parent = nullptr;  // device or null
+    int64_t* cp = nullptr;      // device or null
+    std::vector<int64_t> h_parent;  // host copy until finalize builds the child pointers
+    int ratio = 1, shift = 0, base = 0, period = 0, n_head = 0, n_tail = 0;
+    double* P0 = nullptr;
+    double* P1 = nullptr;
+    int64_t nblk = 0;
+    bool single_parent_uniform = false;  // parent[e] = e / ratio, no P1
+};
+
+}  // namespace
+
+struct amg1d {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    bool own_stream = false;
+    int n_levels = 0;
+    std::vector<Level> L;
+    std::vector<Transfer> T;
+    bool finalized = false;
+    std::string err;
+    // work
+    DVec scratch;          // residual scratch, max level size
+    double* stage = nullptr;  // host-ordered staging for permuted levels
+    int64_t stage_len = 0;
+    double* partial = nullptr;
+    double* d_scal = nullptr;  // device scalars
+    double* h_scal = nullptr;  // pinned host scalars
+    double* coarse_fac = nullptr;
+    // options
+    int opt_fused = 1, opt_graph = 1;
+    int64_t opt_coarse_cta = 1024;
+    // graph cache
+    cudaGraphExec_t gexec = nullptr;
+    int g_pre = -1, g_post = -1;
+    double g_alpha = 0.0;
+    int64_t launches_per_cycle = 0;
+    int64_t launch_counter = 0;
+    int64_t device_bytes = 0;
+    // distributed
+    int rank = 0, nranks = 1;
+};
+
+namespace {
+
+int fail(amg1d* h, int code, const char* fmt, ...) {
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    if (h) h->err = buf; else g_create_error = buf;
+    return code;
+}
+
+#define CK(call)                                                                          \
+    do {                                                                                  \
+        cudaError_t e_ = (call);                                                          \
+        if (e_ != cudaSuccess)                                                            \
+            return fail(h, e_ == cudaErrorMemoryAllocation ? AMG1D_ERR_NOMEM : AMG1D_ERR_CUDA, \
+                        "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); \
+    } while (0)
+
+#define RET(expr)                \
+    do {                         \
+        int rc_ = (expr);        \
+        if (rc_ != AMG1D_OK) return rc_; \
+    } while (0)
+
+int dev_alloc(amg1d* h, void** p, int64_t bytes) {
+    if (bytes <= 0) bytes = 8;
+    CK(cudaMalloc(p, (size_t)bytes));
+    h->device_bytes += bytes;
+    return AMG1D_OK;
+}
+
+int vec_alloc(amg1d* h, DVec& v, int64_t n, int m) {
+    v.len = n * m;
+    const int64_t total = PAD_FRONT + v.len + PAD_BACK;
+    RET(dev_alloc(h, (void**)&v.raw, total * 8));
+    CK(cudaMemsetAsync(v.raw, 0, (size_t)total * 8, h->stream));
+    v.p = v.raw + PAD_FRONT;
+    return AMG1D_OK;
+}
+
+void vec_free(DVec& v) {
+    if (v.raw) cudaFree(v.raw);
+    v.raw = v.p = nullptr;
+}
+
+inline dim3 gblock(int m) {
+    int z = 256 / (AMG1D_TILE * m);
+    if (z < 1) z = 1;
+    return dim3(AMG1D_TILE, m, z);
+}
+inline unsigned ggrid(int64_t n, int m) {
+    const int z = gblock(m).z;
+    return (unsigned)((amg1d_tiles(n) + z - 1) / z);
+}
+
+#define LAUNCH_CHECK() CK(cudaGetLastError())
+
+bool valid_level(amg1d* h, int l) { return h && l >= 0 && l < h->n_levels; }
+
+TransferMap make_map(const Transfer& t) {
+    TransferMap tm;
+    tm.parent = t.parent;
+    tm.cp = t.cp;
+    tm.n_fine = t.n_fine;
+    tm.n_coarse = t.n_coarse;
+    tm.ratio = t.ratio;
+    tm.shift = t.shift;
+    tm.base = t.base;
+    tm.period = t.period;
+    tm.n_head = t.n_head;
+    tm.n_tail = t.n_tail;
+    return tm;
+}
+
+// ---- elementary enqueued operations ---------------------------------------------------------------
+int op_sweep(amg1d* h, int l, const double* b, const double* xin, double* xout, double alpha,
+             int zero_guess) {
+    Level& lv = h->L[l];
+    if (h->opt_fused && fused_sweep(lv.m, lv.diag, lv.mat, b, xin, xout, lv.n, alpha, zero_guess,
+                                    h->stream)) {
+        h->launch_counter++;
+        LAUNCH_CHECK();
+        return AMG1D_OK;
+    }
+    const dim3 blk = gblock(lv.m);
+    const size_t sm = (size_t)blk.z * lv.m * AMG1D_TILE * sizeof(double);
+    g_sweep<<<ggrid(lv.n, lv.m), blk, sm, h->stream>>>(lv.mat, lv.m, lv.diag, lv.K, b, xin, xout,
+                                                        lv.n, alpha, zero_guess);
+    h->launch_counter++;
+    LAUNCH_CHECK();
+    return AMG1D_OK;
+}
+
+int op_apply(amg1d* h, int l, const double* b, const double* x, double* out, int mode) {
+    Level& lv = h->L[l];
+    g_apply<<<ggrid(lv.n, lv.m), gblock(lv.m), 0, h->stream>>>(lv.mat, lv.m, lv.K, b, x, out, lv.n,
+                                                               mode);
+    h->launch_counter++;
+    LAUNCH_CHECK();
+    return AMG1D_OK;
+}
+
+int op_restrict(amg1d* h, int l, const double* rf, double* rc) {
+    Transfer& t = h->T[l];
+    const int64_t total = t.n_coarse * t.mc;
+    g_restrict<<<(unsigned)((total + 255) / 256), 256, 0, h->stream>>>(make_map(t), t.mf, t.mc, t.P0,
+                                                                       t.P1, rf, rc);
+    h->launch_counter++;
+    LAUNCH_CHECK();
+    return AMG1D_OK;
+}
+
+int op_prolong(amg1d* h, int l, const double* xc, double* xf, int add) {
+    Transfer& t = h->T[l];
+    const int64_t total = t.n_fine * t.mf;
+    g_prolong<<<(unsigned)((total + 255) / 256), 256, 0, h->stream>>>(make_map(t), t.mf, t.mc, t.P0,
+                                                                      t.P1, xc, xf, add);
+    h->launch_counter++;
+    LAUNCH_CHECK();
+    return AMG1D_OK;
+}
+
+int op_coarse(amg1d* h, const double* b, double* x) {
+    Level& lv = h->L[h->n_levels - 1];
+    g_coarse_solve<<<1, 32, 2 * lv.m * sizeof(double), h->stream>>>(h->coarse_fac, lv.m, lv.n, b, x);
+    h->launch_counter++;
+    LAUNCH_CHECK();
+    return AMG1D_OK;
+}
+
+// out slot <- || a - c ||_2 (c may be null)
+int op_norm(amg1d* h, const double* a, const double* c, int64_t n, int slot) {
+    int nb = (int)std::min<int64_t>(AMG1D_RED_BLOCKS, (n + AMG1D_RED_THREADS - 1) / AMG1D_RED_THREADS);
+    if (nb < 1) nb = 1;
+    k_sqdiff_partial<<<nb, AMG1D_RED_THREADS, 0, h->stream>>>(a, c, n, h->partial);
+    k_reduce_final<<<1, AMG1D_RED_THREADS, 0, h->stream>>>(h->partial, nb, h->d_scal, slot, 1);
+    h->launch_counter += 2;
+    LAUNCH_CHECK();
+    return AMG1D_OK;
+}
+
+// || b - A x ||_2 on level l into slot
+int op_resnorm(amg1d* h, int l, int slot) {
+    Level& lv = h->L[l];
+    if (h->opt_fused) {
+        int nb = 0;
+        if (fused_resnorm(lv.m, lv.mat, lv.b.p, lv.x[lv.cur].p, lv.n, h->partial, &nb, h->stream)) {
+            k_reduce_final<<<1, AMG1D_RED_THREADS, 0, h->stream>>>(h->partial, nb, h->d_scal, slot, 1);
+            h->launch_counter += 2;
+            LAUNCH_CHECK();
+            return AMG1D_OK;
+        }
+    }
+    RET(op_apply(h, l, lv.b.p, lv.x[lv.cur].p, h->scratch.p, 1));
+    return op_norm(h, h->scratch.p, nullptr, lv.n * lv.m, slot);
+}
+
+// ---- the V-cycle (src/solvers.jl:19-50) ------------------------------------------------------------
+int enqueue_vcycle(amg1d* h, int nPre, int nPost, double alpha) {
+    const int nl = h->n_levels;
+    for (int l = 0; l < nl - 1; ++l) {
+        Level& lv = h->L[l];
+        Transfer& t = h->T[l];
+        Level& lc = h->L[l + 1];
+        bool zero = l > 0;
+        if (zero) lv.cur = 0;
+        // fused down-leg: nPre sweeps + residual + restriction in one pass over the operator
+        if (h->opt_fused && t.single_parent_uniform) {
+            int outbuf = -1;
+            if (fused_down(lv.m, t.mc, lv.diag, t.ratio, t.period, nPre, zero, lv.mat, lv.b.p,
+                           lv.x[lv.cur].p, lv.x[1 - lv.cur].p, t.P0, lc.b.p, lv.n, alpha, lv.cur,
+                           &outbuf, h->stream)) {
+                lv.cur = outbuf;
+                h->launch_counter++;
+                LAUNCH_CHECK();
+                continue;
+            }
+        }
+        if (zero && nPre == 0)
+            CK(cudaMemsetAsync(lv.x[0].p, 0, (size_t)lv.x[0].len * 8, h->stream));
+        for (int s = 0; s < nPre; ++s) {
+            if (zero && s == 0) {
+                RET(op_sweep(h, l, lv.b.p, lv.x[0].p, lv.x[0].p, alpha, 1));  // x = alpha Dinv b
+            } else {
+                RET(op_sweep(h, l, lv.b.p, lv.x[lv.cur].p, lv.x[1 - lv.cur].p, alpha, 0));
+                lv.cur = 1 - lv.cur;
+            }
+        }
+        if (h->opt_fused && t.single_parent_uniform &&
+            fused_residual_restrict(lv.m, t.mc, t.ratio, t.period, lv.mat, lv.b.p, lv.x[lv.cur].p,
+                                    t.P0, lc.b.p, lv.n, h->stream)) {
+            h->launch_counter++;
+            LAUNCH_CHECK();
+        } else {
+            RET(op_apply(h, l, lv.b.p, lv.x[lv.cur].p, h->scratch.p, 1));
+            RET(op_restrict(h, l, h->scratch.p, lc.b.p));
+        }
+    }
+    {
+        Level& lv = h->L[nl - 1];
+        if (nl > 1) lv.cur = 0;
+        // single level: x = A \ b overwrites the current x
+        RET(op_coarse(h, lv.b.p, lv.x[lv.cur].p));
+    }
+    for (int l = nl - 2; l >= 0; --l) {
+        Level& lv = h->L[l];
+        Transfer& t = h->T[l];
+        Level& lc = h->L[l + 1];
+        if (h->opt_fused && t.single_parent_uniform) {
+            int outbuf = -1;
+            if (fused_up(lv.m, t.mc, lv.diag, t.ratio, t.period, nPost, lv.mat, lv.b.p,
+                         lv.x[lv.cur].p, lv.x[1 - lv.cur].p, t.P0, lc.x[lc.cur].p, lv.n, alpha,
+                         lv.cur, &outbuf, h->stream)) {
+                lv.cur = outbuf;
+                h->launch_counter++;
+                LAUNCH_CHECK();
+                continue;
+            }
+        }
+        RET(op_prolong(h, l, lc.x[lc.cur].p, lv.x[lv.cur].p, 1));
+        for (int s = 0; s < nPost; ++s) {
+            RET(op_sweep(h, l, lv.b.p, lv.x[lv.cur].p, lv.x[1 - lv.cur].p, alpha, 0));
+            lv.cur = 1 - lv.cur;
+        }
+    }
+    Level& l0 = h->L[0];
+    if (l0.cur != 0) {
+        CK(cudaMemcpyAsync(l0.x[0].p, l0.x[1].p, (size_t)l0.x[0].len * 8, cudaMemcpyDeviceToDevice,
+                           h->stream));
+        l0.cur = 0;
+    }
+    return AMG1D_OK;
+}
+
+int run_vcycle(amg1d* h, int nPre, int nPost, double alpha) {
+    if (nPre < 0 || nPost < 0) return fail(h, AMG1D_ERR_ARG, "nPre and nPost must be >= 0");
+    if (!h->opt_graph) {
+        const int64_t c0 = h->launch_counter;
+        RET(enqueue_vcycle(h, nPre, nPost, alpha));
+        h->launches_per_cycle = h->launch_counter - c0;
+        return AMG1D_OK;
+    }
+    if (!h->gexec || h->g_pre != nPre || h->g_post != nPost || h->g_alpha != alpha) {
+        if (h->gexec) { cudaGraphExecDestroy(h->gexec); h->gexec = nullptr; }
+        if (h->L[0].cur != 0) return fail(h, AMG1D_ERR_STATE, "internal: level-0 buffer parity");
+        cudaGraph_t g = nullptr;
+        const int64_t c0 = h->launch_counter;
+        CK(cudaStreamBeginCapture(h->stream, cudaStreamCaptureModeThreadLocal));
+        int rc = enqueue_vcycle(h, nPre, nPost, alpha);
+        cudaError_t ce = cudaStreamEndCapture(h->stream, &g);
+        if (rc != AMG1D_OK) { if (g) cudaGraphDestroy(g); return rc; }
+        if (ce != cudaSuccess) return fail(h, AMG1D_ERR_CUDA, "graph capture failed: %s", cudaGetErrorString(ce));
+        h->launches_per_cycle = h->launch_counter - c0;
+        h->launch_counter = c0;
+        ce = cudaGraphInstantiate(&h->gexec, g, 0);
+        cudaGraphDestroy(g);
+        if (ce != cudaSuccess) return fail(h, AMG1D_ERR_CUDA, "graph instantiate failed: %s", cudaGetErrorString(ce));
+        h->g_pre = nPre; h->g_post = nPost; h->g_alpha = alpha;
+    }
+    CK(cudaGraphLaunch(h->gexec, h->stream));
+    h->launch_counter += h->launches_per_cycle;
+    return AMG1D_OK;
+}
+
+void invalidate_graph(amg1d* h) {
+    if (h->gexec) { cudaGraphExecDestroy(h->gexec); h->gexec = nullptr; }
+    h->g_pre = h->g_post = -1;
+}
+
+// ---- host <-> device vector movement (reference ordering <-> device block ordering) --------------
+int ensure_stage(amg1d* h, int64_t len) {
+    if (h->stage_len >= len) return AMG1D_OK;
+    if (h->stage) { cudaFree(h->stage); h->device_bytes -= h->stage_len * 8; }
+    h->stage = nullptr; h->stage_len = 0;
+    RET(dev_alloc(h, (void**)&h->stage, len * 8));
+    h->stage_len = len;
+    return AMG1D_OK;
+}
+
+int to_device(amg1d* h, int l, const double* host, double* dev) {
+    Level& lv = h->L[l];
+    if (!lv.perm) {
+        CK(cudaMemcpyAsync(dev, host, (size_t)lv.n_host * 8, cudaMemcpyHostToDevice, h->stream));
+        return AMG1D_OK;
+    }
+    RET(ensure_stage(h, lv.n_host));
+    CK(cudaMemcpyAsync(h->stage, host, (size_t)lv.n_host * 8, cudaMemcpyHostToDevice, h->stream));
+    const int64_t ns = lv.n * lv.m;
+    k_gather_perm<<<(unsigned)((ns + 255) / 256), 256, 0, h->stream>>>(lv.perm, h->stage, dev, ns);
+    LAUNCH_CHECK();
+    return AMG1D_OK;
+}
+
+int to_host(amg1d* h, int l, const double* dev, double* host) {
+    Level& lv = h->L[l];
+    if (!lv.perm) {
+        CK(cudaMemcpyAsync(host, dev, (size_t)lv.n_host * 8, cudaMemcpyDeviceToHost, h->stream));
+        CK(cudaStreamSynchronize(h->stream));
+        return AMG1D_OK;
+    }
+    RET(ensure_stage(h, lv.n_host));
+    const int64_t ns = lv.n * lv.m;
+    k_scatter_perm<<<(unsigned)((ns + 255) / 256), 256, 0, h->stream>>>(lv.perm, dev, h->stage, ns);
+    LAUNCH_CHECK();
+    CK(cudaMemcpyAsync(host, h->stage, (size_t)lv.n_host * 8, cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    return AMG1D_OK;
+}
+
+int read_scalars(amg1d* h, int count) {
+    CK(cudaMemcpyAsync(h->h_scal, h->d_scal, sizeof(double) * count, cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    return AMG1D_OK;
+}
+
+// dense m x m inverse with partial pivoting (Gauss-Jordan), column-major; returns false if singular
+bool invert_block(const double* A, double* Ainv, int m) {
+    std::vector<double> a(A, A + m * m);
+    for (int j = 0; j < m; ++j)
+        for (int i = 0; i < m; ++i) Ainv[j * m + i] = (i == j) ? 1.0 : 0.0;
+    for (int c = 0; c < m; ++c) {
+        int piv = c;
+        double best = std::fabs(a[c * m + c]);
+        for (int r = c + 1; r < m; ++r)
+            if (std::fabs(a[c * m + r]) > best) { best = std::fabs(a[c * m + r]); piv = r; }
+        if (best == 0.0) return false;
+        if (piv != c)
+            for (int j = 0; j < m; ++j) {
+                std::swap(a[j * m + c], a[j * m + piv]);
+                std::swap(Ainv[j * m + c], Ainv[j * m + piv]);
+            }
+        const double d = 1.0 / a[c * m + c];
+        for (int j = 0; j < m; ++j) { a[j * m + c] *= d; Ainv[j * m + c] *= d; }
+        for (int r = 0; r < m; ++r) {
+            if (r == c) continue;
+            const double f = a[c * m + r];
+            if (f == 0.0) continue;
+            for (int j = 0; j < m; ++j) {
+                a[j * m + r] -= f * a[j * m + c];
+                Ainv[j * m + r] -= f * Ainv[j * m + c];
+            }
+        }
+    }
+    return true;
+}
+
+void matmul_cm(const double* A, const double* B, double* C, int m) {  // C = A B, column-major
+    for (int j = 0; j < m; ++j)
+        for (int i = 0; i < m; ++i) {
+            double s = 0.0;
+            for (int k = 0; k < m; ++k) s += A[k * m + i] * B[j * m + k];
+            C[j * m + i] = s;
+        }
+}
+
+int factor_coarsest(amg1d* h) {
+    Level& lv = h->L[h->n_levels - 1];
+    if (lv.h_di.empty())
+        return fail(h, AMG1D_ERR_UNSUPPORTED,
+                    "coarsest level has %lld elements: too large for the block-Thomas direct solve "
+                    "(limit 65536); add coarser levels", (long long)lv.n);
+    const int m = lv.m, mm = m * m;
+    std::vector<double> fac((size_t)lv.n * 3 * mm, 0.0), S(mm), tmp(mm), Sinv_prev(mm);
+    for (int64_t k = 0; k < lv.n; ++k) {
+        double* W = &fac[(size_t)k * 3 * mm];
+        double* Sinv = W + mm;
+        double* U = W + 2 * mm;
+        std::copy(&lv.h_di[(size_t)k * mm], &lv.h_di[(size_t)k * mm] + mm, S.begin());
+        if (k > 0) {
+            matmul_cm(&lv.h_lo[(size_t)k * mm], Sinv_prev.data(), W, m);       // W = L_k Sinv_{k-1}
+            matmul_cm(W, &lv.h_up[(size_t)(k - 1) * mm], tmp.data(), m);        // W U_{k-1}
+            for (int q = 0; q < mm; ++q) S[q] -= tmp[q];
+        }
+        if (!invert_block(S.data(), Sinv, m))
+            return fail(h, AMG1D_ERR_ARG, "coarsest level is singular at element %lld", (long long)k);
+        std::copy(&lv.h_up[(size_t)k * mm], &lv.h_up[(size_t)k * mm] + mm, U);
+        std::copy(Sinv, Sinv + mm, Sinv_prev.begin());
+    }
+    RET(dev_alloc(h, (void**)&h->coarse_fac, (int64_t)fac.size() * 8));
+    CK(cudaMemcpy(h->coarse_fac, fac.data(), fac.size() * 8, cudaMemcpyHostToDevice));
+    return AMG1D_OK;
+}
+
+int check_ready(amg1d* h) {
+    if (!h) return AMG1D_ERR_ARG;
+    if (!h->finalized) return fail(h, AMG1D_ERR_STATE, "hierarchy not finalized (call amg1d_finalize)");
+    CK(cudaSetDevice(h->device));
+    return AMG1D_OK;
+}
+
+int alloc_level_common(amg1d* h, int level, int64_t n_elem, int m, int diag, const int64_t* perm,
+                       int64_t n_dof_host) {
+    if (!valid_level(h, level)) return fail(h, AMG1D_ERR_ARG, "level %d out of range", level);
+    if (h->finalized) return fail(h, AMG1D_ERR_STATE, "hierarchy already finalized");
+    if (n_elem < 1 || m < 1 || m > 32) return fail(h, AMG1D_ERR_ARG, "need n_elem >= 1 and 1 <= m <= 32");
+    Level& lv = h->L[level];
+    if (lv.set) return fail(h, AMG1D_ERR_STATE, "level %d already set", level);
+    CK(cudaSetDevice(h->device));
+    lv.n = n_elem; lv.m = m; lv.diag = diag ? 1 : 0; lv.K = amg1d_K(m, lv.diag);
+    lv.n_host = n_dof_host;
+    if (!perm && n_dof_host != n_elem * m)
+        return fail(h, AMG1D_ERR_ARG, "n_dof_host must equal n_elem*m when perm is NULL");
+    lv.mat_bytes = amg1d_tiles(n_elem) * (int64_t)lv.K * AMG1D_TILE * 8;
+    RET(dev_alloc(h, (void**)&lv.mat, lv.mat_bytes));
+    if (perm) {
+        const int64_t ns = n_elem * m;
+        for (int64_t s = 0; s < ns; ++s)
+            if (perm[s] < -1 || perm[s] >= n_dof_host)
+                return fail(h, AMG1D_ERR_ARG, "perm[%lld] out of range", (long long)s);
+        RET(dev_alloc(h, (void**)&lv.perm, ns * 8));
+        CK(cudaMemcpy(lv.perm, perm, (size_t)ns * 8, cudaMemcpyHostToDevice));
+    }
+    return AMG1D_OK;
+}
+
+}  // namespace
+
+// =====================================================================================================
+extern "C" {
+
+int amg1d_version(void) { return AMG1D_VERSION; }
+
+const char* amg1d_last_error(const amg1d_t* h) { return h ? h->err.c_str() : g_create_error.c_str(); }
+
+int amg1d_create(amg1d_t** out, int n_levels, int device, void* stream) {
+    amg1d* h = nullptr;
+    if (!out) return fail(h, AMG1D_ERR_ARG, "null handle pointer");
+    *out = nullptr;
+    if (n_levels < 1) return fail(h, AMG1D_ERR_ARG, "At least one level required.");
+    int ndev = 0;
+    CK(cudaGetDeviceCount(&ndev));
+    if (device < 0 || device >= ndev) return fail(h, AMG1D_ERR_ARG, "device %d not available (%d visible)", device, ndev);
+    CK(cudaSetDevice(device));
+    amg1d* nh = new (std::nothrow) amg1d();
+    if (!nh) return fail(h, AMG1D_ERR_NOMEM, "host allocation failed");
+    nh->device = device;
+    nh->n_levels = n_levels;
+    nh->L.resize(n_levels);
+    nh->T.resize(n_levels > 1 ? n_levels - 1 : 0);
+    if (stream) {
+        nh->stream = (cudaStream_t)stream;
+    } else {
+        cudaError_t e = cudaStreamCreateWithFlags(&nh->stream, cudaStreamNonBlocking);
+        if (e != cudaSuccess) { delete nh; return fail(h, AMG1D_ERR_CUDA, "cudaStreamCreate: %s", cudaGetErrorString(e)); }
+        nh->own_stream = true;
+    }
+    *out = nh;
+    return AMG1D_OK;
+}
+
+int amg1d_nccl_unique_id(void* id128) {
+    (void)id128;
+    return fail(nullptr, AMG1D_ERR_UNSUPPORTED, "multi-GPU support not built in this version");
+}
+
+int amg1d_create_dist(amg1d_t** out, int n_levels, int device, void* stream, int rank, int nranks,
+                      const void* nccl_id) {
+    (void)nccl_id;
+    if (nranks == 1 && rank == 0) return amg1d_create(out, n_levels, device, stream);
+    return fail(nullptr, AMG1D_ERR_UNSUPPORTED, "multi-GPU support not built in this version");
+}
+
+int amg1d_destroy(amg1d_t* h) {
+    if (!h) return AMG1D_OK;
+    cudaSetDevice(h->device);
+    cudaStreamSynchronize(h->stream);
+    if (h->gexec) cudaGraphExecDestroy(h->gexec);
+    for (auto& lv : h->L) {
+        if (lv.mat) cudaFree(lv.mat);
+        if (lv.perm) cudaFree(lv.perm);
+        vec_free(lv.x[0]); vec_free(lv.x[1]); vec_free(lv.b);
+    }
+    for (auto& t : h->T) {
+        if (t.parent) cudaFree(t.parent);
+        if (t.cp) cudaFree(t.cp);
+        if (t.P0) cudaFree(t.P0);
+        if (t.P1) cudaFree(t.P1);
+    }
+    vec_free(h->scratch);
+    if (h->stage) cudaFree(h->stage);
+    if (h->partial) cudaFree(h->partial);
+    if (h->d_scal) cudaFree(h->d_scal);
+    if (h->h_scal) cudaFreeHost(h->h_scal);
+    if (h->coarse_fac) cudaFree(h->coarse_fac);
+    if (h->own_stream) cudaStreamDestroy(h->stream);
+    delete h;
+    return AMG1D_OK;
+}
+
+int amg1d_set_level(amg1d_t* h, int level, int64_t n_elem, int m, const double* A_lo,
+                    const double* A_di, const double* A_up, const double* Dinv,
+                    int dinv_is_diagonal, const int64_t* perm, int64_t n_dof_host) {
+    if (!h) return AMG1D_ERR_ARG;
+    if (!A_lo || !A_di || !A_up || !Dinv) return fail(h, AMG1D_ERR_ARG, "null operator array");
+    RET(alloc_level_common(h, level, n_elem, m, dinv_is_diagonal, perm, n_dof_host));
+    Level& lv = h->L[level];
+    const int mm = m * m;
+    const int dsz = lv.diag ? m : mm;
+    for (int q = 0; q < mm; ++q)
+        if (A_lo[q] != 0.0 || A_up[(size_t)(n_elem - 1) * mm + q] != 0.0)
+            return fail(h, AMG1D_ERR_ARG, "A_lo[0] and A_up[n-1] must be zero blocks");
+    const int64_t chunk = 1 << 18;  // elements per staging chunk (multiple of 32)
+    const int64_t c = std::min(chunk, (n_elem + 31) / 32 * 32);
+    double *d_lo, *d_di, *d_up, *d_dv;
+    CK(cudaMalloc(&d_lo, (size_t)c * mm * 8));
+    CK(cudaMalloc(&d_di, (size_t)c * mm * 8));
+    CK(cudaMalloc(&d_up, (size_t)c * mm * 8));
+    CK(cudaMalloc(&d_dv, (size_t)c * dsz * 8));
+    int rc = AMG1D_OK;
+    for (int64_t e0 = 0; e0 < n_elem && rc == AMG1D_OK; e0 += c) {
+        const int64_t cnt = std::min(c, n_elem - e0);
+        cudaMemcpyAsync(d_lo, A_lo + e0 * mm, (size_t)cnt * mm * 8, cudaMemcpyHostToDevice, h->stream);
+        cudaMemcpyAsync(d_di, A_di + e0 * mm, (size_t)cnt * mm * 8, cudaMemcpyHostToDevice, h->stream);
+        cudaMemcpyAsync(d_up, A_up + e0 * mm, (size_t)cnt * mm * 8, cudaMemcpyHostToDevice, h->stream);
+        cudaMemcpyAsync(d_dv, Dinv + e0 * dsz, (size_t)cnt * dsz * 8, cudaMemcpyHostToDevice, h->stream);
+        const int64_t total = amg1d_tiles(cnt) * (int64_t)lv.K * AMG1D_TILE;
+        k_repack<<<(unsigned)((total + 255) / 256), 256, 0, h->stream>>>(d_lo, d_di, d_up, d_dv, m,
+                                                                         lv.diag, lv.K, e0, cnt, lv.mat);
+        cudaError_t e = cudaStreamSynchronize(h->stream);
+        if (e == cudaSuccess) e = cudaGetLastError();
+        if (e != cudaSuccess) rc = fail(h, AMG1D_ERR_CUDA, "level upload failed: %s", cudaGetErrorString(e));
+    }
+    cudaFree(d_lo); cudaFree(d_di); cudaFree(d_up); cudaFree(d_dv);
+    RET(rc);
+    if (n_elem <= 65536) {
+        lv.h_lo.assign(A_lo, A_lo + (size_t)n_elem * mm);
+        lv.h_di.assign(A_di, A_di + (size_t)n_elem * mm);
+        lv.h_up.assign(A_up, A_up + (size_t)n_elem * mm);
+    }
+    lv.set = true;
+    return AMG1D_OK;
+}
+
+int amg1d_set_level_pattern(amg1d_t* h, int level, int64_t n_elem, int m, int n_head, int n_tail,
+                            const double* A_lo, const double* A_di, const double* A_up,
+                            const double* Dinv, int dinv_is_diagonal) {
+    if (!h) return AMG1D_ERR_ARG;
+    if (!A_lo || !A_di || !A_up || !Dinv) return fail(h, AMG1D_ERR_ARG, "null operator array");
+    if (n_head < 0 || n_tail < 0 || (int64_t)n_head + n_tail > n_elem)
+        return fail(h, AMG1D_ERR_ARG, "need n_head + n_tail <= n_elem");
+    RET(alloc_level_common(h, level, n_elem, m, dinv_is_diagonal, nullptr, n_elem * m));
+    Level& lv = h->L[level];
+    const int mm = m * m;
+    const int dsz = lv.diag ? m : mm;
+    const int nb = n_head + 1 + n_tail;
+    double *d_lo, *d_di, *d_up, *d_dv;
+    CK(cudaMalloc(&d_lo, (size_t)nb * mm * 8));
+    CK(cudaMalloc(&d_di, (size_t)nb * mm * 8));
+    CK(cudaMalloc(&d_up, (size_t)nb * mm * 8));
+    CK(cudaMalloc(&d_dv, (size_t)nb * dsz * 8));
+    cudaMemcpyAsync(d_lo, A_lo, (size_t)nb * mm * 8, cudaMemcpyHostToDevice, h->stream);
+    cudaMemcpyAsync(d_di, A_di, (size_t)nb * mm * 8, cudaMemcpyHostToDevice, h->stream);
+    cudaMemcpyAsync(d_up, A_up, (size_t)nb * mm * 8, cudaMemcpyHostToDevice, h->stream);
+    cudaMemcpyAsync(d_dv, Dinv, (size_t)nb * dsz * 8, cudaMemcpyHostToDevice, h->stream);
+    const int64_t total = amg1d_tiles(n_elem) * (int64_t)lv.K * AMG1D_TILE;
+    k_fill_pattern<<<(unsigned)((total + 255) / 256), 256, 0, h->stream>>>(
+        d_lo, d_di, d_up, d_dv, m, lv.diag, lv.K, n_elem, n_head, n_tail, lv.mat);
+    cudaError_t e = cudaStreamSynchronize(h->stream);
+    if (e == cudaSuccess) e = cudaGetLastError();
+    cudaFree(d_lo); cudaFree(d_di); cudaFree(d_up); cudaFree(d_dv);
+    if (e != cudaSuccess) return fail(h, AMG1D_ERR_CUDA, "pattern fill failed: %s", cudaGetErrorString(e));
+    if (n_elem <= 65536) {
+        lv.h_lo.resize((size_t)n_elem * mm); lv.h_di.resize((size_t)n_elem * mm); lv.h_up.resize((size_t)n_elem * mm);
+        for (int64_t el = 0; el < n_elem; ++el) {
+            int64_t s = el < n_head ? el : (el >= n_elem - n_tail ? n_head + 1 + (el - (n_elem - n_tail)) : n_head);
+            std::copy(A_lo + s * mm, A_lo + (s + 1) * mm, &lv.h_lo[(size_t)el * mm]);
+            std::copy(A_di + s * mm, A_di + (s + 1) * mm, &lv.h_di[(size_t)el * mm]);
+            std::copy(A_up + s * mm, A_up + (s + 1) * mm, &lv.h_up[(size_t)el * mm]);
+        }
+    }
+    lv.set = true;
+    return AMG1D_OK;
+}
+
+static int transfer_common(amg1d_t* h, int level, int64_t n_fine, int mf, int mc) {
+    if (!h) return AMG1D_ERR_ARG;
+    if (level < 0 || level >= h->n_levels - 1) return fail(h, AMG1D_ERR_ARG, "transfer %d out of range", level);
+    if (h->finalized) return fail(h, AMG1D_ERR_STATE, "hierarchy already finalized");
+    if (h->T[level].set) return fail(h, AMG1D_ERR_STATE, "transfer %d already set", level);
+    if (n_fine < 1 || mf < 1 || mc < 1 || mf > 32 || mc > 32) return fail(h, AMG1D_ERR_ARG, "bad transfer shape");
+    CK(cudaSetDevice(h->device));
+    return AMG1D_OK;
+}
+
+int amg1d_set_transfer(amg1d_t* h, int level, int64_t n_fine_elem, int m_f, int m_c,
+                       const int64_t* parent, const double* P0, const double* P1) {
+    RET(transfer_common(h, level, n_fine_elem, m_f, m_c));
+    if (!parent || !P0) return fail(h, AMG1D_ERR_ARG, "null transfer array");
+    Transfer& t = h->T[level];
+    t.n_fine = n_fine_elem; t.mf = m_f; t.mc = m_c; t.period = 0;
+    int64_t maxp = -1;
+    for (int64_t e = 0; e < n_fine_elem; ++e) {
+        if (parent[e] < -1 || (e > 0 && parent[e] < parent[e - 1]))
+            return fail(h, AMG1D_ERR_ARG, "parent map must be non-decreasing and >= -1 (element %lld)", (long long)e);
+        maxp = std::max(maxp, parent[e]);
+    }
+    t.n_coarse = maxp + 1;  // validated against the coarse level at finalize (P1 may reach maxp + 1)
+    // uniform single-parent detection: parent[e] = e / ratio
+    bool uniform = (P1 == nullptr) && parent[0] == 0;
+    int ratio = 1;
+    if (uniform) {
+        int64_t r = 1;
+        while (r < n_fine_elem && parent[r] == 0) ++r;
+        ratio = (int)r;
+        for (int64_t e = 0; e < n_fine_elem && uniform; ++e) uniform = parent[e] == e / ratio;
+    }
+    t.single_parent_uniform = uniform;
+    t.ratio = uniform ? ratio : 1; t.shift = 0; t.base = 0;
+    const int bs = m_f * m_c;
+    RET(dev_alloc(h, (void**)&t.P0, n_fine_elem * bs * 8));
+    CK(cudaMemcpy(t.P0, P0, (size_t)n_fine_elem * bs * 8, cudaMemcpyHostToDevice));
+    if (P1) {
+        RET(dev_alloc(h, (void**)&t.P1, n_fine_elem * bs * 8));
+        CK(cudaMemcpy(t.P1, P1, (size_t)n_fine_elem * bs * 8, cudaMemcpyHostToDevice));
+    }
+    t.nblk = n_fine_elem;
+    RET(dev_alloc(h, (void**)&t.parent, n_fine_elem * 8));
+    CK(cudaMemcpy(t.parent, parent, (size_t)n_fine_elem * 8, cudaMemcpyHostToDevice));
+    t.set = true;
+    // child pointers are built at finalize once the coarse element count is known
+    t.h_parent.assign(parent, parent + n_fine_elem);
+    return AMG1D_OK;
+}
+
+int amg1d_set_transfer_pattern(amg1d_t* h, int level, int64_t n_fine_elem, int m_f, int m_c,
+                               int ratio, int shift, int base, int period, int n_head, int n_tail,
+                               const double* P0_pat, const double* P1_pat) {
+    RET(transfer_common(h, level, n_fine_elem, m_f, m_c));
+    if (!P0_pat) return fail(h, AMG1D_ERR_ARG, "null transfer array");
+    if (ratio < 1 || period < 1 || shift < 0 || n_head < 0 || n_tail < 0 ||
+        (int64_t)n_head + n_tail > n_fine_elem)
+        return fail(h, AMG1D_ERR_ARG, "bad transfer pattern");
+    Transfer& t = h->T[level];
+    t.n_fine = n_fine_elem; t.mf = m_f; t.mc = m_c;
+    t.ratio = ratio; t.shift = shift; t.base = base; t.period = period; t.n_head = n_head; t.n_tail = n_tail;
+    t.n_coarse = (n_fine_elem - 1 + shift) / ratio + base + 1;
+    t.single_parent_uniform = (P1_pat == nullptr) && shift == 0 && base == 0;
+    const int bs = m_f * m_c;
+    t.nblk = n_head + period + n_tail;
+    RET(dev_alloc(h, (void**)&t.P0, t.nblk * bs * 8));
+    CK(cudaMemcpy(t.P0, P0_pat, (size_t)t.nblk * bs * 8, cudaMemcpyHostToDevice));
+    if (P1_pat) {
+        RET(dev_alloc(h, (void**)&t.P1, t.nblk * bs * 8));
+        CK(cudaMemcpy(t.P1, P1_pat, (size_t)t.nblk * bs * 8, cudaMemcpyHostToDevice));
+    }
+    t.set = true;
+    return AMG1D_OK;
+}
+
+int amg1d_finalize(amg1d_t* h) {
+    if (!h) return AMG1D_ERR_ARG;
+    if (h->finalized) return fail(h, AMG1D_ERR_STATE, "hierarchy already finalized");
+    CK(cudaSetDevice(h->device));
+    for (int l = 0; l < h->n_levels; ++l)
+        if (!h->L[l].set) return fail(h, AMG1D_ERR_STATE, "level %d was never set", l);
+    int64_t maxlen = 0;
+    int maxm = 1;
+    for (int l = 0; l < h->n_levels - 1; ++l) {
+        Transfer& t = h->T[l];
+        if (!t.set) return fail(h, AMG1D_ERR_STATE, "transfer %d was never set", l);
+        Level& lf = h->L[l];
+        Level& lc = h->L[l + 1];
+        if (t.n_fine != lf.n || t.mf != lf.m || t.mc != lc.m)
+            return fail(h, AMG1D_ERR_ARG, "transfer %d does not match its levels (n_fine %lld vs %lld, m_f %d vs %d, m_c %d vs %d)",
+                        l, (long long)t.n_fine, (long long)lf.n, t.mf, lf.m, t.mc, lc.m);
+        const int64_t need = t.n_coarse + (t.P1 ? 1 : 0);
+        if (t.n_coarse > lc.n || need < lc.n)
+            return fail(h, AMG1D_ERR_ARG, "transfer %d reaches coarse element %lld but level %d has %lld elements",
+                        l, (long long)t.n_coarse - 1, l + 1, (long long)lc.n);
+        t.n_coarse = lc.n;
+        if (t.parent) {  // build child pointers: cp[q] = first e with parent[e] >= q - 1, q = 0..n_coarse+1
+            std::vector<int64_t> cp((size_t)lc.n + 2);
+            int64_t e = 0;
+            for (int64_t q = 0; q < lc.n + 2; ++q) {
+                while (e < t.n_fine && t.h_parent[e] < q - 1) ++e;
+                cp[q] = e;
+            }
+            t.h_parent.clear();
+            t.h_parent.shrink_to_fit();
+            RET(dev_alloc(h, (void**)&t.cp, (int64_t)cp.size() * 8));
+            CK(cudaMemcpy(t.cp, cp.data(), cp.size() * 8, cudaMemcpyHostToDevice));
+        }
+    }
+    for (int l = 0; l < h->n_levels; ++l) {
+        Level& lv = h->L[l];
+        RET(vec_alloc(h, lv.x[0], lv.n, lv.m));
+        RET(vec_alloc(h, lv.x[1], lv.n, lv.m));
+        RET(vec_alloc(h, lv.b, lv.n, lv.m));
+        maxlen = std::max(maxlen, lv.n * lv.m);
+        maxm = std::max(maxm, lv.m);
+    }
+    RET(vec_alloc(h, h->scratch, maxlen, 1));
+    RET(dev_alloc(h, (void**)&h->partial, (AMG1D_RED_BLOCKS + 8) * 8 * 4));
+    RET(dev_alloc(h, (void**)&h->d_scal, 64 * 8));
+    CK(cudaMallocHost(&h->h_scal, 64 * 8));
+    RET(factor_coarsest(h));
+    CK(cudaStreamSynchronize(h->stream));
+    h->finalized = true;
+    return AMG1D_OK;
+}
+
+// ---- hot path ----------------------------------------------------------------------------------------
+int amg1d_dev_set_problem(amg1d_t* h, const double* x0, const double* b) {
+    RET(check_ready(h));
+    Level& l0 = h->L[0];
+    if (b) RET(to_device(h, 0, b, l0.b.p));
+    if (l0.cur != 0) l0.cur = 0;
+    if (x0) RET(to_device(h, 0, x0, l0.x[0].p));
+    else CK(cudaMemsetAsync(l0.x[0].p, 0, (size_t)l0.x[0].len * 8, h->stream));
+    return AMG1D_OK;
+}
+
+int amg1d_dev_fill_rhs_random(amg1d_t* h, uint64_t seed) {
+    RET(check_ready(h));
+    Level& l0 = h->L[0];
+    if (l0.perm) return fail(h, AMG1D_ERR_UNSUPPORTED, "random rhs only for unpermuted (DG) fine levels");
+    k_fill_random<<<1184, 256, 0, h->stream>>>(l0.b.p, l0.b.len, seed);
+    LAUNCH_CHECK();
+    l0.cur = 0;
+    CK(cudaMemsetAsync(l0.x[0].p, 0, (size_t)l0.x[0].len * 8, h->stream));
+    return AMG1D_OK;
+}
+
+int amg1d_dev_vcycle(amg1d_t* h, int nPre, int nPost, double alpha) {
+    RET(check_ready(h));
+    return run_vcycle(h, nPre, nPost, alpha);
+}
+
+int amg1d_dev_residual_norm(amg1d_t* h, double* res) {
+    RET(check_ready(h));
+    RET(op_resnorm(h, 0, 0));
+    RET(read_scalars(h, 1));
+    if (res) *res = h->h_scal[0];
+    return AMG1D_OK;
+}
+
+int amg1d_dev_rhs_norm(amg1d_t* h, double* nb) {
+    RET(check_ready(h));
+    RET(op_norm(h, h->L[0].b.p, nullptr, h->L[0].b.len, 0));
+    RET(read_scalars(h, 1));
+    if (nb) *nb = h->h_scal[0];
+    return AMG1D_OK;
+}
+
+int amg1d_dev_get_solution(amg1d_t* h, double* x) {
+    RET(check_ready(h));
+    if (!x) return fail(h, AMG1D_ERR_ARG, "null x");
+    return to_host(h, 0, h->L[0].x[h->L[0].cur].p, x);
+}
+
+int amg1d_synchronize(amg1d_t* h) {
+    if (!h) return AMG1D_ERR_ARG;
+    CK(cudaStreamSynchronize(h->stream));
+    return AMG1D_OK;
+}
+
+void* amg1d_stream(amg1d_t* h) { return h ? (void*)h->stream : nullptr; }
+
+void* amg1d_dev_ptr(amg1d_t* h, int level, int which) {
+    if (!valid_level(h, level) || !h->finalized) return nullptr;
+    Level& lv = h->L[level];
+    switch (which) {
+        case AMG1D_VEC_X: return lv.x[lv.cur].p;
+        case AMG1D_VEC_B: return lv.b.p;
+        case AMG1D_VEC_R: return h->scratch.p;
+        default: return nullptr;
+    }
+}
+
+int amg1d_vcycle(amg1d_t* h, double* x, const double* b, int nPre, int nPost, double alpha) {
+    RET(check_ready(h));
+    if (!x || !b) return fail(h, AMG1D_ERR_ARG, "null vector");
+    RET(amg1d_dev_set_problem(h, x, b));
+    RET(run_vcycle(h, nPre, nPost, alpha));
+    return to_host(h, 0, h->L[0].x[h->L[0].cur].p, x);
+}
+
+int amg1d_solve(amg1d_t* h, double* x, const double* b, int maxiter, double tol, int nPre,
+                int nPost, double alpha, int* iters, double* res, double* err,
+                const double* u_exact) {
+    RET(check_ready(h));
+    if (!x || !b || !res || !iters) return fail(h, AMG1D_ERR_ARG, "null argument");
+    if (maxiter < 0) return fail(h, AMG1D_ERR_ARG, "maxiter must be >= 0");
+    Level& l0 = h->L[0];
+    RET(amg1d_dev_set_problem(h, x, b));
+    double* d_exact = nullptr;
+    if (err && u_exact) {
+        // u_exact lives in the scratch-free second buffer of a dedicated allocation
+        CK(cudaMalloc(&d_exact, (size_t)(l0.x[0].len + 8) * 8));
+        int rc = to_device(h, 0, u_exact, d_exact);
+        if (rc != AMG1D_OK) { cudaFree(d_exact); return rc; }
+    }
+    int rc = op_norm(h, l0.b.p, nullptr, l0.b.len, 2);
+    int it = 0;
+    for (int i = 0; i < maxiter && rc == AMG1D_OK; ++i) {
+        rc = run_vcycle(h, nPre, nPost, alpha);
+        if (rc != AMG1D_OK) break;
+        rc = op_resnorm(h, 0, 0);
+        if (rc != AMG1D_OK) break;
+        if (d_exact) {
+            rc = op_norm(h, l0.x[l0.cur].p, d_exact, l0.x[0].len, 1);
+            if (rc != AMG1D_OK) break;
+        }
+        rc = read_scalars(h, 3);
+        if (rc != AMG1D_OK) break;
+        res[i] = h->h_scal[0];
+        if (err) err[i] = d_exact ? h->h_scal[1] : NAN;
+        it = i + 1;
+        if (res[i] < tol * h->h_scal[2]) break;
+    }
+    if (d_exact) cudaFree(d_exact);
+    RET(rc);
+    *iters = it;
+    return to_host(h, 0, l0.x[l0.cur].p, x);
+}
+
+int amg1d_apply_smoother(amg1d_t* h, int level, double* Y, const double* B, int64_t n_rhs,
+                         double alpha) {
+    RET(check_ready(h));
+    if (!valid_level(h, level)) return fail(h, AMG1D_ERR_ARG, "level %d out of range", level);
+    if (!Y || !B || n_rhs < 1) return fail(h, AMG1D_ERR_ARG, "bad arguments");
+    Level& lv = h->L[level];
+    double* in = lv.x[1 - lv.cur].p;  // free ping-pong buffer as input staging
+    for (int64_t c = 0; c < n_rhs; ++c) {
+        RET(to_device(h, level, B + c * lv.n_host, in));
+        g_apply_smoother<<<ggrid(lv.n, lv.m), gblock(lv.m), 0, h->stream>>>(
+            lv.mat, lv.m, lv.diag, lv.K, in, h->scratch.p, lv.n, alpha);
+        LAUNCH_CHECK();
+        RET(to_host(h, level, h->scratch.p, Y + c * lv.n_host));
+    }
+    return AMG1D_OK;
+}
+
+int amg1d_smoother_solve(amg1d_t* h, int level, double* x, const double* b, int maxiter, double tol,
+                         double alpha, int* iters, double* res, double* err, const double* u_exact) {
+    RET(check_ready(h));
+    if (!valid_level(h, level)) return fail(h, AMG1D_ERR_ARG, "level %d out of range", level);
+    if (!x || !b || !res || !iters) return fail(h, AMG1D_ERR_ARG, "null argument");
+    Level& lv = h->L[level];
+    invalidate_graph(h);
+    lv.cur = 0;
+    RET(to_device(h, level, b, lv.b.p));
+    RET(to_device(h, level, x, lv.x[0].p));
+    double* d_exact = nullptr;
+    if (err && u_exact) {
+        CK(cudaMalloc(&d_exact, (size_t)(lv.x[0].len + 8) * 8));
+        int rc = to_device(h, level, u_exact, d_exact);
+        if (rc != AMG1D_OK) { cudaFree(d_exact); return rc; }
+    }
+    int rc = op_norm(h, lv.b.p, nullptr, lv.b.len, 2);
+    int it = 0;
+    for (int i = 0; i < maxiter && rc == AMG1D_OK; ++i) {
+        rc = op_sweep(h, level, lv.b.p, lv.x[lv.cur].p, lv.x[1 - lv.cur].p, alpha, 0);
+        if (rc != AMG1D_OK) break;
+        lv.cur = 1 - lv.cur;
+        rc = op_resnorm(h, level, 0);
+        if (rc != AMG1D_OK) break;
+        if (d_exact) {
+            rc = op_norm(h, lv.x[lv.cur].p, d_exact, lv.x[0].len, 1);
+            if (rc != AMG1D_OK) break;
+        }
+        rc = read_scalars(h, 3);
+        if (rc != AMG1D_OK) break;
+        res[i] = h->h_scal[0];
+        if (err) err[i] = d_exact ? h->h_scal[1] : NAN;
+        it = i + 1;
+        if (res[i] < tol * h->h_scal[2]) break;
+    }
+    if (d_exact) cudaFree(d_exact);
+    RET(rc);
+    *iters = it;
+    rc = to_host(h, level, lv.x[lv.cur].p, x);
+    if (lv.cur != 0) {
+        CK(cudaMemcpyAsync(lv.x[0].p, lv.x[1].p, (size_t)lv.x[0].len * 8, cudaMemcpyDeviceToDevice, h->stream));
+        lv.cur = 0;
+    }
+    return rc;
+}
+
+static int apply_common(amg1d_t* h, int level, double* out, const double* x, const double* b, int mode) {
+    RET(check_ready(h));
+    if (!valid_level(h, level)) return fail(h, AMG1D_ERR_ARG, "level %d out of range", level);
+    if (!out || !x || (mode && !b)) return fail(h, AMG1D_ERR_ARG, "null vector");
+    Level& lv = h->L[level];
+    invalidate_graph(h);
+    double* xin = lv.x[1 - lv.cur].p;
+    RET(to_device(h, level, x, xin));
+    double* bin = lv.b.p;  // clobbers the level rhs; the next vcycle / solve re-uploads it
+    if (mode) RET(to_device(h, level, b, bin));
+    RET(op_apply(h, level, bin, xin, h->scratch.p, mode));
+    return to_host(h, level, h->scratch.p, out);
+}
+
+int amg1d_matvec(amg1d_t* h, int level, double* y, const double* x) {
+    return apply_common(h, level, y, x, nullptr, 0);
+}
+
+int amg1d_residual(amg1d_t* h, int level, double* r, const double* x, const double* b) {
+    return apply_common(h, level, r, x, b, 1);
+}
+
+int amg1d_restrict(amg1d_t* h, int level, double* rc, const double* rf) {
+    RET(check_ready(h));
+    if (level < 0 || level >= h->n_levels - 1) return fail(h, AMG1D_ERR_ARG, "transfer %d out of range", level);
+    if (!rc || !rf) return fail(h, AMG1D_ERR_ARG, "null vector");
+    invalidate_graph(h);
+    Level& lf = h->L[level];
+    Level& lc = h->L[level + 1];
+    double* fin = lf.x[1 - lf.cur].p;
+    RET(to_device(h, level, rf, fin));
+    RET(op_restrict(h, level, fin, lc.b.p));
+    return to_host(h, level + 1, lc.b.p, rc);
+}
+
+int amg1d_prolong(amg1d_t* h, int level, double* xf, const double* xc) {
+    RET(check_ready(h));
+    if (level < 0 || level >= h->n_levels - 1) return fail(h, AMG1D_ERR_ARG, "transfer %d out of range", level);
+    if (!xf || !xc) return fail(h, AMG1D_ERR_ARG, "null vector");
+    invalidate_graph(h);
+    Level& lf = h->L[level];
+    Level& lc = h->L[level + 1];
+    double* cin = lc.x[1 - lc.cur].p;
+    RET(to_device(h, level + 1, xc, cin));
+    RET(op_prolong(h, level, cin, h->scratch.p, 0));
+    return to_host(h, level, h->scratch.p, xf);
+}
+
+int amg1d_coarse_solve(amg1d_t* h, double* x, const double* b) {
+    RET(check_ready(h));
+    if (!x || !b) return fail(h, AMG1D_ERR_ARG, "null vector");
+    invalidate_graph(h);
+    const int l = h->n_levels - 1;
+    Level& lv = h->L[l];
+    double* bin = lv.x[1 - lv.cur].p;
+    RET(to_device(h, l, b, bin));
+    RET(op_coarse(h, bin, h->scratch.p));
+    return to_host(h, l, h->scratch.p, x);
+}
+
+int amg1d_set_option(amg1d_t* h, const char* key, int64_t value) {
+    if (!h || !key) return AMG1D_ERR_ARG;
+    invalidate_graph(h);
+    if (!strcmp(key, "fused")) h->opt_fused = (int)value;
+    else if (!strcmp(key, "graph")) h->opt_graph = (int)value;
+    else if (!strcmp(key, "coarse_cta_elems")) h->opt_coarse_cta = value;
+    else return fail(h, AMG1D_ERR_ARG, "unknown option '%s'", key);
+    return AMG1D_OK;
+}
+
+int64_t amg1d_get_info(amg1d_t* h, const char* key) {
+    if (!h || !key) return -1;
+    if (!strcmp(key, "kernel_launches")) return h->launch_counter;
+    if (!strcmp(key, "launches_per_cycle")) return h->launches_per_cycle;
+    if (!strcmp(key, "device_bytes")) return h->device_bytes;
+    if (!strcmp(key, "n_levels")) return h->n_levels;
+    if (!strcmp(key, "dof_updates_per_sweep")) {
+        int64_t s = 0;
+        for (int l = 0; l < h->n_levels - 1; ++l) s += h->L[l].n_host;
+        return s;
+    }
+    return -1;
+}
+
+int amg1d_host_alloc(void** p, int64_t bytes) {
+    amg1d* h = nullptr;
+    if (!p || bytes < 0) return fail(h, AMG1D_ERR_ARG, "bad arguments");
+    CK(cudaMallocHost(p, (size_t)std::max<int64_t>(bytes, 8)));
+    return AMG1D_OK;
+}
+
+int amg1d_host_free(void* p) {
+    amg1d* h = nullptr;
+    if (p) CK(cudaFreeHost(p));
+    return AMG1D_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,160 @@
+"""MeshHierarchy: host mirror of src/mesh_heirarchy.jl (the reference's spelling), plus the upload.
+
+Both reference constructors are kept:
+  * ``MeshHierarchy(mMeshes, mesh, mBdConds, A, nCG=, nDG=, nAgg=, CDir=)``   (:30-138, CG first)
+  * ``MeshHierarchy(mMeshes, mBdConds, A, G, D, C, nDG=, nAgg=)``             (:140-181, DG first)
+The second one accepts ``nAgg`` in the reference but never builds the agglomerated levels; here it
+does, mirroring :89-106 (needed by the BASELINE configs; an extension, flagged in DESIGN.md).
+
+Set-up (Galerkin products L'XL, A = C - D (M \\ G), smoother extraction) runs on the host with scipy
+exactly as in the reference; at the end of construction every level is converted to element blocks
+and uploaded once (``H.device``).  The solver entry points in solvers.py then run on the GPU.
+"""
+import scipy.sparse as sp
+
+from . import blocks as blk
+from .agglomerated_dg_mesh import AgglomeratedDgMesh1, AgglomeratedDgMeshN, agg_dg_flux_operators
+from .cg_mesh import CgMesh
+from .device import DeviceHierarchy
+from .dg_mesh import DgMesh
+from .dg_mesh import dg_flux_operators as _dg_flux_operators
+from .interpolation import (aggdg_aggdg_interpolation, aggdg_cg_interpolation,
+                            aggdg_dg_interpolation, cg_cg_interpolation, dg_cg_interpolation,
+                            dg_dg_interpolation)
+from .smoother import cg_smoother, dg_smoother, smoother_inverse
+
+
+def dg_flux_operators(dgMesh, mesh_or_base, bdCond, CDir):
+    """Dispatch like the reference's two methods (src/dg_mesh.jl:144, agglomerated_dg_mesh.jl:641)."""
+    if isinstance(dgMesh, AgglomeratedDgMesh1):
+        return agg_dg_flux_operators(dgMesh, mesh_or_base, bdCond, CDir)
+    if isinstance(dgMesh, DgMesh):
+        return _dg_flux_operators(dgMesh, mesh_or_base, bdCond, CDir)
+    raise TypeError("dg_flux_operators needs a DgMesh or an AgglomeratedDgMesh1")
+
+
+def _galerkin(L, X):
+    return (L.T @ X @ L).tocsc()
+
+
+def _dg_level(mesh, G, D, C):
+    A = (C - D @ mesh.mMassMatrixLU.solve(G)).tocsc()
+    return A, dg_smoother(mesh, A, "blockJac")
+
+
+class MeshHierarchy:
+    """Fields as in src/mesh_heirarchy.jl:17-28: mMeshes, mStiffness, mGradient, mDivergence, mC,
+    mSmoothers, mInterpolation, mBdConds; plus ``device`` (the uploaded hierarchy)."""
+
+    def __init__(self, mMeshes, *args, nCG=None, nDG=None, nAgg=0, CDir=1.0, device=0, upload=True,
+                 stream=None):
+        self.mMeshes = list(mMeshes)
+        if len(args) == 3:                      # (mesh, mBdConds, A): CG-first constructor
+            mesh, mBdConds, A = args
+            self._build_cg_first(mesh, mBdConds, A, 1 if nCG is None else nCG,
+                                 0 if nDG is None else nDG, nAgg, CDir)
+        elif len(args) == 5:                    # (mBdConds, A, G, D, C): DG-first constructor
+            mBdConds, A, G, D, C = args
+            self._build_dg_first(mBdConds, A, G, D, C, 1 if nDG is None else nDG, nAgg)
+        else:
+            raise TypeError("MeshHierarchy(mMeshes, mesh, mBdConds, A; ...) or "
+                            "MeshHierarchy(mMeshes, mBdConds, A, G, D, C; ...)")
+        self.device = None
+        if upload:
+            self.upload(device=device, stream=stream)
+
+    # ---- src/mesh_heirarchy.jl:30-138 -----------------------------------------------------------
+    def _build_cg_first(self, mesh, mBdConds, A, nCG, nDG, nAgg, CDir):
+        M = self.mMeshes
+        if nCG <= 0:
+            raise ValueError("At least one CG mesh required.")
+        if len(M) != nCG + nDG + nAgg:
+            raise ValueError("Length of vector of meshes does not match inputed number of CG, DG, "
+                             "and agglomerated meshes.")
+        nL = nCG + nDG + nAgg
+        S, Sm, I = [None] * nL, [None] * nL, [None] * (nL - 1)
+        Gs, Ds, Cs = ([None] * (nDG + nAgg) for _ in range(3))
+        S[0] = sp.csc_matrix(A)
+        Sm[0] = cg_smoother(M[0], S[0], "jac")
+        for i in range(1, nCG):
+            I[i - 1] = cg_cg_interpolation(M[i], M[i - 1])
+            S[i] = _galerkin(I[i - 1], S[i - 1])
+            Sm[i] = cg_smoother(M[i], S[i], "jac")
+
+        def project(g, L):
+            Gs[g], Ds[g], Cs[g] = (_galerkin(L, Gs[g - 1]), _galerkin(L, Ds[g - 1]),
+                                   _galerkin(L, Cs[g - 1]))
+
+        if nDG >= 1:
+            I[nCG - 1] = dg_cg_interpolation(M[nCG], M[nCG - 1], mesh, 1)
+            Gs[0], Ds[0], Cs[0] = dg_flux_operators(M[nCG], mesh, mBdConds[nCG], CDir)
+            S[nCG], Sm[nCG] = _dg_level(M[nCG], Gs[0], Ds[0], Cs[0])
+            for i in range(1, nDG):
+                I[nCG + i - 1] = dg_dg_interpolation(M[nCG + i], M[nCG + i - 1])
+                project(i, I[nCG + i - 1])
+                S[nCG + i], Sm[nCG + i] = _dg_level(M[nCG + i], Gs[i], Ds[i], Cs[i])
+            for i in range(nAgg):
+                k = nCG + nDG + i
+                if i == 0:
+                    I[k - 1] = aggdg_dg_interpolation(M[k], M[k - 1])
+                else:
+                    I[k - 1] = aggdg_aggdg_interpolation(M[k], M[k - 1], M[nCG + nDG - 1])
+                project(nDG + i, I[k - 1])
+                S[k], Sm[k] = _dg_level(M[k], Gs[nDG + i], Ds[nDG + i], Cs[nDG + i])
+        elif nAgg >= 1:
+            I[nCG - 1] = aggdg_cg_interpolation(M[nCG], M[nCG - 1], mesh, 1)
+            Gs[0], Ds[0], Cs[0] = dg_flux_operators(M[nCG], M[nCG - 1], mBdConds[nCG], CDir)
+            S[nCG], Sm[nCG] = _dg_level(M[nCG], Gs[0], Ds[0], Cs[0])
+            for i in range(1, nAgg):
+                I[nCG + i - 1] = aggdg_aggdg_interpolation(M[nCG + i], M[nCG + i - 1], M[nCG - 1])
+                project(i, I[nCG + i - 1])
+                S[nCG + i], Sm[nCG + i] = _dg_level(M[nCG + i], Gs[i], Ds[i], Cs[i])
+        self._set(S, Gs, Ds, Cs, Sm, I, mBdConds)
+
+    # ---- src/mesh_heirarchy.jl:140-181 (+ agglomerated tail) -------------------------------------
+    def _build_dg_first(self, mBdConds, A, G, D, C, nDG, nAgg):
+        M = self.mMeshes
+        if nDG <= 0:
+            raise ValueError("At least one DG mesh required.")
+        if len(M) != nDG + nAgg:
+            raise ValueError("Length of vector of meshes does not match inputed number of DG and "
+                             "agglomerated meshes.")
+        nL = nDG + nAgg
+        S, Sm, I = [None] * nL, [None] * nL, [None] * (nL - 1)
+        Gs, Ds, Cs = ([None] * nL for _ in range(3))
+        Gs[0], Ds[0], Cs[0] = sp.csc_matrix(G), sp.csc_matrix(D), sp.csc_matrix(C)
+        S[0] = sp.csc_matrix(A)
+        Sm[0] = dg_smoother(M[0], S[0], "blockJac")
+        for k in range(1, nL):
+            if k < nDG:
+                I[k - 1] = dg_dg_interpolation(M[k], M[k - 1])
+            elif k == nDG:
+                I[k - 1] = aggdg_dg_interpolation(M[k], M[k - 1])
+            else:
+                I[k - 1] = aggdg_aggdg_interpolation(M[k], M[k - 1], M[nDG - 1])
+            L = I[k - 1]
+            Gs[k], Ds[k], Cs[k] = _galerkin(L, Gs[k - 1]), _galerkin(L, Ds[k - 1]), _galerkin(L, Cs[k - 1])
+            S[k], Sm[k] = _dg_level(M[k], Gs[k], Ds[k], Cs[k])
+        self._set(S, Gs, Ds, Cs, Sm, I, mBdConds)
+
+    def _set(self, S, Gs, Ds, Cs, Sm, I, mBdConds):
+        self.mStiffness, self.mGradient, self.mDivergence, self.mC = S, Gs, Ds, Cs
+        self.mSmoothers, self.mInterpolation, self.mBdConds = Sm, I, list(mBdConds)
+
+    # ---- upload (stands in for the end of construction) ------------------------------------------
+    def upload(self, device=0, stream=None):
+        nL = len(self.mMeshes)
+        dev = DeviceHierarchy(nL, device=device, stream=stream)
+        slots = [blk.level_slots(m) for m in self.mMeshes]
+        for l in range(nL):
+            lo, di, up = blk.csc_to_blocks(self.mStiffness[l], slots[l])
+            dinv, is_diag = smoother_inverse(self.mSmoothers[l], slots[l])
+            dev.set_level_blocks(l, lo, di, up, dinv, is_diag, slots[l], self.mStiffness[l].shape[0])
+            self.mSmoothers[l]._owner = (dev, l)
+        for l in range(nL - 1):
+            parent, P0, P1 = blk.transfer_to_blocks(self.mInterpolation[l], slots[l], slots[l + 1])
+            dev.set_transfer_blocks(l, parent, P0, P1)
+        dev.finalize()
+        self.device = dev
+        self.mSlots = slots
+        return dev

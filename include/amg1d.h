@@ -1,0 +1,167 @@
+/* amg1d.h - C ABI of libamg1d.so: the B200 (sm_100a) multigrid V-cycle of AgglomerationMultigrid1D.
+ *
+ * The reference (mheinz757/AgglomerationMultigrid1D, pure Julia) has no FFI; its boundary is Julia
+ * dispatch on MeshHierarchy / BlockJacobi / JacobiSmoother.  Each entry point below names the
+ * reference call it stands in for (file:line relative to the reference tree).  A host module (Julia
+ * `ccall`, Python `ctypes`, C) assembles the operators at set-up - as the reference does - and uploads
+ * them once per level; everything in src/solvers.jl then runs on the GPU.
+ *
+ * Conventions
+ *   - every function returns an int status (AMG1D_OK = 0); text via amg1d_last_error().  Nothing
+ *     throws or exits across this boundary.
+ *   - all pointers are HOST pointers unless the name says `dev`; the caller owns them; the library
+ *     copies what it needs before returning and never keeps a host pointer.
+ *   - all floating point is FP64, all indices int64_t and 0-based (reference value - 1).
+ *   - a "level" is a block-tridiagonal operator: n_elem element blocks of size m x m (m = p + 1).
+ *     Blocks are column-major inside (entry (i,j) at [j*m + i]) and element-major outside, i.e. the
+ *     block of element e starts at [e*m*m] (BSR-like).  Level 0 is the finest.
+ *   - one handle = one CUDA stream; calls on one handle are not re-entrant.
+ */
+#ifndef AMG1D_H
+#define AMG1D_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct amg1d amg1d_t;
+
+enum {
+    AMG1D_OK = 0,
+    AMG1D_ERR_ARG = 1,      /* invalid argument / wrong call order (reference: ArgumentError) */
+    AMG1D_ERR_CUDA = 2,     /* CUDA runtime error */
+    AMG1D_ERR_NCCL = 3,     /* NCCL error */
+    AMG1D_ERR_NOMEM = 4,    /* host or device allocation failed */
+    AMG1D_ERR_STATE = 5,    /* hierarchy incomplete / not finalized */
+    AMG1D_ERR_UNSUPPORTED = 6
+};
+
+/* Which device vector amg1d_dev_ptr() returns. */
+enum { AMG1D_VEC_X = 0, AMG1D_VEC_B = 1, AMG1D_VEC_R = 2 };
+
+/* ---- life cycle ------------------------------------------------------------------------------
+ * Stands in for the end of MeshHierarchy(...) construction (src/mesh_heirarchy.jl:136-137,
+ * :179-180): the host has built mStiffness / mSmoothers / mInterpolation and hands them over.
+ * `stream` is a cudaStream_t to run on (e.g. the caller's current stream) or NULL to let the
+ * library create its own. */
+int amg1d_create(amg1d_t** h, int n_levels, int device, void* stream);
+int amg1d_destroy(amg1d_t* h);
+const char* amg1d_last_error(const amg1d_t* h); /* h may be NULL: error of the last failed create */
+int amg1d_version(void);
+
+/* Multi-GPU variant: contiguous element slabs, one rank per GPU.  `nccl_id` is the
+ * 128-byte ncclUniqueId made by amg1d_nccl_unique_id() on rank 0 and broadcast by the host. */
+int amg1d_nccl_unique_id(void* id128);
+int amg1d_create_dist(amg1d_t** h, int n_levels, int device, void* stream, int rank, int nranks,
+                      const void* nccl_id);
+
+/* ---- per-level upload ------------------------------------------------------------------------
+ * mStiffness[l] as block-tridiagonal blocks plus mSmoothers[l] as explicit inverse blocks:
+ *   A_lo[e] couples element e to e-1 (A_lo[0] must be 0), A_di[e] is the diagonal block,
+ *   A_up[e] couples e to e+1 (A_up[n-1] must be 0); each array n_elem*m*m doubles.
+ *   Dinv: inverse of the smoother block - n_elem*m*m doubles (BlockJacobi, src/smoother.jl:64-81,
+ *   :154-164) or, with dinv_is_diagonal = 1, n_elem*m reciprocals of diag(A) (JacobiSmoother,
+ *   src/smoother.jl:52-58, :92-98).
+ *   perm: NULL when device slot s holds host DOF s (DG / agglomerated levels); otherwise n_elem*m
+ *   entries mapping device slot -> host DOF, -1 for a padding slot (CG levels, whose vertex-first
+ *   numbering, src/cg_mesh.jl:35-45, is regrouped into [vertex_k, interior_k] blocks).
+ *   n_dof_host: length of the reference's vectors on this level (size(mStiffness[l], 1)). */
+int amg1d_set_level(amg1d_t* h, int level, int64_t n_elem, int m, const double* A_lo,
+                    const double* A_di, const double* A_up, const double* Dinv,
+                    int dinv_is_diagonal, const int64_t* perm, int64_t n_dof_host);
+
+/* Same operator given as a translation-invariant pattern (uniform meshes at 2^20..2^26 elements,
+ * where per-element host arrays would be tens of GB): the first n_head and last n_tail elements are
+ * explicit, every element in between repeats the single `interior` block set.  Arrays hold
+ * n_head + 1 + n_tail blocks in that order.  The device still stores every element's blocks. */
+int amg1d_set_level_pattern(amg1d_t* h, int level, int64_t n_elem, int m, int n_head, int n_tail,
+                            const double* A_lo, const double* A_di, const double* A_up,
+                            const double* Dinv, int dinv_is_diagonal);
+
+/* mInterpolation[l] (prolongation from level l+1 to level l; restriction is its transpose,
+ * src/solvers.jl:36,42) as element-local blocks: fine element e has parent element parent[e]
+ * (non-decreasing) and
+ *     x_f[e] += P0[e] * x_c[parent[e]]  (+ P1[e] * x_c[parent[e]+1] when P1 != NULL)
+ * with m_f x m_c column-major blocks, n_fine_elem of them per array.  P1 carries the second parent of
+ * the CG-type transfers (cg_cg / dg_cg / aggdg_cg, src/interpolation.jl:33-52, :158-216, :340-406),
+ * NULL for dg_dg / aggdg_dg / aggdg_aggdg (:91-109, :226-292). */
+int amg1d_set_transfer(amg1d_t* h, int level, int64_t n_fine_elem, int m_f, int m_c,
+                       const int64_t* parent, const double* P0, const double* P1);
+
+/* parent[e] may be -1 and parent[e] + 1 may equal the coarse element count: both address ghost
+ * elements that hold zeros (the matching P block must be zero).
+ *
+ * Pattern form for uniform meshes: parent[e] = (e + shift) / ratio + base, and the block of element
+ * e is   P_pat[e]                                       for e <  n_head,
+ *        P_pat[n_head + (e - n_head) % period]          in between,
+ *        P_pat[n_head + period + e - (n - n_tail)]      for e >= n - n_tail
+ * (n_head + period + n_tail blocks per array; P1_pat NULL for single-parent transfers). */
+int amg1d_set_transfer_pattern(amg1d_t* h, int level, int64_t n_fine_elem, int m_f, int m_c,
+                               int ratio, int shift, int base, int period, int n_head, int n_tail,
+                               const double* P0_pat, const double* P1_pat);
+
+/* Allocates work vectors, factorises the coarsest level (block Thomas; replaces the sparse direct
+ * solve of src/solvers.jl:39) and validates that the hierarchy is complete. */
+int amg1d_finalize(amg1d_t* h);
+
+/* ---- the hot path ----------------------------------------------------------------------------
+ * multigrid_v_cycle(H, x0, b; nPre, nPost, alpha) - src/solvers.jl:19-50.  x: in x0, out x. */
+int amg1d_vcycle(amg1d_t* h, double* x, const double* b, int nPre, int nPost, double alpha);
+
+/* multigrid(H, x0, b, maxiter, tol) - src/solvers.jl:116-139.  res / err: maxiter doubles (err and
+ * u_exact may be NULL: the reference computes u_exact = A \ b itself, here the host supplies it).
+ * The reference always cycles with nPre = nPost = 3, alpha = 2/3; they are arguments here. */
+int amg1d_solve(amg1d_t* h, double* x, const double* b, int maxiter, double tol, int nPre,
+                int nPost, double alpha, int* iters, double* res, double* err,
+                const double* u_exact);
+
+/* apply_smoother(S, B; alpha) - src/smoother.jl:52-58, :69-81.  Y = alpha * S^-1 * B, B and Y are
+ * n_dof_host x n_rhs column-major (the scripts also pass matrices, tests/dg_smoother_test.jl:105). */
+int amg1d_apply_smoother(amg1d_t* h, int level, double* Y, const double* B, int64_t n_rhs,
+                         double alpha);
+
+/* iterative_smoother_solve(A, smoother, x0, b; maxiter, tol, alpha) - src/solvers.jl:189-213. */
+int amg1d_smoother_solve(amg1d_t* h, int level, double* x, const double* b, int maxiter, double tol,
+                         double alpha, int* iters, double* res, double* err, const double* u_exact);
+
+/* The stdlib operations the scripts use directly on hierarchy members:
+ *   amg1d_matvec        y  = mStiffness[l] * x
+ *   amg1d_residual      r  = b - mStiffness[l] * x          (src/solvers.jl:33)
+ *   amg1d_restrict      rc = mInterpolation[l]' * rf        (src/solvers.jl:36)
+ *   amg1d_prolong       xf = mInterpolation[l] * xc         (src/solvers.jl:42, without the add)
+ *   amg1d_coarse_solve  x  = mStiffness[end] \ b            (src/solvers.jl:39) */
+int amg1d_matvec(amg1d_t* h, int level, double* y, const double* x);
+int amg1d_residual(amg1d_t* h, int level, double* r, const double* x, const double* b);
+int amg1d_restrict(amg1d_t* h, int level, double* rc, const double* rf);
+int amg1d_prolong(amg1d_t* h, int level, double* xf, const double* xc);
+int amg1d_coarse_solve(amg1d_t* h, double* x, const double* b);
+
+/* ---- device-resident path (no host copies; what bench.py times as `value`) -------------------- */
+int amg1d_dev_set_problem(amg1d_t* h, const double* x0, const double* b); /* host -> device, x0 NULL = 0 */
+int amg1d_dev_fill_rhs_random(amg1d_t* h, uint64_t seed);          /* b[i] ~ U(-1,1) on the device, x = 0 */
+int amg1d_dev_vcycle(amg1d_t* h, int nPre, int nPost, double alpha); /* asynchronous on the stream */
+int amg1d_dev_residual_norm(amg1d_t* h, double* res);              /* ||A x - b||_2, synchronises */
+int amg1d_dev_rhs_norm(amg1d_t* h, double* nb);                    /* ||b||_2, synchronises */
+int amg1d_dev_get_solution(amg1d_t* h, double* x);                 /* device -> host */
+int amg1d_synchronize(amg1d_t* h);
+void* amg1d_stream(amg1d_t* h);                                    /* the cudaStream_t in use */
+void* amg1d_dev_ptr(amg1d_t* h, int level, int which);             /* raw device pointer (AMG1D_VEC_*) */
+
+/* ---- options and introspection ------------------------------------------------------------------
+ * amg1d_set_option keys: "fused" (1 = fused multi-sweep kernels where available, default 1),
+ * "graph" (1 = replay the V-cycle as a CUDA graph, default 1), "coarse_cta_elems" (levels with at
+ * most this many elements run inside the single-CTA coarse kernel, default 1024). */
+int amg1d_set_option(amg1d_t* h, const char* key, int64_t value);
+int64_t amg1d_get_info(amg1d_t* h, const char* key); /* "kernel_launches", "dof_updates_per_cycle",
+                                                        "bytes_per_cycle", "device_bytes", "n_levels" */
+
+/* Pinned host memory helpers for callers that want asynchronous, full-bandwidth copies. */
+int amg1d_host_alloc(void** p, int64_t bytes);
+int amg1d_host_free(void* p);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* AMG1D_H */

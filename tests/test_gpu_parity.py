@@ -1,0 +1,186 @@
+"""GPU parity tests proper: the CUDA path (through the C ABI) against the CPU oracle.
+
+The oracle builds its hierarchy with its own literal restatement of the reference; the GPU side is
+fed by the product's host package.  Both are built from the same parameters.
+
+Tolerances (north_star): per-cycle residual norms within 1e-10 relative, identical V-cycle counts,
+bit-exact index maps (the latter is a CPU test, tests/test_assembly_parity.py).  Residual norms that
+have reached the FP64 rounding floor of the problem (eps * ||A|| * ||x||) are compared against that
+floor instead - a relative 1e-10 on pure rounding noise is not meaningful in any implementation.
+"""
+import numpy as np
+import pytest
+import scipy.sparse as sp
+
+from oracle import solvers as osolv
+from oracle import smoother as osm
+
+import agglomerationmultigrid1d_b200 as aggmg
+from shapes import SHAPES, build_oracle, build_package
+
+pytestmark = pytest.mark.gpu
+
+REL = 1e-10
+
+
+def rounding_floor(H, x):
+    A = sp.csr_matrix(H.mStiffness[0])
+    return 64 * np.finfo(float).eps * abs(A).sum(axis=1).max() * np.abs(x).max() * np.sqrt(A.shape[0])
+
+
+@pytest.fixture(scope="module", params=sorted(SHAPES))
+def case(request):
+    kw = SHAPES[request.param]
+    Ho, x0, bo, _ = build_oracle(**kw)
+    Hp, _, bp = build_package(**kw)
+    yield request.param, Ho, bo, Hp, bp
+    Hp.device.close()
+
+
+def test_level_operations(case):
+    """A*u, rhs - A*u, L'*r, L*u, apply_smoother, A_n \\ rhs on every level (src/solvers.jl:33-44)."""
+    name, Ho, bo, Hp, bp = case
+    dev = Hp.device
+    rng = np.random.default_rng(0)
+    nL = len(Ho.mMeshes)
+    for l in range(nL):
+        A = Ho.mStiffness[l]
+        N = A.shape[0]
+        x = rng.standard_normal(N)
+        b = rng.standard_normal(N)
+        scale = abs(A).sum(axis=1).max() * np.abs(x).max()
+        assert np.abs(dev.matvec(l, x) - A @ x).max() <= 1e-13 * scale
+        assert np.abs(dev.residual(l, x, b) - (b - A @ x)).max() <= 1e-13 * scale
+        y_or = osm.apply_smoother(Ho.mSmoothers[l], b, alpha=2.0 / 3.0)
+        y = dev.apply_smoother(l, b, alpha=2.0 / 3.0)
+        assert np.abs(y - y_or).max() <= 1e-11 * np.abs(y_or).max()
+        if l < nL - 1:
+            L = sp.csc_matrix(Ho.mInterpolation[l])
+            xc = rng.standard_normal(L.shape[1])
+            assert np.abs(dev.restrict(l, x) - L.T @ x).max() <= 1e-13 * abs(L).sum(axis=0).max() * np.abs(x).max()
+            assert np.abs(dev.prolong(l, xc) - L @ xc).max() <= 1e-13 * abs(L).sum(axis=1).max() * np.abs(xc).max()
+    A = Ho.mStiffness[-1]
+    b = rng.standard_normal(A.shape[0])
+    x_or = osolv._direct_solve(A, b)
+    assert np.abs(dev.coarse_solve(b) - x_or).max() <= 1e-10 * np.abs(x_or).max()
+
+
+def test_apply_smoother_matrix_rhs(case):
+    """apply_smoother(S, A) with a (sparse) matrix right-hand side, tests/dg_smoother_test.jl:105."""
+    name, Ho, bo, Hp, bp = case
+    l = len(Ho.mMeshes) - 1
+    A = Ho.mStiffness[l]
+    Y_or = osm.apply_smoother(Ho.mSmoothers[l], A, alpha=0.5)
+    Y = aggmg.apply_smoother(Hp.mSmoothers[l], Hp.mStiffness[l], alpha=0.5)
+    assert Y.shape == Y_or.shape
+    assert np.abs(Y - Y_or).max() <= 1e-11 * np.abs(Y_or).max()
+
+
+def test_single_vcycle(case):
+    name, Ho, bo, Hp, bp = case
+    x_or = osolv.multigrid_v_cycle(Ho, np.zeros(len(bo)), bo)
+    x = aggmg.multigrid_v_cycle(Hp, np.zeros(len(bp)), bp)
+    assert np.abs(x - x_or).max() <= 1e-11 * np.abs(x_or).max()
+    # non-default smoothing parameters and a non-zero initial guess
+    rng = np.random.default_rng(1)
+    x0 = rng.standard_normal(len(bo)) * np.abs(x_or).max()
+    for nPre, nPost, alpha in ((1, 2, 0.5), (0, 3, 2.0 / 3.0), (2, 0, 0.8), (0, 0, 1.0)):
+        x_or = osolv.multigrid_v_cycle(Ho, x0, bo, nPre=nPre, nPost=nPost, alpha=alpha)
+        x = aggmg.multigrid_v_cycle(Hp, x0, bp, nPre=nPre, nPost=nPost, alpha=alpha)
+        assert np.abs(x - x_or).max() <= 1e-10 * np.abs(x_or).max(), (nPre, nPost, alpha)
+
+
+def test_ldiv(case):
+    name, Ho, bo, Hp, bp = case
+    y = np.zeros(len(bp))
+    aggmg.ldiv(y, Hp, bp)
+    y_or = osolv.ldiv(Ho, bo)
+    assert np.abs(y - y_or).max() <= 1e-11 * np.abs(y_or).max()
+    b2 = bp.copy()
+    aggmg.ldiv(Hp, b2)
+    assert np.array_equal(b2, y)
+
+
+def test_multigrid_histories(case):
+    """multigrid(H, x0, b, maxiter, tol): identical cycle counts, residual histories within 1e-10
+    relative (src/solvers.jl:116-139; scripts: maxiter 100, tol 1e-10)."""
+    name, Ho, bo, Hp, bp = case
+    x_or, it_or, res_or, err_or = osolv.multigrid(Ho, np.zeros(len(bo)), bo, 100, 1e-10)
+    x, it, res, err = aggmg.multigrid(Hp, np.zeros(len(bp)), bp, 100, 1e-10)
+    assert it == it_or, (name, it, it_or)
+    floor = rounding_floor(Ho, x_or)
+    tol = np.maximum(REL * res_or, floor)
+    assert np.all(np.abs(res - res_or) <= tol), (name, res, res_or, floor)
+    assert np.abs(x - x_or).max() <= 1e-9 * np.abs(x_or).max()
+    # error history against the direct solve (both sides use their own A \ b)
+    assert np.all(np.abs(err - err_or) <= np.maximum(1e-8 * err_or, 1e-9 * np.linalg.norm(x_or)))
+
+
+def test_fused_and_generic_tiers_agree(case):
+    """The fast kernel tier must reproduce the generic tier (same arithmetic per element)."""
+    name, Ho, bo, Hp, bp = case
+    dev = Hp.device
+    out = {}
+    for fused in (0, 1):
+        for graph in (0, 1):
+            dev.set_option("fused", fused)
+            dev.set_option("graph", graph)
+            out[(fused, graph)] = dev.solve(np.zeros(len(bp)), bp, 30, 1e-10)
+    dev.set_option("fused", 1)
+    dev.set_option("graph", 1)
+    ref = out[(0, 0)]
+    for key, val in out.items():
+        assert val[1] == ref[1], key
+        assert np.allclose(val[2], ref[2], rtol=1e-11, atol=rounding_floor(Ho, ref[0])), key
+
+
+def test_iterative_smoother_solve():
+    """tests/dg_smoother_test.jl:16-48 shape: n = 16, p = 2, Dirichlet both ends, f = 1."""
+    from oracle import dg as odg, refmesh, smoother
+    n, p = 16, 2
+    CDir = 1000.0 * n
+    u = lambda x: -0.5 * x * x + x
+    mesh_o = refmesh.create_uniform_mesh(n, 0.0, 1.0)
+    bd_o = refmesh.set_boundary(mesh_o, 0.0, 1.0, [("dir", u(0.0)), ("dir", u(1.0))])
+    dgo = odg.DgMesh(mesh_o, p)
+    A_o, b_o, *_ = odg.dg_operator_and_rhs(dgo, mesh_o, lambda x: 1.0, bd_o, CDir)
+    for kind, alpha in (("blockJac", 2.0 / 3.0), ("jac", 2.0 / 3.0)):
+        s_o = smoother.dg_smoother(dgo, A_o, kind)
+        x_o, it_o, res_o, err_o = osolv.iterative_smoother_solve(A_o, s_o, np.zeros(len(b_o)), b_o,
+                                                                 maxiter=10 ** 4, alpha=alpha)
+        mesh = aggmg.create_uniform_mesh(n, 0.0, 1.0)
+        bd = aggmg.set_boundary(mesh, 0.0, 1.0, [("dir", u(0.0)), ("dir", u(1.0))])
+        dgm = aggmg.DgMesh(mesh, p)
+        G, D, C = aggmg.dg_flux_operators(dgm, mesh, bd, CDir)
+        A = (C - D @ dgm.mMassMatrixLU.solve(G)).tocsc()
+        f, r = aggmg.dg_flux_rhs(dgm, mesh, lambda x: 1.0, bd, CDir)
+        b = f - D @ dgm.mMassMatrixLU.solve(r)
+        s = aggmg.dg_smoother(dgm, A, kind)
+        x, it, res, err = aggmg.iterative_smoother_solve(A, s, np.zeros(len(b)), b, maxiter=10 ** 4,
+                                                         alpha=alpha)
+        assert it == it_o, (kind, it, it_o)
+        assert np.allclose(res, res_o, rtol=1e-9, atol=1e-12 * np.linalg.norm(b_o))
+        assert np.abs(x - x_o).max() <= 1e-9 * np.abs(x_o).max()
+
+
+def test_error_behaviour(lib):
+    """Status codes instead of exceptions across the ABI; argument errors mirror the reference's
+    ArgumentError sites (src/mesh_heirarchy.jl:33-39, :142-148)."""
+    import ctypes as C
+    from agglomerationmultigrid1d_b200 import _capi as capi
+    h = C.c_void_p()
+    assert lib.amg1d_create(C.byref(h), 0, 0, None) == capi.ERR_ARG
+    assert b"least one level" in lib.amg1d_last_error(None)
+    assert lib.amg1d_create(C.byref(h), 2, 0, None) == capi.OK
+    x = np.zeros(4)
+    assert lib.amg1d_vcycle(h, capi.dptr(x), capi.dptr(x), 3, 3, 0.5) == capi.ERR_STATE
+    assert lib.amg1d_finalize(h) == capi.ERR_STATE            # levels never set
+    blk = np.zeros(4)
+    one = np.ones(4)
+    assert lib.amg1d_set_level(h, 5, 1, 2, capi.dptr(blk), capi.dptr(one), capi.dptr(blk),
+                               capi.dptr(one), 0, None, 2) == capi.ERR_ARG
+    assert lib.amg1d_set_level(h, 0, 1, 2, capi.dptr(one), capi.dptr(one), capi.dptr(blk),
+                               capi.dptr(one), 0, None, 2) == capi.ERR_ARG   # A_lo[0] != 0
+    assert lib.amg1d_destroy(h) == capi.OK
+    with pytest.raises(ValueError):
+        build_package(8, dg_orders=[2, 1], agg_factors=[2], pAgg=2, upload=False)   # p in {0,1} only
