@@ -34,7 +34,7 @@ SHAPES = {
     "C3_dg4_agg": dict(n=32, dg_orders=[4, 2, 1], agg_factors=[2] * 5),
     "C4_cg3_dg1_agg": dict(n=32, cg_orders=[3, 1], dg_orders=[1], agg_factors=[2] * 5),
     "dg_p0_agg0": dict(n=16, dg_orders=[1], agg_factors=[2, 2], pAgg=0),
-    "ragged_n24": dict(n=24, dg_orders=[2, 1], agg_factors=[3, 2, 2, 2]),
+    "factor3_n24": dict(n=24, dg_orders=[2, 1], agg_factors=[3, 2, 2, 2]),
 }
 
 
