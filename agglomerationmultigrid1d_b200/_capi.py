@@ -48,7 +48,7 @@ PROTOTYPES = {
     "amg1d_coarse_solve": (C.c_int, [_h, _pd, _pd]),
     "amg1d_dev_set_problem": (C.c_int, [_h, _pd, _pd]),
     "amg1d_dev_fill_rhs_random": (C.c_int, [_h, C.c_uint64]),
-    "amg1d_dev_vcycle": (C.c_int, [_h, C.c_int, C.c_int, C.c_double]),
+    "amg1d_dev_vcycle": (C.c_int, [_h, C.c_int, C.c_int, C.c_double, C.c_int]),
     "amg1d_dev_residual_norm": (C.c_int, [_h, _pd]),
     "amg1d_dev_rhs_norm": (C.c_int, [_h, _pd]),
     "amg1d_dev_get_solution": (C.c_int, [_h, _pd]),
@@ -57,6 +57,7 @@ PROTOTYPES = {
     "amg1d_dev_ptr": (C.c_void_p, [_h, C.c_int, C.c_int]),
     "amg1d_set_option": (C.c_int, [_h, C.c_char_p, C.c_int64]),
     "amg1d_get_info": (C.c_int64, [_h, C.c_char_p]),
+    "amg1d_get_profile": (C.c_int, [_h, C.c_int, C.c_int, _pd, C.POINTER(C.c_int)]),
     "amg1d_host_alloc": (C.c_int, [C.POINTER(C.c_void_p), C.c_int64]),
     "amg1d_host_free": (C.c_int, [C.c_void_p]),
 }

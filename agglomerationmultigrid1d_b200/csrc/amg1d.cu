@@ -77,6 +77,8 @@ struct amg1d {
     double* stage = nullptr;  // host-ordered staging for permuted levels
     int64_t stage_len = 0;
     double* partial = nullptr;
+    int64_t partial_cap = 0;
+    bool norm_valid = false;   // d_scal[0] holds ||b - A x|| of the current level-0 iterate
     double* d_scal = nullptr;  // device scalars
     double* h_scal = nullptr;  // pinned host scalars
     double* coarse_fac = nullptr;
@@ -85,11 +87,15 @@ struct amg1d {
     int64_t opt_coarse_cta = 1024;
     // graph cache
     cudaGraphExec_t gexec = nullptr;
-    int g_pre = -1, g_post = -1;
+    int g_pre = -1, g_post = -1, g_norm = -1;
     double g_alpha = 0.0;
     int64_t launches_per_cycle = 0;
     int64_t launch_counter = 0;
     int64_t device_bytes = 0;
+    // per-kernel event profiling (option "profile"): one (start, stop) pair per launch of a leg
+    int opt_profile = 0;
+    struct Prof { std::vector<cudaEvent_t> ev; };
+    std::vector<Prof> prof;   // index = level * 2 + leg (0 = down, 1 = up)
     // distributed
     int rank = 0, nranks = 1;
 };
@@ -242,7 +248,8 @@ int op_resnorm(amg1d* h, int l, int slot) {
     Level& lv = h->L[l];
     if (h->opt_fused) {
         int nb = 0;
-        if (fused_resnorm(lv.m, lv.mat, lv.b.p, lv.x[lv.cur].p, lv.n, h->partial, &nb, h->stream)) {
+        if (fused_resnorm(lv.m, lv.diag, lv.mat, lv.b.p, lv.x[lv.cur].p, lv.n, h->partial,
+                          h->partial_cap, &nb, h->stream)) {
             k_reduce_final<<<1, AMG1D_RED_THREADS, 0, h->stream>>>(h->partial, nb, h->d_scal, slot, 1);
             h->launch_counter += 2;
             LAUNCH_CHECK();
@@ -253,24 +260,36 @@ int op_resnorm(amg1d* h, int l, int slot) {
     return op_norm(h, h->scratch.p, nullptr, lv.n * lv.m, slot);
 }
 
+int prof_mark(amg1d* h, int level, int leg) {
+    if (!h->opt_profile) return AMG1D_OK;
+    if (h->prof.size() < (size_t)h->n_levels * 2) h->prof.resize((size_t)h->n_levels * 2);
+    cudaEvent_t ev;
+    CK(cudaEventCreate(&ev));
+    CK(cudaEventRecord(ev, h->stream));
+    h->prof[level * 2 + leg].ev.push_back(ev);
+    return AMG1D_OK;
+}
+
 // ---- the V-cycle (src/solvers.jl:19-50) ------------------------------------------------------------
-int enqueue_vcycle(amg1d* h, int nPre, int nPost, double alpha) {
+int enqueue_vcycle(amg1d* h, int nPre, int nPost, double alpha, bool want_norm) {
     const int nl = h->n_levels;
+    bool norm_done = false;
     for (int l = 0; l < nl - 1; ++l) {
         Level& lv = h->L[l];
         Transfer& t = h->T[l];
         Level& lc = h->L[l + 1];
         bool zero = l > 0;
         if (zero) lv.cur = 0;
+        RET(prof_mark(h, l, 0));
         // fused down-leg: nPre sweeps + residual + restriction in one pass over the operator
         if (h->opt_fused && t.single_parent_uniform) {
-            int outbuf = -1;
-            if (fused_down(lv.m, t.mc, lv.diag, t.ratio, t.period, nPre, zero, lv.mat, lv.b.p,
-                           lv.x[lv.cur].p, lv.x[1 - lv.cur].p, t.P0, lc.b.p, lv.n, alpha, lv.cur,
-                           &outbuf, h->stream)) {
-                lv.cur = outbuf;
+            const int ob = zero ? 0 : 1 - lv.cur;
+            if (fused_down(lv.m, t.mc, lv.diag, make_map(t), nPre, zero, lv.mat, lv.b.p,
+                           lv.x[lv.cur].p, lv.x[ob].p, t.P0, lc.b.p, lv.n, alpha, h->stream)) {
+                lv.cur = ob;
                 h->launch_counter++;
                 LAUNCH_CHECK();
+                RET(prof_mark(h, l, 0));
                 continue;
             }
         }
@@ -285,7 +304,7 @@ int enqueue_vcycle(amg1d* h, int nPre, int nPost, double alpha) {
             }
         }
         if (h->opt_fused && t.single_parent_uniform &&
-            fused_residual_restrict(lv.m, t.mc, t.ratio, t.period, lv.mat, lv.b.p, lv.x[lv.cur].p,
+            fused_residual_restrict(lv.m, t.mc, lv.K, make_map(t), lv.mat, lv.b.p, lv.x[lv.cur].p,
                                     t.P0, lc.b.p, lv.n, h->stream)) {
             h->launch_counter++;
             LAUNCH_CHECK();
@@ -293,6 +312,7 @@ int enqueue_vcycle(amg1d* h, int nPre, int nPost, double alpha) {
             RET(op_apply(h, l, lv.b.p, lv.x[lv.cur].p, h->scratch.p, 1));
             RET(op_restrict(h, l, h->scratch.p, lc.b.p));
         }
+        RET(prof_mark(h, l, 0));
     }
     {
         Level& lv = h->L[nl - 1];
@@ -304,14 +324,23 @@ int enqueue_vcycle(amg1d* h, int nPre, int nPost, double alpha) {
         Level& lv = h->L[l];
         Transfer& t = h->T[l];
         Level& lc = h->L[l + 1];
+        RET(prof_mark(h, l, 1));
         if (h->opt_fused && t.single_parent_uniform) {
-            int outbuf = -1;
-            if (fused_up(lv.m, t.mc, lv.diag, t.ratio, t.period, nPost, lv.mat, lv.b.p,
-                         lv.x[lv.cur].p, lv.x[1 - lv.cur].p, t.P0, lc.x[lc.cur].p, lv.n, alpha,
-                         lv.cur, &outbuf, h->stream)) {
-                lv.cur = outbuf;
+            const bool fuse_norm = want_norm && l == 0;
+            int nb = 0;
+            if (fused_up(lv.m, t.mc, lv.diag, make_map(t), nPost, lv.mat, lv.b.p, lv.x[lv.cur].p,
+                         lv.x[1 - lv.cur].p, t.P0, lc.x[lc.cur].p, lv.n, alpha,
+                         fuse_norm ? h->partial : nullptr, h->partial_cap, &nb, h->stream)) {
+                lv.cur = 1 - lv.cur;
                 h->launch_counter++;
                 LAUNCH_CHECK();
+                RET(prof_mark(h, l, 1));
+                if (fuse_norm) {
+                    k_reduce_final<<<1, AMG1D_RED_THREADS, 0, h->stream>>>(h->partial, nb, h->d_scal, 0, 1);
+                    h->launch_counter++;
+                    LAUNCH_CHECK();
+                    norm_done = true;
+                }
                 continue;
             }
         }
@@ -320,6 +349,7 @@ int enqueue_vcycle(amg1d* h, int nPre, int nPost, double alpha) {
             RET(op_sweep(h, l, lv.b.p, lv.x[lv.cur].p, lv.x[1 - lv.cur].p, alpha, 0));
             lv.cur = 1 - lv.cur;
         }
+        RET(prof_mark(h, l, 1));
     }
     Level& l0 = h->L[0];
     if (l0.cur != 0) {
@@ -327,24 +357,27 @@ int enqueue_vcycle(amg1d* h, int nPre, int nPost, double alpha) {
                            h->stream));
         l0.cur = 0;
     }
+    if (want_norm && !norm_done) RET(op_resnorm(h, 0, 0));
     return AMG1D_OK;
 }
 
-int run_vcycle(amg1d* h, int nPre, int nPost, double alpha) {
+int run_vcycle(amg1d* h, int nPre, int nPost, double alpha, bool want_norm) {
     if (nPre < 0 || nPost < 0) return fail(h, AMG1D_ERR_ARG, "nPre and nPost must be >= 0");
-    if (!h->opt_graph) {
+    if (!h->opt_graph || h->opt_profile) {
         const int64_t c0 = h->launch_counter;
-        RET(enqueue_vcycle(h, nPre, nPost, alpha));
+        RET(enqueue_vcycle(h, nPre, nPost, alpha, want_norm));
         h->launches_per_cycle = h->launch_counter - c0;
+        h->norm_valid = want_norm;
         return AMG1D_OK;
     }
-    if (!h->gexec || h->g_pre != nPre || h->g_post != nPost || h->g_alpha != alpha) {
+    if (!h->gexec || h->g_pre != nPre || h->g_post != nPost || h->g_alpha != alpha ||
+        h->g_norm != (int)want_norm) {
         if (h->gexec) { cudaGraphExecDestroy(h->gexec); h->gexec = nullptr; }
         if (h->L[0].cur != 0) return fail(h, AMG1D_ERR_STATE, "internal: level-0 buffer parity");
         cudaGraph_t g = nullptr;
         const int64_t c0 = h->launch_counter;
         CK(cudaStreamBeginCapture(h->stream, cudaStreamCaptureModeThreadLocal));
-        int rc = enqueue_vcycle(h, nPre, nPost, alpha);
+        int rc = enqueue_vcycle(h, nPre, nPost, alpha, want_norm);
         cudaError_t ce = cudaStreamEndCapture(h->stream, &g);
         if (rc != AMG1D_OK) { if (g) cudaGraphDestroy(g); return rc; }
         if (ce != cudaSuccess) return fail(h, AMG1D_ERR_CUDA, "graph capture failed: %s", cudaGetErrorString(ce));
@@ -353,16 +386,18 @@ int run_vcycle(amg1d* h, int nPre, int nPost, double alpha) {
         ce = cudaGraphInstantiate(&h->gexec, g, 0);
         cudaGraphDestroy(g);
         if (ce != cudaSuccess) return fail(h, AMG1D_ERR_CUDA, "graph instantiate failed: %s", cudaGetErrorString(ce));
-        h->g_pre = nPre; h->g_post = nPost; h->g_alpha = alpha;
+        h->g_pre = nPre; h->g_post = nPost; h->g_alpha = alpha; h->g_norm = (int)want_norm;
     }
     CK(cudaGraphLaunch(h->gexec, h->stream));
     h->launch_counter += h->launches_per_cycle;
+    h->norm_valid = want_norm;
     return AMG1D_OK;
 }
 
 void invalidate_graph(amg1d* h) {
     if (h->gexec) { cudaGraphExecDestroy(h->gexec); h->gexec = nullptr; }
-    h->g_pre = h->g_post = -1;
+    h->g_pre = h->g_post = h->g_norm = -1;
+    h->norm_valid = false;
 }
 
 // ---- host <-> device vector movement (reference ordering <-> device block ordering) --------------
@@ -563,6 +598,7 @@ int amg1d_destroy(amg1d_t* h) {
     cudaSetDevice(h->device);
     cudaStreamSynchronize(h->stream);
     if (h->gexec) cudaGraphExecDestroy(h->gexec);
+    for (auto& pr : h->prof) for (auto ev : pr.ev) cudaEventDestroy(ev);
     for (auto& lv : h->L) {
         if (lv.mat) cudaFree(lv.mat);
         if (lv.perm) cudaFree(lv.perm);
@@ -788,7 +824,10 @@ int amg1d_finalize(amg1d_t* h) {
         maxm = std::max(maxm, lv.m);
     }
     RET(vec_alloc(h, h->scratch, maxlen, 1));
-    RET(dev_alloc(h, (void**)&h->partial, (AMG1D_RED_BLOCKS + 8) * 8 * 4));
+    h->partial_cap = std::max<int64_t>(AMG1D_RED_BLOCKS, h->L[0].n / (FUSED_B / 2) + 16);
+    for (int l = 0; l < h->n_levels; ++l)
+        h->partial_cap = std::max<int64_t>(h->partial_cap, h->L[l].n / (FUSED_B / 2) + 16);
+    RET(dev_alloc(h, (void**)&h->partial, h->partial_cap * 8));
     RET(dev_alloc(h, (void**)&h->d_scal, 64 * 8));
     CK(cudaMallocHost(&h->h_scal, 64 * 8));
     RET(factor_coarsest(h));
@@ -801,6 +840,7 @@ int amg1d_finalize(amg1d_t* h) {
 int amg1d_dev_set_problem(amg1d_t* h, const double* x0, const double* b) {
     RET(check_ready(h));
     Level& l0 = h->L[0];
+    h->norm_valid = false;
     if (b) RET(to_device(h, 0, b, l0.b.p));
     if (l0.cur != 0) l0.cur = 0;
     if (x0) RET(to_device(h, 0, x0, l0.x[0].p));
@@ -812,6 +852,7 @@ int amg1d_dev_fill_rhs_random(amg1d_t* h, uint64_t seed) {
     RET(check_ready(h));
     Level& l0 = h->L[0];
     if (l0.perm) return fail(h, AMG1D_ERR_UNSUPPORTED, "random rhs only for unpermuted (DG) fine levels");
+    h->norm_valid = false;
     k_fill_random<<<1184, 256, 0, h->stream>>>(l0.b.p, l0.b.len, seed);
     LAUNCH_CHECK();
     l0.cur = 0;
@@ -819,14 +860,14 @@ int amg1d_dev_fill_rhs_random(amg1d_t* h, uint64_t seed) {
     return AMG1D_OK;
 }
 
-int amg1d_dev_vcycle(amg1d_t* h, int nPre, int nPost, double alpha) {
+int amg1d_dev_vcycle(amg1d_t* h, int nPre, int nPost, double alpha, int with_residual_norm) {
     RET(check_ready(h));
-    return run_vcycle(h, nPre, nPost, alpha);
+    return run_vcycle(h, nPre, nPost, alpha, with_residual_norm != 0);
 }
 
 int amg1d_dev_residual_norm(amg1d_t* h, double* res) {
     RET(check_ready(h));
-    RET(op_resnorm(h, 0, 0));
+    if (!h->norm_valid) RET(op_resnorm(h, 0, 0));
     RET(read_scalars(h, 1));
     if (res) *res = h->h_scal[0];
     return AMG1D_OK;
@@ -869,7 +910,7 @@ int amg1d_vcycle(amg1d_t* h, double* x, const double* b, int nPre, int nPost, do
     RET(check_ready(h));
     if (!x || !b) return fail(h, AMG1D_ERR_ARG, "null vector");
     RET(amg1d_dev_set_problem(h, x, b));
-    RET(run_vcycle(h, nPre, nPost, alpha));
+    RET(run_vcycle(h, nPre, nPost, alpha, false));
     return to_host(h, 0, h->L[0].x[h->L[0].cur].p, x);
 }
 
@@ -891,9 +932,7 @@ int amg1d_solve(amg1d_t* h, double* x, const double* b, int maxiter, double tol,
     int rc = op_norm(h, l0.b.p, nullptr, l0.b.len, 2);
     int it = 0;
     for (int i = 0; i < maxiter && rc == AMG1D_OK; ++i) {
-        rc = run_vcycle(h, nPre, nPost, alpha);
-        if (rc != AMG1D_OK) break;
-        rc = op_resnorm(h, 0, 0);
+        rc = run_vcycle(h, nPre, nPost, alpha, true);
         if (rc != AMG1D_OK) break;
         if (d_exact) {
             rc = op_norm(h, l0.x[l0.cur].p, d_exact, l0.x[0].len, 1);
@@ -1041,6 +1080,10 @@ int amg1d_set_option(amg1d_t* h, const char* key, int64_t value) {
     if (!strcmp(key, "fused")) h->opt_fused = (int)value;
     else if (!strcmp(key, "graph")) h->opt_graph = (int)value;
     else if (!strcmp(key, "coarse_cta_elems")) h->opt_coarse_cta = value;
+    else if (!strcmp(key, "profile")) {
+        h->opt_profile = (int)value;
+        for (auto& pr : h->prof) { for (auto ev : pr.ev) cudaEventDestroy(ev); pr.ev.clear(); }
+    }
     else return fail(h, AMG1D_ERR_ARG, "unknown option '%s'", key);
     return AMG1D_OK;
 }
@@ -1057,6 +1100,23 @@ int64_t amg1d_get_info(amg1d_t* h, const char* key) {
         return s;
     }
     return -1;
+}
+
+int amg1d_get_profile(amg1d_t* h, int level, int leg, double* total_ms, int* launches) {
+    if (!h || !total_ms || !launches) return AMG1D_ERR_ARG;
+    if (!valid_level(h, level) || leg < 0 || leg > 1) return fail(h, AMG1D_ERR_ARG, "bad level / leg");
+    *total_ms = 0.0;
+    *launches = 0;
+    if (h->prof.size() <= (size_t)(level * 2 + leg)) return AMG1D_OK;
+    CK(cudaStreamSynchronize(h->stream));
+    auto& ev = h->prof[level * 2 + leg].ev;
+    for (size_t i = 0; i + 1 < ev.size(); i += 2) {
+        float ms = 0.f;
+        CK(cudaEventElapsedTime(&ms, ev[i], ev[i + 1]));
+        *total_ms += ms;
+        *launches += 1;
+    }
+    return AMG1D_OK;
 }
 
 int amg1d_host_alloc(void** p, int64_t bytes) {

@@ -175,8 +175,8 @@ class DeviceHierarchy:
     def dev_fill_rhs_random(self, seed=0):
         self._ck(self._lib.amg1d_dev_fill_rhs_random(self._h, seed))
 
-    def dev_vcycle(self, nPre=3, nPost=3, alpha=2.0 / 3.0):
-        self._ck(self._lib.amg1d_dev_vcycle(self._h, nPre, nPost, alpha))
+    def dev_vcycle(self, nPre=3, nPost=3, alpha=2.0 / 3.0, with_residual_norm=False):
+        self._ck(self._lib.amg1d_dev_vcycle(self._h, nPre, nPost, alpha, int(with_residual_norm)))
 
     def dev_residual_norm(self):
         v = C.c_double(0.0)
@@ -201,6 +201,12 @@ class DeviceHierarchy:
 
     def info(self, key):
         return int(self._lib.amg1d_get_info(self._h, key.encode()))
+
+    def profile(self, level, leg):
+        """(total device ms, launches) of one leg of one level since option 'profile' was set."""
+        ms, cnt = C.c_double(0.0), C.c_int(0)
+        self._ck(self._lib.amg1d_get_profile(self._h, level, leg, C.byref(ms), C.byref(cnt)))
+        return ms.value, cnt.value
 
     @property
     def stream(self):

@@ -1,0 +1,318 @@
+#!/usr/bin/env python
+"""bench.py - headline benchmark of the B200 V-cycle (contract: see the task statement / DESIGN.md).
+
+A "step" is one pass of the hot path over one batch: ONE V-cycle (nPre = nPost = 3, alpha = 2/3)
+plus the convergence check ||A x - b||_2 that ``multigrid`` performs after every cycle
+(src/solvers.jl:124-131).  `value` = smoother DOF-updates per second with x, b and the hierarchy
+resident in HBM; `e2e` = the same metric through the reference-facing call
+``multigrid_v_cycle(H, x0, b)`` (amg1d_vcycle) with pinned HOST vectors, copies inside the timing.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--workload T|C2|C3|C5|C1] [--impl reference]
+"""
+import argparse
+import json
+import math
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+METRIC = "FP64 V-cycle DOF-updates/s"
+UNIT = "DOF-updates/s"
+
+# name -> (log2 n, DG orders, description)
+WORKLOADS = {
+    "T": (26, [3, 1], "DG p=3, 2^26 elements, DG 3->1 then pAgg=1 factor-2 agglomeration to one element (28 levels)"),
+    "C2": (20, [3, 1], "DG p=3, 2^20 elements, full hierarchy (22 levels)"),
+    "C3": (24, [4, 2, 1], "DG p=4, 2^24 elements, DG 4->2->1 then factor-2 agglomeration (27 levels)"),
+    "C5": (24, [3, 1], "DG p=3, 2^24 elements per GPU, full hierarchy"),
+    "S": (14, [3, 1], "DG p=3, 2^14 elements (smoke-sized)"),
+}
+
+
+def problem(n):
+    """Domain [0, n] (h = 1), CDir = 1000, u = cos(2 pi x / 64): FP64 can reach 1e-10 at any n
+    (SURVEY section 7); Neumann left, Dirichlet right as in the reference's hierarchy scripts."""
+    w = 2.0 * math.pi / 64.0
+    return dict(xin=0.0, xout=float(n), CDir=1000.0,
+                func=lambda x: w * w * np.cos(w * x),
+                bc_values=[-w * math.sin(0.0), math.cos(w * n)])
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the timed region (profiling recipe)."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index=0):
+        self.lines = []
+        self.proc = None
+        self.index = index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+                 "-i", str(self.index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append((time.time(), line.strip()))
+
+    def stop(self, t0, t1):
+        if self.proc is None:
+            return None
+        time.sleep(0.15)
+        self.proc.terminate()
+        rows = [l.split(", ") for (t, l) in self.lines if t0 <= t <= t1 + 0.2] or \
+               [l.split(", ") for (t, l) in self.lines[-3:]]
+        sm, mx, reasons = [], [], set()
+        for r in rows:
+            try:
+                sm.append(float(r[0])); mx.append(float(r[1]))
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown",
+                                    "sw_power_cap"), r[3:7]):
+                    if v.strip().lower().startswith("active"):
+                        reasons.add(name)
+            except Exception:
+                pass
+        if not sm:
+            return None
+        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)), "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+def measured_peak():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+# ---- CPU reference arm: the oracle's restatement of multigrid_v_cycle on the host cores ------------
+def cpu_reference(orders, nsteps, log2n_sample=11):
+    """Times the CPU oracle (literal numpy/scipy restatement: CSC SpMV, per-element LU solves,
+    sparse L'/L products, sparse direct coarse solve) on a bounded sample of the same hierarchy
+    shape; DOF-updates/s is size independent for this O(N) method, so the sample is scaled only in n."""
+    from oracle import drivers, solvers
+    n = 2 ** log2n_sample
+    pr = problem(n)
+    w = 2.0 * math.pi / 64.0
+    nAgg = int(round(math.log2(n)))
+    H, x0, b, _ = drivers.build_problem(
+        n, dg_orders=orders, agg_factors=[2] * nAgg, xin=0.0, xout=float(n), CDir=1000.0,
+        func=lambda x: w * w * math.cos(w * x), u_exact=lambda x: math.cos(w * x),
+        ux_exact=lambda x: -w * math.sin(w * x))
+    upd = 6 * sum(S.shape[0] for S in H.mStiffness[:-1])
+    x = x0
+    solvers.multigrid_v_cycle(H, x, b)          # warm-up
+    t0 = time.perf_counter()
+    for _ in range(nsteps):
+        x = solvers.multigrid_v_cycle(H, x, b)
+        np.linalg.norm(H.mStiffness[0] @ x - b)
+    dt = (time.perf_counter() - t0) / nsteps
+    return upd / dt, dt, f"{nsteps} V-cycles of the same hierarchy shape at n = 2^{log2n_sample} elements " \
+                         f"({upd} DOF-updates per cycle), single thread numpy/scipy oracle"
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    log2n, orders, desc = WORKLOADS[args.workload]
+    steps = max(1, min(args.steps, 5))
+    val, dt, sample = cpu_reference(orders, steps)
+    line = {
+        "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus,
+        "steps": steps, "warmup": 1, "ms_per_step": dt * 1e3, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": f"{args.workload}: {desc}", "note": "Julia is not installed here; this is the "
+                   "CPU oracle port of the reference algorithm, timed on a bounded sample"},
+        "cpu_baseline": {"value": val, "unit": UNIT, "cores": 1, "kind": "port", "sample": sample},
+        "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ---- GPU arm ----------------------------------------------------------------------------------------
+def run_gpu(args):
+    import torch
+    import agglomerationmultigrid1d_b200 as aggmg          # raises if libamg1d.so is missing
+    from agglomerationmultigrid1d_b200 import uniform, _capi as capi
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world > 1:
+        raise SystemExit("multi-GPU slab sharding is not wired into bench.py yet")
+    torch.cuda.set_device(local)
+    stream = torch.cuda.current_stream().cuda_stream
+
+    log2n, orders, desc = WORKLOADS[args.workload]
+    n = 2 ** log2n
+    pr = problem(n)
+    t_setup = time.perf_counter()
+    U = uniform.UniformDgHierarchy(n, orders, [2] * log2n, pAgg=1, xin=pr["xin"], xout=pr["xout"],
+                                   CDir=pr["CDir"])
+    dev = U.upload(device=local, stream=stream)
+    dev.synchronize()
+    t_setup = time.perf_counter() - t_setup
+    N0 = U.levels[0].n * U.levels[0].m
+    upd = U.dof_updates_per_cycle()
+
+    # ---- value: device-resident steps (random rhs; throughput does not depend on the data) --------
+    dev.dev_fill_rhs_random(0)
+    for _ in range(args.warmup):
+        dev.dev_vcycle(with_residual_norm=True)
+    dev.synchronize()
+    launches0 = dev.info("kernel_launches")
+    sampler = ClockSampler(local)
+    sampler.start()
+    time.sleep(0.25)
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
+    tw0 = time.time()
+    ev0.record()
+    for _ in range(args.steps):
+        dev.dev_vcycle(with_residual_norm=True)
+    ev1.record()
+    torch.cuda.synchronize()
+    tw1 = time.time()
+    clocks = sampler.stop(tw0, tw1)
+    ms_step = ev0.elapsed_time(ev1) / args.steps
+    launches = dev.info("kernel_launches") - launches0
+    value = upd / (ms_step * 1e-3)
+    res_after = dev.dev_residual_norm()
+
+    # ---- roofline of the dominant kernel, CUDA events around each launch (un-graphed pass) --------
+    peak, peak_src = measured_peak()
+    dev.set_option("profile", 1)
+    for _ in range(args.steps):
+        dev.dev_vcycle(with_residual_norm=True)
+    dev.synchronize()
+    legs = {}
+    for l in range(min(3, len(U.levels) - 1)):
+        for leg, nm in ((0, "down"), (1, "up")):
+            ms, cnt = dev.profile(l, leg)
+            legs[f"L{l}_{nm}"] = ms / max(cnt, 1)
+    dev.set_option("profile", 0)
+    lv0, lv1 = U.levels[0], U.levels[1]
+    m, mc = lv0.m, lv1.m
+    fused_kernel = m <= 4
+    if fused_kernel:
+        bytes_up = 8 * (lv0.n * (4 * m * m + 3 * m) + lv1.n * mc)           # f_up at level 0 (+ norm)
+        kern = f"f_up<{m},{mc},128> level 0 (prolong + 3 sweeps + ||b-Ax||^2)"
+        t_k = legs["L0_up"]
+    else:
+        bytes_up = 3 * 8 * lv0.n * (4 * m * m + 3 * m) + 8 * (lv1.n * mc + 2 * lv0.n * m)
+        kern = f"level-0 up leg (g_prolong + 3 x f_sweep<{m}>)"
+        t_k = legs["L0_up"]
+    achieved = bytes_up / (t_k * 1e-3) / 1e9
+    cyc_bytes = U.bytes_per_cycle_fused() if fused_kernel else U.bytes_per_cycle_reference_model()
+    roofline = {
+        "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+        "traffic": None, "kernel": kern, "algorithmic_bytes_per_launch": bytes_up,
+        "avg_launch_ms": t_k, "peak_source": peak_src,
+        "whole_cycle": {"algorithmic_bytes": cyc_bytes, "GBps": cyc_bytes / (ms_step * 1e-3) / 1e9,
+                        "frac": cyc_bytes / (ms_step * 1e-3) / 1e9 / peak,
+                        "B_ref_bytes": U.bytes_per_cycle_reference_model(),
+                        "B_ref_equiv_GBps": U.bytes_per_cycle_reference_model() / (ms_step * 1e-3) / 1e9},
+        "leg_ms": legs,
+    }
+
+    # ---- e2e: the reference-facing call with pinned host vectors, copies inside the timed region ---
+    lib = capi.load()
+    import ctypes as C
+    bufs = []
+    for _ in range(2):
+        p = C.c_void_p()
+        capi.check(None, lib.amg1d_host_alloc(C.byref(p), N0 * 8))
+        bufs.append(p)
+    xh = np.ctypeslib.as_array(C.cast(bufs[0], C.POINTER(C.c_double)), shape=(N0,))
+    bh = np.ctypeslib.as_array(C.cast(bufs[1], C.POINTER(C.c_double)), shape=(N0,))
+    t_rhs = time.perf_counter()
+    bh[:] = U.rhs(pr["func"], pr["bc_values"])
+    t_rhs = time.perf_counter() - t_rhs
+    xh[:] = 0.0
+    e2e_steps = max(1, min(args.steps, 5))
+    capi.check(dev._h, lib.amg1d_vcycle(dev._h, capi.dptr(xh), capi.dptr(bh), 3, 3, 2.0 / 3.0))  # warm
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        capi.check(dev._h, lib.amg1d_vcycle(dev._h, capi.dptr(xh), capi.dptr(bh), 3, 3, 2.0 / 3.0))
+    t_e2e = (time.perf_counter() - t0) / e2e_steps
+    e2e = {"value": upd / t_e2e, "unit": UNIT, "h2d_bytes_per_step": 2 * N0 * 8,
+           "d2h_bytes_per_step": N0 * 8, "ms_per_step": t_e2e * 1e3, "steps": e2e_steps,
+           "call": "amg1d_vcycle (multigrid_v_cycle(H, x0, b)) with pinned host x0, b"}
+
+    # ---- time-to-1e-10: full multigrid() solve through the ABI (host vectors in, solution out) ----
+    xh[:] = 0.0
+    res = np.zeros(100)
+    it = C.c_int(0)
+    t0 = time.perf_counter()
+    capi.check(dev._h, lib.amg1d_solve(dev._h, capi.dptr(xh), capi.dptr(bh), 100, 1e-10, 3, 3, 2.0 / 3.0,
+                                        C.byref(it), capi.dptr(res), None, None))
+    t_solve = time.perf_counter() - t0
+    nb = float(np.linalg.norm(bh))
+    solve = {"iters": it.value, "seconds_e2e": t_solve, "final_relative_residual": float(res[it.value - 1] / nb),
+             "call": "amg1d_solve (multigrid(H, x0, b, 100, 1e-10)), host b in / host x out"}
+
+    # ---- CPU baseline beside it (oracle port, bounded sample) ----------------------------------------
+    cpu = None
+    if not args.no_cpu:
+        v, dt, sample = cpu_reference(orders, 2)
+        cpu = {"value": v, "unit": UNIT, "cores": 1, "kind": "port", "sample": sample,
+               "host_cores_available": os.cpu_count()}
+
+    for p in bufs:
+        lib.amg1d_host_free(p)
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": f"{args.workload}: {desc}", "n_elements": n, "fine_dofs": N0,
+                   "levels": len(U.levels), "nPre": 3, "nPost": 3, "alpha": 2.0 / 3.0,
+                   "dof_updates_per_step": upd, "step": "one V-cycle + ||Ax-b|| check, CUDA graph replay",
+                   "l2": "inputs larger than L2 (operators + vectors of the fine levels are GBs)"
+                   if N0 * 8 > 2 ** 27 else "fine level fits L2; no flush (working set re-read each step)",
+                   "device_bytes": dev.info("device_bytes"), "setup_s": t_setup, "rhs_assembly_s": t_rhs,
+                   "residual_after_timed_steps": res_after},
+        "roofline": roofline, "cpu_baseline": cpu, "clocks": clocks, "e2e": e2e,
+        "time_to_1e-10": solve, "gpu_launches": int(launches),
+        "fine_dof_cycles_per_s": N0 / (ms_step * 1e-3),
+    }
+    print(json.dumps(line), flush=True)
+    dev.close()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="T", choices=sorted(WORKLOADS))
+    ap.add_argument("--no-cpu", action="store_true", help="skip the CPU baseline leg")
+    args = ap.parse_args()
+    if args.warmup < 3 and args.impl == "b200":
+        args.warmup = 3
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_gpu(args)
+
+
+if __name__ == "__main__":
+    main()

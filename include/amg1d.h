@@ -141,7 +141,9 @@ int amg1d_coarse_solve(amg1d_t* h, double* x, const double* b);
 /* ---- device-resident path (no host copies; what bench.py times as `value`) -------------------- */
 int amg1d_dev_set_problem(amg1d_t* h, const double* x0, const double* b); /* host -> device, x0 NULL = 0 */
 int amg1d_dev_fill_rhs_random(amg1d_t* h, uint64_t seed);          /* b[i] ~ U(-1,1) on the device, x = 0 */
-int amg1d_dev_vcycle(amg1d_t* h, int nPre, int nPost, double alpha); /* asynchronous on the stream */
+/* asynchronous on the stream; with_residual_norm = 1 also leaves ||A x - b||_2 of the new iterate on the
+ * device (fused into the last kernel of the cycle), which amg1d_dev_residual_norm then just reads */
+int amg1d_dev_vcycle(amg1d_t* h, int nPre, int nPost, double alpha, int with_residual_norm);
 int amg1d_dev_residual_norm(amg1d_t* h, double* res);              /* ||A x - b||_2, synchronises */
 int amg1d_dev_rhs_norm(amg1d_t* h, double* nb);                    /* ||b||_2, synchronises */
 int amg1d_dev_get_solution(amg1d_t* h, double* x);                 /* device -> host */
@@ -152,10 +154,16 @@ void* amg1d_dev_ptr(amg1d_t* h, int level, int which);             /* raw device
 /* ---- options and introspection ------------------------------------------------------------------
  * amg1d_set_option keys: "fused" (1 = fused multi-sweep kernels where available, default 1),
  * "graph" (1 = replay the V-cycle as a CUDA graph, default 1), "coarse_cta_elems" (levels with at
- * most this many elements run inside the single-CTA coarse kernel, default 1024). */
+ * most this many elements run inside the single-CTA coarse kernel, default 1024), "profile" (see
+ * amg1d_get_profile; setting it clears earlier samples). */
 int amg1d_set_option(amg1d_t* h, const char* key, int64_t value);
 int64_t amg1d_get_info(amg1d_t* h, const char* key); /* "kernel_launches", "dof_updates_per_cycle",
                                                         "bytes_per_cycle", "device_bytes", "n_levels" */
+
+/* With option "profile" = 1 every V-cycle runs un-graphed and brackets each level's down leg (leg 0:
+ * pre-smoothing + residual + restriction) and up leg (leg 1: prolongation + post-smoothing) with CUDA
+ * events on the handle's stream; this returns the summed device time and the number of brackets. */
+int amg1d_get_profile(amg1d_t* h, int level, int leg, double* total_ms, int* launches);
 
 /* Pinned host memory helpers for callers that want asynchronous, full-bandwidth copies. */
 int amg1d_host_alloc(void** p, int64_t bytes);

@@ -132,6 +132,8 @@ def test_fused_and_generic_tiers_agree(case):
     for key, val in out.items():
         assert val[1] == ref[1], key
         assert np.allclose(val[2], ref[2], rtol=1e-11, atol=rounding_floor(Ho, ref[0])), key
+        # same arithmetic in the same order per element: the iterate itself is bit-identical
+        assert np.array_equal(val[0], ref[0]), key
 
 
 def test_iterative_smoother_solve():
