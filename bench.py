@@ -159,7 +159,12 @@ def run_gpu(args):
     if world > 1:
         raise SystemExit("multi-GPU slab sharding is not wired into bench.py yet")
     torch.cuda.set_device(local)
-    stream = torch.cuda.current_stream().cuda_stream
+    # a non-default stream: its handle is non-zero, so the library runs on exactly the stream that
+    # torch.cuda.Event records on (handle 0 would make the library create a stream of its own)
+    tstream = torch.cuda.Stream(device=local)
+    torch.cuda.set_stream(tstream)
+    stream = tstream.cuda_stream
+    assert stream != 0
 
     log2n, orders, desc = WORKLOADS[args.workload]
     n = 2 ** log2n
