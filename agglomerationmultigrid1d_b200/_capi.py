@@ -9,7 +9,7 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libamg1d.so")
+LIB_PATH = os.environ.get("AMG1D_LIB") or os.path.join(_HERE, "libamg1d.so")   # AMG1D_LIB: tuning builds
 
 OK, ERR_ARG, ERR_CUDA, ERR_NCCL, ERR_NOMEM, ERR_STATE, ERR_UNSUPPORTED = range(7)
 VEC_X, VEC_B, VEC_R = 0, 1, 2

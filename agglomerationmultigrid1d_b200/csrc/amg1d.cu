@@ -243,6 +243,22 @@ int op_norm(amg1d* h, const double* a, const double* c, int64_t n, int slot) {
     return AMG1D_OK;
 }
 
+// d_scal[slot] = sqrt(sum partial[0..np)); long arrays go through a second stage of 256 partial sums
+int op_reduce_partials(amg1d* h, int64_t np, int slot) {
+    const double* src = h->partial;
+    if (np > 8192) {
+        double* stage2 = h->partial + h->partial_cap;   // 256 extra slots behind the first stage
+        k_sum_partial<<<256, AMG1D_RED_THREADS, 0, h->stream>>>(h->partial, np, stage2);
+        h->launch_counter++;
+        src = stage2;
+        np = 256;
+    }
+    k_reduce_final<<<1, AMG1D_RED_THREADS, 0, h->stream>>>(src, (int)np, h->d_scal, slot, 1);
+    h->launch_counter++;
+    LAUNCH_CHECK();
+    return AMG1D_OK;
+}
+
 // || b - A x ||_2 on level l into slot
 int op_resnorm(amg1d* h, int l, int slot) {
     Level& lv = h->L[l];
@@ -250,10 +266,9 @@ int op_resnorm(amg1d* h, int l, int slot) {
         int nb = 0;
         if (fused_resnorm(lv.m, lv.diag, lv.mat, lv.b.p, lv.x[lv.cur].p, lv.n, h->partial,
                           h->partial_cap, &nb, h->stream)) {
-            k_reduce_final<<<1, AMG1D_RED_THREADS, 0, h->stream>>>(h->partial, nb, h->d_scal, slot, 1);
-            h->launch_counter += 2;
+            h->launch_counter++;
             LAUNCH_CHECK();
-            return AMG1D_OK;
+            return op_reduce_partials(h, nb, slot);
         }
     }
     RET(op_apply(h, l, lv.b.p, lv.x[lv.cur].p, h->scratch.p, 1));
@@ -336,9 +351,7 @@ int enqueue_vcycle(amg1d* h, int nPre, int nPost, double alpha, bool want_norm) 
                 LAUNCH_CHECK();
                 RET(prof_mark(h, l, 1));
                 if (fuse_norm) {
-                    k_reduce_final<<<1, AMG1D_RED_THREADS, 0, h->stream>>>(h->partial, nb, h->d_scal, 0, 1);
-                    h->launch_counter++;
-                    LAUNCH_CHECK();
+                    RET(op_reduce_partials(h, nb, 0));
                     norm_done = true;
                 }
                 continue;
@@ -827,7 +840,7 @@ int amg1d_finalize(amg1d_t* h) {
     h->partial_cap = std::max<int64_t>(AMG1D_RED_BLOCKS, h->L[0].n / (FUSED_B / 2) + 16);
     for (int l = 0; l < h->n_levels; ++l)
         h->partial_cap = std::max<int64_t>(h->partial_cap, h->L[l].n / (FUSED_B / 2) + 16);
-    RET(dev_alloc(h, (void**)&h->partial, h->partial_cap * 8));
+    RET(dev_alloc(h, (void**)&h->partial, (h->partial_cap + 256) * 8));
     RET(dev_alloc(h, (void**)&h->d_scal, 64 * 8));
     CK(cudaMallocHost(&h->h_scal, 64 * 8));
     RET(factor_coarsest(h));

@@ -23,7 +23,12 @@
 #include "kernels_generic.cuh"
 #include "layout.cuh"
 
+#ifndef FUSED_B
 #define FUSED_B 128  // window (threads) per CTA of f_down / f_up
+#endif
+#ifndef FUSED_MINB
+#define FUSED_MINB 3   // __launch_bounds__ min CTAs per SM for f_down / f_up
+#endif
 
 // ---- small helpers ---------------------------------------------------------------------------------
 template <int M>
@@ -159,8 +164,9 @@ __device__ __forceinline__ void exch_init(Exchange<M, B>& ex) {
 }
 
 // one damped block-Jacobi sweep on register-resident blocks; same operation order as g_sweep
-template <int M>
-__device__ __forceinline__ void reg_sweep(const double (&A)[3 * M * M], const double (&Dv)[M * M],
+// Dinv is read from shared memory: dcol points at this thread's column of ds[k][thread], stride DS.
+template <int M, int DS>
+__device__ __forceinline__ void reg_sweep(const double (&A)[3 * M * M], const double* __restrict__ dcol,
                                           const double (&bb)[M], const double (&xl)[M],
                                           double (&xc)[M], const double (&xr)[M], double alpha,
                                           bool zero_guess) {
@@ -193,9 +199,18 @@ __device__ __forceinline__ void reg_sweep(const double (&A)[3 * M * M], const do
 #pragma unroll
     for (int j = 0; j < M; ++j)
 #pragma unroll
-        for (int i = 0; i < M; ++i) z[i] = fma(Dv[j * M + i], r[j], z[i]);
+        for (int i = 0; i < M; ++i) z[i] = fma(dcol[(j * M + i) * DS], r[j], z[i]);
 #pragma unroll
     for (int i = 0; i < M; ++i) xc[i] = __dadd_rn(xc[i], __dmul_rn(alpha, z[i]));
+}
+
+__device__ __forceinline__ void cp_async8(double* smem_dst, const double* gmem_src) {
+    const unsigned sa = (unsigned)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(sa), "l"(gmem_src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit_wait_all() {
+    asm volatile("cp.async.commit_group;" ::: "memory");
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
 }
 
 template <int M>
@@ -236,21 +251,24 @@ __device__ __forceinline__ void exchange(Exchange<M, B>& ex, int buf, const doub
     }
 }
 
+// A_lo / A_di / A_up go to registers; Dinv (used once per sweep) is copied global -> shared with
+// cp.async, i.e. without register staging, into this thread's own column ds[k][thread].
 template <int M, int B>
 __device__ __forceinline__ void load_blocks(const double* __restrict__ mat, int64_t e, bool active,
-                                            double (&A)[3 * M * M], double (&Dv)[M * M]) {
+                                            double (&A)[3 * M * M], double (*ds)[B]) {
     constexpr int K = 4 * M * M;
+    const int t = threadIdx.x;
     if (active) {
         const double* T = mat + (e >> 5) * (int64_t)(K * AMG1D_TILE) + (e & 31);
 #pragma unroll
-        for (int k = 0; k < 3 * M * M; ++k) A[k] = T[k * AMG1D_TILE];
+        for (int k = 0; k < M * M; ++k) cp_async8(&ds[k][t], T + (3 * M * M + k) * AMG1D_TILE);
 #pragma unroll
-        for (int k = 0; k < M * M; ++k) Dv[k] = T[(3 * M * M + k) * AMG1D_TILE];
+        for (int k = 0; k < 3 * M * M; ++k) A[k] = T[k * AMG1D_TILE];
     } else {
 #pragma unroll
-        for (int k = 0; k < 3 * M * M; ++k) A[k] = 0.0;
+        for (int k = 0; k < M * M; ++k) ds[k][t] = 0.0;
 #pragma unroll
-        for (int k = 0; k < M * M; ++k) Dv[k] = 0.0;
+        for (int k = 0; k < 3 * M * M; ++k) A[k] = 0.0;
     }
 }
 
@@ -258,19 +276,20 @@ __device__ __forceinline__ void load_blocks(const double* __restrict__ mat, int6
 //   halo = nsweep + 1 window elements on each side are recomputed; out = elements emitted per CTA
 //   (a multiple of the agglomeration ratio).
 template <int M, int MC, int B>
-__global__ void __launch_bounds__(B, 2)
+__global__ void __launch_bounds__(B, FUSED_MINB)
 f_down(const double* __restrict__ mat, const double* __restrict__ b, const double* __restrict__ xin,
        double* __restrict__ xout, const double* __restrict__ P0, TransferMap tm,
        double* __restrict__ rc, int64_t n, double alpha, int nsweep, int zero_guess, int out) {
     __shared__ Exchange<M, B> ex;
     __shared__ double rs[M][B + 8];
+    __shared__ double ds[M * M][B];
     const int t = threadIdx.x;
     const int halo = nsweep + 1;
     const int64_t e = (int64_t)blockIdx.x * out - halo + t;
     const bool active = e >= 0 && e < n;
     exch_init<M, B>(ex);
-    double A[3 * M * M], Dv[M * M], bb[M], xc[M], xl[M], xr[M];
-    load_blocks<M, B>(mat, e, active, A, Dv);
+    double A[3 * M * M], bb[M], xc[M], xl[M], xr[M];
+    load_blocks<M, B>(mat, e, active, A, ds);
     if (active) {
         load_vec<M>(b + e * M, bb);
         if (zero_guess) {
@@ -283,7 +302,8 @@ f_down(const double* __restrict__ mat, const double* __restrict__ b, const doubl
 #pragma unroll
         for (int i = 0; i < M; ++i) { bb[i] = 0.0; xc[i] = 0.0; }
     }
-    __syncthreads();  // exch_init visible
+    cp_async_commit_wait_all();  // this thread's Dinv column has landed (only this thread reads it)
+    __syncthreads();             // exch_init visible
     int buf = 0;
     for (int s = 0; s < nsweep; ++s) {
         const bool zg = zero_guess && s == 0;
@@ -291,7 +311,7 @@ f_down(const double* __restrict__ mat, const double* __restrict__ b, const doubl
             exchange<M, B>(ex, buf, xc, xl, xr);
             buf ^= 1;
         }
-        reg_sweep<M>(A, Dv, bb, xl, xc, xr, alpha, zg);
+        reg_sweep<M, B>(A, &ds[0][t], bb, xl, xc, xr, alpha, zg);
     }
     const bool emit = active && t >= halo && t < halo + out;
     if (emit) store_vec<M>(xout + e * M, xc);
@@ -322,19 +342,20 @@ f_down(const double* __restrict__ mat, const double* __restrict__ b, const doubl
 
 // prolongation + correction, nsweep post-smoothing sweeps, optional || b - A x ||^2 partial sums.
 template <int M, int MC, int B>
-__global__ void __launch_bounds__(B, 2)
+__global__ void __launch_bounds__(B, FUSED_MINB)
 f_up(const double* __restrict__ mat, const double* __restrict__ b, const double* __restrict__ xin,
      double* __restrict__ xout, const double* __restrict__ P0, TransferMap tm,
      const double* __restrict__ xcoarse, int64_t n, double alpha, int nsweep, int out,
      double* __restrict__ partial) {
     __shared__ Exchange<M, B> ex;
+    __shared__ double ds[M * M][B];
     const int t = threadIdx.x;
     const int halo = nsweep + 1;
     const int64_t e = (int64_t)blockIdx.x * out - halo + t;
     const bool active = e >= 0 && e < n;
     exch_init<M, B>(ex);
-    double A[3 * M * M], Dv[M * M], bb[M], xc[M], xl[M], xr[M];
-    load_blocks<M, B>(mat, e, active, A, Dv);
+    double A[3 * M * M], bb[M], xc[M], xl[M], xr[M];
+    load_blocks<M, B>(mat, e, active, A, ds);
     if (active) {
         load_vec<M>(b + e * M, bb);
         load_vec<M>(xin + e * M, xc);
@@ -356,12 +377,13 @@ f_up(const double* __restrict__ mat, const double* __restrict__ b, const double*
 #pragma unroll
         for (int i = 0; i < M; ++i) { bb[i] = 0.0; xc[i] = 0.0; }
     }
+    cp_async_commit_wait_all();
     __syncthreads();
     int buf = 0;
     for (int s = 0; s < nsweep; ++s) {
         exchange<M, B>(ex, buf, xc, xl, xr);
         buf ^= 1;
-        reg_sweep<M>(A, Dv, bb, xl, xc, xr, alpha, false);
+        reg_sweep<M, B>(A, &ds[0][t], bb, xl, xc, xr, alpha, false);
     }
     const bool emit = active && t >= halo && t < halo + out;
     if (emit) store_vec<M>(xout + e * M, xc);

@@ -246,6 +246,16 @@ __global__ void k_sqdiff_partial(const double* __restrict__ a, const double* __r
     if (threadIdx.x == 0) partial[blockIdx.x] = s;
 }
 
+// second-stage partial sums for long partial arrays: out[b] = sum of a fixed grid-stride slice
+__global__ void k_sum_partial(const double* __restrict__ partial, int64_t np, double* __restrict__ out) {
+    double s = 0.0;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < np;
+         i += (int64_t)gridDim.x * blockDim.x)
+        s += partial[i];
+    s = block_sum(s);
+    if (threadIdx.x == 0) out[blockIdx.x] = s;
+}
+
 // out[slot] = sqrt(sum partial[0..np))
 __global__ void k_reduce_final(const double* __restrict__ partial, int np, double* __restrict__ out,
                                int slot, int take_sqrt) {
