@@ -82,7 +82,7 @@ def load():
             f"{LIB_PATH} not found: the CUDA library is not built. Run "
             "`python -c 'import __graft_entry__ as g; g.build()'` at the repo root. "
             "There is no CPU fallback for the V-cycle.")
-    lib = C.CDLL(LIB_PATH, mode=C.RTLD_GLOBAL)
+    lib = C.CDLL(LIB_PATH)
     for name, (res, args) in PROTOTYPES.items():
         fn = getattr(lib, name)      # AttributeError here = header / library mismatch
         fn.restype = res

@@ -13,12 +13,17 @@
 #include <string>
 #include <vector>
 
+#ifdef AMG1D_WITH_NCCL
+#include <dlfcn.h>
+#include <nccl.h>   // types and prototypes only: the library is dlopen'ed, never linked
+#endif
+
 #include "../../include/amg1d.h"
 #include "kernels_generic.cuh"
 #include "kernels_fused.cuh"
 
 #define AMG1D_VERSION 100
-#define PAD_FRONT 32  // doubles in front of element 0 (ghost element lives in the last m of them)
+#define PAD_FRONT 64  // doubles in front of element 0 (ghost elements live at the end of them)
 #define PAD_BACK 64
 
 namespace {
@@ -33,7 +38,14 @@ struct DVec {
 
 struct Level {
     bool set = false;
-    int64_t n = 0;  // elements (device blocks)
+    int64_t n = 0;       // elements held by this rank (== n_glob unless the level is sharded)
+    int64_t n_glob = 0;  // elements of the whole level
+    int64_t start = 0;   // global index of local element 0
+    int gl = 0, gr = 0;  // ghost elements on the left / right slab edge (sharded levels only)
+    bool sharded = false;  // split into contiguous element slabs, one per rank
+    bool present = true;   // this rank holds the level's operator (sharded, or rank 0)
+    bool proxy = false;    // vectors only: a non-root rank's slab of the first gathered level
+    double* mat_alloc = nullptr;
     int m = 0;
     int diag = 0;
     int K = 0;
@@ -96,8 +108,14 @@ struct amg1d {
     int opt_profile = 0;
     struct Prof { std::vector<cudaEvent_t> ev; };
     std::vector<Prof> prof;   // index = level * 2 + leg (0 = down, 1 = up)
-    // distributed
+    // distributed (contiguous element slabs)
     int rank = 0, nranks = 1;
+    int ghost_depth = 4;          // elements per slab edge = max(nPre, nPost) + 1
+    int64_t shard_min = 8192;     // a level is sharded while it has >= nranks * shard_min elements
+    int gather_level = -1;        // first level that lives on rank 0 only (-1: single GPU)
+#ifdef AMG1D_WITH_NCCL
+    ncclComm_t comm = nullptr;
+#endif
 };
 
 namespace {
@@ -176,6 +194,135 @@ TransferMap make_map(const Transfer& t) {
     return tm;
 }
 
+#ifdef AMG1D_WITH_NCCL
+// NCCL is resolved at run time (dlopen by SONAME) when a multi-GPU handle is created, so that a
+// process that already loaded an NCCL (e.g. the one bundled with PyTorch) keeps using exactly that
+// one, and single-GPU use never loads NCCL at all.  $AMG1D_NCCL_LIB overrides the library path.
+struct NcclApi {
+    void* lib = nullptr;
+    decltype(&ncclGetUniqueId) GetUniqueId = nullptr;
+    decltype(&ncclCommInitRank) CommInitRank = nullptr;
+    decltype(&ncclCommDestroy) CommDestroy = nullptr;
+    decltype(&ncclSend) Send = nullptr;
+    decltype(&ncclRecv) Recv = nullptr;
+    decltype(&ncclAllReduce) AllReduce = nullptr;
+    decltype(&ncclGroupStart) GroupStart = nullptr;
+    decltype(&ncclGroupEnd) GroupEnd = nullptr;
+    decltype(&ncclGetErrorString) GetErrorString = nullptr;
+};
+NcclApi g_nccl;
+
+const char* load_nccl() {
+    if (g_nccl.lib) return nullptr;
+    const char* env = getenv("AMG1D_NCCL_LIB");
+    void* lib = env ? dlopen(env, RTLD_NOW | RTLD_LOCAL) : nullptr;
+    if (!lib) lib = dlopen("libnccl.so.2", RTLD_NOW | RTLD_LOCAL);
+    if (!lib) lib = dlopen("libnccl.so", RTLD_NOW | RTLD_LOCAL);
+    if (!lib) return "cannot dlopen libnccl.so.2";
+#define NSYM(field, name)                                                    \
+    g_nccl.field = reinterpret_cast<decltype(g_nccl.field)>(dlsym(lib, name)); \
+    if (!g_nccl.field) return "libnccl lacks " name;
+    NSYM(GetUniqueId, "ncclGetUniqueId") NSYM(CommInitRank, "ncclCommInitRank")
+    NSYM(CommDestroy, "ncclCommDestroy") NSYM(Send, "ncclSend") NSYM(Recv, "ncclRecv")
+    NSYM(AllReduce, "ncclAllReduce") NSYM(GroupStart, "ncclGroupStart") NSYM(GroupEnd, "ncclGroupEnd")
+    NSYM(GetErrorString, "ncclGetErrorString")
+#undef NSYM
+    g_nccl.lib = lib;
+    return nullptr;
+}
+#endif
+
+Slab make_slab(amg1d* h, int l) {
+    Slab sl;
+    const Level& lv = h->L[l];
+    sl.gl = lv.gl;
+    sl.gr = lv.gr;
+    sl.e_off = lv.start;
+    sl.c_off = (l + 1 < h->n_levels) ? h->L[l + 1].start : 0;
+    return sl;
+}
+
+#ifdef AMG1D_WITH_NCCL
+#define NCK(call)                                                                              \
+    do {                                                                                       \
+        ncclResult_t r_ = (call);                                                              \
+        if (r_ != ncclSuccess)                                                                 \
+            return fail(h, AMG1D_ERR_NCCL, "%s failed: %s (%s:%d)", #call, g_nccl.GetErrorString(r_), \
+                        __FILE__, __LINE__);                                                   \
+    } while (0)
+
+// Exchange ghost_depth edge elements of a slab vector with both neighbour ranks.
+// v points at local element 0; n = owned elements; m = block size.
+int op_halo(amg1d* h, double* v, int64_t n, int m) {
+    const int64_t cnt = (int64_t)h->ghost_depth * m;
+    NCK(g_nccl.GroupStart());
+    if (h->rank > 0) {
+        NCK(g_nccl.Send(v, cnt, ncclDouble, h->rank - 1, h->comm, h->stream));
+        NCK(g_nccl.Recv(v - cnt, cnt, ncclDouble, h->rank - 1, h->comm, h->stream));
+    }
+    if (h->rank < h->nranks - 1) {
+        NCK(g_nccl.Send(v + (n - h->ghost_depth) * m, cnt, ncclDouble, h->rank + 1, h->comm, h->stream));
+        NCK(g_nccl.Recv(v + n * m, cnt, ncclDouble, h->rank + 1, h->comm, h->stream));
+    }
+    NCK(g_nccl.GroupEnd());
+    h->launch_counter++;
+    return AMG1D_OK;
+}
+
+// rank r's slab of the gather level's right-hand side -> rank 0 (which owns the whole level)
+int op_gather_rhs(amg1d* h, int g) {
+    Level& lg = h->L[g];
+    const int64_t per = (lg.n_glob / h->nranks) * lg.m;
+    NCK(g_nccl.GroupStart());
+    if (h->rank == 0) {
+        for (int r = 1; r < h->nranks; ++r)
+            NCK(g_nccl.Recv(lg.b.p + r * per, per, ncclDouble, r, h->comm, h->stream));
+    } else {
+        NCK(g_nccl.Send(lg.b.p, per, ncclDouble, 0, h->comm, h->stream));
+    }
+    NCK(g_nccl.GroupEnd());
+    h->launch_counter++;
+    return AMG1D_OK;
+}
+
+// rank 0's solution of the gather level -> every rank's slab (with ghost elements)
+int op_scatter_sol(amg1d* h, int g) {
+    Level& lg = h->L[g];
+    const int64_t nloc = lg.n_glob / h->nranks;
+    const int gd = h->ghost_depth;
+    NCK(g_nccl.GroupStart());
+    if (h->rank == 0) {
+        const double* x = lg.x[lg.cur].p;
+        for (int r = 1; r < h->nranks; ++r) {
+            const int64_t e0 = r * nloc - gd;
+            const int64_t e1 = (r + 1) * nloc + (r < h->nranks - 1 ? gd : 0);
+            NCK(g_nccl.Send(x + e0 * lg.m, (e1 - e0) * lg.m, ncclDouble, r, h->comm, h->stream));
+        }
+    } else {
+        const int64_t cnt = (nloc + gd + (h->rank < h->nranks - 1 ? gd : 0)) * lg.m;
+        NCK(g_nccl.Recv(lg.x[0].p - (int64_t)gd * lg.m, cnt, ncclDouble, 0, h->comm, h->stream));
+    }
+    NCK(g_nccl.GroupEnd());
+    h->launch_counter++;
+    return AMG1D_OK;
+}
+
+// d_scal[slot] currently holds a local SUM OF SQUARES: make it the global 2-norm
+__global__ void k_sqrt_inplace(double* v, int slot) { v[slot] = sqrt(v[slot]); }
+int op_allreduce_norm(amg1d* h, int slot) {
+    NCK(g_nccl.AllReduce(h->d_scal + slot, h->d_scal + slot, 1, ncclDouble, ncclSum, h->comm, h->stream));
+    k_sqrt_inplace<<<1, 1, 0, h->stream>>>(h->d_scal, slot);
+    h->launch_counter += 2;
+    LAUNCH_CHECK();
+    return AMG1D_OK;
+}
+#else
+int op_halo(amg1d* h, double*, int64_t, int) { return fail(h, AMG1D_ERR_UNSUPPORTED, "built without NCCL"); }
+int op_gather_rhs(amg1d* h, int) { return fail(h, AMG1D_ERR_UNSUPPORTED, "built without NCCL"); }
+int op_scatter_sol(amg1d* h, int) { return fail(h, AMG1D_ERR_UNSUPPORTED, "built without NCCL"); }
+int op_allreduce_norm(amg1d* h, int) { return fail(h, AMG1D_ERR_UNSUPPORTED, "built without NCCL"); }
+#endif
+
 // ---- elementary enqueued operations ---------------------------------------------------------------
 int op_sweep(amg1d* h, int l, const double* b, const double* xin, double* xout, double alpha,
              int zero_guess) {
@@ -237,9 +384,11 @@ int op_norm(amg1d* h, const double* a, const double* c, int64_t n, int slot) {
     int nb = (int)std::min<int64_t>(AMG1D_RED_BLOCKS, (n + AMG1D_RED_THREADS - 1) / AMG1D_RED_THREADS);
     if (nb < 1) nb = 1;
     k_sqdiff_partial<<<nb, AMG1D_RED_THREADS, 0, h->stream>>>(a, c, n, h->partial);
-    k_reduce_final<<<1, AMG1D_RED_THREADS, 0, h->stream>>>(h->partial, nb, h->d_scal, slot, 1);
+    k_reduce_final<<<1, AMG1D_RED_THREADS, 0, h->stream>>>(h->partial, nb, h->d_scal, slot,
+                                                           h->nranks > 1 ? 0 : 1);
     h->launch_counter += 2;
     LAUNCH_CHECK();
+    if (h->nranks > 1) RET(op_allreduce_norm(h, slot));
     return AMG1D_OK;
 }
 
@@ -253,15 +402,18 @@ int op_reduce_partials(amg1d* h, int64_t np, int slot) {
         src = stage2;
         np = 256;
     }
-    k_reduce_final<<<1, AMG1D_RED_THREADS, 0, h->stream>>>(src, (int)np, h->d_scal, slot, 1);
+    k_reduce_final<<<1, AMG1D_RED_THREADS, 0, h->stream>>>(src, (int)np, h->d_scal, slot,
+                                                           h->nranks > 1 ? 0 : 1);
     h->launch_counter++;
     LAUNCH_CHECK();
+    if (h->nranks > 1) RET(op_allreduce_norm(h, slot));
     return AMG1D_OK;
 }
 
 // || b - A x ||_2 on level l into slot
 int op_resnorm(amg1d* h, int l, int slot) {
     Level& lv = h->L[l];
+    if (lv.sharded) RET(op_halo(h, lv.x[lv.cur].p, lv.n, lv.m));
     if (h->opt_fused) {
         int nb = 0;
         if (fused_resnorm(lv.m, lv.diag, lv.mat, lv.b.p, lv.x[lv.cur].p, lv.n, h->partial,
@@ -286,83 +438,116 @@ int prof_mark(amg1d* h, int level, int leg) {
 }
 
 // ---- the V-cycle (src/solvers.jl:19-50) ------------------------------------------------------------
-int enqueue_vcycle(amg1d* h, int nPre, int nPost, double alpha, bool want_norm) {
-    const int nl = h->n_levels;
-    bool norm_done = false;
-    for (int l = 0; l < nl - 1; ++l) {
-        Level& lv = h->L[l];
-        Transfer& t = h->T[l];
-        Level& lc = h->L[l + 1];
-        bool zero = l > 0;
-        if (zero) lv.cur = 0;
-        RET(prof_mark(h, l, 0));
-        // fused down-leg: nPre sweeps + residual + restriction in one pass over the operator
-        if (h->opt_fused && t.single_parent_uniform) {
-            const int ob = zero ? 0 : 1 - lv.cur;
-            if (fused_down(lv.m, t.mc, lv.diag, make_map(t), nPre, zero, lv.mat, lv.b.p,
-                           lv.x[lv.cur].p, lv.x[ob].p, t.P0, lc.b.p, lv.n, alpha, h->stream)) {
-                lv.cur = ob;
-                h->launch_counter++;
-                LAUNCH_CHECK();
-                RET(prof_mark(h, l, 0));
-                continue;
-            }
-        }
-        if (zero && nPre == 0)
-            CK(cudaMemsetAsync(lv.x[0].p, 0, (size_t)lv.x[0].len * 8, h->stream));
-        for (int s = 0; s < nPre; ++s) {
-            if (zero && s == 0) {
-                RET(op_sweep(h, l, lv.b.p, lv.x[0].p, lv.x[0].p, alpha, 1));  // x = alpha Dinv b
-            } else {
-                RET(op_sweep(h, l, lv.b.p, lv.x[lv.cur].p, lv.x[1 - lv.cur].p, alpha, 0));
-                lv.cur = 1 - lv.cur;
-            }
-        }
-        if (h->opt_fused && t.single_parent_uniform &&
-            fused_residual_restrict(lv.m, t.mc, lv.K, make_map(t), lv.mat, lv.b.p, lv.x[lv.cur].p,
-                                    t.P0, lc.b.p, lv.n, h->stream)) {
+// Down leg of level l: nPre sweeps (zero guess on l > 0), residual, restriction into level l+1's rhs.
+int leg_down(amg1d* h, int l, int nPre, double alpha) {
+    Level& lv = h->L[l];
+    Transfer& t = h->T[l];
+    Level& lc = h->L[l + 1];
+    const bool zero = l > 0;
+    if (zero) lv.cur = 0;
+    RET(prof_mark(h, l, 0));
+    if (lv.sharded && !zero) RET(op_halo(h, lv.x[lv.cur].p, lv.n, lv.m));   // ghosts of the incoming iterate
+    // fused: nPre sweeps + residual + restriction in one pass over the operator
+    if (h->opt_fused && t.single_parent_uniform) {
+        const int ob = zero ? 0 : 1 - lv.cur;
+        if (fused_down(lv.m, t.mc, lv.diag, make_map(t), nPre, zero, lv.mat, lv.b.p, lv.x[lv.cur].p,
+                       lv.x[ob].p, t.P0, lc.b.p, lv.n, alpha, make_slab(h, l), h->stream)) {
+            lv.cur = ob;
             h->launch_counter++;
             LAUNCH_CHECK();
+            RET(prof_mark(h, l, 0));
+            return AMG1D_OK;
+        }
+    }
+    if (lv.sharded)
+        return fail(h, AMG1D_ERR_UNSUPPORTED, "level %d: sharded levels need the fused kernels "
+                    "(block size <= 4, single-parent transfer, option fused = 1)", l);
+    if (zero && nPre == 0) CK(cudaMemsetAsync(lv.x[0].p, 0, (size_t)lv.x[0].len * 8, h->stream));
+    for (int s = 0; s < nPre; ++s) {
+        if (zero && s == 0) {
+            RET(op_sweep(h, l, lv.b.p, lv.x[0].p, lv.x[0].p, alpha, 1));  // x = alpha Dinv b
         } else {
-            RET(op_apply(h, l, lv.b.p, lv.x[lv.cur].p, h->scratch.p, 1));
-            RET(op_restrict(h, l, h->scratch.p, lc.b.p));
-        }
-        RET(prof_mark(h, l, 0));
-    }
-    {
-        Level& lv = h->L[nl - 1];
-        if (nl > 1) lv.cur = 0;
-        // single level: x = A \ b overwrites the current x
-        RET(op_coarse(h, lv.b.p, lv.x[lv.cur].p));
-    }
-    for (int l = nl - 2; l >= 0; --l) {
-        Level& lv = h->L[l];
-        Transfer& t = h->T[l];
-        Level& lc = h->L[l + 1];
-        RET(prof_mark(h, l, 1));
-        if (h->opt_fused && t.single_parent_uniform) {
-            const bool fuse_norm = want_norm && l == 0;
-            int nb = 0;
-            if (fused_up(lv.m, t.mc, lv.diag, make_map(t), nPost, lv.mat, lv.b.p, lv.x[lv.cur].p,
-                         lv.x[1 - lv.cur].p, t.P0, lc.x[lc.cur].p, lv.n, alpha,
-                         fuse_norm ? h->partial : nullptr, h->partial_cap, &nb, h->stream)) {
-                lv.cur = 1 - lv.cur;
-                h->launch_counter++;
-                LAUNCH_CHECK();
-                RET(prof_mark(h, l, 1));
-                if (fuse_norm) {
-                    RET(op_reduce_partials(h, nb, 0));
-                    norm_done = true;
-                }
-                continue;
-            }
-        }
-        RET(op_prolong(h, l, lc.x[lc.cur].p, lv.x[lv.cur].p, 1));
-        for (int s = 0; s < nPost; ++s) {
             RET(op_sweep(h, l, lv.b.p, lv.x[lv.cur].p, lv.x[1 - lv.cur].p, alpha, 0));
             lv.cur = 1 - lv.cur;
         }
-        RET(prof_mark(h, l, 1));
+    }
+    if (h->opt_fused && t.single_parent_uniform &&
+        fused_residual_restrict(lv.m, t.mc, lv.K, make_map(t), lv.mat, lv.b.p, lv.x[lv.cur].p, t.P0,
+                                lc.b.p, lv.n, h->stream)) {
+        h->launch_counter++;
+        LAUNCH_CHECK();
+    } else {
+        RET(op_apply(h, l, lv.b.p, lv.x[lv.cur].p, h->scratch.p, 1));
+        RET(op_restrict(h, l, h->scratch.p, lc.b.p));
+    }
+    return prof_mark(h, l, 0);
+}
+
+// Up leg of level l: x += L x_c, nPost sweeps; optionally ||b - A x|| of the result (level 0).
+int leg_up(amg1d* h, int l, int nPost, double alpha, bool fuse_norm, bool* norm_done) {
+    Level& lv = h->L[l];
+    Transfer& t = h->T[l];
+    Level& lc = h->L[l + 1];
+    RET(prof_mark(h, l, 1));
+    if (h->opt_fused && t.single_parent_uniform) {
+        int nb = 0;
+        if (fused_up(lv.m, t.mc, lv.diag, make_map(t), nPost, lv.mat, lv.b.p, lv.x[lv.cur].p,
+                     lv.x[1 - lv.cur].p, t.P0, lc.x[lc.cur].p, lv.n, alpha,
+                     fuse_norm ? h->partial : nullptr, h->partial_cap, &nb, make_slab(h, l),
+                     h->stream)) {
+            lv.cur = 1 - lv.cur;
+            h->launch_counter++;
+            LAUNCH_CHECK();
+            RET(prof_mark(h, l, 1));
+            if (fuse_norm) {
+                RET(op_reduce_partials(h, nb, 0));
+                *norm_done = true;
+            }
+            return AMG1D_OK;
+        }
+    }
+    if (lv.sharded)
+        return fail(h, AMG1D_ERR_UNSUPPORTED, "level %d: sharded levels need the fused kernels", l);
+    RET(op_prolong(h, l, lc.x[lc.cur].p, lv.x[lv.cur].p, 1));
+    for (int s = 0; s < nPost; ++s) {
+        RET(op_sweep(h, l, lv.b.p, lv.x[lv.cur].p, lv.x[1 - lv.cur].p, alpha, 0));
+        lv.cur = 1 - lv.cur;
+    }
+    return prof_mark(h, l, 1);
+}
+
+int enqueue_vcycle(amg1d* h, int nPre, int nPost, double alpha, bool want_norm) {
+    const int nl = h->n_levels;
+    const int g = h->gather_level;          // -1 on a single GPU: every level is local
+    bool norm_done = false;
+    if (g >= 0 && std::max(nPre, nPost) + 1 > h->ghost_depth)
+        return fail(h, AMG1D_ERR_ARG, "nPre / nPost need ghost_depth >= %d", std::max(nPre, nPost) + 1);
+    // ---- down ----
+    for (int l = 0; l < nl - 1; ++l) {
+        Level& lv = h->L[l];
+        if (!lv.present) break;                       // ranks > 0 stop at the gather level
+        RET(leg_down(h, l, nPre, alpha));
+        if (lv.sharded) {
+            Level& lc = h->L[l + 1];
+            RET(op_halo(h, lv.x[lv.cur].p, lv.n, lv.m));              // pre-smoothed iterate, for the up leg
+            if (lc.sharded) RET(op_halo(h, lc.b.p, lc.n, lc.m));      // coarse rhs ghosts
+            else RET(op_gather_rhs(h, l + 1));                        // slabs -> rank 0
+        }
+    }
+    // ---- coarsest level: exact solve (src/solvers.jl:39) ----
+    if (h->L[nl - 1].present) {
+        Level& lv = h->L[nl - 1];
+        if (nl > 1) lv.cur = 0;
+        RET(op_coarse(h, lv.b.p, lv.x[lv.cur].p));   // single level: x = A \ b overwrites x
+    }
+    // ---- up ----
+    for (int l = nl - 2; l >= 0; --l) {
+        Level& lv = h->L[l];
+        Level& lc = h->L[l + 1];
+        if (!lv.present) continue;
+        if (lv.sharded && !lc.sharded) RET(op_scatter_sol(h, l + 1));   // rank 0 -> slabs (+ ghosts)
+        RET(leg_up(h, l, nPost, alpha, want_norm && l == 0, &norm_done));
+        if (lv.sharded && l > 0) RET(op_halo(h, lv.x[lv.cur].p, lv.n, lv.m));  // for level l-1's prolongation
     }
     Level& l0 = h->L[0];
     if (l0.cur != 0) {
@@ -542,12 +727,36 @@ int alloc_level_common(amg1d* h, int level, int64_t n_elem, int m, int diag, con
     Level& lv = h->L[level];
     if (lv.set) return fail(h, AMG1D_ERR_STATE, "level %d already set", level);
     CK(cudaSetDevice(h->device));
-    lv.n = n_elem; lv.m = m; lv.diag = diag ? 1 : 0; lv.K = amg1d_K(m, lv.diag);
-    lv.n_host = n_dof_host;
+    lv.m = m; lv.diag = diag ? 1 : 0; lv.K = amg1d_K(m, lv.diag);
+    lv.n_glob = n_elem;
     if (!perm && n_dof_host != n_elem * m)
         return fail(h, AMG1D_ERR_ARG, "n_dof_host must equal n_elem*m when perm is NULL");
-    lv.mat_bytes = amg1d_tiles(n_elem) * (int64_t)lv.K * AMG1D_TILE * 8;
-    RET(dev_alloc(h, (void**)&lv.mat, lv.mat_bytes));
+    // slab decision: shard while the level is large, otherwise it lives on rank 0
+    lv.sharded = h->nranks > 1 && !perm && n_elem % h->nranks == 0 &&
+                 n_elem / h->nranks >= h->shard_min &&
+                 (level == 0 || h->L[level - 1].sharded);
+    if (h->nranks > 1 && level == 0 && !lv.sharded)
+        return fail(h, AMG1D_ERR_UNSUPPORTED, "multi-GPU: the finest level must be shardable (DG-type, "
+                    "n_elem divisible by the rank count, >= %lld elements per rank)", (long long)h->shard_min);
+    if (lv.sharded) {
+        lv.n = n_elem / h->nranks;
+        lv.start = lv.n * h->rank;
+        lv.gl = h->rank > 0 ? h->ghost_depth : 0;
+        lv.gr = h->rank < h->nranks - 1 ? h->ghost_depth : 0;
+        lv.present = true;
+        n_dof_host = lv.n * m;                    // host vectors are the rank's slab
+    } else {
+        lv.n = n_elem; lv.start = 0; lv.gl = lv.gr = 0;
+        lv.present = h->rank == 0;
+        if (h->nranks > 1 && h->gather_level < 0) h->gather_level = level;
+    }
+    lv.n_host = n_dof_host;
+    if (!lv.present) return AMG1D_OK;             // ranks > 0 hold nothing of gathered levels
+    // one spare tile in front of element 0 (ghost elements have negative local indices)
+    lv.mat_bytes = (amg1d_tiles(lv.n + lv.gr) + 1) * (int64_t)lv.K * AMG1D_TILE * 8;
+    RET(dev_alloc(h, (void**)&lv.mat_alloc, lv.mat_bytes));
+    CK(cudaMemsetAsync(lv.mat_alloc, 0, (size_t)lv.K * AMG1D_TILE * 8, h->stream));
+    lv.mat = lv.mat_alloc + (int64_t)lv.K * AMG1D_TILE;
     if (perm) {
         const int64_t ns = n_elem * m;
         for (int64_t s = 0; s < ns; ++s)
@@ -595,15 +804,44 @@ int amg1d_create(amg1d_t** out, int n_levels, int device, void* stream) {
 }
 
 int amg1d_nccl_unique_id(void* id128) {
-    (void)id128;
-    return fail(nullptr, AMG1D_ERR_UNSUPPORTED, "multi-GPU support not built in this version");
+    amg1d* h = nullptr;
+    if (!id128) return fail(h, AMG1D_ERR_ARG, "null id buffer");
+#ifdef AMG1D_WITH_NCCL
+    static_assert(sizeof(ncclUniqueId) == 128, "ncclUniqueId is expected to be 128 bytes");
+    if (const char* e = load_nccl()) return fail(h, AMG1D_ERR_NCCL, "%s", e);
+    ncclUniqueId id;
+    NCK(g_nccl.GetUniqueId(&id));
+    memcpy(id128, &id, sizeof id);
+    return AMG1D_OK;
+#else
+    return fail(h, AMG1D_ERR_UNSUPPORTED, "libamg1d was built without NCCL");
+#endif
 }
 
 int amg1d_create_dist(amg1d_t** out, int n_levels, int device, void* stream, int rank, int nranks,
                       const void* nccl_id) {
-    (void)nccl_id;
     if (nranks == 1 && rank == 0) return amg1d_create(out, n_levels, device, stream);
-    return fail(nullptr, AMG1D_ERR_UNSUPPORTED, "multi-GPU support not built in this version");
+    amg1d* h = nullptr;
+    if (nranks < 1 || rank < 0 || rank >= nranks) return fail(h, AMG1D_ERR_ARG, "bad rank / nranks");
+    if (!nccl_id) return fail(h, AMG1D_ERR_ARG, "null NCCL id");
+#ifdef AMG1D_WITH_NCCL
+    if (const char* e = load_nccl()) return fail(h, AMG1D_ERR_NCCL, "%s", e);
+    RET(amg1d_create(out, n_levels, device, stream));
+    amg1d* nh = *out;
+    nh->rank = rank;
+    nh->nranks = nranks;
+    ncclUniqueId id;
+    memcpy(&id, nccl_id, sizeof id);
+    ncclResult_t r = g_nccl.CommInitRank(&nh->comm, nranks, id, rank);
+    if (r != ncclSuccess) {
+        amg1d_destroy(nh);
+        *out = nullptr;
+        return fail(h, AMG1D_ERR_NCCL, "ncclCommInitRank failed: %s", g_nccl.GetErrorString(r));
+    }
+    return AMG1D_OK;
+#else
+    return fail(h, AMG1D_ERR_UNSUPPORTED, "libamg1d was built without NCCL");
+#endif
 }
 
 int amg1d_destroy(amg1d_t* h) {
@@ -613,7 +851,7 @@ int amg1d_destroy(amg1d_t* h) {
     if (h->gexec) cudaGraphExecDestroy(h->gexec);
     for (auto& pr : h->prof) for (auto ev : pr.ev) cudaEventDestroy(ev);
     for (auto& lv : h->L) {
-        if (lv.mat) cudaFree(lv.mat);
+        if (lv.mat_alloc) cudaFree(lv.mat_alloc);
         if (lv.perm) cudaFree(lv.perm);
         vec_free(lv.x[0]); vec_free(lv.x[1]); vec_free(lv.b);
     }
@@ -629,6 +867,9 @@ int amg1d_destroy(amg1d_t* h) {
     if (h->d_scal) cudaFree(h->d_scal);
     if (h->h_scal) cudaFreeHost(h->h_scal);
     if (h->coarse_fac) cudaFree(h->coarse_fac);
+#ifdef AMG1D_WITH_NCCL
+    if (h->comm) g_nccl.CommDestroy(h->comm);
+#endif
     if (h->own_stream) cudaStreamDestroy(h->stream);
     delete h;
     return AMG1D_OK;
@@ -646,30 +887,45 @@ int amg1d_set_level(amg1d_t* h, int level, int64_t n_elem, int m, const double* 
     for (int q = 0; q < mm; ++q)
         if (A_lo[q] != 0.0 || A_up[(size_t)(n_elem - 1) * mm + q] != 0.0)
             return fail(h, AMG1D_ERR_ARG, "A_lo[0] and A_up[n-1] must be zero blocks");
+    if (!lv.present) { lv.set = true; return AMG1D_OK; }
+    // local range of elements to store: [-gl, n + gr) in local indices = [g0, g1) in global ones
+    const int64_t g0 = lv.start - lv.gl, g1 = lv.start + lv.n + lv.gr;
     const int64_t chunk = 1 << 18;  // elements per staging chunk (multiple of 32)
-    const int64_t c = std::min(chunk, (n_elem + 31) / 32 * 32);
+    const int64_t c = std::min(chunk, (lv.n + lv.gr + 63) / 32 * 32);
     double *d_lo, *d_di, *d_up, *d_dv;
     CK(cudaMalloc(&d_lo, (size_t)c * mm * 8));
     CK(cudaMalloc(&d_di, (size_t)c * mm * 8));
     CK(cudaMalloc(&d_up, (size_t)c * mm * 8));
     CK(cudaMalloc(&d_dv, (size_t)c * dsz * 8));
     int rc = AMG1D_OK;
-    for (int64_t e0 = 0; e0 < n_elem && rc == AMG1D_OK; e0 += c) {
-        const int64_t cnt = std::min(c, n_elem - e0);
-        cudaMemcpyAsync(d_lo, A_lo + e0 * mm, (size_t)cnt * mm * 8, cudaMemcpyHostToDevice, h->stream);
-        cudaMemcpyAsync(d_di, A_di + e0 * mm, (size_t)cnt * mm * 8, cudaMemcpyHostToDevice, h->stream);
-        cudaMemcpyAsync(d_up, A_up + e0 * mm, (size_t)cnt * mm * 8, cudaMemcpyHostToDevice, h->stream);
-        cudaMemcpyAsync(d_dv, Dinv + e0 * dsz, (size_t)cnt * dsz * 8, cudaMemcpyHostToDevice, h->stream);
+    // chunks are aligned to tiles of the local storage; the first one starts at local element -32 when
+    // the slab has left ghosts (those tiles are zero-filled outside [g0, g1))
+    const int64_t l_begin = lv.gl ? -AMG1D_TILE : 0;
+    for (int64_t le0 = l_begin; le0 < lv.n + lv.gr && rc == AMG1D_OK; le0 += c) {
+        const int64_t cnt = std::min<int64_t>(c, lv.n + lv.gr - le0);
+        // global elements of this chunk that exist: [a, b)
+        const int64_t a = std::max(g0, lv.start + le0), b = std::min(g1, lv.start + le0 + cnt);
+        const int64_t off = a - (lv.start + le0);       // leading elements of the chunk left at zero
+        cudaMemsetAsync(d_lo, 0, (size_t)cnt * mm * 8, h->stream);
+        cudaMemsetAsync(d_di, 0, (size_t)cnt * mm * 8, h->stream);
+        cudaMemsetAsync(d_up, 0, (size_t)cnt * mm * 8, h->stream);
+        cudaMemsetAsync(d_dv, 0, (size_t)cnt * dsz * 8, h->stream);
+        if (b > a) {
+            cudaMemcpyAsync(d_lo + off * mm, A_lo + a * mm, (size_t)(b - a) * mm * 8, cudaMemcpyHostToDevice, h->stream);
+            cudaMemcpyAsync(d_di + off * mm, A_di + a * mm, (size_t)(b - a) * mm * 8, cudaMemcpyHostToDevice, h->stream);
+            cudaMemcpyAsync(d_up + off * mm, A_up + a * mm, (size_t)(b - a) * mm * 8, cudaMemcpyHostToDevice, h->stream);
+            cudaMemcpyAsync(d_dv + off * dsz, Dinv + a * dsz, (size_t)(b - a) * dsz * 8, cudaMemcpyHostToDevice, h->stream);
+        }
         const int64_t total = amg1d_tiles(cnt) * (int64_t)lv.K * AMG1D_TILE;
         k_repack<<<(unsigned)((total + 255) / 256), 256, 0, h->stream>>>(d_lo, d_di, d_up, d_dv, m,
-                                                                         lv.diag, lv.K, e0, cnt, lv.mat);
+                                                                         lv.diag, lv.K, le0, cnt, lv.mat);
         cudaError_t e = cudaStreamSynchronize(h->stream);
         if (e == cudaSuccess) e = cudaGetLastError();
         if (e != cudaSuccess) rc = fail(h, AMG1D_ERR_CUDA, "level upload failed: %s", cudaGetErrorString(e));
     }
     cudaFree(d_lo); cudaFree(d_di); cudaFree(d_up); cudaFree(d_dv);
     RET(rc);
-    if (n_elem <= 65536) {
+    if (n_elem <= 65536 && !lv.sharded) {
         lv.h_lo.assign(A_lo, A_lo + (size_t)n_elem * mm);
         lv.h_di.assign(A_di, A_di + (size_t)n_elem * mm);
         lv.h_up.assign(A_up, A_up + (size_t)n_elem * mm);
@@ -690,6 +946,7 @@ int amg1d_set_level_pattern(amg1d_t* h, int level, int64_t n_elem, int m, int n_
     const int mm = m * m;
     const int dsz = lv.diag ? m : mm;
     const int nb = n_head + 1 + n_tail;
+    if (!lv.present) { lv.set = true; return AMG1D_OK; }
     double *d_lo, *d_di, *d_up, *d_dv;
     CK(cudaMalloc(&d_lo, (size_t)nb * mm * 8));
     CK(cudaMalloc(&d_di, (size_t)nb * mm * 8));
@@ -699,14 +956,17 @@ int amg1d_set_level_pattern(amg1d_t* h, int level, int64_t n_elem, int m, int n_
     cudaMemcpyAsync(d_di, A_di, (size_t)nb * mm * 8, cudaMemcpyHostToDevice, h->stream);
     cudaMemcpyAsync(d_up, A_up, (size_t)nb * mm * 8, cudaMemcpyHostToDevice, h->stream);
     cudaMemcpyAsync(d_dv, Dinv, (size_t)nb * dsz * 8, cudaMemcpyHostToDevice, h->stream);
-    const int64_t total = amg1d_tiles(n_elem) * (int64_t)lv.K * AMG1D_TILE;
+    // fill every stored tile, including the spare front tile that holds the left ghost elements
+    const int64_t ntiles = amg1d_tiles(lv.n + lv.gr) + 1;
+    const int64_t total = ntiles * (int64_t)lv.K * AMG1D_TILE;
     k_fill_pattern<<<(unsigned)((total + 255) / 256), 256, 0, h->stream>>>(
-        d_lo, d_di, d_up, d_dv, m, lv.diag, lv.K, n_elem, n_head, n_tail, lv.mat);
+        d_lo, d_di, d_up, d_dv, m, lv.diag, lv.K, n_elem, n_head, n_tail, lv.start, -(int64_t)lv.gl,
+        lv.n + lv.gr, ntiles, lv.mat_alloc);
     cudaError_t e = cudaStreamSynchronize(h->stream);
     if (e == cudaSuccess) e = cudaGetLastError();
     cudaFree(d_lo); cudaFree(d_di); cudaFree(d_up); cudaFree(d_dv);
     if (e != cudaSuccess) return fail(h, AMG1D_ERR_CUDA, "pattern fill failed: %s", cudaGetErrorString(e));
-    if (n_elem <= 65536) {
+    if (n_elem <= 65536 && !lv.sharded) {
         lv.h_lo.resize((size_t)n_elem * mm); lv.h_di.resize((size_t)n_elem * mm); lv.h_up.resize((size_t)n_elem * mm);
         for (int64_t el = 0; el < n_elem; ++el) {
             int64_t s = el < n_head ? el : (el >= n_elem - n_tail ? n_head + 1 + (el - (n_elem - n_tail)) : n_head);
@@ -733,6 +993,9 @@ int amg1d_set_transfer(amg1d_t* h, int level, int64_t n_fine_elem, int m_f, int 
                        const int64_t* parent, const double* P0, const double* P1) {
     RET(transfer_common(h, level, n_fine_elem, m_f, m_c));
     if (!parent || !P0) return fail(h, AMG1D_ERR_ARG, "null transfer array");
+    if (h->L[level].set && h->L[level].sharded)
+        return fail(h, AMG1D_ERR_UNSUPPORTED, "transfer %d: a sharded level needs a pattern transfer "
+                    "(amg1d_set_transfer_pattern)", level);
     Transfer& t = h->T[level];
     t.n_fine = n_fine_elem; t.mf = m_f; t.mc = m_c; t.period = 0;
     int64_t maxp = -1;
@@ -800,25 +1063,35 @@ int amg1d_finalize(amg1d_t* h) {
     CK(cudaSetDevice(h->device));
     for (int l = 0; l < h->n_levels; ++l)
         if (!h->L[l].set) return fail(h, AMG1D_ERR_STATE, "level %d was never set", l);
+    if (h->nranks > 1 && h->gather_level < 0)
+        return fail(h, AMG1D_ERR_UNSUPPORTED, "multi-GPU: the coarsest levels must fall below the shard "
+                    "threshold (%lld elements per rank) so that they can be gathered", (long long)h->shard_min);
     int64_t maxlen = 0;
-    int maxm = 1;
     for (int l = 0; l < h->n_levels - 1; ++l) {
         Transfer& t = h->T[l];
         if (!t.set) return fail(h, AMG1D_ERR_STATE, "transfer %d was never set", l);
         Level& lf = h->L[l];
         Level& lc = h->L[l + 1];
-        if (t.n_fine != lf.n || t.mf != lf.m || t.mc != lc.m)
+        if (t.n_fine != lf.n_glob || t.mf != lf.m || t.mc != lc.m)
             return fail(h, AMG1D_ERR_ARG, "transfer %d does not match its levels (n_fine %lld vs %lld, m_f %d vs %d, m_c %d vs %d)",
-                        l, (long long)t.n_fine, (long long)lf.n, t.mf, lf.m, t.mc, lc.m);
+                        l, (long long)t.n_fine, (long long)lf.n_glob, t.mf, lf.m, t.mc, lc.m);
         const int64_t need = t.n_coarse + (t.P1 ? 1 : 0);
-        if (t.n_coarse > lc.n || need < lc.n)
+        if (t.n_coarse > lc.n_glob || need < lc.n_glob)
             return fail(h, AMG1D_ERR_ARG, "transfer %d reaches coarse element %lld but level %d has %lld elements",
-                        l, (long long)t.n_coarse - 1, l + 1, (long long)lc.n);
-        t.n_coarse = lc.n;
+                        l, (long long)t.n_coarse - 1, l + 1, (long long)lc.n_glob);
+        t.n_coarse = lc.n_glob;
+        if (lf.sharded) {
+            if (!t.single_parent_uniform || t.period == 0)
+                return fail(h, AMG1D_ERR_UNSUPPORTED, "transfer %d: sharded levels need a single-parent "
+                            "pattern transfer", l);
+            if (lf.n % t.ratio || lf.n < 2 * h->ghost_depth || lc.n_glob % h->nranks)
+                return fail(h, AMG1D_ERR_UNSUPPORTED, "transfer %d: slab of %lld elements is not aligned "
+                            "to the agglomeration ratio %d", l, (long long)lf.n, t.ratio);
+        }
         if (t.parent) {  // build child pointers: cp[q] = first e with parent[e] >= q - 1, q = 0..n_coarse+1
-            std::vector<int64_t> cp((size_t)lc.n + 2);
+            std::vector<int64_t> cp((size_t)lc.n_glob + 2);
             int64_t e = 0;
-            for (int64_t q = 0; q < lc.n + 2; ++q) {
+            for (int64_t q = 0; q < lc.n_glob + 2; ++q) {
                 while (e < t.n_fine && t.h_parent[e] < q - 1) ++e;
                 cp[q] = e;
             }
@@ -828,22 +1101,28 @@ int amg1d_finalize(amg1d_t* h) {
             CK(cudaMemcpy(t.cp, cp.data(), cp.size() * 8, cudaMemcpyHostToDevice));
         }
     }
+    // a non-root rank keeps only its slab of the first gathered level (vectors, no operator)
+    if (h->nranks > 1 && h->rank > 0) {
+        Level& lg = h->L[h->gather_level];
+        lg.proxy = true;
+        lg.n = lg.n_glob / h->nranks;
+        lg.start = lg.n * h->rank;
+    }
+    h->partial_cap = AMG1D_RED_BLOCKS;
     for (int l = 0; l < h->n_levels; ++l) {
         Level& lv = h->L[l];
+        if (!lv.present && !lv.proxy) continue;
         RET(vec_alloc(h, lv.x[0], lv.n, lv.m));
-        RET(vec_alloc(h, lv.x[1], lv.n, lv.m));
         RET(vec_alloc(h, lv.b, lv.n, lv.m));
+        if (lv.present) RET(vec_alloc(h, lv.x[1], lv.n, lv.m));
         maxlen = std::max(maxlen, lv.n * lv.m);
-        maxm = std::max(maxm, lv.m);
+        h->partial_cap = std::max<int64_t>(h->partial_cap, lv.n / (FUSED_B / 2) + 16);
     }
     RET(vec_alloc(h, h->scratch, maxlen, 1));
-    h->partial_cap = std::max<int64_t>(AMG1D_RED_BLOCKS, h->L[0].n / (FUSED_B / 2) + 16);
-    for (int l = 0; l < h->n_levels; ++l)
-        h->partial_cap = std::max<int64_t>(h->partial_cap, h->L[l].n / (FUSED_B / 2) + 16);
     RET(dev_alloc(h, (void**)&h->partial, (h->partial_cap + 256) * 8));
     RET(dev_alloc(h, (void**)&h->d_scal, 64 * 8));
     CK(cudaMallocHost(&h->h_scal, 64 * 8));
-    RET(factor_coarsest(h));
+    if (h->L[h->n_levels - 1].present) RET(factor_coarsest(h));
     CK(cudaStreamSynchronize(h->stream));
     h->finalized = true;
     return AMG1D_OK;
@@ -854,7 +1133,10 @@ int amg1d_dev_set_problem(amg1d_t* h, const double* x0, const double* b) {
     RET(check_ready(h));
     Level& l0 = h->L[0];
     h->norm_valid = false;
-    if (b) RET(to_device(h, 0, b, l0.b.p));
+    if (b) {
+        RET(to_device(h, 0, b, l0.b.p));
+        if (l0.sharded) RET(op_halo(h, l0.b.p, l0.n, l0.m));
+    }
     if (l0.cur != 0) l0.cur = 0;
     if (x0) RET(to_device(h, 0, x0, l0.x[0].p));
     else CK(cudaMemsetAsync(l0.x[0].p, 0, (size_t)l0.x[0].len * 8, h->stream));
@@ -866,8 +1148,9 @@ int amg1d_dev_fill_rhs_random(amg1d_t* h, uint64_t seed) {
     Level& l0 = h->L[0];
     if (l0.perm) return fail(h, AMG1D_ERR_UNSUPPORTED, "random rhs only for unpermuted (DG) fine levels");
     h->norm_valid = false;
-    k_fill_random<<<1184, 256, 0, h->stream>>>(l0.b.p, l0.b.len, seed);
+    k_fill_random<<<1184, 256, 0, h->stream>>>(l0.b.p, l0.b.len, seed, l0.start * l0.m);
     LAUNCH_CHECK();
+    if (l0.sharded) RET(op_halo(h, l0.b.p, l0.n, l0.m));
     l0.cur = 0;
     CK(cudaMemsetAsync(l0.x[0].p, 0, (size_t)l0.x[0].len * 8, h->stream));
     return AMG1D_OK;
@@ -967,6 +1250,7 @@ int amg1d_solve(amg1d_t* h, double* x, const double* b, int maxiter, double tol,
 int amg1d_apply_smoother(amg1d_t* h, int level, double* Y, const double* B, int64_t n_rhs,
                          double alpha) {
     RET(check_ready(h));
+    if (h->nranks > 1) return fail(h, AMG1D_ERR_UNSUPPORTED, "per-level host operations are single-GPU only");
     if (!valid_level(h, level)) return fail(h, AMG1D_ERR_ARG, "level %d out of range", level);
     if (!Y || !B || n_rhs < 1) return fail(h, AMG1D_ERR_ARG, "bad arguments");
     Level& lv = h->L[level];
@@ -984,6 +1268,7 @@ int amg1d_apply_smoother(amg1d_t* h, int level, double* Y, const double* B, int6
 int amg1d_smoother_solve(amg1d_t* h, int level, double* x, const double* b, int maxiter, double tol,
                          double alpha, int* iters, double* res, double* err, const double* u_exact) {
     RET(check_ready(h));
+    if (h->nranks > 1) return fail(h, AMG1D_ERR_UNSUPPORTED, "per-level host operations are single-GPU only");
     if (!valid_level(h, level)) return fail(h, AMG1D_ERR_ARG, "level %d out of range", level);
     if (!x || !b || !res || !iters) return fail(h, AMG1D_ERR_ARG, "null argument");
     Level& lv = h->L[level];
@@ -1029,6 +1314,7 @@ int amg1d_smoother_solve(amg1d_t* h, int level, double* x, const double* b, int 
 
 static int apply_common(amg1d_t* h, int level, double* out, const double* x, const double* b, int mode) {
     RET(check_ready(h));
+    if (h->nranks > 1) return fail(h, AMG1D_ERR_UNSUPPORTED, "per-level host operations are single-GPU only");
     if (!valid_level(h, level)) return fail(h, AMG1D_ERR_ARG, "level %d out of range", level);
     if (!out || !x || (mode && !b)) return fail(h, AMG1D_ERR_ARG, "null vector");
     Level& lv = h->L[level];
@@ -1051,6 +1337,7 @@ int amg1d_residual(amg1d_t* h, int level, double* r, const double* x, const doub
 
 int amg1d_restrict(amg1d_t* h, int level, double* rc, const double* rf) {
     RET(check_ready(h));
+    if (h->nranks > 1) return fail(h, AMG1D_ERR_UNSUPPORTED, "per-level host operations are single-GPU only");
     if (level < 0 || level >= h->n_levels - 1) return fail(h, AMG1D_ERR_ARG, "transfer %d out of range", level);
     if (!rc || !rf) return fail(h, AMG1D_ERR_ARG, "null vector");
     invalidate_graph(h);
@@ -1064,6 +1351,7 @@ int amg1d_restrict(amg1d_t* h, int level, double* rc, const double* rf) {
 
 int amg1d_prolong(amg1d_t* h, int level, double* xf, const double* xc) {
     RET(check_ready(h));
+    if (h->nranks > 1) return fail(h, AMG1D_ERR_UNSUPPORTED, "per-level host operations are single-GPU only");
     if (level < 0 || level >= h->n_levels - 1) return fail(h, AMG1D_ERR_ARG, "transfer %d out of range", level);
     if (!xf || !xc) return fail(h, AMG1D_ERR_ARG, "null vector");
     invalidate_graph(h);
@@ -1077,6 +1365,7 @@ int amg1d_prolong(amg1d_t* h, int level, double* xf, const double* xc) {
 
 int amg1d_coarse_solve(amg1d_t* h, double* x, const double* b) {
     RET(check_ready(h));
+    if (h->nranks > 1) return fail(h, AMG1D_ERR_UNSUPPORTED, "per-level host operations are single-GPU only");
     if (!x || !b) return fail(h, AMG1D_ERR_ARG, "null vector");
     invalidate_graph(h);
     const int l = h->n_levels - 1;
@@ -1093,6 +1382,12 @@ int amg1d_set_option(amg1d_t* h, const char* key, int64_t value) {
     if (!strcmp(key, "fused")) h->opt_fused = (int)value;
     else if (!strcmp(key, "graph")) h->opt_graph = (int)value;
     else if (!strcmp(key, "coarse_cta_elems")) h->opt_coarse_cta = value;
+    else if (!strcmp(key, "ghost_depth") || !strcmp(key, "shard_min")) {
+        for (auto& lv : h->L)
+            if (lv.set) return fail(h, AMG1D_ERR_STATE, "'%s' must be set before the first level", key);
+        if (value < 1) return fail(h, AMG1D_ERR_ARG, "'%s' must be >= 1", key);
+        if (!strcmp(key, "ghost_depth")) h->ghost_depth = (int)value; else h->shard_min = value;
+    }
     else if (!strcmp(key, "profile")) {
         h->opt_profile = (int)value;
         for (auto& pr : h->prof) { for (auto ev : pr.ev) cudaEventDestroy(ev); pr.ev.clear(); }
@@ -1107,9 +1402,15 @@ int64_t amg1d_get_info(amg1d_t* h, const char* key) {
     if (!strcmp(key, "launches_per_cycle")) return h->launches_per_cycle;
     if (!strcmp(key, "device_bytes")) return h->device_bytes;
     if (!strcmp(key, "n_levels")) return h->n_levels;
+    if (!strcmp(key, "local_elements")) return h->L[0].n;
+    if (!strcmp(key, "local_dofs")) return h->L[0].n * h->L[0].m;
+    if (!strcmp(key, "local_offset_dofs")) return h->L[0].start * h->L[0].m;
+    if (!strcmp(key, "gather_level")) return h->gather_level;
+    if (!strcmp(key, "rank")) return h->rank;
+    if (!strcmp(key, "nranks")) return h->nranks;
     if (!strcmp(key, "dof_updates_per_sweep")) {
         int64_t s = 0;
-        for (int l = 0; l < h->n_levels - 1; ++l) s += h->L[l].n_host;
+        for (int l = 0; l < h->n_levels - 1; ++l) s += h->L[l].n_glob * h->L[l].m;
         return s;
     }
     return -1;

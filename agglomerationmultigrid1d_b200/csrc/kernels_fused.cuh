@@ -23,6 +23,14 @@
 #include "kernels_generic.cuh"
 #include "layout.cuh"
 
+// Position of a rank's slab inside its level (single GPU: all zero).  Local element index e runs over
+// [-gl, n + gr): gl / gr ghost elements (with operator blocks, rhs and iterate) on the left / right
+// slab edge; e_off = global index of local element 0; c_off = global index of local coarse element 0.
+struct Slab {
+    int gl, gr;
+    int64_t e_off, c_off;
+};
+
 #ifndef FUSED_B
 #define FUSED_B 128  // window (threads) per CTA of f_down / f_up
 #endif
@@ -279,14 +287,15 @@ template <int M, int MC, int B>
 __global__ void __launch_bounds__(B, FUSED_MINB)
 f_down(const double* __restrict__ mat, const double* __restrict__ b, const double* __restrict__ xin,
        double* __restrict__ xout, const double* __restrict__ P0, TransferMap tm,
-       double* __restrict__ rc, int64_t n, double alpha, int nsweep, int zero_guess, int out) {
+       double* __restrict__ rc, int64_t n, double alpha, int nsweep, int zero_guess, int out,
+       Slab sl) {
     __shared__ Exchange<M, B> ex;
     __shared__ double rs[M][B + 8];
     __shared__ double ds[M * M][B];
     const int t = threadIdx.x;
     const int halo = nsweep + 1;
-    const int64_t e = (int64_t)blockIdx.x * out - halo + t;
-    const bool active = e >= 0 && e < n;
+    const int64_t e = (int64_t)blockIdx.x * out - halo + t;     // local element index (ghosts < 0, >= n)
+    const bool active = e >= -(int64_t)sl.gl && e < n + sl.gr;
     exch_init<M, B>(ex);
     double A[3 * M * M], bb[M], xc[M], xl[M], xr[M];
     load_blocks<M, B>(mat, e, active, A, ds);
@@ -313,7 +322,7 @@ f_down(const double* __restrict__ mat, const double* __restrict__ b, const doubl
         }
         reg_sweep<M, B>(A, &ds[0][t], bb, xl, xc, xr, alpha, zg);
     }
-    const bool emit = active && t >= halo && t < halo + out;
+    const bool emit = e >= 0 && e < n && t >= halo && t < halo + out;
     if (emit) store_vec<M>(xout + e * M, xc);
     // residual with the final iterate, then restriction
     exchange<M, B>(ex, buf, xc, xl, xr);
@@ -323,18 +332,19 @@ f_down(const double* __restrict__ mat, const double* __restrict__ b, const doubl
     for (int i = 0; i < M; ++i) rs[i][t] = r[i];
     __syncthreads();
     const int ratio = tm.ratio;
-    if (emit && (e % ratio) == 0) {
+    const int64_t eg = e + sl.e_off;                           // global element index
+    if (emit && (eg % ratio) == 0) {
         double acc[MC];
 #pragma unroll
         for (int j = 0; j < MC; ++j) acc[j] = 0.0;
         for (int c = 0; c < ratio && e + c < n; ++c) {
-            const double* P = P0 + tm.blk(e + c) * (M * MC);
+            const double* P = P0 + tm.blk(eg + c) * (M * MC);
 #pragma unroll
             for (int j = 0; j < MC; ++j)
 #pragma unroll
                 for (int i = 0; i < M; ++i) acc[j] = fma(P[j * M + i], rs[i][t + c], acc[j]);
         }
-        const int64_t Kc = e / ratio;
+        const int64_t Kc = eg / ratio - sl.c_off;              // local coarse element index
 #pragma unroll
         for (int j = 0; j < MC; ++j) rc[Kc * MC + j] = acc[j];
     }
@@ -346,13 +356,13 @@ __global__ void __launch_bounds__(B, FUSED_MINB)
 f_up(const double* __restrict__ mat, const double* __restrict__ b, const double* __restrict__ xin,
      double* __restrict__ xout, const double* __restrict__ P0, TransferMap tm,
      const double* __restrict__ xcoarse, int64_t n, double alpha, int nsweep, int out,
-     double* __restrict__ partial) {
+     double* __restrict__ partial, Slab sl) {
     __shared__ Exchange<M, B> ex;
     __shared__ double ds[M * M][B];
     const int t = threadIdx.x;
     const int halo = nsweep + 1;
     const int64_t e = (int64_t)blockIdx.x * out - halo + t;
-    const bool active = e >= 0 && e < n;
+    const bool active = e >= -(int64_t)sl.gl && e < n + sl.gr;
     exch_init<M, B>(ex);
     double A[3 * M * M], bb[M], xc[M], xl[M], xr[M];
     load_blocks<M, B>(mat, e, active, A, ds);
@@ -360,8 +370,9 @@ f_up(const double* __restrict__ mat, const double* __restrict__ b, const double*
         load_vec<M>(b + e * M, bb);
         load_vec<M>(xin + e * M, xc);
         // x += P x_c   (same operation order as g_prolong: y = sum_j P(i,j) xc_j, then x + y)
-        const double* P = P0 + tm.blk(e) * (M * MC);
-        const double* c0 = xcoarse + (e / tm.ratio) * MC;
+        const int64_t eg = e + sl.e_off;
+        const double* P = P0 + tm.blk(eg) * (M * MC);
+        const double* c0 = xcoarse + (eg / tm.ratio - sl.c_off) * MC;
         double y[M];
 #pragma unroll
         for (int i = 0; i < M; ++i) y[i] = 0.0;
@@ -385,7 +396,7 @@ f_up(const double* __restrict__ mat, const double* __restrict__ b, const double*
         buf ^= 1;
         reg_sweep<M, B>(A, &ds[0][t], bb, xl, xc, xr, alpha, false);
     }
-    const bool emit = active && t >= halo && t < halo + out;
+    const bool emit = e >= 0 && e < n && t >= halo && t < halo + out;
     if (emit) store_vec<M>(xout + e * M, xc);
     if (partial) {
         exchange<M, B>(ex, buf, xc, xl, xr);
@@ -489,7 +500,8 @@ inline int fused_out_per_cta(int nsweep, int ratio) {
 
 inline bool fused_down(int m, int mc, int diag, const TransferMap& tm, int nsweep, bool zero,
                        const double* mat, const double* b, const double* xin, double* xout,
-                       const double* P0, double* rc, int64_t n, double alpha, cudaStream_t st) {
+                       const double* P0, double* rc, int64_t n, double alpha, const Slab& sl,
+                       cudaStream_t st) {
     if (diag) return false;
     const int out = fused_out_per_cta(nsweep, tm.ratio);
     if (out < tm.ratio || out < FUSED_B / 2) return false;
@@ -498,7 +510,7 @@ inline bool fused_down(int m, int mc, int diag, const TransferMap& tm, int nswee
 #define X(MM, MCC)                                                                                     \
     case MM * 16 + MCC:                                                                                \
         f_down<MM, MCC, FUSED_B><<<grid, FUSED_B, 0, st>>>(mat, b, xin, xout, P0, tm, rc, n, alpha,   \
-                                                            nsweep, zero ? 1 : 0, out);               \
+                                                            nsweep, zero ? 1 : 0, out, sl);           \
         return true;
         FUSED_PAIRS(X)
 #undef X
@@ -509,7 +521,7 @@ inline bool fused_down(int m, int mc, int diag, const TransferMap& tm, int nswee
 inline bool fused_up(int m, int mc, int diag, const TransferMap& tm, int nsweep, const double* mat,
                      const double* b, const double* xin, double* xout, const double* P0,
                      const double* xcoarse, int64_t n, double alpha, double* partial,
-                     int64_t partial_cap, int* nblocks, cudaStream_t st) {
+                     int64_t partial_cap, int* nblocks, const Slab& sl, cudaStream_t st) {
     if (diag) return false;
     const int out = fused_out_per_cta(nsweep, tm.ratio);
     if (out < tm.ratio || out < FUSED_B / 2) return false;
@@ -520,7 +532,7 @@ inline bool fused_up(int m, int mc, int diag, const TransferMap& tm, int nsweep,
 #define X(MM, MCC)                                                                                      \
     case MM * 16 + MCC:                                                                                 \
         f_up<MM, MCC, FUSED_B><<<(unsigned)grid, FUSED_B, 0, st>>>(mat, b, xin, xout, P0, tm, xcoarse, \
-                                                                    n, alpha, nsweep, out, partial);   \
+                                                                    n, alpha, nsweep, out, partial, sl); \
         return true;
         FUSED_PAIRS(X)
 #undef X

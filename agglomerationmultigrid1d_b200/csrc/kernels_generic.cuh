@@ -273,6 +273,7 @@ __global__ void k_repack(const double* __restrict__ lo, const double* __restrict
                          int diag, int K, int64_t e0, int64_t cnt, double* __restrict__ mat) {
     const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     // t enumerates (tile_local, k, lane) over the tiles touched by [e0, e0+cnt); e0 % 32 == 0
+    // (e0 = -32 addresses the spare front tile of a slab with left ghost elements)
     const int64_t per_tile = (int64_t)K * AMG1D_TILE;
     const int64_t tl = t / per_tile;
     const int k = (int)((t % per_tile) / AMG1D_TILE);
@@ -292,23 +293,28 @@ __global__ void k_repack(const double* __restrict__ lo, const double* __restrict
     mat[(e0 / AMG1D_TILE + tl) * per_tile + (int64_t)k * AMG1D_TILE + lane] = v;
 }
 
-// Fill the tiles from a head / interior / tail pattern of n_head + 1 + n_tail element block sets.
+// Fill the stored tiles of a (slab of a) level from a head / interior / tail pattern of
+// n_head + 1 + n_tail element block sets.  `store` starts one tile before local element 0; local
+// element e = stored index - 32 maps to global element start + e; only local elements in
+// [e_lo, e_hi) that exist globally are filled, everything else is zero.
 __global__ void k_fill_pattern(const double* __restrict__ lo, const double* __restrict__ di,
                                const double* __restrict__ up, const double* __restrict__ dinv,
-                               int m, int diag, int K, int64_t n, int n_head, int n_tail,
-                               double* __restrict__ mat) {
+                               int m, int diag, int K, int64_t n_glob, int n_head, int n_tail,
+                               int64_t start, int64_t e_lo, int64_t e_hi, int64_t ntiles,
+                               double* __restrict__ store) {
     const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const int64_t per_tile = (int64_t)K * AMG1D_TILE;
     const int64_t tile = t / per_tile;
-    if (tile >= amg1d_tiles(n)) return;
+    if (tile >= ntiles) return;
     const int k = (int)((t % per_tile) / AMG1D_TILE);
     const int lane = (int)(t % AMG1D_TILE);
-    const int64_t e = tile * AMG1D_TILE + lane;
+    const int64_t e = tile * AMG1D_TILE + lane - AMG1D_TILE;   // local element index
+    const int64_t eg = start + e;                              // global element index
     double v = 0.0;
-    if (e < n) {
+    if (e >= e_lo && e < e_hi && eg >= 0 && eg < n_glob) {
         int64_t s;
-        if (e < n_head) s = e;
-        else if (e >= n - n_tail) s = n_head + 1 + (e - (n - n_tail));
+        if (eg < n_head) s = eg;
+        else if (eg >= n_glob - n_tail) s = n_head + 1 + (eg - (n_glob - n_tail));
         else s = n_head;
         const int mm = m * m;
         if (k < mm) v = lo[s * mm + k];
@@ -316,7 +322,7 @@ __global__ void k_fill_pattern(const double* __restrict__ lo, const double* __re
         else if (k < 3 * mm) v = up[s * mm + (k - 2 * mm)];
         else v = diag ? dinv[s * m + (k - 3 * mm)] : dinv[s * mm + (k - 3 * mm)];
     }
-    mat[t] = v;
+    store[t] = v;
 }
 
 // device slot s <- host-ordered vector (perm[s] = host DOF, -1 = padding)
@@ -337,10 +343,10 @@ __global__ void k_scatter_perm(const int64_t* __restrict__ perm, const double* _
 }
 
 // b[i] = uniform(-1, 1) from a counter-based hash (splitmix64); x = 0
-__global__ void k_fill_random(double* __restrict__ b, int64_t n, uint64_t seed) {
+__global__ void k_fill_random(double* __restrict__ b, int64_t n, uint64_t seed, int64_t offset) {
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n;
          i += (int64_t)gridDim.x * blockDim.x) {
-        uint64_t z = seed + 0x9E3779B97F4A7C15ull * (uint64_t)(i + 1);
+        uint64_t z = seed + 0x9E3779B97F4A7C15ull * (uint64_t)(i + offset + 1);   // global DOF index
         z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
         z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
         z = z ^ (z >> 31);

@@ -245,44 +245,55 @@ class UniformDgHierarchy:
         return lv.ops[name] if lv.explicit else lv.ops[name].expand(lv.n)
 
     # ---- right-hand side b = f - D (M \ r) on level 0 (src/dg_mesh.jl:342-457) ---------------------
-    def rhs(self, func, bc_values, chunk=1 << 20):
+    def rhs(self, func, bc_values, chunk=1 << 20, elem_range=None):
+        """b on level 0; ``elem_range = (e_begin, e_end)`` returns only that slab (multi-GPU)."""
         p0 = self.dg_orders[0]
         m = p0 + 1
         ref = ReferenceElement(p0)
         n, h = self.n, self.h
-        b = np.empty(n * m)
+        lo_e, hi_e = (0, n) if elem_range is None else elem_range
+        b = np.empty((hi_e - lo_e) * m)
         W = ref.mGaussQuadWeights[:, None] * ref.mBasisGQFunVal          # (nq, m)
-        for e0 in range(0, n, chunk):
-            e1 = min(n, e0 + chunk)
+        for e0 in range(lo_e, hi_e, chunk):
+            e1 = min(hi_e, e0 + chunk)
             i = np.arange(e0, e1, dtype=np.float64)
             xl = self.xin + (i / n) * (self.xout - self.xin)
             xr = self.xin + ((i + 1) / n) * (self.xout - self.xin)
             hh, xc = xr - xl, (xl + xr) / 2.0
             xq = xc[:, None] + (hh / 2.0)[:, None] * ref.mGaussQuadNodes[None, :]
-            b[e0 * m:e1 * m] = ((hh / 2.0)[:, None] * (eval_func(func, xq) @ W)).ravel()
+            b[(e0 - lo_e) * m:(e1 - lo_e) * m] = ((hh / 2.0)[:, None] * (eval_func(func, xq) @ W)).ravel()
         lv = self.levels[0]
         Dlo, Ddi, Dup = lv.ops["D"] if lv.explicit else lv.ops["D"].expand(min(n, NV))
         Minv = np.linalg.inv(lv.mass)
         e1, e2 = 0, (1 if p0 >= 1 else 0)
+        def add(el, vec):                                   # b[el] += vec if el lies in the slab
+            if lo_e <= el < hi_e:
+                b[(el - lo_e) * m:(el - lo_e + 1) * m] += vec
+
         for side, el, loc, sgn in ((0, 0, e1, -1.0), (1, n - 1, e2, 1.0)):
             val = bc_values[side]
+            unit = np.zeros(m)
+            unit[loc] = 1.0
             if self.bc_kinds[side] == "dir":
-                b[el * m + loc] += self.CDir * val
-                r = np.zeros(m)
-                r[loc] = sgn * val
-                s = Minv @ r
+                add(el, self.CDir * val * unit)
+                s = Minv @ (sgn * val * unit)
                 w = el if side == 0 else Ddi.shape[0] - 1            # same block in the window
-                b[el * m:(el + 1) * m] -= Ddi[w] @ s
+                add(el, -(Ddi[w] @ s))
                 if side == 1 and n > 1:
-                    b[(el - 1) * m:el * m] -= Dup[w - 1] @ s
+                    add(el - 1, -(Dup[w - 1] @ s))
             else:
-                b[el * m + loc] += sgn * val
+                add(el, sgn * val * unit)
         return b
 
     # ---- upload --------------------------------------------------------------------------------------
-    def upload(self, device=0, stream=None):
+    def upload(self, device=0, stream=None, dist=None, options=None):
+        """dist = (rank, nranks, nccl_id_bytes) shards the large levels into contiguous element slabs
+        (the library decides per level; see amg1d.h).  options: dict for amg1d_set_option, applied
+        before the first level (e.g. {"shard_min": 1024})."""
         nL = len(self.levels)
-        dev = DeviceHierarchy(nL, device=device, stream=stream)
+        dev = DeviceHierarchy(nL, device=device, stream=stream, dist=dist)
+        for k, v in (options or {}).items():
+            dev.set_option(k, v)
         for l, lv in enumerate(self.levels):
             lo, di, up = lv.ops["A"] if lv.explicit else (lv.ops["A"].lo, lv.ops["A"].di, lv.ops["A"].up)
             dinv = blk.to_abi(np.linalg.inv(di))
@@ -293,6 +304,8 @@ class UniformDgHierarchy:
         for l, (P, ratio) in enumerate(self.transfers):
             dev.set_transfer_pattern(l, self.levels[l].n, P, None, ratio=ratio, period=P.shape[0])
         dev.finalize()
+        if dist is not None and dist[1] > 1:
+            dev.n_dof[0] = dev.info("local_dofs")          # host vectors are the rank's slab
         self.device = dev
         return dev
 

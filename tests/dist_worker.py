@@ -1,0 +1,82 @@
+"""Worker for the multi-GPU parity test (run under torch.distributed.run, one rank per GPU).
+
+Each rank builds the same uniform hierarchy, uploads its slab through amg1d_create_dist and solves;
+rank 0 also solves the whole problem on a single-GPU handle.  The sharded run must give the same
+V-cycle count, the same residual history (up to the order of the norm's final sum) and - because the
+per-element arithmetic is identical - bit-identical solution slabs."""
+import ctypes as C
+import json
+import math
+import os
+import sys
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from agglomerationmultigrid1d_b200 import _capi as capi, uniform   # noqa: E402
+
+
+def main():
+    out = sys.argv[1]
+    log2n = int(sys.argv[2]) if len(sys.argv) > 2 else 15
+    dist.init_process_group("gloo")
+    rank, world = dist.get_rank(), dist.get_world_size()
+    torch.cuda.set_device(rank)
+    lib = capi.load()
+    ids = [None]
+    if rank == 0:
+        buf = C.create_string_buffer(128)
+        capi.check(None, lib.amg1d_nccl_unique_id(C.cast(buf, C.c_void_p)))
+        ids[0] = buf.raw
+    dist.broadcast_object_list(ids, src=0)
+    n = 2 ** log2n
+    w = 2.0 * math.pi / 64.0
+    func = lambda x: w * w * np.cos(w * x)                       # noqa: E731
+    vals = [0.0, math.cos(w * n)]
+    U = uniform.UniformDgHierarchy(n, [3, 1], [2] * log2n, xin=0.0, xout=float(n), CDir=1000.0)
+    dev = U.upload(device=rank, dist=(rank, world, ids[0]), options={"shard_min": 512})
+    nloc = n // world
+    b_loc = U.rhs(func, vals, elem_range=(rank * nloc, (rank + 1) * nloc))
+    report = {"rank": rank, "gather_level": dev.info("gather_level"), "local_dofs": dev.info("local_dofs")}
+    results = {}
+    x, it, res, _ = dev.solve(np.zeros(len(b_loc)), b_loc, 100, 1e-10)
+    results["solve"] = (x, it, res)
+    rng = np.random.default_rng(5)
+    x0_glob = rng.standard_normal(n * 4)
+    x0_loc = x0_glob[rank * nloc * 4:(rank + 1) * nloc * 4]
+    for key, (nPre, nPost, alpha) in {"v312": (3, 1, 0.5), "v023": (0, 2, 2.0 / 3.0), "v330": (3, 3, 0.8)}.items():
+        results[key] = (dev.vcycle(x0_loc, b_loc, nPre=nPre, nPost=nPost, alpha=alpha), 0, np.zeros(0))
+    gathered = [None] * world
+    dist.gather_object({k: v for k, v in results.items()}, gathered if rank == 0 else None, dst=0)
+    ok, msgs = True, []
+    if rank == 0:
+        U1 = uniform.UniformDgHierarchy(n, [3, 1], [2] * log2n, xin=0.0, xout=float(n), CDir=1000.0)
+        d1 = U1.upload(device=0)
+        b = U1.rhs(func, vals)
+        x1, it1, res1, _ = d1.solve(np.zeros(len(b)), b, 100, 1e-10)
+        xs = np.concatenate([g["solve"][0] for g in gathered])
+        it_d, res_d = gathered[0]["solve"][1], gathered[0]["solve"][2]
+        if it_d != it1:
+            ok = False; msgs.append(f"iters {it_d} vs {it1}")
+        elif not np.allclose(res_d, res1, rtol=1e-12, atol=0):
+            ok = False; msgs.append(f"res {res_d} vs {res1}")
+        if not np.array_equal(xs, x1):
+            ok = False; msgs.append(f"solve x max diff {np.abs(xs - x1).max():.3e}")
+        for key, (nPre, nPost, alpha) in {"v312": (3, 1, 0.5), "v023": (0, 2, 2.0 / 3.0), "v330": (3, 3, 0.8)}.items():
+            ref = d1.vcycle(x0_glob, b, nPre=nPre, nPost=nPost, alpha=alpha)
+            got = np.concatenate([g[key][0] for g in gathered])
+            if not np.array_equal(got, ref):
+                ok = False; msgs.append(f"{key} x max diff {np.abs(got - ref).max():.3e}")
+        report.update(ok=ok, msgs=msgs, iters=int(it1), world=world, res_last=float(res1[-1]))
+        json.dump(report, open(out, "w"))
+        d1.close()
+    dev.close()
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

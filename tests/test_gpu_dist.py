@@ -1,0 +1,30 @@
+"""Multi-GPU (slab-sharded) parity: needs >= 2 GPUs on the box; skipped otherwise."""
+import json
+import os
+import subprocess
+import sys
+
+import pytest
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _ngpu():
+    import torch
+    return torch.cuda.device_count()
+
+
+@pytest.mark.parametrize("world", [2, 4])
+def test_sharded_solve_matches_single_gpu(world, tmp_path):
+    if _ngpu() < world:
+        pytest.skip(f"needs {world} GPUs")
+    out = tmp_path / "dist.json"
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}",
+           "--master-addr", "127.0.0.1", "--master-port", str(29500 + world),
+           os.path.join(ROOT, "tests", "dist_worker.py"), str(out), "15"]
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
+    rep = json.load(open(out))
+    assert rep["ok"], rep
+    assert rep["gather_level"] > 0
