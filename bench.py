@@ -156,9 +156,34 @@ def run_gpu(args):
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
-    if world > 1:
-        raise SystemExit("multi-GPU slab sharding is not wired into bench.py yet")
+    if world & (world - 1):
+        raise SystemExit("the weak-scaling workloads need a power-of-two rank count")
     torch.cuda.set_device(local)
+    dist_arg = None
+    if world > 1:
+        import ctypes as C0
+        import torch.distributed as tdist
+        tdist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        ids = [None]
+        if rank == 0:
+            buf = C0.create_string_buffer(128)
+            capi.check(None, capi.load().amg1d_nccl_unique_id(C0.cast(buf, C0.c_void_p)))
+            ids[0] = buf.raw
+        tdist.broadcast_object_list(ids, src=0)
+        dist_arg = (rank, world, ids[0])
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            tdist.barrier()
+
+    def max_over_ranks(v):
+        if world == 1:
+            return v
+        t = torch.tensor([v], dtype=torch.float64, device="cuda")
+        tdist.all_reduce(t, op=tdist.ReduceOp.MAX)
+        return float(t.item())
+
     # a non-default stream: its handle is non-zero, so the library runs on exactly the stream that
     # torch.cuda.Event records on (handle 0 would make the library create a stream of its own)
     tstream = torch.cuda.Stream(device=local)
@@ -167,16 +192,18 @@ def run_gpu(args):
     assert stream != 0
 
     log2n, orders, desc = WORKLOADS[args.workload]
-    n = 2 ** log2n
+    log2w = world.bit_length() - 1
+    n = 2 ** (log2n + log2w)                      # weak scaling: 2^log2n elements per GPU
+    nloc = n // world
     pr = problem(n)
     t_setup = time.perf_counter()
-    U = uniform.UniformDgHierarchy(n, orders, [2] * log2n, pAgg=1, xin=pr["xin"], xout=pr["xout"],
-                                   CDir=pr["CDir"])
-    dev = U.upload(device=local, stream=stream)
+    U = uniform.UniformDgHierarchy(n, orders, [2] * (log2n + log2w), pAgg=1, xin=pr["xin"],
+                                   xout=pr["xout"], CDir=pr["CDir"])
+    dev = U.upload(device=local, stream=stream, dist=dist_arg)
     dev.synchronize()
     t_setup = time.perf_counter() - t_setup
-    N0 = U.levels[0].n * U.levels[0].m
-    upd = U.dof_updates_per_cycle()
+    N0 = nloc * U.levels[0].m                     # DOFs of this rank's slab of the fine level
+    upd = U.dof_updates_per_cycle()               # whole job
 
     # ---- value: device-resident steps (random rhs; throughput does not depend on the data) --------
     dev.dev_fill_rhs_random(0)
@@ -188,16 +215,16 @@ def run_gpu(args):
     sampler.start()
     time.sleep(0.25)
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    torch.cuda.synchronize()
+    barrier()
     tw0 = time.time()
     ev0.record()
     for _ in range(args.steps):
         dev.dev_vcycle(with_residual_norm=True)
     ev1.record()
-    torch.cuda.synchronize()
+    barrier()
     tw1 = time.time()
     clocks = sampler.stop(tw0, tw1)
-    ms_step = ev0.elapsed_time(ev1) / args.steps
+    ms_step = max_over_ranks(ev0.elapsed_time(ev1)) / args.steps
     launches = dev.info("kernel_launches") - launches0
     value = upd / (ms_step * 1e-3)
     res_after = dev.dev_residual_norm()
@@ -218,11 +245,11 @@ def run_gpu(args):
     m, mc = lv0.m, lv1.m
     fused_kernel = m <= 4
     if fused_kernel:
-        bytes_up = 8 * (lv0.n * (4 * m * m + 3 * m) + lv1.n * mc)           # f_up at level 0 (+ norm)
+        bytes_up = 8 * (lv0.n * (4 * m * m + 3 * m) + lv1.n * mc) // world   # f_up at level 0 (+ norm), this rank
         kern = f"f_up<{m},{mc},128> level 0 (prolong + 3 sweeps + ||b-Ax||^2)"
         t_k = legs["L0_up"]
     else:
-        bytes_up = 3 * 8 * lv0.n * (4 * m * m + 3 * m) + 8 * (lv1.n * mc + 2 * lv0.n * m)
+        bytes_up = (3 * 8 * lv0.n * (4 * m * m + 3 * m) + 8 * (lv1.n * mc + 2 * lv0.n * m)) // world
         kern = f"level-0 up leg (g_prolong + 3 x f_sweep<{m}>)"
         t_k = legs["L0_up"]
     achieved = bytes_up / (t_k * 1e-3) / 1e9
@@ -232,7 +259,7 @@ def run_gpu(args):
         "traffic": None, "kernel": kern, "algorithmic_bytes_per_launch": bytes_up,
         "avg_launch_ms": t_k, "peak_source": peak_src,
         "whole_cycle": {"algorithmic_bytes": cyc_bytes, "GBps": cyc_bytes / (ms_step * 1e-3) / 1e9,
-                        "frac": cyc_bytes / (ms_step * 1e-3) / 1e9 / peak,
+                        "frac": cyc_bytes / (ms_step * 1e-3) / 1e9 / (peak * world),
                         "B_ref_bytes": U.bytes_per_cycle_reference_model(),
                         "B_ref_equiv_GBps": U.bytes_per_cycle_reference_model() / (ms_step * 1e-3) / 1e9},
         "leg_ms": legs,
@@ -249,34 +276,38 @@ def run_gpu(args):
     xh = np.ctypeslib.as_array(C.cast(bufs[0], C.POINTER(C.c_double)), shape=(N0,))
     bh = np.ctypeslib.as_array(C.cast(bufs[1], C.POINTER(C.c_double)), shape=(N0,))
     t_rhs = time.perf_counter()
-    bh[:] = U.rhs(pr["func"], pr["bc_values"])
+    bh[:] = U.rhs(pr["func"], pr["bc_values"], elem_range=(rank * nloc, (rank + 1) * nloc))
     t_rhs = time.perf_counter() - t_rhs
     xh[:] = 0.0
     e2e_steps = max(1, min(args.steps, 5))
     capi.check(dev._h, lib.amg1d_vcycle(dev._h, capi.dptr(xh), capi.dptr(bh), 3, 3, 2.0 / 3.0))  # warm
+    barrier()
     t0 = time.perf_counter()
     for _ in range(e2e_steps):
         capi.check(dev._h, lib.amg1d_vcycle(dev._h, capi.dptr(xh), capi.dptr(bh), 3, 3, 2.0 / 3.0))
-    t_e2e = (time.perf_counter() - t0) / e2e_steps
-    e2e = {"value": upd / t_e2e, "unit": UNIT, "h2d_bytes_per_step": 2 * N0 * 8,
-           "d2h_bytes_per_step": N0 * 8, "ms_per_step": t_e2e * 1e3, "steps": e2e_steps,
+    barrier()
+    t_e2e = max_over_ranks(time.perf_counter() - t0) / e2e_steps
+    e2e = {"value": upd / t_e2e, "unit": UNIT, "h2d_bytes_per_step": 2 * N0 * 8 * world,
+           "d2h_bytes_per_step": N0 * 8 * world, "ms_per_step": t_e2e * 1e3, "steps": e2e_steps,
            "call": "amg1d_vcycle (multigrid_v_cycle(H, x0, b)) with pinned host x0, b"}
 
     # ---- time-to-1e-10: full multigrid() solve through the ABI (host vectors in, solution out) ----
     xh[:] = 0.0
     res = np.zeros(100)
     it = C.c_int(0)
+    barrier()
     t0 = time.perf_counter()
     capi.check(dev._h, lib.amg1d_solve(dev._h, capi.dptr(xh), capi.dptr(bh), 100, 1e-10, 3, 3, 2.0 / 3.0,
                                         C.byref(it), capi.dptr(res), None, None))
-    t_solve = time.perf_counter() - t0
-    nb = float(np.linalg.norm(bh))
+    barrier()
+    t_solve = max_over_ranks(time.perf_counter() - t0)
+    nb = dev.dev_rhs_norm()
     solve = {"iters": it.value, "seconds_e2e": t_solve, "final_relative_residual": float(res[it.value - 1] / nb),
              "call": "amg1d_solve (multigrid(H, x0, b, 100, 1e-10)), host b in / host x out"}
 
     # ---- CPU baseline beside it (oracle port, bounded sample) ----------------------------------------
     cpu = None
-    if not args.no_cpu:
+    if not args.no_cpu and world == 1:
         v, dt, sample = cpu_reference(orders, 2)
         cpu = {"value": v, "unit": UNIT, "cores": 1, "kind": "port", "sample": sample,
                "host_cores_available": os.cpu_count()}
@@ -287,7 +318,9 @@ def run_gpu(args):
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": f"{args.workload}: {desc}", "n_elements": n, "fine_dofs": N0,
+        "config": {"workload": f"{args.workload}: {desc}" + (f" x {world} GPUs (2^{log2n} elements per GPU, slab-sharded)" if world > 1 else ""),
+                   "n_elements": n, "fine_dofs": N0 * world, "elements_per_gpu": nloc,
+                   "parallelism": f"slab{world}" if world > 1 else "single",
                    "levels": len(U.levels), "nPre": 3, "nPost": 3, "alpha": 2.0 / 3.0,
                    "dof_updates_per_step": upd, "step": "one V-cycle + ||Ax-b|| check, CUDA graph replay",
                    "l2": "inputs larger than L2 (operators + vectors of the fine levels are GBs)"
@@ -296,10 +329,14 @@ def run_gpu(args):
                    "residual_after_timed_steps": res_after},
         "roofline": roofline, "cpu_baseline": cpu, "clocks": clocks, "e2e": e2e,
         "time_to_1e-10": solve, "gpu_launches": int(launches),
-        "fine_dof_cycles_per_s": N0 / (ms_step * 1e-3),
+        "fine_dof_cycles_per_s": N0 * world / (ms_step * 1e-3),
     }
-    print(json.dumps(line), flush=True)
+    if rank == 0:
+        print(json.dumps(line), flush=True)
     dev.close()
+    if world > 1:
+        tdist.barrier()
+        tdist.destroy_process_group()
 
 
 def main():
