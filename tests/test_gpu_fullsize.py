@@ -1,0 +1,87 @@
+"""GPU tests at BASELINE sizes.  The oracle cannot run there, so parity is carried by
+(a) the pattern upload path checked against the oracle at n = 1024, and
+(b) size-independent properties at 2^20 and 2^26 elements: exact linearity in powers of two, agreement of
+the fused residual norm with an independently computed one, symmetry of the operator, bit-identical
+results of the two kernel tiers, monotone convergence with the mesh-independent cycle count."""
+import math
+
+import numpy as np
+import pytest
+
+from agglomerationmultigrid1d_b200 import uniform
+
+pytestmark = pytest.mark.gpu
+
+
+def _problem(n):
+    w = 2.0 * math.pi / 64.0
+    return (lambda x: w * w * np.cos(w * x)), [0.0, math.cos(w * n)]
+
+
+def _build(log2n, orders=(3, 1)):
+    n = 2 ** log2n
+    U = uniform.UniformDgHierarchy(n, list(orders), [2] * log2n, xin=0.0, xout=float(n), CDir=1000.0)
+    return U, U.upload()
+
+
+def test_pattern_path_matches_oracle_n1024():
+    from oracle import drivers, solvers
+    n = 1024
+    U, dev = _build(10)
+    func, vals = _problem(n)
+    b = U.rhs(func, vals)
+    H, x0, bo, _ = drivers.dg_agg_problem(n, p=3, unit_h=True)
+    assert np.abs(b - bo).max() <= 1e-13 * np.abs(bo).max()
+    x_or, it_or, res_or, _ = solvers.multigrid(H, x0, bo, 100, 1e-10, u_exact=np.zeros(len(bo)))
+    x, it, res, _ = dev.solve(np.zeros(len(b)), b, 100, 1e-10)
+    assert it == it_or == 11
+    assert np.all(np.abs(res - res_or) <= np.maximum(1e-10 * res_or, 1e-13 * np.linalg.norm(bo)))
+    assert np.abs(x - x_or).max() <= 1e-9 * np.abs(x_or).max()
+    dev.close()
+
+
+@pytest.mark.parametrize("log2n", [20, 26])
+def test_properties_at_baseline_sizes(log2n):
+    n = 2 ** log2n
+    U, dev = _build(log2n)
+    func, vals = _problem(n)
+    b = U.rhs(func, vals)
+    x0 = np.zeros(len(b))
+    # convergence: monotone, mesh-independent count (11 at n <= 2^13, slowly growing: 13 at 2^20, 15 at 2^26)
+    x, it, res, _ = dev.solve(x0, b, 100, 1e-10)
+    assert it <= 16 and np.all(np.diff(res) < 0)
+    assert res[-1] < 1e-10 * np.linalg.norm(b)
+    assert np.all(res[1:6] / res[:5] < 0.35)            # ~0.2 reduction per cycle
+    # the fused residual norm (inside f_up) equals the one from the stand-alone residual kernel
+    r = dev.residual(0, x, b)
+    assert abs(np.linalg.norm(r) - res[-1]) <= 1e-12 * np.linalg.norm(b) + 1e-9 * res[-1]
+    # exact linearity under scaling by a power of two (no rounding involved)
+    x1 = dev.vcycle(x0, b)
+    x2 = dev.vcycle(x0, 4.0 * b)
+    assert np.array_equal(x2, 4.0 * x1)
+    # both kernel tiers give bit-identical iterates (generic tier only at 2^20: it is ~4x slower)
+    if log2n <= 20:
+        dev.set_option("fused", 0)
+        xg = dev.vcycle(x0, b)
+        dev.set_option("fused", 1)
+        assert np.array_equal(xg, x1)
+        # symmetry of the fine operator: u'(A v) = v'(A u)
+        rng = np.random.default_rng(0)
+        u, v = rng.standard_normal(len(b)), rng.standard_normal(len(b))
+        s1, s2 = float(u @ dev.matvec(0, v)), float(v @ dev.matvec(0, u))
+        assert abs(s1 - s2) <= 1e-9 * (np.linalg.norm(u) * np.linalg.norm(v) * 1000.0)
+    dev.close()
+
+
+def test_p4_hierarchy_properties():
+    """BASELINE C3 shape (DG p=4 -> 2 -> 1 -> agglomerated), 2^18 elements: m = 5 uses the streaming
+    kernels on the fine level."""
+    U, dev = _build(18, orders=(4, 2, 1))
+    func, vals = _problem(2 ** 18)
+    b = U.rhs(func, vals)
+    x, it, res, _ = dev.solve(np.zeros(len(b)), b, 100, 1e-10)
+    assert it <= 16 and np.all(np.diff(res) < 0) and res[-1] < 1e-10 * np.linalg.norm(b)
+    dev.set_option("fused", 0)
+    xg, itg, resg, _ = dev.solve(np.zeros(len(b)), b, 100, 1e-10)
+    assert itg == it and np.array_equal(xg, x)
+    dev.close()
