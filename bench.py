@@ -102,29 +102,49 @@ def measured_peak():
 
 
 # ---- CPU reference arm: the oracle's restatement of multigrid_v_cycle on the host cores ------------
-def cpu_reference(orders, nsteps, log2n_sample=11):
-    """Times the CPU oracle (literal numpy/scipy restatement: CSC SpMV, per-element LU solves,
-    sparse L'/L products, sparse direct coarse solve) on a bounded sample of the same hierarchy
-    shape; DOF-updates/s is size independent for this O(N) method, so the sample is scaled only in n."""
-    from oracle import drivers, solvers
+def cpu_reference(orders, nsteps, log2n_sample=18, threads=0):
+    """Times the oracle's plain-C restatement of the reference algorithm (oracle/vcycle_ref.c: sparse
+    SpMV for A*u, one partial-pivoting LU solve per element for block Jacobi, sparse L' / L products,
+    direct coarse solve, fresh temporaries per expression as in src/solvers.jl:19-50) on a bounded
+    sample of the same hierarchy shape.  The method is O(N), so DOF-updates/s does not depend on n;
+    the sample is the same hierarchy at 2^log2n_sample elements.  Returns (all-thread value, seconds
+    per cycle, sample text, threads used, single-thread value)."""
+    import scipy.linalg  # noqa: F401
+    from oracle import cref
+    from oracle.hierarchy import MeshHierarchy
+    from oracle.smoother import BlockJacobi
+    from agglomerationmultigrid1d_b200 import blocks as blk, uniform
     n = 2 ** log2n_sample
     pr = problem(n)
-    w = 2.0 * math.pi / 64.0
-    nAgg = int(round(math.log2(n)))
-    H, x0, b, _ = drivers.build_problem(
-        n, dg_orders=orders, agg_factors=[2] * nAgg, xin=0.0, xout=float(n), CDir=1000.0,
-        func=lambda x: w * w * math.cos(w * x), u_exact=lambda x: math.cos(w * x),
-        ux_exact=lambda x: -w * math.sin(w * x))
-    upd = 6 * sum(S.shape[0] for S in H.mStiffness[:-1])
-    x = x0
-    solvers.multigrid_v_cycle(H, x, b)          # warm-up
-    t0 = time.perf_counter()
-    for _ in range(nsteps):
-        x = solvers.multigrid_v_cycle(H, x, b)
-        np.linalg.norm(H.mStiffness[0] @ x - b)
-    dt = (time.perf_counter() - t0) / nsteps
-    return upd / dt, dt, f"{nsteps} V-cycles of the same hierarchy shape at n = 2^{log2n_sample} elements " \
-                         f"({upd} DOF-updates per cycle), single thread numpy/scipy oracle"
+    U = uniform.UniformDgHierarchy(n, orders, [2] * log2n_sample, pAgg=1, xin=pr["xin"], xout=pr["xout"],
+                                   CDir=pr["CDir"])
+    S, Sm, I = [], [], []
+    for l, lv in enumerate(U.levels):
+        lo, di, up = U.level_blocks(l)
+        slots = np.arange(lv.n * lv.m, dtype=np.int64).reshape(lv.n, lv.m)
+        S.append(blk.blocks_to_csc(lo, di, up, slots, lv.n * lv.m))
+        Sm.append(BlockJacobi(None, slots.T))                 # the C side factorises A's diagonal blocks
+    for l, (P, ratio) in enumerate(U.transfers):
+        I.append(uniform._transfer_csc(P, U.levels[l].n, ratio))
+    H = MeshHierarchy([None] * len(S), S, None, None, None, Sm, I, None)
+    c = cref.CRefHierarchy(H)
+    b = U.rhs(pr["func"], pr["bc_values"])
+    upd = U.dof_updates_per_cycle()
+    out = {}
+    for key, thr in (("single", 1), ("all", threads or (os.cpu_count() or 1))):
+        used = c.set_threads(thr)
+        x = c.vcycle(np.zeros(len(b)), b)                     # warm-up
+        t0 = time.perf_counter()
+        for _ in range(nsteps):
+            x = c.vcycle(x, b)
+            c.residual_norm(x, b)
+        out[key] = ((time.perf_counter() - t0) / nsteps, used)
+    c.close()
+    dt, used = out["all"]
+    sample = (f"{nsteps} V-cycles (+ residual check) of the same hierarchy shape at n = 2^{log2n_sample} elements "
+              f"({upd} DOF-updates per cycle); oracle/vcycle_ref.c (C port of the reference algorithm, "
+              f"OpenMP over rows / elements, {used} threads); single thread: {upd / out['single'][0]:.3e} DOF-updates/s")
+    return upd / dt, dt, sample, used, upd / out["single"][0]
 
 
 def run_reference(args):
@@ -132,15 +152,16 @@ def run_reference(args):
     if rank != 0:
         return
     log2n, orders, desc = WORKLOADS[args.workload]
-    steps = max(1, min(args.steps, 5))
-    val, dt, sample = cpu_reference(orders, steps)
+    steps = max(1, min(args.steps, 10))
+    val, dt, sample, used, single = cpu_reference(orders, steps)
     line = {
         "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus,
         "steps": steps, "warmup": 1, "ms_per_step": dt * 1e3, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": {"workload": f"{args.workload}: {desc}", "note": "Julia is not installed here; this is the "
-                   "CPU oracle port of the reference algorithm, timed on a bounded sample"},
-        "cpu_baseline": {"value": val, "unit": UNIT, "cores": 1, "kind": "port", "sample": sample},
+                   "C port of the reference algorithm (oracle/vcycle_ref.c), timed on a bounded sample with all host threads"},
+        "cpu_baseline": {"value": val, "unit": UNIT, "cores": used, "kind": "port", "sample": sample,
+                         "single_thread_value": single},
         "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -308,9 +329,9 @@ def run_gpu(args):
     # ---- CPU baseline beside it (oracle port, bounded sample) ----------------------------------------
     cpu = None
     if not args.no_cpu and world == 1:
-        v, dt, sample = cpu_reference(orders, 2)
-        cpu = {"value": v, "unit": UNIT, "cores": 1, "kind": "port", "sample": sample,
-               "host_cores_available": os.cpu_count()}
+        v, dt, sample, used, single = cpu_reference(orders, 3)
+        cpu = {"value": v, "unit": UNIT, "cores": used, "kind": "port", "sample": sample,
+               "single_thread_value": single, "host_cores_available": os.cpu_count()}
 
     for p in bufs:
         lib.amg1d_host_free(p)

@@ -195,3 +195,20 @@ def test_batched_solve_equals_lu_loop():
     y2 = np.zeros_like(b)
     y2[idx] = np.linalg.solve(blocks, b[idx][:, :, None])[:, :, 0]
     assert np.abs(y - y2).max() <= 1e-14 * np.abs(y).max()
+
+
+def test_c_restatement_matches_python_oracle():
+    """oracle/vcycle_ref.c (the timed CPU baseline) against the literal Python oracle."""
+    from oracle import cref
+    for build in (lambda: drivers.dg_agg_problem(64, p=3, unit_h=True), lambda: drivers.full_heirarchy_test(n=32),
+                  lambda: drivers.dg_cg_heirarchy_test(n=16)):
+        H, x0, b, _ = build()
+        c = cref.CRefHierarchy(H)
+        rng = np.random.default_rng(0)
+        xs = rng.standard_normal(len(b))
+        for nPre, nPost, alpha in ((3, 3, 2.0 / 3.0), (1, 2, 0.5)):
+            x_py = solvers.multigrid_v_cycle(H, xs, b, nPre=nPre, nPost=nPost, alpha=alpha)
+            x_c = c.vcycle(xs, b, nPre=nPre, nPost=nPost, alpha=alpha)
+            assert np.abs(x_c - x_py).max() <= 1e-11 * np.abs(x_py).max()
+        assert abs(c.residual_norm(x_c, b) - np.linalg.norm(H.mStiffness[0] @ x_c - b)) <= 1e-9 * np.linalg.norm(b)
+        c.close()
