@@ -284,7 +284,7 @@ __device__ __forceinline__ void load_blocks(const double* __restrict__ mat, int6
 //   halo = nsweep + 1 window elements on each side are recomputed; out = elements emitted per CTA
 //   (a multiple of the agglomeration ratio).
 template <int M, int MC, int B>
-__global__ void __launch_bounds__(B, FUSED_MINB)
+__global__ void __launch_bounds__(B, (M >= 5 ? 2 : FUSED_MINB))
 f_down(const double* __restrict__ mat, const double* __restrict__ b, const double* __restrict__ xin,
        double* __restrict__ xout, const double* __restrict__ P0, TransferMap tm,
        double* __restrict__ rc, int64_t n, double alpha, int nsweep, int zero_guess, int out,
@@ -352,7 +352,7 @@ f_down(const double* __restrict__ mat, const double* __restrict__ b, const doubl
 
 // prolongation + correction, nsweep post-smoothing sweeps, optional || b - A x ||^2 partial sums.
 template <int M, int MC, int B>
-__global__ void __launch_bounds__(B, FUSED_MINB)
+__global__ void __launch_bounds__(B, (M >= 5 ? 2 : FUSED_MINB))
 f_up(const double* __restrict__ mat, const double* __restrict__ b, const double* __restrict__ xin,
      double* __restrict__ xout, const double* __restrict__ P0, TransferMap tm,
      const double* __restrict__ xcoarse, int64_t n, double alpha, int nsweep, int out,
@@ -491,7 +491,7 @@ inline bool fused_resnorm(int m, int diag, const double* mat, const double* b, c
 }
 
 // (M, MC) pairs with a register-resident multi-sweep kernel
-#define FUSED_PAIRS(X) X(1, 1) X(2, 1) X(2, 2) X(3, 1) X(3, 2) X(4, 2) X(4, 3)
+#define FUSED_PAIRS(X) X(1, 1) X(2, 1) X(2, 2) X(3, 1) X(3, 2) X(4, 2) X(4, 3) X(5, 3)
 
 inline int fused_out_per_cta(int nsweep, int ratio) {
     const int out = ((FUSED_B - 2 * (nsweep + 1)) / ratio) * ratio;
@@ -552,7 +552,7 @@ inline bool fused_residual_restrict(int m, int mc, int K, const TransferMap& tm,
         f_residual_restrict<MM, MCC, FUSED_B><<<grid, FUSED_B, 0, st>>>(mat, K, b, x, P0, tm, rc, n, out); \
         return true;
         FUSED_PAIRS(X)
-        X(5, 3) X(9, 5) X(5, 2) X(9, 2)
+        X(9, 5) X(5, 2) X(9, 2)
 #undef X
         default: return false;
     }

@@ -29,6 +29,7 @@ SHAPES = {
     "full_heirarchy": dict(n=32, cg_orders=halving(8, 4), agg_factors=[4, 2, 2, 2]),
     # BASELINE configs, scaled down
     "C1_cg1_agg": dict(n=64, cg_orders=[1], agg_factors=[2]),
+    "C1_cg1_agg_n1024": dict(n=1024, cg_orders=[1], agg_factors=[2]),        # BASELINE configs[0] at its own size
     "C2_dg3_agg": dict(n=64, dg_orders=[3, 1], agg_factors=[2] * 6),
     "C2_dg3_agg_unit_h": dict(n=64, dg_orders=[3, 1], agg_factors=[2] * 6, unit_h=True),
     "C3_dg4_agg": dict(n=32, dg_orders=[4, 2, 1], agg_factors=[2] * 5),

@@ -73,11 +73,12 @@ def test_properties_at_baseline_sizes(log2n):
     dev.close()
 
 
-def test_p4_hierarchy_properties():
-    """BASELINE C3 shape (DG p=4 -> 2 -> 1 -> agglomerated), 2^18 elements: m = 5 uses the streaming
-    kernels on the fine level."""
-    U, dev = _build(18, orders=(4, 2, 1))
-    func, vals = _problem(2 ** 18)
+@pytest.mark.parametrize("log2n", [18, 24])
+def test_p4_hierarchy_properties(log2n):
+    """BASELINE C3 shape (DG p=4 -> 2 -> 1 -> agglomerated) at 2^18 and at its full 2^24 elements:
+    fused kernels with 5x5 blocks against the generic tier."""
+    U, dev = _build(log2n, orders=(4, 2, 1))
+    func, vals = _problem(2 ** log2n)
     b = U.rhs(func, vals)
     x, it, res, _ = dev.solve(np.zeros(len(b)), b, 100, 1e-10)
     assert it <= 16 and np.all(np.diff(res) < 0) and res[-1] < 1e-10 * np.linalg.norm(b)
