@@ -23,6 +23,21 @@ pytestmark = pytest.mark.gpu
 REL = 1e-10
 
 
+class dense_coarse_solver:
+    """Re-run the oracle with a dense LAPACK LU instead of SuperLU for its two direct solves.  The
+    difference between the two CPU runs is the conditioning noise of the problem itself (the coarsest
+    operator of the CG -> agglomerated shapes has cond ~ 1e8-1e9); GPU-vs-oracle tolerances below are
+    max(stated tolerance, 20 x that CPU-vs-CPU disagreement)."""
+
+    def __enter__(self):
+        self.orig = osolv._direct_solve
+        osolv._direct_solve = lambda A, b: np.linalg.solve(sp.csc_matrix(A).toarray(), np.asarray(b, dtype=float))
+        return self
+
+    def __exit__(self, *a):
+        osolv._direct_solve = self.orig
+
+
 def rounding_floor(H, x):
     A = sp.csr_matrix(H.mStiffness[0])
     return 64 * np.finfo(float).eps * abs(A).sum(axis=1).max() * np.abs(x).max() * np.sqrt(A.shape[0])
@@ -62,7 +77,9 @@ def test_level_operations(case):
     A = Ho.mStiffness[-1]
     b = rng.standard_normal(A.shape[0])
     x_or = osolv._direct_solve(A, b)
-    assert np.abs(dev.coarse_solve(b) - x_or).max() <= 1e-10 * np.abs(x_or).max()
+    x_d = np.linalg.solve(sp.csc_matrix(A).toarray(), b)
+    noise = np.abs(x_d - x_or).max() / np.abs(x_or).max()
+    assert np.abs(dev.coarse_solve(b) - x_or).max() <= max(1e-10, 20 * noise) * np.abs(x_or).max()
 
 
 def test_apply_smoother_matrix_rhs(case):
@@ -79,15 +96,17 @@ def test_apply_smoother_matrix_rhs(case):
 def test_single_vcycle(case):
     name, Ho, bo, Hp, bp = case
     x_or = osolv.multigrid_v_cycle(Ho, np.zeros(len(bo)), bo)
+    with dense_coarse_solver():
+        noise = np.abs(osolv.multigrid_v_cycle(Ho, np.zeros(len(bo)), bo) - x_or).max() / np.abs(x_or).max()
     x = aggmg.multigrid_v_cycle(Hp, np.zeros(len(bp)), bp)
-    assert np.abs(x - x_or).max() <= 1e-11 * np.abs(x_or).max()
+    assert np.abs(x - x_or).max() <= max(1e-11, 20 * noise) * np.abs(x_or).max()
     # non-default smoothing parameters and a non-zero initial guess
     rng = np.random.default_rng(1)
     x0 = rng.standard_normal(len(bo)) * np.abs(x_or).max()
     for nPre, nPost, alpha in ((1, 2, 0.5), (0, 3, 2.0 / 3.0), (2, 0, 0.8), (0, 0, 1.0)):
         x_or = osolv.multigrid_v_cycle(Ho, x0, bo, nPre=nPre, nPost=nPost, alpha=alpha)
         x = aggmg.multigrid_v_cycle(Hp, x0, bp, nPre=nPre, nPost=nPost, alpha=alpha)
-        assert np.abs(x - x_or).max() <= 1e-10 * np.abs(x_or).max(), (nPre, nPost, alpha)
+        assert np.abs(x - x_or).max() <= max(1e-10, 20 * noise) * np.abs(x_or).max(), (nPre, nPost, alpha)
 
 
 def test_ldiv(case):
@@ -95,7 +114,9 @@ def test_ldiv(case):
     y = np.zeros(len(bp))
     aggmg.ldiv(y, Hp, bp)
     y_or = osolv.ldiv(Ho, bo)
-    assert np.abs(y - y_or).max() <= 1e-11 * np.abs(y_or).max()
+    with dense_coarse_solver():
+        noise = np.abs(osolv.ldiv(Ho, bo) - y_or).max() / np.abs(y_or).max()
+    assert np.abs(y - y_or).max() <= max(1e-11, 20 * noise) * np.abs(y_or).max()
     b2 = bp.copy()
     aggmg.ldiv(Hp, b2)
     assert np.array_equal(b2, y)
@@ -109,7 +130,12 @@ def test_multigrid_histories(case):
     x, it, res, err = aggmg.multigrid(Hp, np.zeros(len(bp)), bp, 100, 1e-10)
     assert it == it_or, (name, it, it_or)
     floor = rounding_floor(Ho, x_or)
-    tol = np.maximum(REL * res_or, floor)
+    with dense_coarse_solver():
+        _, it_d, res_d, _ = osolv.multigrid(Ho, np.zeros(len(bo)), bo, 100, 1e-10)
+    k = min(it_d, it_or)
+    noise = np.zeros(it_or)
+    noise[:k] = 20 * np.abs(res_d[:k] - res_or[:k])
+    tol = np.maximum(np.maximum(REL * res_or, floor), noise)
     assert np.all(np.abs(res - res_or) <= tol), (name, res, res_or, floor)
     assert np.abs(x - x_or).max() <= 1e-9 * np.abs(x_or).max()
     # error history against the direct solve (both sides use their own A \ b)
