@@ -162,6 +162,46 @@ def _level_from_window(level, G, D, C, Mblock):
     level.mass = Mblock
 
 
+def extend_chain(levels, transfers, steps, n_cur, H, p_cur, is_agg, pAgg):
+    """Append the DG-type levels below levels[-1] (which must carry G, D, C): p-coarsened DG levels
+    ("dg", p) and agglomerated levels ("agg", factor), each by L'(G,D,C)L and A = C - D (M \\ G) on a
+    virtual window (src/mesh_heirarchy.jl:75-106).  transfers gets (P blocks, ratio) per step."""
+    for kind, val in steps:
+        fine = levels[-1]
+        if kind == "dg":
+            P, ratio, m_c = dg_dg_blocks(val, p_cur), 1, val + 1
+            Mblock = (H / 2.0) * ReferenceElement(val).mMassMatrix
+            p_cur = val
+        else:
+            ratio, m_c = val, pAgg + 1
+            if n_cur % ratio:
+                raise ValueError("agglomeration factor does not divide the element count")
+            P = aggdg_aggdg_blocks(pAgg, ratio) if is_agg else aggdg_dg_blocks(pAgg, p_cur, ratio)
+            H *= ratio
+            Mblock = agg_mass_block(pAgg, H)
+            is_agg = True
+        n_next = n_cur // ratio
+        coarse = UniformLevel(n_next, m_c)
+        # window of the fine level on which this coarsening step is evaluated
+        if coarse.explicit and not fine.explicit:
+            nwf = n_cur                              # last pattern level: expand it fully
+            ops = {k: fine.ops[k].expand(nwf) for k in ("G", "D", "C")}
+        elif fine.explicit:
+            nwf = n_cur
+            ops = {k: fine.ops[k] for k in ("G", "D", "C")}
+        else:
+            nwf = NV * ratio
+            ops = {k: fine.ops[k].expand(nwf) for k in ("G", "D", "C")}
+        L = _transfer_csc(P, nwf, ratio)
+        proj = {k: (L.T @ _csc(*ops[k]) @ L).tocsc() for k in ("G", "D", "C")}
+        assert nwf // ratio == coarse.window_size()
+        _level_from_window(coarse, proj["G"], proj["D"], proj["C"], Mblock)
+        levels.append(coarse)
+        transfers.append((P, ratio))
+        n_cur = n_next
+    return n_cur, H
+
+
 class UniformDgHierarchy:
     """DG(p_0) -> DG(p_1) -> ... -> agglomerated(pAgg) levels on a uniform mesh of n elements.
 
@@ -202,42 +242,8 @@ class UniformDgHierarchy:
         G, D, C = dg_flux_operators(dgm, mesh, bd, self.CDir)
         _level_from_window(lv, G, D, C, dgm.mMassMatrix.mBlocks[nw // 2])
         self.levels.append(lv)
-        n_cur, H = self.n, self.h
         steps = [("dg", p) for p in self.dg_orders[1:]] + [("agg", f) for f in self.agg_factors]
-        p_cur, is_agg = p0, False
-        for kind, val in steps:
-            fine = self.levels[-1]
-            if kind == "dg":
-                P, ratio, m_c = dg_dg_blocks(val, p_cur), 1, val + 1
-                Mblock = (H / 2.0) * ReferenceElement(val).mMassMatrix
-                p_cur = val
-            else:
-                ratio, m_c = val, self.pAgg + 1
-                if n_cur % ratio:
-                    raise ValueError("agglomeration factor does not divide the element count")
-                P = aggdg_aggdg_blocks(self.pAgg, ratio) if is_agg else aggdg_dg_blocks(self.pAgg, p_cur, ratio)
-                H *= ratio
-                Mblock = agg_mass_block(self.pAgg, H)
-                is_agg = True
-            n_next = n_cur // ratio
-            coarse = UniformLevel(n_next, m_c)
-            # window of the fine level on which this coarsening step is evaluated
-            if coarse.explicit and not fine.explicit:
-                nwf = n_cur                              # last pattern level: expand it fully
-                ops = {k: fine.ops[k].expand(nwf) for k in ("G", "D", "C")}
-            elif fine.explicit:
-                nwf = n_cur
-                ops = {k: fine.ops[k] for k in ("G", "D", "C")}
-            else:
-                nwf = NV * ratio
-                ops = {k: fine.ops[k].expand(nwf) for k in ("G", "D", "C")}
-            L = _transfer_csc(P, nwf, ratio)
-            proj = {k: (L.T @ _csc(*ops[k]) @ L).tocsc() for k in ("G", "D", "C")}
-            assert nwf // ratio == coarse.window_size()
-            _level_from_window(coarse, proj["G"], proj["D"], proj["C"], Mblock)
-            self.levels.append(coarse)
-            self.transfers.append((P, ratio))
-            n_cur = n_next
+        extend_chain(self.levels, self.transfers, steps, self.n, self.h, p0, False, self.pAgg)
 
     # ---- explicit blocks of any level (for tests / small levels) -----------------------------------
     def level_blocks(self, l, name="A"):
@@ -340,3 +346,240 @@ class UniformDgHierarchy:
             up = n * (4 * m * m + 3 * m) + nc * mc
             total += 8 * (down + up)
         return total
+
+
+# =====================================================================================================
+# CG-first hierarchies on uniform meshes:  CG(p_0) -> ... -> CG(p_k) -> DG / agglomerated levels
+# =====================================================================================================
+def normalise_transfer(parent, P0, P1, ratio, shift, base):
+    """Rewrite explicit transfer blocks for the closed-form parent map
+    parent[e] = (e + shift) // ratio + base used by amg1d_set_transfer_pattern.  An element whose only
+    parent is the *second* one of the formula gets its block moved from P0 to P1."""
+    nf = len(parent)
+    pf = (np.arange(nf) + shift) // ratio + base
+    Q0 = P0.copy()
+    Q1 = np.zeros_like(P0) if P1 is None else P1.copy()
+    late = parent == pf + 1
+    if np.any((parent != pf) & ~late):
+        raise RuntimeError("transfer does not follow the closed-form parent map")
+    if np.any(late):
+        if np.abs(Q1[late]).max() > 0:
+            raise RuntimeError("cannot move a block into an occupied second-parent slot")
+        Q1[late] = Q0[late]
+        Q0[late] = 0.0
+    return Q0, (Q1 if np.abs(Q1).max() > 0 else None)
+
+
+def compress_transfer(P, period, n_head, n_tail, what=""):
+    """(n_fine, mf, mc) explicit blocks -> (n_head + period + n_tail, mf, mc) pattern, checking that
+    the interior is periodic."""
+    nf = P.shape[0]
+    e = np.arange(n_head, nf - n_tail)
+    ref = P[n_head + (e - n_head) % period]
+    dev = np.abs(P[e] - ref).max() / max(np.abs(P).max(), 1e-300)
+    if dev > 1e-11:
+        raise RuntimeError(f"{what}: interior transfer blocks are not periodic ({dev:.2e})")
+    return np.concatenate([P[:n_head], P[n_head:n_head + period], P[nf - n_tail:]])
+
+
+def expand_transfer(Ppat, nf, period, n_head, n_tail):
+    e = np.arange(nf)
+    idx = np.where(e < n_head, e, np.where(e >= nf - n_tail, n_head + period + e - (nf - n_tail),
+                                           n_head + (e - n_head) % period))
+    return Ppat[idx]
+
+
+class UniformCgHierarchy:
+    """CG(p_0) -> ... -> CG(p_k) -> [DG(q_0) -> ...] -> [agglomerated levels] on a uniform mesh: the
+    hierarchy of ``MeshHierarchy(mMeshes, mesh, mBdConds, A; nCG, nDG, nAgg, CDir)``
+    (src/mesh_heirarchy.jl:30-138; shapes of tests/cg_heirarchy_test.jl, dg_cg_heirarchy_test.jl,
+    full_heirarchy_test.jl and BASELINE C1 / C4) in pattern form.
+
+    CG levels change the polynomial order on a FIXED mesh, so their operators, point-Jacobi diagonals
+    and transfers are read off a literal small replica built by the general path (same h, same boundary
+    conditions) and compressed to head / interior / tail patterns; the first DG-type level is assembled
+    directly on that replica as in the reference, and the levels below it continue with
+    ``extend_chain``.  Vectors of CG levels are in *group order*: block k = [vertex k, interior nodes of
+    element k] (n + 1 blocks of size p, the last one padded with zeros), see ``blocks.level_slots``.
+    """
+
+    HEAD = 8        # explicit head / tail blocks of the CG-side transfers
+
+    def __init__(self, n, cg_orders, dg_orders=(), agg_factors=(), pAgg=1, xin=0.0, xout=1.0,
+                 CDir=None, bc_kinds=("neu", "dir")):
+        from .agglomerated_dg_mesh import AgglomeratedDgMesh1, uniform_agglomeration
+        from .cg_mesh import CgMesh, cg_stiffness
+        from .mesh_hierarchy import MeshHierarchy
+        self.n = int(n)
+        self.cg_orders, self.dg_orders = list(cg_orders), list(dg_orders)
+        self.agg_factors, self.pAgg = list(agg_factors), pAgg
+        self.xin, self.xout = float(xin), float(xout)
+        self.h = (self.xout - self.xin) / self.n
+        self.CDir = 1000.0 * n if CDir is None else float(CDir)
+        self.bc_kinds = tuple(bc_kinds)
+        if not self.cg_orders:
+            raise ValueError("At least one CG mesh required.")
+        nCG = len(self.cg_orders)
+        first_is_dg = bool(self.dg_orders)
+        f0 = 1 if first_is_dg or not self.agg_factors else self.agg_factors[0]
+        ns = NV * f0
+        if self.n < 2 * ns or self.n % f0:
+            raise ValueError(f"UniformCgHierarchy needs n >= {2 * ns} (use MeshHierarchy for small meshes)")
+        # ---- literal replica by the general path -------------------------------------------------
+        mesh = create_uniform_mesh(ns, self.xin, self.xin + ns * self.h)
+        bd = set_boundary(mesh, self.xin, self.xin + ns * self.h,
+                          [(self.bc_kinds[0], 0.0), (self.bc_kinds[1], 0.0)])
+        meshes = [CgMesh(mesh, p) for p in self.cg_orders]
+        nDG = nAgg = 0
+        if first_is_dg:
+            meshes.append(DgMesh(mesh, self.dg_orders[0])); nDG = 1
+        elif self.agg_factors:
+            meshes.append(AgglomeratedDgMesh1(pAgg, uniform_agglomeration(ns, f0), mesh, meshes[0])); nAgg = 1
+        A0 = cg_stiffness(meshes[0], bd)
+        Hr = MeshHierarchy(meshes, mesh, [bd] * len(meshes), A0, nCG=nCG, nDG=nDG, nAgg=nAgg,
+                           CDir=self.CDir, upload=False)
+        self.levels, self.cg_transfers, self.transfers = [], [], []
+        slots = [blk.level_slots(m) for m in meshes]
+        for l in range(nCG):
+            p = self.cg_orders[l]
+            lv = UniformLevel(self.n + 1, p)
+            lv.explicit = False
+            lv.is_cg = True
+            lo, di, up = blk.csc_to_blocks(Hr.mStiffness[l], slots[l])
+            lv.ops["A"] = compress(lo, di, up, f"CG level {l}")
+            self.levels.append(lv)
+        # ---- CG-side transfers (two-parent), in the closed-form parent convention ------------------
+        for l in range(len(meshes) - 1):
+            parent, P0, P1 = blk.transfer_to_blocks(Hr.mInterpolation[l], slots[l], slots[l + 1])
+            if l < nCG - 1:
+                ratio, shift, base, period = 1, 0, 0, 1            # cg_cg: group k <- groups k, k+1
+            elif first_is_dg:
+                ratio, shift, base, period = 1, 0, -1, 1           # dg_cg: group k <- elements k-1, k
+            else:
+                ratio, shift, base, period = f0, f0 - 1, -1, f0    # aggdg_cg: k <- ceil(k/f)-1, +1
+            Q0, Q1 = normalise_transfer(parent, P0, P1, ratio, shift, base)
+            nh = nt = max(self.HEAD, 2 * period)
+            tr = dict(ratio=ratio, shift=shift, base=base, period=period, n_head=nh, n_tail=nt,
+                      P0=compress_transfer(Q0, period, nh, nt, f"transfer {l} P0"),
+                      P1=None if Q1 is None else compress_transfer(Q1, period, nh, nt, f"transfer {l} P1"))
+            self.cg_transfers.append(tr)
+        # ---- first DG-type level, then the usual chain -----------------------------------------------
+        if len(meshes) > nCG:
+            m_d = meshes[nCG].mP + 1
+            lv = UniformLevel(self.n // f0, m_d)
+            if lv.explicit:
+                raise ValueError("mesh too small for the pattern path")
+            if first_is_dg:
+                Mblock = meshes[nCG].mMassMatrix.mBlocks[NV // 2]
+            else:
+                Mblock = agg_mass_block(pAgg, f0 * self.h)
+            _level_from_window(lv, Hr.mGradient[0], Hr.mDivergence[0], Hr.mC[0], Mblock)
+            # the reference assembles this level directly; keep ITS operator, not the recomputed one
+            lo, di, up = _blocks(Hr.mStiffness[nCG], NV, m_d)
+            lv.ops["A"] = compress(lo, di, up, "first DG-type level")
+            self.levels.append(lv)
+            if first_is_dg:
+                steps = [("dg", q) for q in self.dg_orders[1:]] + [("agg", f) for f in self.agg_factors]
+                extend_chain(self.levels, self.transfers, steps, self.n, self.h, self.dg_orders[0], False, pAgg)
+            else:
+                steps = [("agg", f) for f in self.agg_factors[1:]]
+                extend_chain(self.levels, self.transfers, steps, self.n // f0, f0 * self.h, None, True, pAgg)
+        self.nCG = nCG
+        self._meshes_replica = meshes
+
+    # ---- explicit forms (tests) --------------------------------------------------------------------
+    def level_blocks(self, l, name="A"):
+        lv = self.levels[l]
+        return lv.ops[name] if lv.explicit else lv.ops[name].expand(lv.n)
+
+    def transfer_blocks(self, l):
+        """(parent, P0, P1) explicit for transfer l (any kind)."""
+        nf = self.levels[l].n
+        if l < len(self.cg_transfers):
+            t = self.cg_transfers[l]
+            parent = (np.arange(nf) + t["shift"]) // t["ratio"] + t["base"]
+            ex = lambda P: None if P is None else expand_transfer(P, nf, t["period"], t["n_head"], t["n_tail"])  # noqa: E731
+            return parent, ex(t["P0"]), ex(t["P1"])
+        P, ratio = self.transfers[l - len(self.cg_transfers)]
+        e = np.arange(nf)
+        return e // ratio, P[e % ratio], None
+
+    def group_slots(self, l=0):
+        """Host DOF (reference numbering, src/cg_mesh.jl:35-45) of every group slot of CG level l."""
+        n, p = self.n, self.cg_orders[l]
+        s = np.full((n + 1, p), -1, dtype=np.int64)
+        s[:, 0] = np.arange(n + 1)
+        if p > 1:
+            s[:n, 1:] = (n + 1) + np.arange(n)[:, None] * (p - 1) + np.arange(p - 1)[None, :]
+        return s
+
+    # ---- right-hand side of cg_stiffness_and_rhs in group order (src/cg_mesh.jl:125-185) -------------
+    def rhs(self, func, bc_values, chunk=1 << 20):
+        p = self.cg_orders[0]
+        ref = ReferenceElement(p)
+        n = self.n
+        b = np.zeros((n + 1, p))
+        W = ref.mGaussQuadWeights[:, None] * ref.mBasisGQFunVal            # (nq, p+1)
+        for e0 in range(0, n, chunk):
+            e1 = min(n, e0 + chunk)
+            i = np.arange(e0, e1, dtype=np.float64)
+            xl = self.xin + (i / n) * (self.xout - self.xin)
+            xr = self.xin + ((i + 1) / n) * (self.xout - self.xin)
+            hh, xc = xr - xl, (xl + xr) / 2.0
+            xq = xc[:, None] + (hh / 2.0)[:, None] * ref.mGaussQuadNodes[None, :]
+            fe = (hh / 2.0)[:, None] * (eval_func(func, xq) @ W)           # (chunk, p+1)
+            b[e0:e1, 0] += fe[:, 0]
+            b[e0 + 1:e1 + 1, 0] += fe[:, 1]
+            if p > 1:
+                b[e0:e1, 1:] = fe[:, 2:]
+        kref = np.einsum("l,li,lj->ij", ref.mGaussQuadWeights, ref.mBasisGQDerivVal, ref.mBasisGQDerivVal)
+        for side in (0, 1):                                               # Neumann terms first (:164-174)
+            if self.bc_kinds[side] == "neu":
+                b[0 if side == 0 else n, 0] += (-1.0 if side == 0 else 1.0) * bc_values[side]
+        for side in (0, 1):                                               # strong Dirichlet (:177-182)
+            if self.bc_kinds[side] != "dir":
+                continue
+            el = 0 if side == 0 else n - 1
+            xl = self.xin + (el / n) * (self.xout - self.xin)
+            xr = self.xin + ((el + 1) / n) * (self.xout - self.xin)
+            col = (1.0 / ((xr - xl) / 2.0)) * kref[:, side] * bc_values[side]    # A[:, dir] * val on this element
+            b[el, 0] -= col[0]
+            b[el + 1, 0] -= col[1]
+            if p > 1:
+                b[el, 1:] -= col[2:]
+        for side in (0, 1):
+            if self.bc_kinds[side] == "dir":
+                b[0 if side == 0 else n, 0] = bc_values[side]
+        return b.ravel()
+
+    # ---- upload ------------------------------------------------------------------------------------------
+    def upload(self, device=0, stream=None):
+        nL = len(self.levels)
+        dev = DeviceHierarchy(nL, device=device, stream=stream)
+        for l, lv in enumerate(self.levels):
+            if getattr(lv, "is_cg", False):
+                pat = lv.ops["A"]
+                dinv = np.ascontiguousarray(1.0 / np.einsum("eii->ei", pat.di))       # point Jacobi
+                dev.set_level_pattern(l, lv.n, pat.lo, pat.di, pat.up, dinv, True, NB, NB)
+            else:
+                lo, di, up = lv.ops["A"] if lv.explicit else (lv.ops["A"].lo, lv.ops["A"].di, lv.ops["A"].up)
+                dinv = blk.to_abi(np.linalg.inv(di))
+                if lv.explicit:
+                    dev.set_level_blocks(l, lo, di, up, dinv, False)
+                else:
+                    dev.set_level_pattern(l, lv.n, lo, di, up, dinv, False, NB, NB)
+        for l, t in enumerate(self.cg_transfers):
+            dev.set_transfer_pattern(l, self.levels[l].n, t["P0"], t["P1"], ratio=t["ratio"], shift=t["shift"],
+                                     base=t["base"], period=t["period"], n_head=t["n_head"], n_tail=t["n_tail"])
+        for k, (P, ratio) in enumerate(self.transfers):
+            l = len(self.cg_transfers) + k
+            dev.set_transfer_pattern(l, self.levels[l].n, P, None, ratio=ratio, period=P.shape[0])
+        dev.finalize()
+        self.device = dev
+        return dev
+
+    def dof_updates_per_cycle(self, nPre=3, nPost=3):
+        tot = 0
+        for l, lv in enumerate(self.levels[:-1]):
+            tot += (lv.n - 1) * lv.m + 1 if getattr(lv, "is_cg", False) else lv.n * lv.m   # real CG DOFs
+        return (nPre + nPost) * tot

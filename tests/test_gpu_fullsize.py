@@ -86,3 +86,49 @@ def test_p4_hierarchy_properties(log2n):
     xg, itg, resg, _ = dev.solve(np.zeros(len(b)), b, 100, 1e-10)
     assert itg == it and np.array_equal(xg, x)
     dev.close()
+
+
+@pytest.mark.parametrize("cg,dg,agg", [([3, 1], [1], [2] * 8), ([8, 4, 2, 1], [], [4] + [2] * 6), ([1], [], [2])])
+def test_cg_pattern_path_matches_oracle(cg, dg, agg):
+    """CG-first hierarchies through the pattern upload path (two-parent pattern transfers, point
+    Jacobi, group-ordered vectors) against the oracle at n = 256 (C4, full_heirarchy, C1 shapes)."""
+    import scipy.sparse as sp
+    from oracle import drivers, solvers
+    from test_gpu_parity import dense_coarse_solver
+    n = 256
+    H, x0, bo, _ = drivers.build_problem(n, cg_orders=cg, dg_orders=dg, agg_factors=agg)
+    U = uniform.UniformCgHierarchy(n, cg, dg, agg, xin=0.0, xout=1.0, CDir=1000.0 * n)
+    dev = U.upload()
+    b = U.rhs(np.cos, [-math.sin(0.0), math.cos(1.0)])
+    s0 = U.group_slots(0)
+    valid = s0.ravel() >= 0
+    x_or, it_or, res_or, _ = solvers.multigrid(H, x0, bo, 100, 1e-10)
+    with dense_coarse_solver():
+        _, it_d, res_d, _ = solvers.multigrid(H, x0, bo, 100, 1e-10)
+    x, it, res, _ = dev.solve(np.zeros(len(b)), b, 100, 1e-10)
+    assert it == it_or
+    k = min(it_d, it_or)
+    noise = np.zeros(it_or)
+    noise[:k] = 20 * np.abs(res_d[:k] - res_or[:k])
+    A = sp.csr_matrix(H.mStiffness[0])
+    floor = 64 * np.finfo(float).eps * abs(A).sum(axis=1).max() * np.abs(x_or).max() * np.sqrt(A.shape[0])
+    assert np.all(np.abs(res - res_or) <= np.maximum(np.maximum(1e-10 * res_or, floor), noise))
+    xh = np.zeros(len(bo))
+    xh[s0.ravel()[valid]] = x[valid]
+    assert np.abs(xh - x_or).max() <= 1e-8 * np.abs(x_or).max()
+    assert np.all(x[~valid] == 0.0)
+    dev.close()
+
+
+def test_c4_shape_at_scale():
+    """BASELINE C4 (CG 3 -> 1 -> DG 1 -> agglomerated) at 2^22 elements: convergence properties."""
+    n = 2 ** 22
+    w = 2.0 * math.pi / 64.0
+    U = uniform.UniformCgHierarchy(n, [3, 1], [1], [2] * 22, xin=0.0, xout=float(n), CDir=1000.0)
+    dev = U.upload()
+    b = U.rhs(lambda x: w * w * np.cos(w * x), [0.0, math.cos(w * n)])
+    x, it, res, _ = dev.solve(np.zeros(len(b)), b, 100, 1e-10)
+    assert it <= 20 and np.all(np.diff(res) < 0) and res[-1] < 1e-10 * np.linalg.norm(b)
+    x1 = dev.vcycle(np.zeros(len(b)), b)
+    assert np.array_equal(dev.vcycle(np.zeros(len(b)), 2.0 * b), 2.0 * x1)
+    dev.close()
