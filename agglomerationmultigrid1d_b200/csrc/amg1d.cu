@@ -48,7 +48,9 @@ struct Level {
     double* mat_alloc = nullptr;
     int m = 0;
     int diag = 0;
-    int K = 0;
+    int K = 0;           // == md.K
+    MatDesc md = {};     // structure class and tile-row offsets (layout.cuh)
+    int64_t base_n = 0;  // sharded: elements per rank (the last rank also holds n_glob % nranks)
     int64_t n_host = 0;  // reference vector length
     double* mat = nullptr;
     int64_t* perm = nullptr;  // device, n*m entries, or null
@@ -71,6 +73,10 @@ struct Transfer {
     double* P1 = nullptr;
     int64_t nblk = 0;
     bool single_parent_uniform = false;  // parent[e] = e / ratio, no P1
+    bool closed = false;     // parent[e] = (e + shift) / ratio + base for every e (pattern or detected)
+    bool fusable = false;    // closed, and every coarse element has a first P0-child (f_down's gather rule)
+    int reach = 0;           // sharded two-parent transfers: fine ghost elements the restriction reads
+    int64_t cover_extra = 0; // sharded: ghost elements right of the slab that own coarse elements of this rank
 };
 
 }  // namespace
@@ -97,6 +103,10 @@ struct amg1d {
     // options
     int opt_fused = 1, opt_graph = 1;
     int64_t opt_coarse_cta = 1024;
+    int opt_compress = 1;         // drop structural zeros of the off-diagonal blocks (layout.cuh)
+    // single-CTA coarse tail (f_tail): levels [tail_start, n_levels)
+    int tail_start = -1;
+    TailLevel* d_tail = nullptr;
     // graph cache
     cudaGraphExec_t gexec = nullptr;
     int g_pre = -1, g_post = -1, g_norm = -1;
@@ -194,6 +204,20 @@ TransferMap make_map(const Transfer& t) {
     return tm;
 }
 
+// closed-form version (no parent / child-pointer arrays): what the fused kernels take
+TransferMap make_map_closed(const Transfer& t) {
+    TransferMap tm = make_map(t);
+    tm.parent = nullptr;
+    tm.cp = nullptr;
+    return tm;
+}
+
+// slab of rank r of a level with n_glob elements split over nranks: [start, start + n)
+inline int64_t slab_start(int64_t n_glob, int nranks, int r) { return (n_glob / nranks) * r; }
+inline int64_t slab_size(int64_t n_glob, int nranks, int r) {
+    return n_glob / nranks + (r == nranks - 1 ? n_glob % nranks : 0);
+}
+
 #ifdef AMG1D_WITH_NCCL
 // NCCL is resolved at run time (dlopen by SONAME) when a multi-GPU handle is created, so that a
 // process that already loaded an NCCL (e.g. the one bundled with PyTorch) keeps using exactly that
@@ -238,7 +262,15 @@ Slab make_slab(amg1d* h, int l) {
     sl.gl = lv.gl;
     sl.gr = lv.gr;
     sl.e_off = lv.start;
-    sl.c_off = (l + 1 < h->n_levels) ? h->L[l + 1].start : 0;
+    sl.c_off = 0;
+    sl.nc = 0;
+    if (l + 1 < h->n_levels) {
+        const Level& lc = h->L[l + 1];
+        // the coarse level is sharded too, or it is the gather level (slabs of its rhs are gathered to
+        // rank 0 afterwards; on a single GPU this is simply the whole level)
+        sl.c_off = lv.sharded ? slab_start(lc.n_glob, h->nranks, h->rank) : 0;
+        sl.nc = lv.sharded ? slab_size(lc.n_glob, h->nranks, h->rank) : lc.n_glob;
+    }
     return sl;
 }
 
@@ -272,13 +304,14 @@ int op_halo(amg1d* h, double* v, int64_t n, int m) {
 // rank r's slab of the gather level's right-hand side -> rank 0 (which owns the whole level)
 int op_gather_rhs(amg1d* h, int g) {
     Level& lg = h->L[g];
-    const int64_t per = (lg.n_glob / h->nranks) * lg.m;
     NCK(g_nccl.GroupStart());
     if (h->rank == 0) {
         for (int r = 1; r < h->nranks; ++r)
-            NCK(g_nccl.Recv(lg.b.p + r * per, per, ncclDouble, r, h->comm, h->stream));
+            NCK(g_nccl.Recv(lg.b.p + slab_start(lg.n_glob, h->nranks, r) * lg.m,
+                            slab_size(lg.n_glob, h->nranks, r) * lg.m, ncclDouble, r, h->comm, h->stream));
     } else {
-        NCK(g_nccl.Send(lg.b.p, per, ncclDouble, 0, h->comm, h->stream));
+        NCK(g_nccl.Send(lg.b.p, slab_size(lg.n_glob, h->nranks, h->rank) * lg.m, ncclDouble, 0, h->comm,
+                        h->stream));
     }
     NCK(g_nccl.GroupEnd());
     h->launch_counter++;
@@ -288,18 +321,19 @@ int op_gather_rhs(amg1d* h, int g) {
 // rank 0's solution of the gather level -> every rank's slab (with ghost elements)
 int op_scatter_sol(amg1d* h, int g) {
     Level& lg = h->L[g];
-    const int64_t nloc = lg.n_glob / h->nranks;
     const int gd = h->ghost_depth;
     NCK(g_nccl.GroupStart());
     if (h->rank == 0) {
         const double* x = lg.x[lg.cur].p;
         for (int r = 1; r < h->nranks; ++r) {
-            const int64_t e0 = r * nloc - gd;
-            const int64_t e1 = (r + 1) * nloc + (r < h->nranks - 1 ? gd : 0);
+            const int64_t e0 = slab_start(lg.n_glob, h->nranks, r) - gd;
+            const int64_t e1 = slab_start(lg.n_glob, h->nranks, r) + slab_size(lg.n_glob, h->nranks, r) +
+                               (r < h->nranks - 1 ? gd : 0);
             NCK(g_nccl.Send(x + e0 * lg.m, (e1 - e0) * lg.m, ncclDouble, r, h->comm, h->stream));
         }
     } else {
-        const int64_t cnt = (nloc + gd + (h->rank < h->nranks - 1 ? gd : 0)) * lg.m;
+        const int64_t cnt = (slab_size(lg.n_glob, h->nranks, h->rank) + gd +
+                             (h->rank < h->nranks - 1 ? gd : 0)) * lg.m;
         NCK(g_nccl.Recv(lg.x[0].p - (int64_t)gd * lg.m, cnt, ncclDouble, 0, h->comm, h->stream));
     }
     NCK(g_nccl.GroupEnd());
@@ -327,16 +361,15 @@ int op_allreduce_norm(amg1d* h, int) { return fail(h, AMG1D_ERR_UNSUPPORTED, "bu
 int op_sweep(amg1d* h, int l, const double* b, const double* xin, double* xout, double alpha,
              int zero_guess) {
     Level& lv = h->L[l];
-    if (h->opt_fused && fused_sweep(lv.m, lv.diag, lv.mat, b, xin, xout, lv.n, alpha, zero_guess,
-                                    h->stream)) {
+    if (h->opt_fused && fused_sweep(lv.md, lv.mat, b, xin, xout, lv.n, alpha, zero_guess, h->stream)) {
         h->launch_counter++;
         LAUNCH_CHECK();
         return AMG1D_OK;
     }
     const dim3 blk = gblock(lv.m);
     const size_t sm = (size_t)blk.z * lv.m * AMG1D_TILE * sizeof(double);
-    g_sweep<<<ggrid(lv.n, lv.m), blk, sm, h->stream>>>(lv.mat, lv.m, lv.diag, lv.K, b, xin, xout,
-                                                        lv.n, alpha, zero_guess);
+    g_sweep<<<ggrid(lv.n, lv.m), blk, sm, h->stream>>>(lv.mat, lv.md, b, xin, xout, lv.n, alpha,
+                                                        zero_guess);
     h->launch_counter++;
     LAUNCH_CHECK();
     return AMG1D_OK;
@@ -344,8 +377,7 @@ int op_sweep(amg1d* h, int l, const double* b, const double* xin, double* xout, 
 
 int op_apply(amg1d* h, int l, const double* b, const double* x, double* out, int mode) {
     Level& lv = h->L[l];
-    g_apply<<<ggrid(lv.n, lv.m), gblock(lv.m), 0, h->stream>>>(lv.mat, lv.m, lv.K, b, x, out, lv.n,
-                                                               mode);
+    g_apply<<<ggrid(lv.n, lv.m), gblock(lv.m), 0, h->stream>>>(lv.mat, lv.md, b, x, out, lv.n, mode);
     h->launch_counter++;
     LAUNCH_CHECK();
     return AMG1D_OK;
@@ -416,8 +448,8 @@ int op_resnorm(amg1d* h, int l, int slot) {
     if (lv.sharded) RET(op_halo(h, lv.x[lv.cur].p, lv.n, lv.m));
     if (h->opt_fused) {
         int nb = 0;
-        if (fused_resnorm(lv.m, lv.diag, lv.mat, lv.b.p, lv.x[lv.cur].p, lv.n, h->partial,
-                          h->partial_cap, &nb, h->stream)) {
+        if (fused_resnorm(lv.md, lv.mat, lv.b.p, lv.x[lv.cur].p, lv.n, h->partial, h->partial_cap, &nb,
+                          h->stream)) {
             h->launch_counter++;
             LAUNCH_CHECK();
             return op_reduce_partials(h, nb, slot);
@@ -448,10 +480,11 @@ int leg_down(amg1d* h, int l, int nPre, double alpha) {
     RET(prof_mark(h, l, 0));
     if (lv.sharded && !zero) RET(op_halo(h, lv.x[lv.cur].p, lv.n, lv.m));   // ghosts of the incoming iterate
     // fused: nPre sweeps + residual + restriction in one pass over the operator
-    if (h->opt_fused && t.single_parent_uniform) {
+    if (h->opt_fused && t.fusable) {
         const int ob = zero ? 0 : 1 - lv.cur;
-        if (fused_down(lv.m, t.mc, lv.diag, make_map(t), nPre, zero, lv.mat, lv.b.p, lv.x[lv.cur].p,
-                       lv.x[ob].p, t.P0, lc.b.p, lv.n, alpha, make_slab(h, l), h->stream)) {
+        if (fused_down(lv.md, t.mc, make_map_closed(t), nPre, zero, lv.mat, lv.b.p, lv.x[lv.cur].p,
+                       lv.x[ob].p, t.P0, t.P1, lc.b.p, lv.n, lv.n + (lv.gr ? t.cover_extra : 0), alpha,
+                       make_slab(h, l), h->stream)) {
             lv.cur = ob;
             h->launch_counter++;
             LAUNCH_CHECK();
@@ -461,7 +494,7 @@ int leg_down(amg1d* h, int l, int nPre, double alpha) {
     }
     if (lv.sharded)
         return fail(h, AMG1D_ERR_UNSUPPORTED, "level %d: sharded levels need the fused kernels "
-                    "(block size <= 4, single-parent transfer, option fused = 1)", l);
+                    "(block size <= 5, closed-form transfer, option fused = 1)", l);
     if (zero && nPre == 0) CK(cudaMemsetAsync(lv.x[0].p, 0, (size_t)lv.x[0].len * 8, h->stream));
     for (int s = 0; s < nPre; ++s) {
         if (zero && s == 0) {
@@ -472,7 +505,7 @@ int leg_down(amg1d* h, int l, int nPre, double alpha) {
         }
     }
     if (h->opt_fused && t.single_parent_uniform &&
-        fused_residual_restrict(lv.m, t.mc, lv.K, make_map(t), lv.mat, lv.b.p, lv.x[lv.cur].p, t.P0,
+        fused_residual_restrict(lv.md, t.mc, make_map_closed(t), lv.mat, lv.b.p, lv.x[lv.cur].p, t.P0,
                                 lc.b.p, lv.n, h->stream)) {
         h->launch_counter++;
         LAUNCH_CHECK();
@@ -489,10 +522,10 @@ int leg_up(amg1d* h, int l, int nPost, double alpha, bool fuse_norm, bool* norm_
     Transfer& t = h->T[l];
     Level& lc = h->L[l + 1];
     RET(prof_mark(h, l, 1));
-    if (h->opt_fused && t.single_parent_uniform) {
+    if (h->opt_fused && t.fusable) {
         int nb = 0;
-        if (fused_up(lv.m, t.mc, lv.diag, make_map(t), nPost, lv.mat, lv.b.p, lv.x[lv.cur].p,
-                     lv.x[1 - lv.cur].p, t.P0, lc.x[lc.cur].p, lv.n, alpha,
+        if (fused_up(lv.md, t.mc, make_map_closed(t), nPost, lv.mat, lv.b.p, lv.x[lv.cur].p,
+                     lv.x[1 - lv.cur].p, t.P0, t.P1, lc.x[lc.cur].p, lv.n, alpha,
                      fuse_norm ? h->partial : nullptr, h->partial_cap, &nb, make_slab(h, l),
                      h->stream)) {
             lv.cur = 1 - lv.cur;
@@ -520,10 +553,18 @@ int enqueue_vcycle(amg1d* h, int nPre, int nPost, double alpha, bool want_norm) 
     const int nl = h->n_levels;
     const int g = h->gather_level;          // -1 on a single GPU: every level is local
     bool norm_done = false;
-    if (g >= 0 && std::max(nPre, nPost) + 1 > h->ghost_depth)
-        return fail(h, AMG1D_ERR_ARG, "nPre / nPost need ghost_depth >= %d", std::max(nPre, nPost) + 1);
+    if (g >= 0) {
+        int need = std::max(nPre, nPost) + 1;         // one halo exchange serves a whole fused leg
+        for (int l = 0; l < nl - 1; ++l)
+            if (h->L[l].sharded) need = std::max(need, std::max(nPre, nPost) + 1 + h->T[l].reach);
+        if (need > h->ghost_depth)
+            return fail(h, AMG1D_ERR_ARG, "nPre / nPost need ghost_depth >= %d (option \"ghost_depth\", "
+                        "before the first level is set)", need);
+    }
+    // levels [ts, nl) run inside the single-CTA tail kernel (rank 0 holds them; ts > gather level)
+    const int ts = (h->tail_start > 0 && h->L[h->tail_start].present) ? h->tail_start : nl;
     // ---- down ----
-    for (int l = 0; l < nl - 1; ++l) {
+    for (int l = 0; l < nl - 1 && l < ts; ++l) {
         Level& lv = h->L[l];
         if (!lv.present) break;                       // ranks > 0 stop at the gather level
         RET(leg_down(h, l, nPre, alpha));
@@ -534,14 +575,20 @@ int enqueue_vcycle(amg1d* h, int nPre, int nPost, double alpha, bool want_norm) 
             else RET(op_gather_rhs(h, l + 1));                        // slabs -> rank 0
         }
     }
-    // ---- coarsest level: exact solve (src/solvers.jl:39) ----
-    if (h->L[nl - 1].present) {
+    // ---- coarse tail in one CTA, or just the coarsest level: exact solve (src/solvers.jl:39) ----
+    if (ts < nl) {
+        for (int l = ts; l < nl; ++l) h->L[l].cur = 0;
+        cudaError_t te = tail_launch(h->L[ts].m, h->d_tail, nl - ts, h->coarse_fac, nPre, nPost, alpha,
+                                     h->stream);
+        if (te != cudaSuccess) return fail(h, AMG1D_ERR_CUDA, "f_tail launch failed: %s", cudaGetErrorString(te));
+        h->launch_counter++;
+    } else if (h->L[nl - 1].present) {
         Level& lv = h->L[nl - 1];
         if (nl > 1) lv.cur = 0;
         RET(op_coarse(h, lv.b.p, lv.x[lv.cur].p));   // single level: x = A \ b overwrites x
     }
     // ---- up ----
-    for (int l = nl - 2; l >= 0; --l) {
+    for (int l = std::min(nl - 2, ts - 1); l >= 0; --l) {
         Level& lv = h->L[l];
         Level& lc = h->L[l + 1];
         if (!lv.present) continue;
@@ -712,6 +759,53 @@ int factor_coarsest(amg1d* h) {
     return AMG1D_OK;
 }
 
+// Single-CTA coarse tail (kernels_fused.cuh, f_tail): the longest suffix of levels [ts, n_levels) that
+// are unsharded, have at most min(coarse_cta_elems, TAIL_B) elements, share one block size, use block
+// smoothers and single-parent closed-form transfers.  Level 0 never joins (it carries the caller's
+// initial guess), and a tail of the coarsest level alone stays with g_coarse_solve.
+int build_tail(amg1d* h) {
+    h->tail_start = -1;
+    if (h->d_tail) { cudaFree(h->d_tail); h->d_tail = nullptr; }
+    const int nl = h->n_levels;
+    if (nl < 3 || h->opt_coarse_cta < 1 || !h->L[nl - 1].present) return AMG1D_OK;
+    const int m = h->L[nl - 1].m;
+    if (!tail_supported(m)) return AMG1D_OK;
+    const int64_t cap = std::min<int64_t>(h->opt_coarse_cta, TAIL_B);
+    int ts = nl;
+    for (int l = nl - 1; l >= 1; --l) {
+        const Level& lv = h->L[l];
+        if (lv.sharded || !lv.present || lv.m != m || lv.n_glob > cap) break;
+        if (l < nl - 1) {
+            const Transfer& t = h->T[l];
+            if (lv.diag || !t.single_parent_uniform || t.P1) break;
+        }
+        ts = l;
+    }
+    if (ts > nl - 2) return AMG1D_OK;
+    std::vector<TailLevel> tl((size_t)(nl - ts));
+    for (int l = ts; l < nl; ++l) {
+        const Level& lv = h->L[l];
+        TailLevel& d = tl[(size_t)(l - ts)];
+        d.md = lv.md;
+        d.mat = lv.mat;
+        d.n = lv.n;
+        d.x = lv.x[0].p;
+        d.b = lv.b.p;
+        d.P0 = nullptr;
+        d.tm = TransferMap();
+        if (l < nl - 1) {
+            d.tm = make_map_closed(h->T[l]);
+            d.P0 = h->T[l].P0;
+        }
+    }
+    cudaError_t e = tail_configure(m);
+    if (e != cudaSuccess) return fail(h, AMG1D_ERR_CUDA, "f_tail configuration failed: %s", cudaGetErrorString(e));
+    RET(dev_alloc(h, (void**)&h->d_tail, (int64_t)(tl.size() * sizeof(TailLevel))));
+    CK(cudaMemcpy(h->d_tail, tl.data(), tl.size() * sizeof(TailLevel), cudaMemcpyHostToDevice));
+    h->tail_start = ts;
+    return AMG1D_OK;
+}
+
 int check_ready(amg1d* h) {
     if (!h) return AMG1D_ERR_ARG;
     if (!h->finalized) return fail(h, AMG1D_ERR_STATE, "hierarchy not finalized (call amg1d_finalize)");
@@ -719,28 +813,56 @@ int check_ready(amg1d* h) {
     return AMG1D_OK;
 }
 
+// Structure class of a level (layout.cuh) from `nb` uploaded off-diagonal block sets.
+void detect_structure(const double* lo, const double* up, int64_t nb, int m, int* st, int* ilo, int* iup) {
+    *st = AMG1D_ST_DENSE; *ilo = 0; *iup = 0;
+    if (m < 2) return;
+    const int mm = m * m;
+    std::vector<char> lo_col(m, 0), lo_row(m, 0), up_col(m, 0), up_row(m, 0);
+    for (int64_t e = 0; e < nb; ++e)
+        for (int j = 0; j < m; ++j)
+            for (int i = 0; i < m; ++i) {
+                if (lo[e * mm + j * m + i] != 0.0) { lo_col[j] = 1; lo_row[i] = 1; }
+                if (up[e * mm + j * m + i] != 0.0) { up_col[j] = 1; up_row[i] = 1; }
+            }
+    auto single = [m](const std::vector<char>& mask, int* idx) {
+        int cnt = 0;
+        *idx = 0;
+        for (int q = 0; q < m; ++q) if (mask[q]) { ++cnt; *idx = q; }
+        return cnt <= 1;
+    };
+    int a, b;
+    if (single(lo_col, &a) && single(up_row, &b)) { *st = AMG1D_ST_COLROW; *ilo = a; *iup = b; return; }
+    if (single(lo_row, &a) && single(up_col, &b)) { *st = AMG1D_ST_ROWCOL; *ilo = a; *iup = b; return; }
+}
+
 int alloc_level_common(amg1d* h, int level, int64_t n_elem, int m, int diag, const int64_t* perm,
-                       int64_t n_dof_host) {
+                       int64_t n_dof_host, int st, int ilo, int iup) {
     if (!valid_level(h, level)) return fail(h, AMG1D_ERR_ARG, "level %d out of range", level);
     if (h->finalized) return fail(h, AMG1D_ERR_STATE, "hierarchy already finalized");
     if (n_elem < 1 || m < 1 || m > 32) return fail(h, AMG1D_ERR_ARG, "need n_elem >= 1 and 1 <= m <= 32");
     Level& lv = h->L[level];
     if (lv.set) return fail(h, AMG1D_ERR_STATE, "level %d already set", level);
     CK(cudaSetDevice(h->device));
-    lv.m = m; lv.diag = diag ? 1 : 0; lv.K = amg1d_K(m, lv.diag);
+    lv.m = m; lv.diag = diag ? 1 : 0;
+    lv.md = amg1d_desc(m, lv.diag, st, ilo, iup);
+    lv.K = lv.md.K;
     lv.n_glob = n_elem;
     if (!perm && n_dof_host != n_elem * m)
         return fail(h, AMG1D_ERR_ARG, "n_dof_host must equal n_elem*m when perm is NULL");
     // slab decision: shard while the level is large, otherwise it lives on rank 0
-    lv.sharded = h->nranks > 1 && !perm && n_elem % h->nranks == 0 &&
+    // (a remainder of one element - the closing vertex group of a CG level, n + 1 groups - goes to
+    // the last rank)
+    lv.sharded = h->nranks > 1 && !perm && n_elem % h->nranks <= 1 &&
                  n_elem / h->nranks >= h->shard_min &&
                  (level == 0 || h->L[level - 1].sharded);
     if (h->nranks > 1 && level == 0 && !lv.sharded)
         return fail(h, AMG1D_ERR_UNSUPPORTED, "multi-GPU: the finest level must be shardable (DG-type, "
                     "n_elem divisible by the rank count, >= %lld elements per rank)", (long long)h->shard_min);
     if (lv.sharded) {
-        lv.n = n_elem / h->nranks;
-        lv.start = lv.n * h->rank;
+        lv.base_n = n_elem / h->nranks;
+        lv.n = slab_size(n_elem, h->nranks, h->rank);
+        lv.start = slab_start(n_elem, h->nranks, h->rank);
         lv.gl = h->rank > 0 ? h->ghost_depth : 0;
         lv.gr = h->rank < h->nranks - 1 ? h->ghost_depth : 0;
         lv.present = true;
@@ -867,6 +989,7 @@ int amg1d_destroy(amg1d_t* h) {
     if (h->d_scal) cudaFree(h->d_scal);
     if (h->h_scal) cudaFreeHost(h->h_scal);
     if (h->coarse_fac) cudaFree(h->coarse_fac);
+    if (h->d_tail) cudaFree(h->d_tail);
 #ifdef AMG1D_WITH_NCCL
     if (h->comm) g_nccl.CommDestroy(h->comm);
 #endif
@@ -880,13 +1003,16 @@ int amg1d_set_level(amg1d_t* h, int level, int64_t n_elem, int m, const double* 
                     int dinv_is_diagonal, const int64_t* perm, int64_t n_dof_host) {
     if (!h) return AMG1D_ERR_ARG;
     if (!A_lo || !A_di || !A_up || !Dinv) return fail(h, AMG1D_ERR_ARG, "null operator array");
-    RET(alloc_level_common(h, level, n_elem, m, dinv_is_diagonal, perm, n_dof_host));
-    Level& lv = h->L[level];
+    if (n_elem < 1 || m < 1 || m > 32) return fail(h, AMG1D_ERR_ARG, "need n_elem >= 1 and 1 <= m <= 32");
     const int mm = m * m;
-    const int dsz = lv.diag ? m : mm;
     for (int q = 0; q < mm; ++q)
         if (A_lo[q] != 0.0 || A_up[(size_t)(n_elem - 1) * mm + q] != 0.0)
             return fail(h, AMG1D_ERR_ARG, "A_lo[0] and A_up[n-1] must be zero blocks");
+    int st = 0, ilo = 0, iup = 0;
+    if (h->opt_compress) detect_structure(A_lo, A_up, n_elem, m, &st, &ilo, &iup);
+    RET(alloc_level_common(h, level, n_elem, m, dinv_is_diagonal, perm, n_dof_host, st, ilo, iup));
+    Level& lv = h->L[level];
+    const int dsz = lv.diag ? m : mm;
     if (!lv.present) { lv.set = true; return AMG1D_OK; }
     // local range of elements to store: [-gl, n + gr) in local indices = [g0, g1) in global ones
     const int64_t g0 = lv.start - lv.gl, g1 = lv.start + lv.n + lv.gr;
@@ -917,8 +1043,8 @@ int amg1d_set_level(amg1d_t* h, int level, int64_t n_elem, int m, const double* 
             cudaMemcpyAsync(d_dv + off * dsz, Dinv + a * dsz, (size_t)(b - a) * dsz * 8, cudaMemcpyHostToDevice, h->stream);
         }
         const int64_t total = amg1d_tiles(cnt) * (int64_t)lv.K * AMG1D_TILE;
-        k_repack<<<(unsigned)((total + 255) / 256), 256, 0, h->stream>>>(d_lo, d_di, d_up, d_dv, m,
-                                                                         lv.diag, lv.K, le0, cnt, lv.mat);
+        k_repack<<<(unsigned)((total + 255) / 256), 256, 0, h->stream>>>(d_lo, d_di, d_up, d_dv, lv.md,
+                                                                         le0, cnt, lv.mat);
         cudaError_t e = cudaStreamSynchronize(h->stream);
         if (e == cudaSuccess) e = cudaGetLastError();
         if (e != cudaSuccess) rc = fail(h, AMG1D_ERR_CUDA, "level upload failed: %s", cudaGetErrorString(e));
@@ -941,11 +1067,14 @@ int amg1d_set_level_pattern(amg1d_t* h, int level, int64_t n_elem, int m, int n_
     if (!A_lo || !A_di || !A_up || !Dinv) return fail(h, AMG1D_ERR_ARG, "null operator array");
     if (n_head < 0 || n_tail < 0 || (int64_t)n_head + n_tail > n_elem)
         return fail(h, AMG1D_ERR_ARG, "need n_head + n_tail <= n_elem");
-    RET(alloc_level_common(h, level, n_elem, m, dinv_is_diagonal, nullptr, n_elem * m));
-    Level& lv = h->L[level];
+    if (n_elem < 1 || m < 1 || m > 32) return fail(h, AMG1D_ERR_ARG, "need n_elem >= 1 and 1 <= m <= 32");
     const int mm = m * m;
-    const int dsz = lv.diag ? m : mm;
     const int nb = n_head + 1 + n_tail;
+    int st = 0, ilo = 0, iup = 0;
+    if (h->opt_compress) detect_structure(A_lo, A_up, nb, m, &st, &ilo, &iup);
+    RET(alloc_level_common(h, level, n_elem, m, dinv_is_diagonal, nullptr, n_elem * m, st, ilo, iup));
+    Level& lv = h->L[level];
+    const int dsz = lv.diag ? m : mm;
     if (!lv.present) { lv.set = true; return AMG1D_OK; }
     double *d_lo, *d_di, *d_up, *d_dv;
     CK(cudaMalloc(&d_lo, (size_t)nb * mm * 8));
@@ -960,7 +1089,7 @@ int amg1d_set_level_pattern(amg1d_t* h, int level, int64_t n_elem, int m, int n_
     const int64_t ntiles = amg1d_tiles(lv.n + lv.gr) + 1;
     const int64_t total = ntiles * (int64_t)lv.K * AMG1D_TILE;
     k_fill_pattern<<<(unsigned)((total + 255) / 256), 256, 0, h->stream>>>(
-        d_lo, d_di, d_up, d_dv, m, lv.diag, lv.K, n_elem, n_head, n_tail, lv.start, -(int64_t)lv.gl,
+        d_lo, d_di, d_up, d_dv, lv.md, n_elem, n_head, n_tail, lv.start, -(int64_t)lv.gl,
         lv.n + lv.gr, ntiles, lv.mat_alloc);
     cudaError_t e = cudaStreamSynchronize(h->stream);
     if (e == cudaSuccess) e = cudaGetLastError();
@@ -1005,17 +1134,26 @@ int amg1d_set_transfer(amg1d_t* h, int level, int64_t n_fine_elem, int m_f, int 
         maxp = std::max(maxp, parent[e]);
     }
     t.n_coarse = maxp + 1;  // validated against the coarse level at finalize (P1 may reach maxp + 1)
-    // uniform single-parent detection: parent[e] = e / ratio
-    bool uniform = (P1 == nullptr) && parent[0] == 0;
-    int ratio = 1;
-    if (uniform) {
-        int64_t r = 1;
-        while (r < n_fine_elem && parent[r] == 0) ++r;
-        ratio = (int)r;
-        for (int64_t e = 0; e < n_fine_elem && uniform; ++e) uniform = parent[e] == e / ratio;
+    // closed-form detection: parent[e] = (e + shift) / ratio + base, with base = parent[0], the first
+    // run of equal parents fixing the shift and the second run the ratio
+    {
+        const int64_t base = parent[0];
+        int64_t c0 = 1;
+        while (c0 < n_fine_elem && parent[c0] == base) ++c0;
+        int64_t c1 = 0;
+        while (c0 + c1 < n_fine_elem && parent[c0 + c1] == base + 1) ++c1;
+        const bool second_run_complete = c0 + c1 < n_fine_elem;
+        int64_t ratio = second_run_complete ? c1 : std::max(c0, c1);
+        if (ratio < 1) ratio = 1;
+        const int64_t shift = ratio - c0;
+        bool closed = ratio <= 1024 && shift >= 0 && shift < ratio;
+        for (int64_t e = 0; e < n_fine_elem && closed; ++e) closed = parent[e] == (e + shift) / ratio + base;
+        t.closed = closed;
+        t.ratio = closed ? (int)ratio : 1;
+        t.shift = closed ? (int)shift : 0;
+        t.base = closed ? (int)base : 0;
     }
-    t.single_parent_uniform = uniform;
-    t.ratio = uniform ? ratio : 1; t.shift = 0; t.base = 0;
+    t.single_parent_uniform = t.closed && P1 == nullptr && t.shift == 0 && t.base == 0;
     const int bs = m_f * m_c;
     RET(dev_alloc(h, (void**)&t.P0, n_fine_elem * bs * 8));
     CK(cudaMemcpy(t.P0, P0, (size_t)n_fine_elem * bs * 8, cudaMemcpyHostToDevice));
@@ -1037,7 +1175,7 @@ int amg1d_set_transfer_pattern(amg1d_t* h, int level, int64_t n_fine_elem, int m
                                const double* P0_pat, const double* P1_pat) {
     RET(transfer_common(h, level, n_fine_elem, m_f, m_c));
     if (!P0_pat) return fail(h, AMG1D_ERR_ARG, "null transfer array");
-    if (ratio < 1 || period < 1 || shift < 0 || n_head < 0 || n_tail < 0 ||
+    if (ratio < 1 || period < 1 || shift < 0 || shift >= ratio || n_head < 0 || n_tail < 0 ||
         (int64_t)n_head + n_tail > n_fine_elem)
         return fail(h, AMG1D_ERR_ARG, "bad transfer pattern");
     Transfer& t = h->T[level];
@@ -1045,6 +1183,7 @@ int amg1d_set_transfer_pattern(amg1d_t* h, int level, int64_t n_fine_elem, int m
     t.ratio = ratio; t.shift = shift; t.base = base; t.period = period; t.n_head = n_head; t.n_tail = n_tail;
     t.n_coarse = (n_fine_elem - 1 + shift) / ratio + base + 1;
     t.single_parent_uniform = (P1_pat == nullptr) && shift == 0 && base == 0;
+    t.closed = true;
     const int bs = m_f * m_c;
     t.nblk = n_head + period + n_tail;
     RET(dev_alloc(h, (void**)&t.P0, t.nblk * bs * 8));
@@ -1080,13 +1219,46 @@ int amg1d_finalize(amg1d_t* h) {
             return fail(h, AMG1D_ERR_ARG, "transfer %d reaches coarse element %lld but level %d has %lld elements",
                         l, (long long)t.n_coarse - 1, l + 1, (long long)lc.n_glob);
         t.n_coarse = lc.n_glob;
+        // f_down gathers coarse element q in the thread of its first P0-child first(q) = (q - base) *
+        // ratio - shift: that child must exist for every q, and first(0) must not be clamped
+        t.fusable = t.closed && (-(int64_t)t.base * t.ratio - t.shift) >= 0 &&
+                    ((lc.n_glob - 1 - t.base) * (int64_t)t.ratio - t.shift) < t.n_fine;
         if (lf.sharded) {
-            if (!t.single_parent_uniform || t.period == 0)
-                return fail(h, AMG1D_ERR_UNSUPPORTED, "transfer %d: sharded levels need a single-parent "
-                            "pattern transfer", l);
-            if (lf.n % t.ratio || lf.n < 2 * h->ghost_depth || lc.n_glob % h->nranks)
-                return fail(h, AMG1D_ERR_UNSUPPORTED, "transfer %d: slab of %lld elements is not aligned "
-                            "to the agglomeration ratio %d", l, (long long)lf.n, t.ratio);
+            if (!t.fusable || t.period == 0)
+                return fail(h, AMG1D_ERR_UNSUPPORTED, "transfer %d: sharded levels need a closed-form "
+                            "pattern transfer (amg1d_set_transfer_pattern)", l);
+            if (lf.n < 2 * h->ghost_depth)
+                return fail(h, AMG1D_ERR_UNSUPPORTED, "transfer %d: slab of %lld elements is too small", l,
+                            (long long)lf.n);
+            // Every rank's coarse slab must be gathered from its own fine slab plus at most `reach`
+            // ghost elements per edge (0 for single-parent transfers aligned to the agglomerates).
+            int64_t reach = 0, extra = 0;
+            for (int r = 0; r < h->nranks; ++r) {
+                const int64_t f0 = slab_start(lf.n_glob, h->nranks, r), f1 = f0 + slab_size(lf.n_glob, h->nranks, r);
+                const int64_t c0 = slab_start(lc.n_glob, h->nranks, r), c1 = c0 + slab_size(lc.n_glob, h->nranks, r);
+                auto first = [&](int64_t q) {
+                    int64_t v = (q - t.base) * (int64_t)t.ratio - t.shift;
+                    return std::min<int64_t>(std::max<int64_t>(v, 0), t.n_fine);
+                };
+                const int64_t lo_child = first(t.P1 ? c0 - 1 : c0);   // first fine element rank r's coarse slab reads
+                const int64_t hi_child = first(c1);                   // one past the last
+                reach = std::max(reach, std::max(f0 - lo_child, hi_child - f1));
+                extra = std::max(extra, first(c1 - 1) + 1 - f1);      // owners (first P0-children) right of the slab
+                const bool plain = !t.P1 && t.shift == 0 && t.base == 0;   // window without extra halo
+                if (plain ? (lo_child != f0 || hi_child != f1)
+                          : (lo_child > f0 + t.ratio || hi_child < f1 - t.ratio || f0 - lo_child > t.ratio ||
+                             hi_child - f1 > t.ratio))
+                    return fail(h, AMG1D_ERR_UNSUPPORTED, "transfer %d: rank %d's slab of level %d [%lld, %lld) "
+                                "is not aligned with its slab of level %d (children [%lld, %lld))", l, r, l,
+                                (long long)f0, (long long)f1, l + 1, (long long)lo_child, (long long)hi_child);
+            }
+            if (reach < 0) reach = 0;
+            if (extra < 0) extra = 0;
+            if (reach > 64)
+                return fail(h, AMG1D_ERR_UNSUPPORTED, "transfer %d: slabs of levels %d and %d are misaligned "
+                            "by %lld elements", l, l, l + 1, (long long)reach);
+            t.reach = (int)reach;
+            t.cover_extra = extra;
         }
         if (t.parent) {  // build child pointers: cp[q] = first e with parent[e] >= q - 1, q = 0..n_coarse+1
             std::vector<int64_t> cp((size_t)lc.n_glob + 2);
@@ -1105,8 +1277,8 @@ int amg1d_finalize(amg1d_t* h) {
     if (h->nranks > 1 && h->rank > 0) {
         Level& lg = h->L[h->gather_level];
         lg.proxy = true;
-        lg.n = lg.n_glob / h->nranks;
-        lg.start = lg.n * h->rank;
+        lg.n = slab_size(lg.n_glob, h->nranks, h->rank);
+        lg.start = slab_start(lg.n_glob, h->nranks, h->rank);
     }
     h->partial_cap = AMG1D_RED_BLOCKS;
     for (int l = 0; l < h->n_levels; ++l) {
@@ -1123,6 +1295,7 @@ int amg1d_finalize(amg1d_t* h) {
     RET(dev_alloc(h, (void**)&h->d_scal, 64 * 8));
     CK(cudaMallocHost(&h->h_scal, 64 * 8));
     if (h->L[h->n_levels - 1].present) RET(factor_coarsest(h));
+    RET(build_tail(h));
     CK(cudaStreamSynchronize(h->stream));
     h->finalized = true;
     return AMG1D_OK;
@@ -1258,7 +1431,7 @@ int amg1d_apply_smoother(amg1d_t* h, int level, double* Y, const double* B, int6
     for (int64_t c = 0; c < n_rhs; ++c) {
         RET(to_device(h, level, B + c * lv.n_host, in));
         g_apply_smoother<<<ggrid(lv.n, lv.m), gblock(lv.m), 0, h->stream>>>(
-            lv.mat, lv.m, lv.diag, lv.K, in, h->scratch.p, lv.n, alpha);
+            lv.mat, lv.md, in, h->scratch.p, lv.n, alpha);
         LAUNCH_CHECK();
         RET(to_host(h, level, h->scratch.p, Y + c * lv.n_host));
     }
@@ -1381,12 +1554,19 @@ int amg1d_set_option(amg1d_t* h, const char* key, int64_t value) {
     invalidate_graph(h);
     if (!strcmp(key, "fused")) h->opt_fused = (int)value;
     else if (!strcmp(key, "graph")) h->opt_graph = (int)value;
-    else if (!strcmp(key, "coarse_cta_elems")) h->opt_coarse_cta = value;
-    else if (!strcmp(key, "ghost_depth") || !strcmp(key, "shard_min")) {
+    else if (!strcmp(key, "coarse_cta_elems")) {
+        h->opt_coarse_cta = value;
+        if (h->finalized) { CK(cudaSetDevice(h->device)); CK(cudaStreamSynchronize(h->stream)); RET(build_tail(h)); }
+    }
+    else if (!strcmp(key, "ghost_depth") || !strcmp(key, "shard_min") || !strcmp(key, "compress")) {
         for (auto& lv : h->L)
             if (lv.set) return fail(h, AMG1D_ERR_STATE, "'%s' must be set before the first level", key);
+        if (!strcmp(key, "compress")) { h->opt_compress = value != 0; return AMG1D_OK; }
         if (value < 1) return fail(h, AMG1D_ERR_ARG, "'%s' must be >= 1", key);
-        if (!strcmp(key, "ghost_depth")) h->ghost_depth = (int)value; else h->shard_min = value;
+        if (!strcmp(key, "ghost_depth")) {
+            if ((value + 2) * 8 > PAD_FRONT) return fail(h, AMG1D_ERR_ARG, "ghost_depth must be <= %d", PAD_FRONT / 8 - 2);
+            h->ghost_depth = (int)value;
+        } else h->shard_min = value;
     }
     else if (!strcmp(key, "profile")) {
         h->opt_profile = (int)value;
@@ -1406,6 +1586,16 @@ int64_t amg1d_get_info(amg1d_t* h, const char* key) {
     if (!strcmp(key, "local_dofs")) return h->L[0].n * h->L[0].m;
     if (!strcmp(key, "local_offset_dofs")) return h->L[0].start * h->L[0].m;
     if (!strcmp(key, "gather_level")) return h->gather_level;
+    if (!strcmp(key, "tail_start")) return h->tail_start;
+    if (!strcmp(key, "ghost_depth")) return h->ghost_depth;
+    if (!strncmp(key, "structure:", 10)) {          // "structure:<level>" -> structure class (layout.cuh)
+        const int l = atoi(key + 10);
+        return valid_level(h, l) && h->L[l].set ? h->L[l].md.st : -1;
+    }
+    if (!strncmp(key, "tile_rows:", 10)) {          // "tile_rows:<level>" -> doubles stored per element
+        const int l = atoi(key + 10);
+        return valid_level(h, l) && h->L[l].set ? h->L[l].md.K : -1;
+    }
     if (!strcmp(key, "rank")) return h->rank;
     if (!strcmp(key, "nranks")) return h->nranks;
     if (!strcmp(key, "dof_updates_per_sweep")) {

@@ -1,34 +1,42 @@
-// Fast kernel tier: templated on the block size M, one thread per element, operator read straight
-// from the element-tile layout with fully coalesced 256-byte warp requests.
+// Fast kernel tier: templated on the block size M and the level's structure class ST (layout.cuh),
+// one thread per element, operator read straight from the element-tile layout with fully coalesced
+// 256-byte warp requests.
 //
 //  f_sweep / f_resnorm / f_residual_restrict  - streaming kernels (one pass over the operator each)
 //  f_down   nPre sweeps + residual + restriction  in ONE pass over the level's operator
 //  f_up     prolongation + correction + nPost sweeps (+ optional ||b - A x||^2)  in ONE pass
+//  f_tail   the whole sub-V-cycle of the coarse levels (<= 1024 elements) in ONE CTA
 //
-// f_down / f_up keep the element's four M x M blocks (A_lo, A_di, A_up, Dinv) in registers for the
-// whole leg and exchange only the M iterate values with the two neighbour threads through shared
-// memory between sweeps (Jacobi needs the *old* neighbour values, so the exchange is double
-// buffered).  A CTA owns a window of B consecutive elements; after s sweeps only the inner
-// [s, B - s) elements are still exact, so the CTA emits the inner B - 2(S+1) elements and adjacent
-// CTAs overlap by the halo (the overlap is re-read through L2, not HBM).  Per element the arithmetic
-// and its order are identical to the generic tier, so both tiers agree bit for bit on x.
+// f_down / f_up keep the element's operator blocks in registers for the whole leg (Dinv in shared
+// memory, staged with cp.async) and exchange only the M iterate values with the two neighbour
+// threads through shared memory between sweeps (Jacobi needs the *old* neighbour values, so the
+// exchange is double buffered).  A CTA owns a window of B consecutive elements; after s sweeps only
+// the inner [s, B - s) elements are still exact, so the CTA emits the inner B - 2 halo elements and
+// adjacent CTAs overlap by the halo (the overlap is re-read through L2, not HBM).  Per element the
+// arithmetic and its order are identical to the generic tier, so both tiers agree bit for bit on x.
 //
-// Algorithmic bytes per element (FP64, M x M blocks, coarse block size MC, ratio R children):
-//   f_sweep               8 (4 M^2 + 3 M)                         [zero guess: 8 (M^2 + 2 M)]
-//   f_down (S sweeps)     8 (4 M^2 + 3 M + MC / R)  (+ P block if it is per-element)
-//   f_up   (S sweeps)     8 (4 M^2 + 3 M + MC / R)  (+ P block if it is per-element)
-// against S * 8 (4 M^2 + 3 M) + 8 (3 M^2 + 2 M + ...) for the unfused sequence (SURVEY 8d B_ref).
+// Both smoother kinds (block Jacobi: Dinv = m x m; point Jacobi: Dinv = m) and both transfer kinds
+// (single parent: dg_dg / aggdg_dg / aggdg_aggdg; two parents: cg_cg / dg_cg / aggdg_cg) are covered,
+// the latter with the closed-form parent map  parent(e) = (e + shift) / ratio + base.
+//
+// Algorithmic bytes per element (FP64; Kop = doubles of the level's structure class, layout.cuh;
+// coarse block size MC, ratio R children):
+//   f_sweep               8 (Kop + 3 M)                           [zero guess: 8 (|Dinv| + 2 M)]
+//   f_down (S sweeps)     8 (Kop + 3 M + MC / R)  (+ P block if it is per-element)
+//   f_up   (S sweeps)     8 (Kop + 3 M + MC / R)  (+ P block if it is per-element)
+// against S * 8 (4 M^2 + 3 M) + 8 (3 M^2 + 2 M + ...) for the unfused dense sequence (SURVEY 8d B_ref).
 #pragma once
 #include <cuda_runtime.h>
 #include "kernels_generic.cuh"
 #include "layout.cuh"
 
-// Position of a rank's slab inside its level (single GPU: all zero).  Local element index e runs over
-// [-gl, n + gr): gl / gr ghost elements (with operator blocks, rhs and iterate) on the left / right
-// slab edge; e_off = global index of local element 0; c_off = global index of local coarse element 0.
+// Position of a rank's slab inside its level (single GPU: gl = gr = e_off = c_off = 0).  Local element
+// index e runs over [-gl, n + gr): gl / gr ghost elements (with operator blocks, rhs and iterate) on the
+// left / right slab edge; e_off = global index of local element 0; c_off = global index of local coarse
+// element 0; nc = coarse elements this rank owns.
 struct Slab {
     int gl, gr;
-    int64_t e_off, c_off;
+    int64_t e_off, c_off, nc;
 };
 
 #ifndef FUSED_B
@@ -37,6 +45,7 @@ struct Slab {
 #ifndef FUSED_MINB
 #define FUSED_MINB 3   // __launch_bounds__ min CTAs per SM for f_down / f_up
 #endif
+#define TAIL_B 1024    // threads (= max elements of the first tail level) of f_tail
 
 // ---- small helpers ---------------------------------------------------------------------------------
 template <int M>
@@ -65,35 +74,82 @@ __device__ __forceinline__ void store_vec(double* __restrict__ p, const double (
     }
 }
 
-// y = A_lo xl + A_di xc + A_up xr, operator streamed from the tile (T points at [tile][0][lane]).
-template <int M>
-__device__ __forceinline__ void stream_Ax(const double* __restrict__ T, const double (&xl)[M],
-                                          const double (&xc)[M], const double (&xr)[M],
-                                          double (&y)[M]) {
+// The fast tier handles ST_COLROW levels whose A_up row is the reference's DG trace row (local node 1,
+// src/dg_mesh.jl:41-46: left end, right end, interior nodes), so that the row is a compile-time
+// register; any other row index stays with the generic tier (fast_tier_ok below).
+#define FUSED_COLROW_IUP 1
+
+// Tile rows of the level's operator part per structure class.
+template <int M, int ST>
+struct OpShape {
+    static constexpr int NO = ST ? M : M * M;           // stored entries of A_lo (and of A_up)
+    static constexpr int O_DI = NO, O_UP = NO + M * M, O_DV = 2 * NO + M * M;
+};
+
+// y = A_lo xl + A_di xc + A_up xr with the operator streamed from the tile (T points at
+// [tile][0][lane]).  Neighbour values: ST_COLROW needs only xl[ilo], passed as xl[0]; ST_ROWCOL needs
+// only xr[iup], passed as xr[0].  Same accumulation order as g_row_Ax.
+template <int M, int ST>
+__device__ __forceinline__ void stream_Ax(const double* __restrict__ T, int ilo, int iup,
+                                          const double (&xl)[M], const double (&xc)[M],
+                                          const double (&xr)[M], double (&y)[M]) {
+    using S = OpShape<M, ST>;
+    if constexpr (ST == AMG1D_ST_DENSE) {
 #pragma unroll
-    for (int i = 0; i < M; ++i) y[i] = 0.0;
+        for (int i = 0; i < M; ++i) y[i] = 0.0;
+#pragma unroll
+        for (int j = 0; j < M; ++j)
+#pragma unroll
+            for (int i = 0; i < M; ++i) y[i] = fma(T[(j * M + i) * AMG1D_TILE], xl[j], y[i]);
+    } else if constexpr (ST == AMG1D_ST_COLROW) {
+#pragma unroll
+        for (int i = 0; i < M; ++i) y[i] = fma(T[i * AMG1D_TILE], xl[0], 0.0);
+    } else {
+        double yr = 0.0;
+#pragma unroll
+        for (int j = 0; j < M; ++j) yr = fma(T[j * AMG1D_TILE], xl[j], yr);
+#pragma unroll
+        for (int i = 0; i < M; ++i) y[i] = (i == ilo) ? yr : 0.0;
+    }
 #pragma unroll
     for (int j = 0; j < M; ++j)
 #pragma unroll
-        for (int i = 0; i < M; ++i) y[i] = fma(T[(j * M + i) * AMG1D_TILE], xl[j], y[i]);
+        for (int i = 0; i < M; ++i) y[i] = fma(T[(S::O_DI + j * M + i) * AMG1D_TILE], xc[j], y[i]);
+    if constexpr (ST == AMG1D_ST_DENSE) {
 #pragma unroll
-    for (int j = 0; j < M; ++j)
+        for (int j = 0; j < M; ++j)
 #pragma unroll
-        for (int i = 0; i < M; ++i) y[i] = fma(T[(M * M + j * M + i) * AMG1D_TILE], xc[j], y[i]);
+            for (int i = 0; i < M; ++i) y[i] = fma(T[(S::O_UP + j * M + i) * AMG1D_TILE], xr[j], y[i]);
+    } else if constexpr (ST == AMG1D_ST_COLROW) {
+        double yr = y[FUSED_COLROW_IUP];
 #pragma unroll
-    for (int j = 0; j < M; ++j)
+        for (int j = 0; j < M; ++j) yr = fma(T[(S::O_UP + j) * AMG1D_TILE], xr[j], yr);
+        y[FUSED_COLROW_IUP] = yr;
+    } else {
 #pragma unroll
-        for (int i = 0; i < M; ++i) y[i] = fma(T[(2 * M * M + j * M + i) * AMG1D_TILE], xr[j], y[i]);
+        for (int i = 0; i < M; ++i) y[i] = fma(T[(S::O_UP + i) * AMG1D_TILE], xr[0], y[i]);
+    }
+}
+
+// Neighbour blocks of element e from a global vector, in the form stream_Ax / reg_Ax expect.
+template <int M, int ST>
+__device__ __forceinline__ void load_neighbours(const double* __restrict__ x, int64_t e, int ilo, int iup,
+                                                double (&xl)[M], double (&xr)[M]) {
+    if constexpr (ST == AMG1D_ST_COLROW) xl[0] = x[(e - 1) * M + ilo];
+    else load_vec<M>(x + (e - 1) * M, xl);
+    if constexpr (ST == AMG1D_ST_ROWCOL) xr[0] = x[(e + 1) * M + iup];
+    else load_vec<M>(x + (e + 1) * M, xr);
 }
 
 // ---- streaming kernels --------------------------------------------------------------------------------
-template <int M, bool DIAG>
-__global__ void __launch_bounds__(256) f_sweep(const double* __restrict__ mat,
+template <int M, bool DIAG, int ST>
+__global__ void __launch_bounds__(256) f_sweep(const double* __restrict__ mat, int ilo, int iup,
                                                const double* __restrict__ b,
                                                const double* __restrict__ xin,
                                                double* __restrict__ xout, int64_t n, double alpha,
                                                int zero_guess) {
-    constexpr int K = 3 * M * M + (DIAG ? M : M * M);
+    using S = OpShape<M, ST>;
+    constexpr int K = S::O_DV + (DIAG ? M : M * M);
     const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (e >= n) return;
     const double* T = mat + (e >> 5) * (int64_t)(K * AMG1D_TILE) + (e & 31);
@@ -104,10 +160,9 @@ __global__ void __launch_bounds__(256) f_sweep(const double* __restrict__ mat,
         for (int i = 0; i < M; ++i) { xc[i] = 0.0; r[i] = bb[i] - 0.0; }
     } else {
         double xl[M], xr[M], y[M];
-        load_vec<M>(xin + (e - 1) * M, xl);
         load_vec<M>(xin + e * M, xc);
-        load_vec<M>(xin + (e + 1) * M, xr);
-        stream_Ax<M>(T, xl, xc, xr, y);
+        load_neighbours<M, ST>(xin, e, ilo, iup, xl, xr);
+        stream_Ax<M, ST>(T, ilo, iup, xl, xc, xr, y);
 #pragma unroll
         for (int i = 0; i < M; ++i) r[i] = bb[i] - y[i];
     }
@@ -115,7 +170,7 @@ __global__ void __launch_bounds__(256) f_sweep(const double* __restrict__ mat,
     if constexpr (DIAG) {
 #pragma unroll
         for (int i = 0; i < M; ++i)
-            xn[i] = __dadd_rn(xc[i], __dmul_rn(alpha, T[(3 * M * M + i) * AMG1D_TILE] * r[i]));
+            xn[i] = __dadd_rn(xc[i], __dmul_rn(alpha, T[(S::O_DV + i) * AMG1D_TILE] * r[i]));
     } else {
         double z[M];
 #pragma unroll
@@ -123,7 +178,7 @@ __global__ void __launch_bounds__(256) f_sweep(const double* __restrict__ mat,
 #pragma unroll
         for (int j = 0; j < M; ++j)
 #pragma unroll
-            for (int i = 0; i < M; ++i) z[i] = fma(T[(3 * M * M + j * M + i) * AMG1D_TILE], r[j], z[i]);
+            for (int i = 0; i < M; ++i) z[i] = fma(T[(S::O_DV + j * M + i) * AMG1D_TILE], r[j], z[i]);
 #pragma unroll
         for (int i = 0; i < M; ++i) xn[i] = __dadd_rn(xc[i], __dmul_rn(alpha, z[i]));
     }
@@ -131,21 +186,20 @@ __global__ void __launch_bounds__(256) f_sweep(const double* __restrict__ mat,
 }
 
 // partial[blockIdx] = sum over the block's elements of || b - A x ||^2
-template <int M, int KK>
-__global__ void __launch_bounds__(256) f_resnorm(const double* __restrict__ mat,
+template <int M, int ST>
+__global__ void __launch_bounds__(256) f_resnorm(const double* __restrict__ mat, int K, int ilo, int iup,
                                                  const double* __restrict__ b,
                                                  const double* __restrict__ x, int64_t n,
                                                  double* __restrict__ partial) {
     const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     double s = 0.0;
     if (e < n) {
-        const double* T = mat + (e >> 5) * (int64_t)(KK * AMG1D_TILE) + (e & 31);
+        const double* T = mat + (e >> 5) * (int64_t)K * AMG1D_TILE + (e & 31);
         double xl[M], xc[M], xr[M], y[M], bb[M];
         load_vec<M>(b + e * M, bb);
-        load_vec<M>(x + (e - 1) * M, xl);
         load_vec<M>(x + e * M, xc);
-        load_vec<M>(x + (e + 1) * M, xr);
-        stream_Ax<M>(T, xl, xc, xr, y);
+        load_neighbours<M, ST>(x, e, ilo, iup, xl, xr);
+        stream_Ax<M, ST>(T, ilo, iup, xl, xc, xr, y);
 #pragma unroll
         for (int i = 0; i < M; ++i) { const double r = bb[i] - y[i]; s = fma(r, r, s); }
     }
@@ -171,45 +225,83 @@ __device__ __forceinline__ void exch_init(Exchange<M, B>& ex) {
     }
 }
 
-// one damped block-Jacobi sweep on register-resident blocks; same operation order as g_sweep
+// The element's A_lo / A_di / A_up in registers (only the stored entries of the structure class).
+template <int M, int ST>
+struct RegOp {
+    double lo[OpShape<M, ST>::NO], di[M * M], up[OpShape<M, ST>::NO];
+};
+
+template <int M, int ST>
+__device__ __forceinline__ void reg_Ax(const RegOp<M, ST>& A, int ilo, int iup, const double (&xl)[M],
+                                       const double (&xc)[M], const double (&xr)[M], double (&y)[M]) {
+    if constexpr (ST == AMG1D_ST_DENSE) {
+#pragma unroll
+        for (int i = 0; i < M; ++i) y[i] = 0.0;
+#pragma unroll
+        for (int j = 0; j < M; ++j)
+#pragma unroll
+            for (int i = 0; i < M; ++i) y[i] = fma(A.lo[j * M + i], xl[j], y[i]);
+    } else if constexpr (ST == AMG1D_ST_COLROW) {
+#pragma unroll
+        for (int i = 0; i < M; ++i) y[i] = fma(A.lo[i], xl[0], 0.0);
+    } else {
+        double yr = 0.0;
+#pragma unroll
+        for (int j = 0; j < M; ++j) yr = fma(A.lo[j], xl[j], yr);
+#pragma unroll
+        for (int i = 0; i < M; ++i) y[i] = (i == ilo) ? yr : 0.0;
+    }
+#pragma unroll
+    for (int j = 0; j < M; ++j)
+#pragma unroll
+        for (int i = 0; i < M; ++i) y[i] = fma(A.di[j * M + i], xc[j], y[i]);
+    if constexpr (ST == AMG1D_ST_DENSE) {
+#pragma unroll
+        for (int j = 0; j < M; ++j)
+#pragma unroll
+            for (int i = 0; i < M; ++i) y[i] = fma(A.up[j * M + i], xr[j], y[i]);
+    } else if constexpr (ST == AMG1D_ST_COLROW) {
+        double yr = y[FUSED_COLROW_IUP];
+#pragma unroll
+        for (int j = 0; j < M; ++j) yr = fma(A.up[j], xr[j], yr);
+        y[FUSED_COLROW_IUP] = yr;
+    } else {
+#pragma unroll
+        for (int i = 0; i < M; ++i) y[i] = fma(A.up[i], xr[0], y[i]);
+    }
+}
+
+// one damped (block-)Jacobi sweep on register-resident blocks; same operation order as g_sweep.
 // Dinv is read from shared memory: dcol points at this thread's column of ds[k][thread], stride DS.
-template <int M, int DS>
-__device__ __forceinline__ void reg_sweep(const double (&A)[3 * M * M], const double* __restrict__ dcol,
-                                          const double (&bb)[M], const double (&xl)[M],
-                                          double (&xc)[M], const double (&xr)[M], double alpha,
-                                          bool zero_guess) {
+template <int M, int ST, bool DIAG, int DS>
+__device__ __forceinline__ void reg_sweep(const RegOp<M, ST>& A, int ilo, int iup,
+                                          const double* __restrict__ dcol, const double (&bb)[M],
+                                          const double (&xl)[M], double (&xc)[M], const double (&xr)[M],
+                                          double alpha, bool zero_guess) {
     double r[M];
     if (zero_guess) {
 #pragma unroll
         for (int i = 0; i < M; ++i) r[i] = bb[i] - 0.0;
     } else {
         double y[M];
-#pragma unroll
-        for (int i = 0; i < M; ++i) y[i] = 0.0;
-#pragma unroll
-        for (int j = 0; j < M; ++j)
-#pragma unroll
-            for (int i = 0; i < M; ++i) y[i] = fma(A[j * M + i], xl[j], y[i]);
-#pragma unroll
-        for (int j = 0; j < M; ++j)
-#pragma unroll
-            for (int i = 0; i < M; ++i) y[i] = fma(A[M * M + j * M + i], xc[j], y[i]);
-#pragma unroll
-        for (int j = 0; j < M; ++j)
-#pragma unroll
-            for (int i = 0; i < M; ++i) y[i] = fma(A[2 * M * M + j * M + i], xr[j], y[i]);
+        reg_Ax<M, ST>(A, ilo, iup, xl, xc, xr, y);
 #pragma unroll
         for (int i = 0; i < M; ++i) r[i] = bb[i] - y[i];
     }
-    double z[M];
+    if constexpr (DIAG) {
 #pragma unroll
-    for (int i = 0; i < M; ++i) z[i] = 0.0;
+        for (int i = 0; i < M; ++i) xc[i] = __dadd_rn(xc[i], __dmul_rn(alpha, dcol[i * DS] * r[i]));
+    } else {
+        double z[M];
 #pragma unroll
-    for (int j = 0; j < M; ++j)
+        for (int i = 0; i < M; ++i) z[i] = 0.0;
 #pragma unroll
-        for (int i = 0; i < M; ++i) z[i] = fma(dcol[(j * M + i) * DS], r[j], z[i]);
+        for (int j = 0; j < M; ++j)
 #pragma unroll
-    for (int i = 0; i < M; ++i) xc[i] = __dadd_rn(xc[i], __dmul_rn(alpha, z[i]));
+            for (int i = 0; i < M; ++i) z[i] = fma(dcol[(j * M + i) * DS], r[j], z[i]);
+#pragma unroll
+        for (int i = 0; i < M; ++i) xc[i] = __dadd_rn(xc[i], __dmul_rn(alpha, z[i]));
+    }
 }
 
 __device__ __forceinline__ void cp_async8(double* smem_dst, const double* gmem_src) {
@@ -221,84 +313,92 @@ __device__ __forceinline__ void cp_async_commit_wait_all() {
     asm volatile("cp.async.wait_group 0;" ::: "memory");
 }
 
-template <int M>
-__device__ __forceinline__ void reg_residual(const double (&A)[3 * M * M], const double (&bb)[M],
-                                             const double (&xl)[M], const double (&xc)[M],
-                                             const double (&xr)[M], double (&r)[M]) {
+template <int M, int ST>
+__device__ __forceinline__ void reg_residual(const RegOp<M, ST>& A, int ilo, int iup,
+                                             const double (&bb)[M], const double (&xl)[M],
+                                             const double (&xc)[M], const double (&xr)[M],
+                                             double (&r)[M]) {
     double y[M];
-#pragma unroll
-    for (int i = 0; i < M; ++i) y[i] = 0.0;
-#pragma unroll
-    for (int j = 0; j < M; ++j)
-#pragma unroll
-        for (int i = 0; i < M; ++i) y[i] = fma(A[j * M + i], xl[j], y[i]);
-#pragma unroll
-    for (int j = 0; j < M; ++j)
-#pragma unroll
-        for (int i = 0; i < M; ++i) y[i] = fma(A[M * M + j * M + i], xc[j], y[i]);
-#pragma unroll
-    for (int j = 0; j < M; ++j)
-#pragma unroll
-        for (int i = 0; i < M; ++i) y[i] = fma(A[2 * M * M + j * M + i], xr[j], y[i]);
+    reg_Ax<M, ST>(A, ilo, iup, xl, xc, xr, y);
 #pragma unroll
     for (int i = 0; i < M; ++i) r[i] = bb[i] - y[i];
 }
 
-// publish x into exchange buffer `buf`, barrier, fetch both neighbours
-template <int M, int B>
-__device__ __forceinline__ void exchange(Exchange<M, B>& ex, int buf, const double (&xc)[M],
-                                         double (&xl)[M], double (&xr)[M]) {
+// publish x into exchange buffer `buf`, barrier, fetch what the structure class needs of both neighbours
+template <int M, int B, int ST>
+__device__ __forceinline__ void exchange(Exchange<M, B>& ex, int buf, int ilo, int iup,
+                                         const double (&xc)[M], double (&xl)[M], double (&xr)[M]) {
     const int t = threadIdx.x;
 #pragma unroll
     for (int i = 0; i < M; ++i) ex.xs[buf][i][t + 1] = xc[i];
     __syncthreads();
+    if constexpr (ST == AMG1D_ST_COLROW) {
+        xl[0] = ex.xs[buf][ilo][t];
+    } else {
 #pragma unroll
-    for (int i = 0; i < M; ++i) {
-        xl[i] = ex.xs[buf][i][t];
-        xr[i] = ex.xs[buf][i][t + 2];
+        for (int i = 0; i < M; ++i) xl[i] = ex.xs[buf][i][t];
+    }
+    if constexpr (ST == AMG1D_ST_ROWCOL) {
+        xr[0] = ex.xs[buf][iup][t + 2];
+    } else {
+#pragma unroll
+        for (int i = 0; i < M; ++i) xr[i] = ex.xs[buf][i][t + 2];
     }
 }
 
 // A_lo / A_di / A_up go to registers; Dinv (used once per sweep) is copied global -> shared with
 // cp.async, i.e. without register staging, into this thread's own column ds[k][thread].
-template <int M, int B>
+template <int M, int B, int ST, bool DIAG>
 __device__ __forceinline__ void load_blocks(const double* __restrict__ mat, int64_t e, bool active,
-                                            double (&A)[3 * M * M], double (*ds)[B]) {
-    constexpr int K = 4 * M * M;
+                                            RegOp<M, ST>& A, double (*ds)[B]) {
+    using S = OpShape<M, ST>;
+    constexpr int ND = DIAG ? M : M * M;
+    constexpr int K = S::O_DV + ND;
     const int t = threadIdx.x;
     if (active) {
         const double* T = mat + (e >> 5) * (int64_t)(K * AMG1D_TILE) + (e & 31);
 #pragma unroll
-        for (int k = 0; k < M * M; ++k) cp_async8(&ds[k][t], T + (3 * M * M + k) * AMG1D_TILE);
+        for (int k = 0; k < ND; ++k) cp_async8(&ds[k][t], T + (S::O_DV + k) * AMG1D_TILE);
 #pragma unroll
-        for (int k = 0; k < 3 * M * M; ++k) A[k] = T[k * AMG1D_TILE];
+        for (int k = 0; k < S::NO; ++k) A.lo[k] = T[k * AMG1D_TILE];
+#pragma unroll
+        for (int k = 0; k < M * M; ++k) A.di[k] = T[(S::O_DI + k) * AMG1D_TILE];
+#pragma unroll
+        for (int k = 0; k < S::NO; ++k) A.up[k] = T[(S::O_UP + k) * AMG1D_TILE];
     } else {
 #pragma unroll
-        for (int k = 0; k < M * M; ++k) ds[k][t] = 0.0;
+        for (int k = 0; k < ND; ++k) ds[k][t] = 0.0;
 #pragma unroll
-        for (int k = 0; k < 3 * M * M; ++k) A[k] = 0.0;
+        for (int k = 0; k < S::NO; ++k) { A.lo[k] = 0.0; A.up[k] = 0.0; }
+#pragma unroll
+        for (int k = 0; k < M * M; ++k) A.di[k] = 0.0;
     }
 }
 
+#define FUSED_BOUNDS(M) __launch_bounds__(B, ((M) >= 5 ? 2 : FUSED_MINB))
+
 // nsweep pre-smoothing sweeps, residual, restriction to the coarse right-hand side.
-//   halo = nsweep + 1 window elements on each side are recomputed; out = elements emitted per CTA
-//   (a multiple of the agglomeration ratio).
-template <int M, int MC, int B>
-__global__ void __launch_bounds__(B, (M >= 5 ? 2 : FUSED_MINB))
-f_down(const double* __restrict__ mat, const double* __restrict__ b, const double* __restrict__ xin,
-       double* __restrict__ xout, const double* __restrict__ P0, TransferMap tm,
-       double* __restrict__ rc, int64_t n, double alpha, int nsweep, int zero_guess, int out,
-       Slab sl) {
+//   halo window elements on each side are recomputed (nsweep + 1, plus `ratio` for two-parent
+//   transfers whose coarse elements also gather from the children of their left neighbour);
+//   out = elements emitted per CTA (a multiple of the agglomeration ratio).
+//   Coarse element Kc is gathered by the thread of its first P0-child, in the order of g_restrict:
+//   the P1 blocks of the children of Kc - 1, then the P0 blocks of its own children.
+template <int M, int MC, int B, int ST, bool DIAG>
+__global__ void FUSED_BOUNDS(M)
+f_down(const double* __restrict__ mat, int ilo, int iup, const double* __restrict__ b,
+       const double* __restrict__ xin, double* __restrict__ xout, const double* __restrict__ P0,
+       const double* __restrict__ P1, TransferMap tm, double* __restrict__ rc, int64_t n, double alpha,
+       int nsweep, int zero_guess, int halo, int out, Slab sl) {
     __shared__ Exchange<M, B> ex;
     __shared__ double rs[M][B + 8];
-    __shared__ double ds[M * M][B];
+    __shared__ double ds[DIAG ? M : M * M][B];
     const int t = threadIdx.x;
-    const int halo = nsweep + 1;
     const int64_t e = (int64_t)blockIdx.x * out - halo + t;     // local element index (ghosts < 0, >= n)
     const bool active = e >= -(int64_t)sl.gl && e < n + sl.gr;
     exch_init<M, B>(ex);
-    double A[3 * M * M], bb[M], xc[M], xl[M], xr[M];
-    load_blocks<M, B>(mat, e, active, A, ds);
+    RegOp<M, ST> A;
+    double bb[M], xc[M], xl[M], xr[M];
+    load_blocks<M, B, ST, DIAG>(mat, e, active, A, ds);
     if (active) {
         load_vec<M>(b + e * M, bb);
         if (zero_guess) {
@@ -317,62 +417,79 @@ f_down(const double* __restrict__ mat, const double* __restrict__ b, const doubl
     for (int s = 0; s < nsweep; ++s) {
         const bool zg = zero_guess && s == 0;
         if (!zg) {
-            exchange<M, B>(ex, buf, xc, xl, xr);
+            exchange<M, B, ST>(ex, buf, ilo, iup, xc, xl, xr);
             buf ^= 1;
         }
-        reg_sweep<M, B>(A, &ds[0][t], bb, xl, xc, xr, alpha, zg);
+        reg_sweep<M, ST, DIAG, B>(A, ilo, iup, &ds[0][t], bb, xl, xc, xr, alpha, zg);
     }
-    const bool emit = e >= 0 && e < n && t >= halo && t < halo + out;
-    if (emit) store_vec<M>(xout + e * M, xc);
+    const bool mine = t >= halo && t < halo + out;              // this CTA's share of the level (e >= 0)
+    if (mine && e < n) store_vec<M>(xout + e * M, xc);
     // residual with the final iterate, then restriction
-    exchange<M, B>(ex, buf, xc, xl, xr);
+    exchange<M, B, ST>(ex, buf, ilo, iup, xc, xl, xr);
     double r[M];
-    reg_residual<M>(A, bb, xl, xc, xr, r);
+    reg_residual<M, ST>(A, ilo, iup, bb, xl, xc, xr, r);
 #pragma unroll
     for (int i = 0; i < M; ++i) rs[i][t] = r[i];
     __syncthreads();
-    const int ratio = tm.ratio;
-    const int64_t eg = e + sl.e_off;                           // global element index
-    if (emit && (eg % ratio) == 0) {
-        double acc[MC];
+    const int64_t eg = e + sl.e_off;                            // global element index
+    if (mine && eg < tm.n_fine) {
+        const int64_t q = eg + tm.shift;
+        if (q % tm.ratio == 0) {
+            const int64_t Kc = q / tm.ratio + tm.base;          // eg == tm.first(Kc)
+            const int64_t Kl = Kc - sl.c_off;                   // local coarse element index
+            if (Kc >= 0 && Kc < tm.n_coarse && Kl >= 0 && Kl < sl.nc) {
+                double acc[MC];
 #pragma unroll
-        for (int j = 0; j < MC; ++j) acc[j] = 0.0;
-        for (int c = 0; c < ratio && e + c < n; ++c) {
-            const double* P = P0 + tm.blk(eg + c) * (M * MC);
+                for (int j = 0; j < MC; ++j) acc[j] = 0.0;
+                if (P1) {
+                    for (int64_t c = tm.first(Kc - 1); c < eg; ++c) {
+                        const double* P = P1 + tm.blk(c) * (M * MC);
+                        const int w = t + (int)(c - eg);
 #pragma unroll
-            for (int j = 0; j < MC; ++j)
+                        for (int j = 0; j < MC; ++j)
 #pragma unroll
-                for (int i = 0; i < M; ++i) acc[j] = fma(P[j * M + i], rs[i][t + c], acc[j]);
+                            for (int i = 0; i < M; ++i) acc[j] = fma(P[j * M + i], rs[i][w], acc[j]);
+                    }
+                }
+                const int64_t c1 = tm.first(Kc + 1);
+                for (int64_t c = eg; c < c1; ++c) {
+                    const double* P = P0 + tm.blk(c) * (M * MC);
+                    const int w = t + (int)(c - eg);
+#pragma unroll
+                    for (int j = 0; j < MC; ++j)
+#pragma unroll
+                        for (int i = 0; i < M; ++i) acc[j] = fma(P[j * M + i], rs[i][w], acc[j]);
+                }
+#pragma unroll
+                for (int j = 0; j < MC; ++j) rc[Kl * MC + j] = acc[j];
+            }
         }
-        const int64_t Kc = eg / ratio - sl.c_off;              // local coarse element index
-#pragma unroll
-        for (int j = 0; j < MC; ++j) rc[Kc * MC + j] = acc[j];
     }
 }
 
 // prolongation + correction, nsweep post-smoothing sweeps, optional || b - A x ||^2 partial sums.
-template <int M, int MC, int B>
-__global__ void __launch_bounds__(B, (M >= 5 ? 2 : FUSED_MINB))
-f_up(const double* __restrict__ mat, const double* __restrict__ b, const double* __restrict__ xin,
-     double* __restrict__ xout, const double* __restrict__ P0, TransferMap tm,
-     const double* __restrict__ xcoarse, int64_t n, double alpha, int nsweep, int out,
-     double* __restrict__ partial, Slab sl) {
+template <int M, int MC, int B, int ST, bool DIAG>
+__global__ void FUSED_BOUNDS(M)
+f_up(const double* __restrict__ mat, int ilo, int iup, const double* __restrict__ b,
+     const double* __restrict__ xin, double* __restrict__ xout, const double* __restrict__ P0,
+     const double* __restrict__ P1, TransferMap tm, const double* __restrict__ xcoarse, int64_t n,
+     double alpha, int nsweep, int halo, int out, double* __restrict__ partial, Slab sl) {
     __shared__ Exchange<M, B> ex;
-    __shared__ double ds[M * M][B];
+    __shared__ double ds[DIAG ? M : M * M][B];
     const int t = threadIdx.x;
-    const int halo = nsweep + 1;
     const int64_t e = (int64_t)blockIdx.x * out - halo + t;
     const bool active = e >= -(int64_t)sl.gl && e < n + sl.gr;
     exch_init<M, B>(ex);
-    double A[3 * M * M], bb[M], xc[M], xl[M], xr[M];
-    load_blocks<M, B>(mat, e, active, A, ds);
+    RegOp<M, ST> A;
+    double bb[M], xc[M], xl[M], xr[M];
+    load_blocks<M, B, ST, DIAG>(mat, e, active, A, ds);
     if (active) {
         load_vec<M>(b + e * M, bb);
         load_vec<M>(xin + e * M, xc);
-        // x += P x_c   (same operation order as g_prolong: y = sum_j P(i,j) xc_j, then x + y)
+        // x += P0 x_c[parent] (+ P1 x_c[parent + 1])   (same operation order as g_prolong)
         const int64_t eg = e + sl.e_off;
-        const double* P = P0 + tm.blk(eg) * (M * MC);
-        const double* c0 = xcoarse + (eg / tm.ratio - sl.c_off) * MC;
+        const int64_t pb = tm.blk(eg) * (M * MC);
+        const double* c0 = xcoarse + (tm.par(eg) - sl.c_off) * MC;
         double y[M];
 #pragma unroll
         for (int i = 0; i < M; ++i) y[i] = 0.0;
@@ -380,7 +497,15 @@ f_up(const double* __restrict__ mat, const double* __restrict__ b, const double*
         for (int j = 0; j < MC; ++j) {
             const double cj = c0[j];
 #pragma unroll
-            for (int i = 0; i < M; ++i) y[i] = fma(P[j * M + i], cj, y[i]);
+            for (int i = 0; i < M; ++i) y[i] = fma(P0[pb + j * M + i], cj, y[i]);
+        }
+        if (P1) {
+#pragma unroll
+            for (int j = 0; j < MC; ++j) {
+                const double cj = c0[MC + j];
+#pragma unroll
+                for (int i = 0; i < M; ++i) y[i] = fma(P1[pb + j * M + i], cj, y[i]);
+            }
         }
 #pragma unroll
         for (int i = 0; i < M; ++i) xc[i] = xc[i] + y[i];
@@ -392,16 +517,16 @@ f_up(const double* __restrict__ mat, const double* __restrict__ b, const double*
     __syncthreads();
     int buf = 0;
     for (int s = 0; s < nsweep; ++s) {
-        exchange<M, B>(ex, buf, xc, xl, xr);
+        exchange<M, B, ST>(ex, buf, ilo, iup, xc, xl, xr);
         buf ^= 1;
-        reg_sweep<M, B>(A, &ds[0][t], bb, xl, xc, xr, alpha, false);
+        reg_sweep<M, ST, DIAG, B>(A, ilo, iup, &ds[0][t], bb, xl, xc, xr, alpha, false);
     }
-    const bool emit = e >= 0 && e < n && t >= halo && t < halo + out;
+    const bool emit = e < n && t >= halo && t < halo + out;     // e >= 0 for these threads
     if (emit) store_vec<M>(xout + e * M, xc);
     if (partial) {
-        exchange<M, B>(ex, buf, xc, xl, xr);
+        exchange<M, B, ST>(ex, buf, ilo, iup, xc, xl, xr);
         double r[M];
-        reg_residual<M>(A, bb, xl, xc, xr, r);
+        reg_residual<M, ST>(A, ilo, iup, bb, xl, xc, xr, r);
         double s2 = 0.0;
         if (emit) {
 #pragma unroll
@@ -412,10 +537,11 @@ f_up(const double* __restrict__ mat, const double* __restrict__ b, const double*
     }
 }
 
-// residual + restriction, streaming (used when the multi-sweep kernel does not apply)
-template <int M, int MC, int B>
+// residual + restriction, streaming (single-parent transfers; used when the multi-sweep kernel does
+// not apply)
+template <int M, int MC, int B, int ST>
 __global__ void __launch_bounds__(B)
-f_residual_restrict(const double* __restrict__ mat, int K, const double* __restrict__ b,
+f_residual_restrict(const double* __restrict__ mat, int K, int ilo, int iup, const double* __restrict__ b,
                     const double* __restrict__ x, const double* __restrict__ P0, TransferMap tm,
                     double* __restrict__ rc, int64_t n, int out) {
     __shared__ double rs[M][B + 8];
@@ -424,13 +550,12 @@ f_residual_restrict(const double* __restrict__ mat, int K, const double* __restr
     const bool active = e < n && t < out;
     double r[M];
     if (e < n) {
-        const double* T = mat + (e >> 5) * (int64_t)(K * AMG1D_TILE) + (e & 31);
+        const double* T = mat + (e >> 5) * (int64_t)K * AMG1D_TILE + (e & 31);
         double xl[M], xc[M], xr[M], y[M], bb[M];
         load_vec<M>(b + e * M, bb);
-        load_vec<M>(x + (e - 1) * M, xl);
         load_vec<M>(x + e * M, xc);
-        load_vec<M>(x + (e + 1) * M, xr);
-        stream_Ax<M>(T, xl, xc, xr, y);
+        load_neighbours<M, ST>(x, e, ilo, iup, xl, xr);
+        stream_Ax<M, ST>(T, ilo, iup, xl, xc, xr, y);
 #pragma unroll
         for (int i = 0; i < M; ++i) r[i] = bb[i] - y[i];
     } else {
@@ -458,102 +583,338 @@ f_residual_restrict(const double* __restrict__ mat, int K, const double* __restr
     }
 }
 
+// ---- single-CTA coarse tail ----------------------------------------------------------------------------
+// The sub-V-cycle of the coarse levels (every level with at most TAIL_B elements, all with the same
+// block size M, block smoother, single-parent closed-form transfers) in ONE CTA: one thread per
+// element, operator blocks in registers per leg, iterates exchanged through shared memory, the coarse
+// right-hand side / correction handed from level to level through shared memory.  Replaces two
+// launches per level (each a few microseconds of latency for a few hundred bytes of work) by one
+// launch for the whole tail.  Arithmetic per element is that of f_down / f_up / g_coarse_solve.
+struct TailLevel {
+    MatDesc md;
+    const double* mat;
+    int64_t n;
+    double* x;          // iterate buffer 0 of the level (element 0)
+    double* b;          // right-hand side
+    TransferMap tm;     // transfer to the next tail level (unused on the last one)
+    const double* P0;
+};
+
+struct TailSmem {
+    template <int M>
+    struct Layout {
+        Exchange<M, TAIL_B> ex;
+        double rs[M][TAIL_B + 8];
+        double ds[M * M][TAIL_B];
+        double cs[M * TAIL_B];   // coarse rhs on the way down, coarse correction on the way up
+        double cw[2 * 32];       // block-Thomas work space
+    };
+};
+
+// Dense register copy of the element's operator whatever the level's structure class (entries that
+// the class does not store are exact zeros, so the dense chains give identical results).
+template <int M>
+__device__ __forceinline__ void tail_load(const TailLevel& L, int t, bool active, RegOp<M, 0>& A,
+                                          double (*ds)[TAIL_B]) {
+    const MatDesc& d = L.md;
+    if (active) {
+        const double* T = L.mat + (t >> 5) * (int64_t)d.K * AMG1D_TILE + (t & 31);
+#pragma unroll
+        for (int k = 0; k < M * M; ++k) ds[k][t] = T[(d.o_dv + k) * AMG1D_TILE];
+#pragma unroll
+        for (int k = 0; k < M * M; ++k) A.di[k] = T[(d.o_di + k) * AMG1D_TILE];
+        if (d.st == AMG1D_ST_DENSE) {
+#pragma unroll
+            for (int k = 0; k < M * M; ++k) { A.lo[k] = T[k * AMG1D_TILE]; A.up[k] = T[(d.o_up + k) * AMG1D_TILE]; }
+        } else {
+#pragma unroll
+            for (int j = 0; j < M; ++j)
+#pragma unroll
+                for (int i = 0; i < M; ++i) {
+                    if (d.st == AMG1D_ST_COLROW) {
+                        A.lo[j * M + i] = (j == d.ilo) ? T[i * AMG1D_TILE] : 0.0;
+                        A.up[j * M + i] = (i == d.iup) ? T[(d.o_up + j) * AMG1D_TILE] : 0.0;
+                    } else {
+                        A.lo[j * M + i] = (i == d.ilo) ? T[j * AMG1D_TILE] : 0.0;
+                        A.up[j * M + i] = (j == d.iup) ? T[(d.o_up + i) * AMG1D_TILE] : 0.0;
+                    }
+                }
+        }
+    } else {
+#pragma unroll
+        for (int k = 0; k < M * M; ++k) { ds[k][t] = 0.0; A.lo[k] = 0.0; A.di[k] = 0.0; A.up[k] = 0.0; }
+    }
+}
+
+template <int M>
+__global__ void __launch_bounds__(TAIL_B, 1)
+f_tail(const TailLevel* __restrict__ lv, int nl, const double* __restrict__ fac, int nPre, int nPost,
+       double alpha) {
+    extern __shared__ __align__(16) unsigned char tail_smem[];
+    using SM = TailSmem::Layout<M>;
+    SM& sm = *reinterpret_cast<SM*>(tail_smem);
+    const int t = threadIdx.x;
+    exch_init<M, TAIL_B>(sm.ex);
+    __syncthreads();
+    RegOp<M, 0> A;
+    double bb[M], xc[M], xl[M], xr[M];
+    int buf = 0;
+    // ---- down: zero guess, nPre sweeps, residual, restriction ----
+    for (int l = 0; l < nl - 1; ++l) {
+        const TailLevel& L = lv[l];
+        const bool active = t < L.n;
+        tail_load<M>(L, t, active, A, sm.ds);
+#pragma unroll
+        for (int i = 0; i < M; ++i) {
+            bb[i] = active ? (l == 0 ? L.b[t * M + i] : sm.cs[t * M + i]) : 0.0;
+            xc[i] = 0.0;
+        }
+        for (int s = 0; s < nPre; ++s) {
+            if (s > 0) {
+                exchange<M, TAIL_B, 0>(sm.ex, buf, 0, 0, xc, xl, xr);
+                buf ^= 1;
+            }
+            reg_sweep<M, 0, false, TAIL_B>(A, 0, 0, &sm.ds[0][t], bb, xl, xc, xr, alpha, s == 0);
+        }
+        if (active) store_vec<M>(L.x + t * M, xc);
+        exchange<M, TAIL_B, 0>(sm.ex, buf, 0, 0, xc, xl, xr);
+        buf ^= 1;
+        double r[M];
+        reg_residual<M, 0>(A, 0, 0, bb, xl, xc, xr, r);
+#pragma unroll
+        for (int i = 0; i < M; ++i) sm.rs[i][t] = r[i];
+        __syncthreads();                                   // rs complete; every read of cs is done
+        const int ratio = L.tm.ratio;
+        if (active && (t % ratio) == 0) {
+            double acc[M];
+#pragma unroll
+            for (int j = 0; j < M; ++j) acc[j] = 0.0;
+            for (int c = 0; c < ratio && t + c < L.n; ++c) {
+                const double* P = L.P0 + L.tm.blk(t + c) * (M * M);
+#pragma unroll
+                for (int j = 0; j < M; ++j)
+#pragma unroll
+                    for (int i = 0; i < M; ++i) acc[j] = fma(P[j * M + i], sm.rs[i][t + c], acc[j]);
+            }
+            const int Kc = t / ratio;
+            double* bc = lv[l + 1].b;
+#pragma unroll
+            for (int j = 0; j < M; ++j) { bc[Kc * M + j] = acc[j]; sm.cs[Kc * M + j] = acc[j]; }
+        }
+        __syncthreads();
+    }
+    // ---- coarsest level: block-Thomas substitution by one warp ----
+    {
+        const TailLevel& L = lv[nl - 1];
+        if (t < 32) coarse_solve_warp(fac, M, L.n, L.b, L.x, sm.cw, sm.cw + 32);
+        __syncthreads();
+        for (int64_t i = t; i < L.n * M; i += TAIL_B) sm.cs[i] = L.x[i];
+        __syncthreads();
+    }
+    // ---- up: prolongation + correction, nPost sweeps ----
+    for (int l = nl - 2; l >= 0; --l) {
+        const TailLevel& L = lv[l];
+        const bool active = t < L.n;
+        tail_load<M>(L, t, active, A, sm.ds);
+        if (active) {
+            load_vec<M>(L.b + t * M, bb);
+            load_vec<M>(L.x + t * M, xc);
+            const double* P = L.P0 + L.tm.blk(t) * (M * M);
+            const double* c0 = sm.cs + (t / L.tm.ratio) * M;
+            double y[M];
+#pragma unroll
+            for (int i = 0; i < M; ++i) y[i] = 0.0;
+#pragma unroll
+            for (int j = 0; j < M; ++j) {
+                const double cj = c0[j];
+#pragma unroll
+                for (int i = 0; i < M; ++i) y[i] = fma(P[j * M + i], cj, y[i]);
+            }
+#pragma unroll
+            for (int i = 0; i < M; ++i) xc[i] = xc[i] + y[i];
+        } else {
+#pragma unroll
+            for (int i = 0; i < M; ++i) { bb[i] = 0.0; xc[i] = 0.0; }
+        }
+        for (int s = 0; s < nPost; ++s) {
+            exchange<M, TAIL_B, 0>(sm.ex, buf, 0, 0, xc, xl, xr);
+            buf ^= 1;
+            reg_sweep<M, 0, false, TAIL_B>(A, 0, 0, &sm.ds[0][t], bb, xl, xc, xr, alpha, false);
+        }
+        __syncthreads();                                   // every read of cs is done
+        if (active) {
+            store_vec<M>(L.x + t * M, xc);
+#pragma unroll
+            for (int i = 0; i < M; ++i) sm.cs[t * M + i] = xc[i];
+        }
+        __syncthreads();
+    }
+}
+
 // ---- host-side dispatch ---------------------------------------------------------------------------------
 #define FUSED_FOR_M(X) X(1) X(2) X(3) X(4) X(5) X(6) X(7) X(8) X(9)
 
-inline bool fused_sweep(int m, int diag, const double* mat, const double* b, const double* xin,
+// structure classes need m >= 2, and ST_COLROW the DG trace row (see FUSED_COLROW_IUP)
+inline bool fast_tier_ok(const MatDesc& d) {
+    if (d.st == AMG1D_ST_DENSE) return true;
+    if (d.m < 2) return false;
+    return d.st != AMG1D_ST_COLROW || d.iup == FUSED_COLROW_IUP;
+}
+
+inline bool fused_sweep(const MatDesc& d, const double* mat, const double* b, const double* xin,
                         double* xout, int64_t n, double alpha, int zero_guess, cudaStream_t st) {
     const unsigned grid = (unsigned)((n + 255) / 256);
-    switch (m * 2 + (diag ? 1 : 0)) {
-#define X(MM)                                                                                   \
-    case MM * 2: f_sweep<MM, false><<<grid, 256, 0, st>>>(mat, b, xin, xout, n, alpha, zero_guess); return true; \
-    case MM * 2 + 1: f_sweep<MM, true><<<grid, 256, 0, st>>>(mat, b, xin, xout, n, alpha, zero_guess); return true;
+    if (!fast_tier_ok(d)) return false;
+    switch ((d.m * 2 + d.diag) * 4 + d.st) {
+#define Y(MM, DG, SS)                                                                                     \
+    case (MM * 2 + DG) * 4 + SS:                                                                          \
+        f_sweep<MM, DG != 0, SS><<<grid, 256, 0, st>>>(mat, d.ilo, d.iup, b, xin, xout, n, alpha, zero_guess); \
+        return true;
+#define X(MM) Y(MM, 0, 0) Y(MM, 1, 0) Y(MM, 0, 1) Y(MM, 1, 1) Y(MM, 0, 2) Y(MM, 1, 2)
         FUSED_FOR_M(X)
 #undef X
+#undef Y
         default: return false;
     }
 }
 
-inline bool fused_resnorm(int m, int diag, const double* mat, const double* b, const double* x,
+inline bool fused_resnorm(const MatDesc& d, const double* mat, const double* b, const double* x,
                           int64_t n, double* partial, int64_t partial_cap, int* nblocks,
                           cudaStream_t st) {
     const int64_t grid = (n + 255) / 256;
-    if (grid > partial_cap) return false;
+    if (grid > partial_cap || !fast_tier_ok(d)) return false;
     *nblocks = (int)grid;
-    switch (m * 2 + (diag ? 1 : 0)) {
-#define X(MM)                                                                                                   \
-    case MM * 2: f_resnorm<MM, 4 * MM * MM><<<(unsigned)grid, 256, 0, st>>>(mat, b, x, n, partial); return true;   \
-    case MM * 2 + 1: f_resnorm<MM, 3 * MM * MM + MM><<<(unsigned)grid, 256, 0, st>>>(mat, b, x, n, partial); return true;
+    switch (d.m * 4 + d.st) {
+#define Y(MM, SS)                                                                                       \
+    case MM * 4 + SS:                                                                                   \
+        f_resnorm<MM, SS><<<(unsigned)grid, 256, 0, st>>>(mat, d.K, d.ilo, d.iup, b, x, n, partial);    \
+        return true;
+#define X(MM) Y(MM, 0) Y(MM, 1) Y(MM, 2)
         FUSED_FOR_M(X)
 #undef X
+#undef Y
         default: return false;
     }
 }
 
-// (M, MC) pairs with a register-resident multi-sweep kernel
-#define FUSED_PAIRS(X) X(1, 1) X(2, 1) X(2, 2) X(3, 1) X(3, 2) X(4, 2) X(4, 3) X(5, 3)
+// (M, MC, ST, DIAG) combinations with a register-resident multi-sweep kernel:
+//   block Jacobi, dense and DG-assembled structure (DG / agglomerated levels);
+//   point Jacobi on CG levels in group form (m = 1: CG p=1; m >= 2: ST_ROWCOL).
+#define FUSED_COMBOS(X)                                                                              \
+    X(1, 1, 0, false) X(2, 1, 0, false) X(2, 2, 0, false) X(3, 1, 0, false) X(3, 2, 0, false)         \
+    X(4, 2, 0, false) X(4, 3, 0, false) X(5, 3, 0, false)                                             \
+    X(2, 1, 1, false) X(2, 2, 1, false) X(3, 1, 1, false) X(3, 2, 1, false)                           \
+    X(4, 2, 1, false) X(4, 3, 1, false) X(5, 3, 1, false)                                             \
+    X(1, 1, 0, true) X(1, 2, 0, true) X(2, 1, 2, true) X(3, 1, 2, true) X(4, 2, 2, true)
 
-inline int fused_out_per_cta(int nsweep, int ratio) {
-    const int out = ((FUSED_B - 2 * (nsweep + 1)) / ratio) * ratio;
-    return out;
+inline int fused_key(int m, int mc, int st, int diag) { return ((m * 16 + mc) * 4 + st) * 2 + (diag ? 1 : 0); }
+
+// halo and elements emitted per CTA for a leg of nsweep sweeps
+inline void fused_window(int nsweep, int ratio, bool two_parent, int* halo, int* out) {
+    *halo = nsweep + 1 + (two_parent ? ratio : 0);
+    *out = ((FUSED_B - 2 * *halo) / ratio) * ratio;
 }
 
-inline bool fused_down(int m, int mc, int diag, const TransferMap& tm, int nsweep, bool zero,
+// tm must be a closed-form map (parent == cp == nullptr); P1 != nullptr selects the two-parent form.
+// n_cover: local elements whose coarse parents this rank may have to gather (n, or n + ratio when the
+// right slab neighbour's first children contribute to this rank's last coarse element).
+inline bool fused_down(const MatDesc& d, int mc, const TransferMap& tm, int nsweep, bool zero,
                        const double* mat, const double* b, const double* xin, double* xout,
-                       const double* P0, double* rc, int64_t n, double alpha, const Slab& sl,
-                       cudaStream_t st) {
-    if (diag) return false;
-    const int out = fused_out_per_cta(nsweep, tm.ratio);
-    if (out < tm.ratio || out < FUSED_B / 2) return false;
-    const unsigned grid = (unsigned)((n + out - 1) / out);
-    switch (m * 16 + mc) {
-#define X(MM, MCC)                                                                                     \
-    case MM * 16 + MCC:                                                                                \
-        f_down<MM, MCC, FUSED_B><<<grid, FUSED_B, 0, st>>>(mat, b, xin, xout, P0, tm, rc, n, alpha,   \
-                                                            nsweep, zero ? 1 : 0, out, sl);           \
+                       const double* P0, const double* P1, double* rc, int64_t n, int64_t n_cover,
+                       double alpha, const Slab& sl, cudaStream_t st) {
+    int halo, out;
+    fused_window(nsweep, tm.ratio, P1 != nullptr || tm.shift != 0 || tm.base != 0, &halo, &out);
+    if (out < tm.ratio || out < FUSED_B / 2 || !fast_tier_ok(d)) return false;
+    const unsigned grid = (unsigned)((n_cover + out - 1) / out);
+    switch (fused_key(d.m, mc, d.st, d.diag)) {
+#define X(MM, MCC, SS, DG)                                                                               \
+    case ((MM * 16 + MCC) * 4 + SS) * 2 + (DG ? 1 : 0):                                                  \
+        f_down<MM, MCC, FUSED_B, SS, DG><<<grid, FUSED_B, 0, st>>>(mat, d.ilo, d.iup, b, xin, xout, P0, P1, \
+                                                                    tm, rc, n, alpha, nsweep, zero ? 1 : 0, \
+                                                                    halo, out, sl);                      \
         return true;
-        FUSED_PAIRS(X)
+        FUSED_COMBOS(X)
 #undef X
         default: return false;
     }
 }
 
-inline bool fused_up(int m, int mc, int diag, const TransferMap& tm, int nsweep, const double* mat,
+inline bool fused_up(const MatDesc& d, int mc, const TransferMap& tm, int nsweep, const double* mat,
                      const double* b, const double* xin, double* xout, const double* P0,
-                     const double* xcoarse, int64_t n, double alpha, double* partial,
+                     const double* P1, const double* xcoarse, int64_t n, double alpha, double* partial,
                      int64_t partial_cap, int* nblocks, const Slab& sl, cudaStream_t st) {
-    if (diag) return false;
-    const int out = fused_out_per_cta(nsweep, tm.ratio);
-    if (out < tm.ratio || out < FUSED_B / 2) return false;
+    int halo, out;
+    fused_window(nsweep, tm.ratio, false, &halo, &out);
+    if (out < tm.ratio || out < FUSED_B / 2 || !fast_tier_ok(d)) return false;
     const int64_t grid = (n + out - 1) / out;
     if (partial && grid > partial_cap) return false;
     if (nblocks) *nblocks = (int)grid;
-    switch (m * 16 + mc) {
-#define X(MM, MCC)                                                                                      \
-    case MM * 16 + MCC:                                                                                 \
-        f_up<MM, MCC, FUSED_B><<<(unsigned)grid, FUSED_B, 0, st>>>(mat, b, xin, xout, P0, tm, xcoarse, \
-                                                                    n, alpha, nsweep, out, partial, sl); \
+    switch (fused_key(d.m, mc, d.st, d.diag)) {
+#define X(MM, MCC, SS, DG)                                                                               \
+    case ((MM * 16 + MCC) * 4 + SS) * 2 + (DG ? 1 : 0):                                                  \
+        f_up<MM, MCC, FUSED_B, SS, DG><<<(unsigned)grid, FUSED_B, 0, st>>>(mat, d.ilo, d.iup, b, xin, xout, \
+                                                                            P0, P1, tm, xcoarse, n, alpha, \
+                                                                            nsweep, halo, out, partial, sl); \
         return true;
-        FUSED_PAIRS(X)
+        FUSED_COMBOS(X)
 #undef X
         default: return false;
     }
 }
 
-inline bool fused_residual_restrict(int m, int mc, int K, const TransferMap& tm, const double* mat,
+// (M, MC) pairs of the streaming residual + restriction kernel (single-parent transfers)
+#define FRR_PAIRS(X) X(1, 1) X(2, 1) X(2, 2) X(3, 1) X(3, 2) X(4, 2) X(4, 3) X(5, 3) X(9, 5) X(5, 2) X(9, 2)
+
+inline bool fused_residual_restrict(const MatDesc& d, int mc, const TransferMap& tm, const double* mat,
                                     const double* b, const double* x, const double* P0, double* rc,
                                     int64_t n, cudaStream_t st) {
     const int out = (FUSED_B / tm.ratio) * tm.ratio;
-    if (out < tm.ratio) return false;
+    if (out < tm.ratio || !fast_tier_ok(d)) return false;
     const unsigned grid = (unsigned)((n + out - 1) / out);
-    switch (m * 16 + mc) {
-#define X(MM, MCC)                                                                                   \
-    case MM * 16 + MCC:                                                                              \
-        f_residual_restrict<MM, MCC, FUSED_B><<<grid, FUSED_B, 0, st>>>(mat, K, b, x, P0, tm, rc, n, out); \
+    switch ((d.m * 16 + mc) * 4 + d.st) {
+#define Y(MM, MCC, SS)                                                                                  \
+    case (MM * 16 + MCC) * 4 + SS:                                                                      \
+        f_residual_restrict<MM, MCC, FUSED_B, SS><<<grid, FUSED_B, 0, st>>>(mat, d.K, d.ilo, d.iup, b, x, P0, \
+                                                                             tm, rc, n, out);           \
         return true;
-        FUSED_PAIRS(X)
-        X(9, 5) X(5, 2) X(9, 2)
+#define X(MM, MCC) Y(MM, MCC, 0) Y(MM, MCC, 1) Y(MM, MCC, 2)
+        FRR_PAIRS(X)
 #undef X
+#undef Y
         default: return false;
+    }
+}
+
+// Block sizes with a single-CTA tail kernel.
+inline bool tail_supported(int m) { return m == 1 || m == 2; }
+
+template <int M>
+inline cudaError_t tail_configure_t() {
+    return cudaFuncSetAttribute(f_tail<M>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                (int)sizeof(TailSmem::Layout<M>));
+}
+
+// once per device context, before the first launch (amg1d_finalize)
+inline cudaError_t tail_configure(int m) {
+    switch (m) {
+        case 1: return tail_configure_t<1>();
+        case 2: return tail_configure_t<2>();
+        default: return cudaErrorInvalidValue;
+    }
+}
+
+template <int M>
+inline cudaError_t tail_launch_t(const TailLevel* lv, int nl, const double* fac, int nPre, int nPost,
+                                 double alpha, cudaStream_t st) {
+    f_tail<M><<<1, TAIL_B, sizeof(TailSmem::Layout<M>), st>>>(lv, nl, fac, nPre, nPost, alpha);
+    return cudaGetLastError();
+}
+
+inline cudaError_t tail_launch(int m, const TailLevel* lv, int nl, const double* fac, int nPre, int nPost,
+                               double alpha, cudaStream_t st) {
+    switch (m) {
+        case 1: return tail_launch_t<1>(lv, nl, fac, nPre, nPost, alpha, st);
+        case 2: return tail_launch_t<2>(lv, nl, fac, nPre, nPost, alpha, st);
+        default: return cudaErrorInvalidValue;
     }
 }

@@ -1,5 +1,5 @@
-// Generic kernel tier: any block size m <= 32, diagonal or block smoother, one- or two-parent
-// transfers with arbitrary (non-decreasing) parent maps.  One thread per (element, row); launch with
+// Generic kernel tier: any block size m <= 32, any structure class (layout.cuh), diagonal or block
+// smoother, one- or two-parent transfers with arbitrary (non-decreasing) parent maps.  One thread per (element, row); launch with
 // blockDim = (32 lanes, m rows, Z tiles).  These are the always-available, always-correct kernels;
 // the templated thread-per-element kernels in kernels_fused.cuh replace them on the hot levels.
 //
@@ -39,84 +39,94 @@ struct TransferMap {
     }
 };
 
+// Row i of  A_lo x_l + A_di x_c + A_up x_r  for one element; T points at [tile][0][lane].  Terms are
+// accumulated in ascending column order, A_lo first, then A_di, then A_up (the order of a CSC SpMV over
+// the reference's DOF numbering); the compressed structure classes skip exact zeros only.
+__device__ __forceinline__ double g_row_Ax(const double* __restrict__ T, const MatDesc& d, int i,
+                                           const double* xl, const double* xc, const double* xr) {
+    const int m = d.m;
+    double y = 0.0;
+    if (d.st == AMG1D_ST_DENSE) {
+        for (int j = 0; j < m; ++j) y = fma(T[(j * m + i) * AMG1D_TILE], xl[j], y);
+    } else if (d.st == AMG1D_ST_COLROW) {
+        y = fma(T[i * AMG1D_TILE], xl[d.ilo], y);
+    } else if (i == d.ilo) {
+        for (int j = 0; j < m; ++j) y = fma(T[j * AMG1D_TILE], xl[j], y);
+    }
+    const double* D = T + (int64_t)d.o_di * AMG1D_TILE;
+    for (int j = 0; j < m; ++j) y = fma(D[(j * m + i) * AMG1D_TILE], xc[j], y);
+    const double* U = T + (int64_t)d.o_up * AMG1D_TILE;
+    if (d.st == AMG1D_ST_DENSE) {
+        for (int j = 0; j < m; ++j) y = fma(U[(j * m + i) * AMG1D_TILE], xr[j], y);
+    } else if (d.st == AMG1D_ST_ROWCOL) {
+        y = fma(U[i * AMG1D_TILE], xr[d.iup], y);
+    } else if (i == d.iup) {
+        for (int j = 0; j < m; ++j) y = fma(U[j * AMG1D_TILE], xr[j], y);
+    }
+    return y;
+}
+
+// Row i of Dinv r (block smoother) or Dinv_i r_i (diagonal smoother); r is the element's residual.
+__device__ __forceinline__ double g_row_Dinv(const double* __restrict__ T, const MatDesc& d, int i,
+                                             const double* r, int rstride) {
+    const double* V = T + (int64_t)d.o_dv * AMG1D_TILE;
+    if (d.diag) return V[i * AMG1D_TILE] * r[i * rstride];
+    double z = 0.0;
+    for (int j = 0; j < d.m; ++j) z = fma(V[(j * d.m + i) * AMG1D_TILE], r[j * rstride], z);
+    return z;
+}
+
 // x_new = x + alpha * Dinv (b - A x).  zero_guess: x is taken as 0 and A is not read.
-__global__ void g_sweep(const double* __restrict__ mat, int m, int diag, int K,
-                        const double* __restrict__ b, const double* __restrict__ xin,
-                        double* __restrict__ xout, int64_t n, double alpha, int zero_guess) {
+__global__ void g_sweep(const double* __restrict__ mat, MatDesc d, const double* __restrict__ b,
+                        const double* __restrict__ xin, double* __restrict__ xout, int64_t n,
+                        double alpha, int zero_guess) {
     extern __shared__ double r_s[];  // [Z][m][32]
+    const int m = d.m;
     const int lane = threadIdx.x, i = threadIdx.y, tz = threadIdx.z;
     const int64_t tile = (int64_t)blockIdx.x * blockDim.z + tz;
     const int64_t e = tile * AMG1D_TILE + lane;
     const bool valid = e < n;
-    const double* T = mat + tile * (int64_t)K * AMG1D_TILE + lane;
-    const int mm = m * m;
+    const double* T = mat + tile * (int64_t)d.K * AMG1D_TILE + lane;
     double r = 0.0;
     if (valid) {
         double y = 0.0;
-        if (!zero_guess) {
-            const double* xl = xin + (e - 1) * m;
-            const double* xc = xin + e * m;
-            const double* xr = xin + (e + 1) * m;
-            for (int j = 0; j < m; ++j) y = fma(T[(j * m + i) * AMG1D_TILE], xl[j], y);
-            for (int j = 0; j < m; ++j) y = fma(T[(mm + j * m + i) * AMG1D_TILE], xc[j], y);
-            for (int j = 0; j < m; ++j) y = fma(T[(2 * mm + j * m + i) * AMG1D_TILE], xr[j], y);
-        }
+        if (!zero_guess) y = g_row_Ax(T, d, i, xin + (e - 1) * m, xin + e * m, xin + (e + 1) * m);
         r = b[e * m + i] - y;
     }
     double* rs = r_s + (size_t)tz * m * AMG1D_TILE;
     rs[i * AMG1D_TILE + lane] = r;
     __syncthreads();
     if (valid) {
-        double z;
-        if (diag) {
-            z = T[(3 * mm + i) * AMG1D_TILE] * r;
-        } else {
-            z = 0.0;
-            for (int j = 0; j < m; ++j)
-                z = fma(T[(3 * mm + j * m + i) * AMG1D_TILE], rs[j * AMG1D_TILE + lane], z);
-        }
+        const double z = g_row_Dinv(T, d, i, rs + lane, AMG1D_TILE);
         const double x0 = zero_guess ? 0.0 : xin[e * m + i];
         xout[e * m + i] = __dadd_rn(x0, __dmul_rn(alpha, z));
     }
 }
 
 // out = A x (mode 0) or out = b - A x (mode 1).
-__global__ void g_apply(const double* __restrict__ mat, int m, int K, const double* __restrict__ b,
+__global__ void g_apply(const double* __restrict__ mat, MatDesc d, const double* __restrict__ b,
                         const double* __restrict__ x, double* __restrict__ out, int64_t n, int mode) {
+    const int m = d.m;
     const int lane = threadIdx.x, i = threadIdx.y, tz = threadIdx.z;
     const int64_t tile = (int64_t)blockIdx.x * blockDim.z + tz;
     const int64_t e = tile * AMG1D_TILE + lane;
     if (e >= n) return;
-    const double* T = mat + tile * (int64_t)K * AMG1D_TILE + lane;
-    const int mm = m * m;
-    const double* xl = x + (e - 1) * m;
-    const double* xc = x + e * m;
-    const double* xr = x + (e + 1) * m;
-    double y = 0.0;
-    for (int j = 0; j < m; ++j) y = fma(T[(j * m + i) * AMG1D_TILE], xl[j], y);
-    for (int j = 0; j < m; ++j) y = fma(T[(mm + j * m + i) * AMG1D_TILE], xc[j], y);
-    for (int j = 0; j < m; ++j) y = fma(T[(2 * mm + j * m + i) * AMG1D_TILE], xr[j], y);
+    const double* T = mat + tile * (int64_t)d.K * AMG1D_TILE + lane;
+    const double y = g_row_Ax(T, d, i, x + (e - 1) * m, x + e * m, x + (e + 1) * m);
     out[e * m + i] = mode ? b[e * m + i] - y : y;
 }
 
 // Y = alpha * Dinv * B  (apply_smoother, src/smoother.jl:52-58, :69-81)
-__global__ void g_apply_smoother(const double* __restrict__ mat, int m, int diag, int K,
+__global__ void g_apply_smoother(const double* __restrict__ mat, MatDesc d,
                                  const double* __restrict__ B, double* __restrict__ Y, int64_t n,
                                  double alpha) {
+    const int m = d.m;
     const int lane = threadIdx.x, i = threadIdx.y, tz = threadIdx.z;
     const int64_t tile = (int64_t)blockIdx.x * blockDim.z + tz;
     const int64_t e = tile * AMG1D_TILE + lane;
     if (e >= n) return;
-    const double* T = mat + tile * (int64_t)K * AMG1D_TILE + lane;
-    const int mm = m * m;
-    double z;
-    if (diag) {
-        z = T[(3 * mm + i) * AMG1D_TILE] * B[e * m + i];
-    } else {
-        z = 0.0;
-        for (int j = 0; j < m; ++j) z = fma(T[(3 * mm + j * m + i) * AMG1D_TILE], B[e * m + j], z);
-    }
-    Y[e * m + i] = __dmul_rn(alpha, z);
+    const double* T = mat + tile * (int64_t)d.K * AMG1D_TILE + lane;
+    Y[e * m + i] = __dmul_rn(alpha, g_row_Dinv(T, d, i, B + e * m, 1));
 }
 
 // rc[Kc] = sum_{parent(e) = Kc-1} P1[e]' rf[e] + sum_{parent(e) = Kc} P0[e]' rf[e]
@@ -174,12 +184,10 @@ __global__ void g_prolong(TransferMap tm, int mf, int mc, const double* __restri
 //   forward  y_k = b_k - W_k y_{k-1}          W_k = A_lo[k] * Sinv_{k-1}
 //   backward x_k = Sinv_k (y_k - A_up[k] x_{k+1})
 // One warp, lane i owns row i (m <= 32).  fac[k] = { W (m*m), Sinv (m*m), U (m*m) } column-major.
-__global__ void g_coarse_solve(const double* __restrict__ fac, int m, int64_t n,
-                               const double* __restrict__ b, double* __restrict__ x) {
-    extern __shared__ double sh[];  // y_prev[m], work[m]
-    double* yp = sh;
-    double* wk = sh + m;
-    const int i = threadIdx.x;
+// yp / wk: m doubles of shared memory each.
+__device__ __forceinline__ void coarse_solve_warp(const double* __restrict__ fac, int m, int64_t n,
+                                                  const double* b, double* x, double* yp, double* wk) {
+    const int i = threadIdx.x & 31;
     const int mm = m * m;
     // forward sweep; y stored temporarily in x
     for (int64_t k = 0; k < n; ++k) {
@@ -213,6 +221,12 @@ __global__ void g_coarse_solve(const double* __restrict__ fac, int m, int64_t n,
         if (i < m) { yp[i] = xi; x[k * m + i] = xi; }
         __syncwarp();
     }
+}
+
+__global__ void g_coarse_solve(const double* __restrict__ fac, int m, int64_t n,
+                               const double* __restrict__ b, double* __restrict__ x) {
+    extern __shared__ double sh[];  // y_prev[m], work[m]
+    coarse_solve_warp(fac, m, n, b, x, sh, sh + m);
 }
 
 // ---- reductions (deterministic: fixed partial layout, fixed final order) -----------------------
@@ -266,15 +280,24 @@ __global__ void k_reduce_final(const double* __restrict__ partial, int np, doubl
 }
 
 // ---- set-up helpers -----------------------------------------------------------------------------
+// Value of tile row k for an element whose uploaded blocks start at lo / di / up (m*m each, column
+// major) and dinv (m*m or m).
+__device__ __forceinline__ double tile_value(const MatDesc& d, int k, const double* lo, const double* di,
+                                             const double* up, const double* dinv) {
+    int which, idx;
+    amg1d_row_source(d, k, &which, &idx);
+    return which == 0 ? lo[idx] : which == 1 ? di[idx] : which == 2 ? up[idx] : dinv[idx];
+}
+
 // Repack element-block host layout (already copied to the device chunk buffers) into element tiles.
 // src arrays hold `cnt` elements starting at element e0; dinv has m*m or m doubles per element.
 __global__ void k_repack(const double* __restrict__ lo, const double* __restrict__ di,
-                         const double* __restrict__ up, const double* __restrict__ dinv, int m,
-                         int diag, int K, int64_t e0, int64_t cnt, double* __restrict__ mat) {
+                         const double* __restrict__ up, const double* __restrict__ dinv, MatDesc d,
+                         int64_t e0, int64_t cnt, double* __restrict__ mat) {
     const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     // t enumerates (tile_local, k, lane) over the tiles touched by [e0, e0+cnt); e0 % 32 == 0
     // (e0 = -32 addresses the spare front tile of a slab with left ghost elements)
-    const int64_t per_tile = (int64_t)K * AMG1D_TILE;
+    const int64_t per_tile = (int64_t)d.K * AMG1D_TILE;
     const int64_t tl = t / per_tile;
     const int k = (int)((t % per_tile) / AMG1D_TILE);
     const int lane = (int)(t % AMG1D_TILE);
@@ -284,13 +307,10 @@ __global__ void k_repack(const double* __restrict__ lo, const double* __restrict
             mat[(e0 / AMG1D_TILE + tl) * per_tile + (int64_t)k * AMG1D_TILE + lane] = 0.0;
         return;
     }
-    const int mm = m * m;
-    double v;
-    if (k < mm) v = lo[el * mm + k];
-    else if (k < 2 * mm) v = di[el * mm + (k - mm)];
-    else if (k < 3 * mm) v = up[el * mm + (k - 2 * mm)];
-    else v = diag ? dinv[el * m + (k - 3 * mm)] : dinv[el * mm + (k - 3 * mm)];
-    mat[(e0 / AMG1D_TILE + tl) * per_tile + (int64_t)k * AMG1D_TILE + lane] = v;
+    const int mm = d.m * d.m;
+    const int dsz = d.diag ? d.m : mm;
+    mat[(e0 / AMG1D_TILE + tl) * per_tile + (int64_t)k * AMG1D_TILE + lane] =
+        tile_value(d, k, lo + el * mm, di + el * mm, up + el * mm, dinv + el * dsz);
 }
 
 // Fill the stored tiles of a (slab of a) level from a head / interior / tail pattern of
@@ -299,11 +319,10 @@ __global__ void k_repack(const double* __restrict__ lo, const double* __restrict
 // [e_lo, e_hi) that exist globally are filled, everything else is zero.
 __global__ void k_fill_pattern(const double* __restrict__ lo, const double* __restrict__ di,
                                const double* __restrict__ up, const double* __restrict__ dinv,
-                               int m, int diag, int K, int64_t n_glob, int n_head, int n_tail,
-                               int64_t start, int64_t e_lo, int64_t e_hi, int64_t ntiles,
-                               double* __restrict__ store) {
+                               MatDesc d, int64_t n_glob, int n_head, int n_tail, int64_t start,
+                               int64_t e_lo, int64_t e_hi, int64_t ntiles, double* __restrict__ store) {
     const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    const int64_t per_tile = (int64_t)K * AMG1D_TILE;
+    const int64_t per_tile = (int64_t)d.K * AMG1D_TILE;
     const int64_t tile = t / per_tile;
     if (tile >= ntiles) return;
     const int k = (int)((t % per_tile) / AMG1D_TILE);
@@ -316,11 +335,9 @@ __global__ void k_fill_pattern(const double* __restrict__ lo, const double* __re
         if (eg < n_head) s = eg;
         else if (eg >= n_glob - n_tail) s = n_head + 1 + (eg - (n_glob - n_tail));
         else s = n_head;
-        const int mm = m * m;
-        if (k < mm) v = lo[s * mm + k];
-        else if (k < 2 * mm) v = di[s * mm + (k - mm)];
-        else if (k < 3 * mm) v = up[s * mm + (k - 2 * mm)];
-        else v = diag ? dinv[s * m + (k - 3 * mm)] : dinv[s * mm + (k - 3 * mm)];
+        const int mm = d.m * d.m;
+        const int dsz = d.diag ? d.m : mm;
+        v = tile_value(d, k, lo + s * mm, di + s * mm, up + s * mm, dinv + s * dsz);
     }
     store[t] = v;
 }

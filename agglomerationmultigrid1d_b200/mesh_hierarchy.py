@@ -142,9 +142,12 @@ class MeshHierarchy:
         self.mSmoothers, self.mInterpolation, self.mBdConds = Sm, I, list(mBdConds)
 
     # ---- upload (stands in for the end of construction) ------------------------------------------
-    def upload(self, device=0, stream=None):
+    def upload(self, device=0, stream=None, options=None):
+        """options: dict for amg1d_set_option, applied before the first level (e.g. {"compress": 0})."""
         nL = len(self.mMeshes)
         dev = DeviceHierarchy(nL, device=device, stream=stream)
+        for k, v in (options or {}).items():
+            dev.set_option(k, v)
         slots = [blk.level_slots(m) for m in self.mMeshes]
         for l in range(nL):
             lo, di, up = blk.csc_to_blocks(self.mStiffness[l], slots[l])

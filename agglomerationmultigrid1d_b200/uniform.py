@@ -334,18 +334,28 @@ class UniformDgHierarchy:
             total += 8 * lv.n * (3 * lv.m * lv.m + 2 * lv.m)
         return total
 
+    def tile_rows(self, l):
+        """Doubles stored per element on level l: what the device reports for its structure class
+        (csrc/layout.cuh) once uploaded, the dense 4 m^2 otherwise."""
+        dev = getattr(self, "device", None)
+        if dev is not None:
+            k = dev.info(f"tile_rows:{l}")
+            if k > 0:
+                return k
+        return 4 * self.levels[l].m ** 2
+
+    def bytes_per_leg_fused(self, l, down):
+        """Algorithmic bytes of one fused leg (f_down / f_up) of level l: the level's operator once
+        (tile_rows), b, x in, x out (3 m; the zero-guess down legs of levels > 0 do not read x) and
+        the coarse vector (m_c per coarse element); transfer blocks are periodic patterns (L1)."""
+        lv, lc = self.levels[l], self.levels[l + 1]
+        vec = 2 if (down and l > 0) else 3
+        return 8 * (lv.n * (self.tile_rows(l) + vec * lv.m) + lc.n * lc.m)
+
     def bytes_per_cycle_fused(self, with_check=True):
-        """Algorithmic bytes of the fused two-kernels-per-level cycle this library runs: per leg the
-        level's operator once (4 m^2), b, x in, x out (3 m) and the coarse vector (m_c / ratio);
-        transfer blocks are periodic patterns (L1-resident).  Zero-guess down-legs do not read x."""
-        total = 0
-        for l, lv in enumerate(self.levels[:-1]):
-            n, m = lv.n, lv.m
-            mc, nc = self.levels[l + 1].m, self.levels[l + 1].n
-            down = n * (4 * m * m + (3 if l == 0 else 2) * m) + nc * mc
-            up = n * (4 * m * m + 3 * m) + nc * mc
-            total += 8 * (down + up)
-        return total
+        """Algorithmic bytes of the fused two-kernels-per-level cycle this library runs."""
+        return sum(self.bytes_per_leg_fused(l, True) + self.bytes_per_leg_fused(l, False)
+                   for l in range(len(self.levels) - 1))
 
 
 # =====================================================================================================
@@ -514,28 +524,40 @@ class UniformCgHierarchy:
         return s
 
     # ---- right-hand side of cg_stiffness_and_rhs in group order (src/cg_mesh.jl:125-185) -------------
-    def rhs(self, func, bc_values, chunk=1 << 20):
+    def rhs(self, func, bc_values, chunk=1 << 20, group_range=None):
+        """Right-hand side in group order; ``group_range = (g_begin, g_end)`` returns only that slab of
+        groups (multi-GPU: every rank assembles its own slab)."""
         p = self.cg_orders[0]
         ref = ReferenceElement(p)
         n = self.n
-        b = np.zeros((n + 1, p))
+        g0, g1 = (0, n + 1) if group_range is None else group_range
+        b = np.zeros((g1 - g0, p))
+
+        def add(g, col, val):                                             # b[g, col] += val if g is in the slab
+            if g0 <= g < g1:
+                b[g - g0, col] += val
+
         W = ref.mGaussQuadWeights[:, None] * ref.mBasisGQFunVal            # (nq, p+1)
-        for e0 in range(0, n, chunk):
-            e1 = min(n, e0 + chunk)
+        for e0 in range(max(g0 - 1, 0), min(g1, n), chunk):                # elements touching the slab
+            e1 = min(min(g1, n), e0 + chunk)
             i = np.arange(e0, e1, dtype=np.float64)
             xl = self.xin + (i / n) * (self.xout - self.xin)
             xr = self.xin + ((i + 1) / n) * (self.xout - self.xin)
             hh, xc = xr - xl, (xl + xr) / 2.0
             xq = xc[:, None] + (hh / 2.0)[:, None] * ref.mGaussQuadNodes[None, :]
             fe = (hh / 2.0)[:, None] * (eval_func(func, xq) @ W)           # (chunk, p+1)
-            b[e0:e1, 0] += fe[:, 0]
-            b[e0 + 1:e1 + 1, 0] += fe[:, 1]
-            if p > 1:
-                b[e0:e1, 1:] = fe[:, 2:]
+            a, z = max(e0, g0), min(e1, g1)                                # own vertex + interior nodes: group e
+            if z > a:
+                b[a - g0:z - g0, 0] += fe[a - e0:z - e0, 0]
+                if p > 1:
+                    b[a - g0:z - g0, 1:] = fe[a - e0:z - e0, 2:]
+            a, z = max(e0 + 1, g0), min(e1 + 1, g1)                        # right vertex: group e + 1
+            if z > a:
+                b[a - g0:z - g0, 0] += fe[a - 1 - e0:z - 1 - e0, 1]
         kref = np.einsum("l,li,lj->ij", ref.mGaussQuadWeights, ref.mBasisGQDerivVal, ref.mBasisGQDerivVal)
         for side in (0, 1):                                               # Neumann terms first (:164-174)
             if self.bc_kinds[side] == "neu":
-                b[0 if side == 0 else n, 0] += (-1.0 if side == 0 else 1.0) * bc_values[side]
+                add(0 if side == 0 else n, 0, (-1.0 if side == 0 else 1.0) * bc_values[side])
         for side in (0, 1):                                               # strong Dirichlet (:177-182)
             if self.bc_kinds[side] != "dir":
                 continue
@@ -543,19 +565,28 @@ class UniformCgHierarchy:
             xl = self.xin + (el / n) * (self.xout - self.xin)
             xr = self.xin + ((el + 1) / n) * (self.xout - self.xin)
             col = (1.0 / ((xr - xl) / 2.0)) * kref[:, side] * bc_values[side]    # A[:, dir] * val on this element
-            b[el, 0] -= col[0]
-            b[el + 1, 0] -= col[1]
-            if p > 1:
-                b[el, 1:] -= col[2:]
+            add(el, 0, -col[0])
+            add(el + 1, 0, -col[1])
+            for q in range(2, p + 1):
+                add(el, q - 1, -col[q])
         for side in (0, 1):
-            if self.bc_kinds[side] == "dir":
-                b[0 if side == 0 else n, 0] = bc_values[side]
+            g = 0 if side == 0 else n
+            if self.bc_kinds[side] == "dir" and g0 <= g < g1:
+                b[g - g0, 0] = bc_values[side]
         return b.ravel()
 
     # ---- upload ------------------------------------------------------------------------------------------
-    def upload(self, device=0, stream=None):
+    def upload(self, device=0, stream=None, dist=None, options=None):
+        """dist = (rank, nranks, nccl_id_bytes): contiguous slabs of groups / elements per rank (the
+        last rank also holds the closing vertex group of the CG levels).  The two-parent CG transfers
+        read ``ratio`` ghost elements more than a fused leg does, hence the deeper default halo."""
         nL = len(self.levels)
-        dev = DeviceHierarchy(nL, device=device, stream=stream)
+        dev = DeviceHierarchy(nL, device=device, stream=stream, dist=dist)
+        options = dict(options or {})
+        if dist is not None and dist[1] > 1:
+            options.setdefault("ghost_depth", 4 + max(t["ratio"] for t in self.cg_transfers))
+        for k, v in options.items():
+            dev.set_option(k, v)
         for l, lv in enumerate(self.levels):
             if getattr(lv, "is_cg", False):
                 pat = lv.ops["A"]
@@ -575,8 +606,45 @@ class UniformCgHierarchy:
             l = len(self.cg_transfers) + k
             dev.set_transfer_pattern(l, self.levels[l].n, P, None, ratio=ratio, period=P.shape[0])
         dev.finalize()
+        if dist is not None and dist[1] > 1:
+            dev.n_dof[0] = dev.info("local_dofs")          # host vectors are the rank's slab of groups
         self.device = dev
         return dev
+
+    def tile_rows(self, l):
+        dev = getattr(self, "device", None)
+        if dev is not None:
+            k = dev.info(f"tile_rows:{l}")
+            if k > 0:
+                return k
+        lv = self.levels[l]
+        return 3 * lv.m ** 2 + (lv.m if getattr(lv, "is_cg", False) else lv.m ** 2)
+
+    def bytes_per_leg_fused(self, l, down):
+        """As UniformDgHierarchy.bytes_per_leg_fused (two-parent transfers read the same coarse
+        vector once: neighbouring fine groups share their parents)."""
+        lv, lc = self.levels[l], self.levels[l + 1]
+        vec = 2 if (down and l > 0) else 3
+        return 8 * (lv.n * (self.tile_rows(l) + vec * lv.m) + lc.n * lc.m)
+
+    def bytes_per_cycle_fused(self, with_check=True):
+        return sum(self.bytes_per_leg_fused(l, True) + self.bytes_per_leg_fused(l, False)
+                   for l in range(len(self.levels) - 1))
+
+    def bytes_per_cycle_reference_model(self, nPre=3, nPost=3, with_check=True):
+        """B_ref of SURVEY 8d on the dense block layout (point-Jacobi levels: Dinv is m entries)."""
+        total = 0
+        for l, lv in enumerate(self.levels[:-1]):
+            n, m = lv.n, lv.m
+            mc, nc = self.levels[l + 1].m, self.levels[l + 1].n
+            dv = m if getattr(lv, "is_cg", False) else m * m
+            total += (nPre + nPost) * 8 * n * (3 * m * m + dv + 3 * m)
+            total += 8 * (n * (3 * m * m + 2 * m) + n * m * mc + nc * mc)
+            total += 8 * (nc * mc + n * m * mc + 2 * n * m)
+        if with_check:
+            lv = self.levels[0]
+            total += 8 * lv.n * (3 * lv.m * lv.m + 2 * lv.m)
+        return total
 
     def dof_updates_per_cycle(self, nPre=3, nPost=3):
         tot = 0

@@ -7,7 +7,7 @@ plus the convergence check ||A x - b||_2 that ``multigrid`` performs after every
 resident in HBM; `e2e` = the same metric through the reference-facing call
 ``multigrid_v_cycle(H, x0, b)`` (amg1d_vcycle) with pinned HOST vectors, copies inside the timing.
 
-  python bench.py [--gpus N] [--steps K] [--warmup W] [--workload T|C2|C3|C5|C1] [--impl reference]
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--workload T|C2|C3|C4|C5|S] [--impl reference]
 """
 import argparse
 import json
@@ -27,14 +27,37 @@ sys.path.insert(0, os.path.join(ROOT, "tests"))
 METRIC = "FP64 V-cycle DOF-updates/s"
 UNIT = "DOF-updates/s"
 
-# name -> (log2 n, DG orders, description)
+# name -> (log2 n per GPU, CG orders, DG orders, description); pAgg = 1, factor-2 agglomeration down to
+# one element in every workload
 WORKLOADS = {
-    "T": (26, [3, 1], "DG p=3, 2^26 elements, DG 3->1 then pAgg=1 factor-2 agglomeration to one element (28 levels)"),
-    "C2": (20, [3, 1], "DG p=3, 2^20 elements, full hierarchy (22 levels)"),
-    "C3": (24, [4, 2, 1], "DG p=4, 2^24 elements, DG 4->2->1 then factor-2 agglomeration (27 levels)"),
-    "C5": (24, [3, 1], "DG p=3, 2^24 elements per GPU, full hierarchy"),
-    "S": (14, [3, 1], "DG p=3, 2^14 elements (smoke-sized)"),
+    "T": (26, [], [3, 1], "DG p=3, 2^26 elements, DG 3->1 then pAgg=1 factor-2 agglomeration to one element (28 levels)"),
+    "C2": (20, [], [3, 1], "DG p=3, 2^20 elements, full hierarchy (22 levels)"),
+    "C3": (24, [], [4, 2, 1], "DG p=4, 2^24 elements, DG 4->2->1 then factor-2 agglomeration (27 levels)"),
+    "C4": (26, [3, 1], [1], "CG p=3 -> CG 1 -> DG 1 -> factor-2 agglomeration, 2^26 elements (dg_cg_heirarchy shape, 29 levels)"),
+    "C5": (24, [], [3, 1], "DG p=3, 2^24 elements per GPU, full hierarchy"),
+    "S": (14, [], [3, 1], "DG p=3, 2^14 elements (smoke-sized)"),
 }
+
+
+def build_hierarchy(workload, n):
+    """The uniform-mesh pattern set-up of one workload at n elements (host side, seconds)."""
+    from agglomerationmultigrid1d_b200 import uniform
+    _, cg, dg, _ = WORKLOADS[workload]
+    pr = problem(n)
+    k = n.bit_length() - 1
+    if cg:
+        return uniform.UniformCgHierarchy(n, cg, dg, [2] * k, pAgg=1, xin=pr["xin"], xout=pr["xout"],
+                                          CDir=pr["CDir"])
+    return uniform.UniformDgHierarchy(n, dg, [2] * k, pAgg=1, xin=pr["xin"], xout=pr["xout"], CDir=pr["CDir"])
+
+
+def rhs_slab(U, pr, rank, world):
+    """This rank's slab of the right-hand side (elements for DG-first, vertex groups for CG-first)."""
+    nloc = U.n // world
+    if hasattr(U, "cg_orders"):
+        return U.rhs(pr["func"], pr["bc_values"],
+                     group_range=(rank * nloc, (rank + 1) * nloc + (1 if rank == world - 1 else 0)))
+    return U.rhs(pr["func"], pr["bc_values"], elem_range=(rank * nloc, (rank + 1) * nloc))
 
 
 def problem(n):
@@ -102,7 +125,7 @@ def measured_peak():
 
 
 # ---- CPU reference arm: the oracle's restatement of multigrid_v_cycle on the host cores ------------
-def cpu_reference(orders, nsteps, log2n_sample=18, threads=0):
+def cpu_reference(workload, nsteps, log2n_sample=18, threads=0):
     """Times the oracle's plain-C restatement of the reference algorithm (oracle/vcycle_ref.c: sparse
     SpMV for A*u, one partial-pivoting LU solve per element for block Jacobi, sparse L' / L products,
     direct coarse solve, fresh temporaries per expression as in src/solvers.jl:19-50) on a bounded
@@ -112,20 +135,43 @@ def cpu_reference(orders, nsteps, log2n_sample=18, threads=0):
     import scipy.linalg  # noqa: F401
     from oracle import cref
     from oracle.hierarchy import MeshHierarchy
-    from oracle.smoother import BlockJacobi
+    from oracle.smoother import BlockJacobi, JacobiSmoother
     from agglomerationmultigrid1d_b200 import blocks as blk, uniform
+    import scipy.sparse as sp
     n = 2 ** log2n_sample
     pr = problem(n)
-    U = uniform.UniformDgHierarchy(n, orders, [2] * log2n_sample, pAgg=1, xin=pr["xin"], xout=pr["xout"],
-                                   CDir=pr["CDir"])
+    U = build_hierarchy(workload, n)
     S, Sm, I = [], [], []
     for l, lv in enumerate(U.levels):
         lo, di, up = U.level_blocks(l)
         slots = np.arange(lv.n * lv.m, dtype=np.int64).reshape(lv.n, lv.m)
         S.append(blk.blocks_to_csc(lo, di, up, slots, lv.n * lv.m))
-        Sm.append(BlockJacobi(None, slots.T))                 # the C side factorises A's diagonal blocks
-    for l, (P, ratio) in enumerate(U.transfers):
-        I.append(uniform._transfer_csc(P, U.levels[l].n, ratio))
+        if getattr(lv, "is_cg", False):                       # point Jacobi (src/smoother.jl:52-58)
+            Sm.append(JacobiSmoother(S[-1].diagonal()))
+        else:
+            Sm.append(BlockJacobi(None, slots.T))             # the C side factorises A's diagonal blocks
+    if hasattr(U, "cg_orders"):
+        for l in range(len(U.levels) - 1):                    # (parent, P0, P1) blocks -> sparse L
+            parent, P0, P1 = U.transfer_blocks(l)
+            nf, mf, mc = P0.shape
+            nc = U.levels[l + 1].n
+            rows, cols, vals = [], [], []
+            for P, off in ((P0, 0), (P1, 1)):
+                if P is None:
+                    continue
+                par = parent + off
+                ok = (par >= 0) & (par < nc)
+                e = np.flatnonzero(ok)
+                rows.append(np.repeat((e[:, None] * mf + np.arange(mf))[:, :, None], mc, axis=2).ravel())
+                cols.append(np.repeat((par[e][:, None] * mc + np.arange(mc))[:, None, :], mf, axis=1).ravel())
+                vals.append(P[e].ravel())
+            L = sp.csc_matrix((np.concatenate(vals), (np.concatenate(rows), np.concatenate(cols))),
+                              shape=(nf * mf, nc * mc))
+            L.eliminate_zeros()
+            I.append(L)
+    else:
+        for l, (P, ratio) in enumerate(U.transfers):
+            I.append(uniform._transfer_csc(P, U.levels[l].n, ratio))
     H = MeshHierarchy([None] * len(S), S, None, None, None, Sm, I, None)
     c = cref.CRefHierarchy(H)
     b = U.rhs(pr["func"], pr["bc_values"])
@@ -151,9 +197,9 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    log2n, orders, desc = WORKLOADS[args.workload]
+    log2n, _, _, desc = WORKLOADS[args.workload]
     steps = max(1, min(args.steps, 10))
-    val, dt, sample, used, single = cpu_reference(orders, steps)
+    val, dt, sample, used, single = cpu_reference(args.workload, steps)
     line = {
         "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus,
         "steps": steps, "warmup": 1, "ms_per_step": dt * 1e3, "higher_is_better": True,
@@ -212,18 +258,18 @@ def run_gpu(args):
     stream = tstream.cuda_stream
     assert stream != 0
 
-    log2n, orders, desc = WORKLOADS[args.workload]
+    log2n, _, _, desc = WORKLOADS[args.workload]
     log2w = world.bit_length() - 1
     n = 2 ** (log2n + log2w)                      # weak scaling: 2^log2n elements per GPU
     nloc = n // world
     pr = problem(n)
     t_setup = time.perf_counter()
-    U = uniform.UniformDgHierarchy(n, orders, [2] * (log2n + log2w), pAgg=1, xin=pr["xin"],
-                                   xout=pr["xout"], CDir=pr["CDir"])
+    U = build_hierarchy(args.workload, n)
     dev = U.upload(device=local, stream=stream, dist=dist_arg)
     dev.synchronize()
     t_setup = time.perf_counter() - t_setup
-    N0 = nloc * U.levels[0].m                     # DOFs of this rank's slab of the fine level
+    N0 = dev.info("local_dofs")                   # DOFs (slots) of this rank's slab of the fine level
+    N0_all = U.levels[0].n * U.levels[0].m        # whole fine level
     upd = U.dof_updates_per_cycle()               # whole job
 
     # ---- value: device-resident steps (random rhs; throughput does not depend on the data) --------
@@ -264,20 +310,22 @@ def run_gpu(args):
     dev.set_option("profile", 0)
     lv0, lv1 = U.levels[0], U.levels[1]
     m, mc = lv0.m, lv1.m
-    fused_kernel = m <= 4
-    if fused_kernel:
-        bytes_up = 8 * (lv0.n * (4 * m * m + 3 * m) + lv1.n * mc) // world   # f_up at level 0 (+ norm), this rank
-        kern = f"f_up<{m},{mc},128> level 0 (prolong + 3 sweeps + ||b-Ax||^2)"
-        t_k = legs["L0_up"]
-    else:
-        bytes_up = (3 * 8 * lv0.n * (4 * m * m + 3 * m) + 8 * (lv1.n * mc + 2 * lv0.n * m)) // world
-        kern = f"level-0 up leg (g_prolong + 3 x f_sweep<{m}>)"
-        t_k = legs["L0_up"]
+    st0 = dev.info("structure:0")
+    # f_up at level 0 (prolongation + 3 sweeps + ||b - A x||^2), this rank's slab: the level's stored
+    # operator once (tile_rows doubles per element for its structure class), b, x in, x out, coarse x
+    bytes_up = U.bytes_per_leg_fused(0, down=False) // world
+    kern = (f"f_up<{m},{mc},128,st={st0},{'point' if getattr(lv0, 'is_cg', False) else 'block'}-Jacobi> level 0 "
+            f"(prolong + 3 sweeps + ||b-Ax||^2; {U.tile_rows(0)} + {3 * m} doubles per element)")
+    t_k = legs["L0_up"]
     achieved = bytes_up / (t_k * 1e-3) / 1e9
-    cyc_bytes = U.bytes_per_cycle_fused() if fused_kernel else U.bytes_per_cycle_reference_model()
+    cyc_bytes = U.bytes_per_cycle_fused()
+    traffic = None                                   # DRAM bytes per launch from the committed ncu capture
+    tpath = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(tpath) and world == 1:
+        traffic = json.load(open(tpath)).get(args.workload, {}).get("dram_bytes_per_launch")
     roofline = {
         "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-        "traffic": None, "kernel": kern, "algorithmic_bytes_per_launch": bytes_up,
+        "traffic": traffic, "kernel": kern, "algorithmic_bytes_per_launch": bytes_up,
         "avg_launch_ms": t_k, "peak_source": peak_src,
         "whole_cycle": {"algorithmic_bytes": cyc_bytes, "GBps": cyc_bytes / (ms_step * 1e-3) / 1e9,
                         "frac": cyc_bytes / (ms_step * 1e-3) / 1e9 / (peak * world),
@@ -297,7 +345,7 @@ def run_gpu(args):
     xh = np.ctypeslib.as_array(C.cast(bufs[0], C.POINTER(C.c_double)), shape=(N0,))
     bh = np.ctypeslib.as_array(C.cast(bufs[1], C.POINTER(C.c_double)), shape=(N0,))
     t_rhs = time.perf_counter()
-    bh[:] = U.rhs(pr["func"], pr["bc_values"], elem_range=(rank * nloc, (rank + 1) * nloc))
+    bh[:] = rhs_slab(U, pr, rank, world)
     t_rhs = time.perf_counter() - t_rhs
     xh[:] = 0.0
     e2e_steps = max(1, min(args.steps, 5))
@@ -308,8 +356,8 @@ def run_gpu(args):
         capi.check(dev._h, lib.amg1d_vcycle(dev._h, capi.dptr(xh), capi.dptr(bh), 3, 3, 2.0 / 3.0))
     barrier()
     t_e2e = max_over_ranks(time.perf_counter() - t0) / e2e_steps
-    e2e = {"value": upd / t_e2e, "unit": UNIT, "h2d_bytes_per_step": 2 * N0 * 8 * world,
-           "d2h_bytes_per_step": N0 * 8 * world, "ms_per_step": t_e2e * 1e3, "steps": e2e_steps,
+    e2e = {"value": upd / t_e2e, "unit": UNIT, "h2d_bytes_per_step": 2 * N0_all * 8,
+           "d2h_bytes_per_step": N0_all * 8, "ms_per_step": t_e2e * 1e3, "steps": e2e_steps,
            "call": "amg1d_vcycle (multigrid_v_cycle(H, x0, b)) with pinned host x0, b"}
 
     # ---- time-to-1e-10: full multigrid() solve through the ABI (host vectors in, solution out) ----
@@ -329,7 +377,7 @@ def run_gpu(args):
     # ---- CPU baseline beside it (oracle port, bounded sample) ----------------------------------------
     cpu = None
     if not args.no_cpu and world == 1:
-        v, dt, sample, used, single = cpu_reference(orders, 3)
+        v, dt, sample, used, single = cpu_reference(args.workload, 3)
         cpu = {"value": v, "unit": UNIT, "cores": used, "kind": "port", "sample": sample,
                "single_thread_value": single, "host_cores_available": os.cpu_count()}
 
@@ -340,17 +388,20 @@ def run_gpu(args):
         "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": {"workload": f"{args.workload}: {desc}" + (f" x {world} GPUs (2^{log2n} elements per GPU, slab-sharded)" if world > 1 else ""),
-                   "n_elements": n, "fine_dofs": N0 * world, "elements_per_gpu": nloc,
+                   "n_elements": n, "fine_dofs": N0_all, "elements_per_gpu": nloc,
                    "parallelism": f"slab{world}" if world > 1 else "single",
                    "levels": len(U.levels), "nPre": 3, "nPost": 3, "alpha": 2.0 / 3.0,
                    "dof_updates_per_step": upd, "step": "one V-cycle + ||Ax-b|| check, CUDA graph replay",
                    "l2": "inputs larger than L2 (operators + vectors of the fine levels are GBs)"
-                   if N0 * 8 > 2 ** 27 else "fine level fits L2; no flush (working set re-read each step)",
+                   if dev.info("device_bytes") > 2 ** 29 else "working set comparable to L2; no flush",
+                   "structure_classes": [dev.info(f"structure:{l}") for l in range(min(4, len(U.levels)))],
+                   "tile_rows": [U.tile_rows(l) for l in range(min(4, len(U.levels)))],
+                   "tail_start": dev.info("tail_start"),
                    "device_bytes": dev.info("device_bytes"), "setup_s": t_setup, "rhs_assembly_s": t_rhs,
                    "residual_after_timed_steps": res_after},
         "roofline": roofline, "cpu_baseline": cpu, "clocks": clocks, "e2e": e2e,
         "time_to_1e-10": solve, "gpu_launches": int(launches),
-        "fine_dof_cycles_per_s": N0 * world / (ms_step * 1e-3),
+        "fine_dof_cycles_per_s": N0_all / (ms_step * 1e-3),
     }
     if rank == 0:
         print(json.dumps(line), flush=True)

@@ -22,6 +22,7 @@ from agglomerationmultigrid1d_b200 import _capi as capi, uniform   # noqa: E402
 def main():
     out = sys.argv[1]
     log2n = int(sys.argv[2]) if len(sys.argv) > 2 else 15
+    kind = sys.argv[3] if len(sys.argv) > 3 else "dg"
     dist.init_process_group("gloo")
     rank, world = dist.get_rank(), dist.get_world_size()
     torch.cuda.set_device(rank)
@@ -36,24 +37,41 @@ def main():
     w = 2.0 * math.pi / 64.0
     func = lambda x: w * w * np.cos(w * x)                       # noqa: E731
     vals = [0.0, math.cos(w * n)]
-    U = uniform.UniformDgHierarchy(n, [3, 1], [2] * log2n, xin=0.0, xout=float(n), CDir=1000.0)
+
+    def build():
+        if kind == "cg":        # BASELINE C4 shape: CG 3 -> 1 -> DG 1 -> agglomerated levels
+            return uniform.UniformCgHierarchy(n, [3, 1], [1], [2] * log2n, xin=0.0, xout=float(n), CDir=1000.0)
+        return uniform.UniformDgHierarchy(n, [3, 1], [2] * log2n, xin=0.0, xout=float(n), CDir=1000.0)
+
+    U = build()
     dev = U.upload(device=rank, dist=(rank, world, ids[0]), options={"shard_min": 512})
     nloc = n // world
-    b_loc = U.rhs(func, vals, elem_range=(rank * nloc, (rank + 1) * nloc))
-    report = {"rank": rank, "gather_level": dev.info("gather_level"), "local_dofs": dev.info("local_dofs")}
+    m0 = U.levels[0].m
+    if kind == "cg":            # slabs of groups; the last rank also holds the closing vertex group
+        lo, hi = rank * nloc, (rank + 1) * nloc + (1 if rank == world - 1 else 0)
+        b_loc = U.rhs(func, vals, group_range=(lo, hi))
+        n_blocks = n + 1
+    else:
+        lo, hi = rank * nloc, (rank + 1) * nloc
+        b_loc = U.rhs(func, vals, elem_range=(lo, hi))
+        n_blocks = n
+    report = {"rank": rank, "gather_level": dev.info("gather_level"), "local_dofs": dev.info("local_dofs"),
+              "ghost_depth": dev.info("ghost_depth")}
     results = {}
     x, it, res, _ = dev.solve(np.zeros(len(b_loc)), b_loc, 100, 1e-10)
     results["solve"] = (x, it, res)
     rng = np.random.default_rng(5)
-    x0_glob = rng.standard_normal(n * 4)
-    x0_loc = x0_glob[rank * nloc * 4:(rank + 1) * nloc * 4]
+    x0_glob = rng.standard_normal(n_blocks * m0)
+    if kind == "cg":
+        x0_glob.reshape(n_blocks, m0)[n, 1:] = 0.0               # padding slots of the closing group
+    x0_loc = x0_glob[lo * m0:hi * m0]
     for key, (nPre, nPost, alpha) in {"v312": (3, 1, 0.5), "v023": (0, 2, 2.0 / 3.0), "v330": (3, 3, 0.8)}.items():
         results[key] = (dev.vcycle(x0_loc, b_loc, nPre=nPre, nPost=nPost, alpha=alpha), 0, np.zeros(0))
     gathered = [None] * world
     dist.gather_object({k: v for k, v in results.items()}, gathered if rank == 0 else None, dst=0)
     ok, msgs = True, []
     if rank == 0:
-        U1 = uniform.UniformDgHierarchy(n, [3, 1], [2] * log2n, xin=0.0, xout=float(n), CDir=1000.0)
+        U1 = build()
         d1 = U1.upload(device=0)
         b = U1.rhs(func, vals)
         x1, it1, res1, _ = d1.solve(np.zeros(len(b)), b, 100, 1e-10)

@@ -59,6 +59,13 @@ def test_properties_at_baseline_sizes(log2n):
     x1 = dev.vcycle(x0, b)
     x2 = dev.vcycle(x0, 4.0 * b)
     assert np.array_equal(x2, 4.0 * x1)
+    # the single-CTA coarse tail replaces ~20 small launches without changing a bit
+    assert dev.info("tail_start") > 0
+    dev.set_option("coarse_cta_elems", 0)
+    assert dev.info("tail_start") < 0
+    assert np.array_equal(dev.vcycle(x0, b), x1)
+    dev.set_option("coarse_cta_elems", 1024)
+    assert dev.info("structure:0") == 1 and dev.info("tile_rows:0") == 40      # 4 + 16 + 4 + 16 doubles
     # both kernel tiers give bit-identical iterates (generic tier only at 2^20: it is ~4x slower)
     if log2n <= 20:
         dev.set_option("fused", 0)
@@ -117,6 +124,29 @@ def test_cg_pattern_path_matches_oracle(cg, dg, agg):
     xh[s0.ravel()[valid]] = x[valid]
     assert np.abs(xh - x_or).max() <= 1e-8 * np.abs(x_or).max()
     assert np.all(x[~valid] == 0.0)
+    # CG levels run in the fused point-Jacobi kernels with two-parent transfers: same bits as the
+    # generic tier, with and without the compressed row / column structure
+    if cg[0] >= 2:
+        assert dev.info("structure:0") == 2
+    dev.set_option("fused", 0)
+    xg, itg, _, _ = dev.solve(np.zeros(len(b)), b, 100, 1e-10)
+    dev.set_option("fused", 1)
+    assert itg == it and np.array_equal(xg, x)
+    dense = U.upload(options={"compress": 0})
+    xd, itd, _, _ = dense.solve(np.zeros(len(b)), b, 100, 1e-10)
+    assert itd == it and np.array_equal(xd, x)
+    rng = np.random.default_rng(2)
+    x0 = rng.standard_normal(len(b))
+    x0[~valid] = 0.0
+    for nPre, nPost in ((3, 3), (0, 2), (2, 0), (1, 4)):
+        ref = None
+        for d_, fused in ((dev, 1), (dev, 0), (dense, 1)):
+            d_.set_option("fused", fused)
+            got = d_.vcycle(x0, b, nPre=nPre, nPost=nPost)
+            ref = got if ref is None else ref
+            assert np.array_equal(got, ref), (nPre, nPost, fused)
+    dev.set_option("fused", 1)
+    dense.close()
     dev.close()
 
 
@@ -131,4 +161,6 @@ def test_c4_shape_at_scale():
     assert it <= 20 and np.all(np.diff(res) < 0) and res[-1] < 1e-10 * np.linalg.norm(b)
     x1 = dev.vcycle(np.zeros(len(b)), b)
     assert np.array_equal(dev.vcycle(np.zeros(len(b)), 2.0 * b), 2.0 * x1)
+    dev.set_option("fused", 0)
+    assert np.array_equal(dev.vcycle(np.zeros(len(b)), b), x1)       # generic tier, same bits
     dev.close()

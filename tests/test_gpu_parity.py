@@ -143,23 +143,79 @@ def test_multigrid_histories(case):
 
 
 def test_fused_and_generic_tiers_agree(case):
-    """The fast kernel tier must reproduce the generic tier (same arithmetic per element)."""
+    """The fast kernel tier (fused legs, single-CTA coarse tail, CUDA graph) must reproduce the generic
+    tier: same arithmetic per element, so the iterate is bit-identical."""
     name, Ho, bo, Hp, bp = case
     dev = Hp.device
     out = {}
     for fused in (0, 1):
         for graph in (0, 1):
-            dev.set_option("fused", fused)
-            dev.set_option("graph", graph)
-            out[(fused, graph)] = dev.solve(np.zeros(len(bp)), bp, 30, 1e-10)
+            for tail in (0, 1024):
+                dev.set_option("fused", fused)
+                dev.set_option("graph", graph)
+                dev.set_option("coarse_cta_elems", tail)
+                out[(fused, graph, tail)] = dev.solve(np.zeros(len(bp)), bp, 30, 1e-10)
     dev.set_option("fused", 1)
     dev.set_option("graph", 1)
-    ref = out[(0, 0)]
+    dev.set_option("coarse_cta_elems", 1024)
+    ref = out[(0, 0, 0)]
     for key, val in out.items():
         assert val[1] == ref[1], key
         assert np.allclose(val[2], ref[2], rtol=1e-11, atol=rounding_floor(Ho, ref[0])), key
         # same arithmetic in the same order per element: the iterate itself is bit-identical
         assert np.array_equal(val[0], ref[0]), key
+    # non-default sweep counts through every tier (nPre = 0 / nPost = 0 take different kernel paths)
+    rng = np.random.default_rng(7)
+    x0 = rng.standard_normal(len(bp))
+    for nPre, nPost, alpha in ((0, 2, 0.7), (2, 0, 0.5), (1, 1, 1.0), (5, 4, 0.6)):
+        got = []
+        for fused, tail in ((0, 0), (1, 0), (1, 1024), (0, 1024)):
+            dev.set_option("fused", fused)
+            dev.set_option("coarse_cta_elems", tail)
+            got.append(dev.vcycle(x0, bp, nPre=nPre, nPost=nPost, alpha=alpha))
+        for g in got[1:]:
+            assert np.array_equal(g, got[0]), (nPre, nPost)
+    dev.set_option("fused", 1)
+    dev.set_option("coarse_cta_elems", 1024)
+
+
+def test_structure_classes_are_exact(case):
+    """Dropping the structural zeros of the off-diagonal blocks (layout.cuh: one column / one row of
+    A_lo and A_up on assembled DG levels and on CG levels in group form) must not change a single bit."""
+    name, Ho, bo, Hp, bp = case
+    dev = Hp.device
+    nL = len(Ho.mMeshes)
+    st = [dev.info(f"structure:{l}") for l in range(nL)]
+    rows = [dev.info(f"tile_rows:{l}") for l in range(nL)]
+    kw = SHAPES[name]
+    if kw.get("dg_orders") and not kw.get("cg_orders") and kw["dg_orders"][0] >= 1:
+        assert st[0] == 1, st                           # assembled DG level: column / row structure
+    if kw.get("cg_orders") and kw["cg_orders"][0] >= 2:
+        assert st[0] == 2, st                           # CG groups: row / column structure
+    x_c, it_c, res_c, _ = dev.solve(np.zeros(len(bp)), bp, 30, 1e-10)
+    owners = [s._owner for s in Hp.mSmoothers]
+    dense = Hp.upload(options={"compress": 0})
+    try:
+        assert all(dense.info(f"structure:{l}") == 0 for l in range(nL))
+        assert all(dense.info(f"tile_rows:{l}") >= rows[l] for l in range(nL))
+        rng = np.random.default_rng(11)
+        x0 = rng.standard_normal(len(bp))
+        for fused in (0, 1):
+            dense.set_option("fused", fused)
+            dev.set_option("fused", fused)
+            x_d, it_d, res_d, _ = dense.solve(np.zeros(len(bp)), bp, 30, 1e-10)
+            assert it_d == it_c and np.array_equal(x_d, x_c), fused
+            assert np.array_equal(dense.vcycle(x0, bp), dev.vcycle(x0, bp)), fused
+            for l in range(nL):
+                N = Ho.mStiffness[l].shape[0]
+                x = rng.standard_normal(N)
+                assert np.array_equal(dense.matvec(l, x), dev.matvec(l, x)), (fused, l)
+    finally:
+        dense.close()
+        Hp.device = dev
+        for s, o in zip(Hp.mSmoothers, owners):
+            s._owner = o
+        dev.set_option("fused", 1)
 
 
 def test_iterative_smoother_solve():
