@@ -104,9 +104,11 @@ struct amg1d {
     int opt_fused = 1, opt_graph = 1;
     int64_t opt_coarse_cta = 1024;
     int opt_compress = 1;         // drop structural zeros of the off-diagonal blocks (layout.cuh)
+    int opt_pdl = 1;              // programmatic dependent launch between the fused kernels
     // single-CTA coarse tail (f_tail): levels [tail_start, n_levels)
     int tail_start = -1;
     TailLevel* d_tail = nullptr;
+    TailPlan tail_plan_ = {};
     // graph cache
     cudaGraphExec_t gexec = nullptr;
     int g_pre = -1, g_post = -1, g_norm = -1;
@@ -484,7 +486,7 @@ int leg_down(amg1d* h, int l, int nPre, double alpha) {
         const int ob = zero ? 0 : 1 - lv.cur;
         if (fused_down(lv.md, t.mc, make_map_closed(t), nPre, zero, lv.mat, lv.b.p, lv.x[lv.cur].p,
                        lv.x[ob].p, t.P0, t.P1, lc.b.p, lv.n, lv.n + (lv.gr ? t.cover_extra : 0), alpha,
-                       make_slab(h, l), h->stream)) {
+                       make_slab(h, l), h->stream, h->opt_pdl != 0)) {
             lv.cur = ob;
             h->launch_counter++;
             LAUNCH_CHECK();
@@ -527,7 +529,7 @@ int leg_up(amg1d* h, int l, int nPost, double alpha, bool fuse_norm, bool* norm_
         if (fused_up(lv.md, t.mc, make_map_closed(t), nPost, lv.mat, lv.b.p, lv.x[lv.cur].p,
                      lv.x[1 - lv.cur].p, t.P0, t.P1, lc.x[lc.cur].p, lv.n, alpha,
                      fuse_norm ? h->partial : nullptr, h->partial_cap, &nb, make_slab(h, l),
-                     h->stream)) {
+                     h->stream, h->opt_pdl != 0)) {
             lv.cur = 1 - lv.cur;
             h->launch_counter++;
             LAUNCH_CHECK();
@@ -579,7 +581,7 @@ int enqueue_vcycle(amg1d* h, int nPre, int nPost, double alpha, bool want_norm) 
     if (ts < nl) {
         for (int l = ts; l < nl; ++l) h->L[l].cur = 0;
         cudaError_t te = tail_launch(h->L[ts].m, h->d_tail, nl - ts, h->coarse_fac, nPre, nPost, alpha,
-                                     h->stream);
+                                     h->tail_plan_, h->stream, h->opt_pdl != 0);
         if (te != cudaSuccess) return fail(h, AMG1D_ERR_CUDA, "f_tail launch failed: %s", cudaGetErrorString(te));
         h->launch_counter++;
     } else if (h->L[nl - 1].present) {
@@ -761,8 +763,9 @@ int factor_coarsest(amg1d* h) {
 
 // Single-CTA coarse tail (kernels_fused.cuh, f_tail): the longest suffix of levels [ts, n_levels) that
 // are unsharded, have at most min(coarse_cta_elems, TAIL_B) elements, share one block size, use block
-// smoothers and single-parent closed-form transfers.  Level 0 never joins (it carries the caller's
-// initial guess), and a tail of the coarsest level alone stays with g_coarse_solve.
+// smoothers and single-parent closed-form transfers, and whose operators + vectors fit the CTA's
+// shared memory.  Level 0 never joins (it carries the caller's initial guess), and a tail of the
+// coarsest level alone stays with g_coarse_solve.
 int build_tail(amg1d* h) {
     h->tail_start = -1;
     if (h->d_tail) { cudaFree(h->d_tail); h->d_tail = nullptr; }
@@ -772,33 +775,46 @@ int build_tail(amg1d* h) {
     if (!tail_supported(m)) return AMG1D_OK;
     const int64_t cap = std::min<int64_t>(h->opt_coarse_cta, TAIL_B);
     int ts = nl;
-    for (int l = nl - 1; l >= 1; --l) {
+    int op_total = 0, vec_total = 0, p_total = 0;
+    for (int l = nl - 1; l >= 1 && nl - l < TAIL_MAXL; --l) {
         const Level& lv = h->L[l];
         if (lv.sharded || !lv.present || lv.m != m || lv.n_glob > cap) break;
+        int p_len = 0;
         if (l < nl - 1) {
             const Transfer& t = h->T[l];
             if (lv.diag || !t.single_parent_uniform || t.P1) break;
+            p_len = (int)(t.nblk * m * m);
         }
+        const int op_len = (int)(amg1d_tiles(lv.n) * lv.K * AMG1D_TILE);
+        const TailPlan trial = tail_plan(m, op_total + op_len, vec_total + (int)lv.n * m, p_total + p_len);
+        if ((size_t)trial.total * 8 > TAIL_SMEM_MAX) break;
+        op_total += op_len; vec_total += (int)lv.n * m; p_total += p_len;
         ts = l;
     }
     if (ts > nl - 2) return AMG1D_OK;
     std::vector<TailLevel> tl((size_t)(nl - ts));
+    int op_off = 0, vec_off = 0, p_off = 0;
     for (int l = ts; l < nl; ++l) {
         const Level& lv = h->L[l];
         TailLevel& d = tl[(size_t)(l - ts)];
+        memset(&d, 0, sizeof d);
         d.md = lv.md;
         d.mat = lv.mat;
         d.n = lv.n;
         d.x = lv.x[0].p;
         d.b = lv.b.p;
-        d.P0 = nullptr;
-        d.tm = TransferMap();
+        d.op_off = op_off; d.op_len = (int)(amg1d_tiles(lv.n) * lv.K * AMG1D_TILE);
+        d.vec_off = vec_off;
+        d.p_off = p_off; d.p_len = 0;
         if (l < nl - 1) {
             d.tm = make_map_closed(h->T[l]);
             d.P0 = h->T[l].P0;
+            d.p_len = (int)(h->T[l].nblk * m * m);
         }
+        op_off += d.op_len; vec_off += (int)lv.n * m; p_off += d.p_len;
     }
-    cudaError_t e = tail_configure(m);
+    h->tail_plan_ = tail_plan(m, op_off, vec_off, p_off);
+    cudaError_t e = tail_configure(m, (size_t)h->tail_plan_.total * 8);
     if (e != cudaSuccess) return fail(h, AMG1D_ERR_CUDA, "f_tail configuration failed: %s", cudaGetErrorString(e));
     RET(dev_alloc(h, (void**)&h->d_tail, (int64_t)(tl.size() * sizeof(TailLevel))));
     CK(cudaMemcpy(h->d_tail, tl.data(), tl.size() * sizeof(TailLevel), cudaMemcpyHostToDevice));
@@ -1554,6 +1570,7 @@ int amg1d_set_option(amg1d_t* h, const char* key, int64_t value) {
     invalidate_graph(h);
     if (!strcmp(key, "fused")) h->opt_fused = (int)value;
     else if (!strcmp(key, "graph")) h->opt_graph = (int)value;
+    else if (!strcmp(key, "pdl")) h->opt_pdl = (int)value;
     else if (!strcmp(key, "coarse_cta_elems")) {
         h->opt_coarse_cta = value;
         if (h->finalized) { CK(cudaSetDevice(h->device)); CK(cudaStreamSynchronize(h->stream)); RET(build_tail(h)); }

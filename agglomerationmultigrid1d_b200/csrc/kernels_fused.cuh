@@ -5,7 +5,7 @@
 //  f_sweep / f_resnorm / f_residual_restrict  - streaming kernels (one pass over the operator each)
 //  f_down   nPre sweeps + residual + restriction  in ONE pass over the level's operator
 //  f_up     prolongation + correction + nPost sweeps (+ optional ||b - A x||^2)  in ONE pass
-//  f_tail   the whole sub-V-cycle of the coarse levels (<= 1024 elements) in ONE CTA
+//  f_tail   the whole sub-V-cycle of the coarse levels (<= 512 elements) in ONE CTA, out of shared memory
 //
 // f_down / f_up keep the element's operator blocks in registers for the whole leg (Dinv in shared
 // memory, staged with cp.async) and exchange only the M iterate values with the two neighbour
@@ -39,13 +39,63 @@ struct Slab {
     int64_t e_off, c_off, nc;
 };
 
+// Per-launch constants of a fused leg, computed on the host so that the per-thread index arithmetic
+// (parent element, owner test, transfer-block index) is 32-bit: with out % ratio == 0 the CTA's first
+// thread has (e_global + shift) = ratio * (blockIdx * opr + qdiv0) + qmod0.
+struct WinIdx {
+    int halo, out;     // recomputed window elements per side; elements emitted per CTA
+    int opr;           // out / ratio
+    int qmod0;         // floormod(e_off + shift - halo, ratio)
+    int64_t qdiv0;     // floordiv(e_off + shift - halo, ratio)
+    int pmod0;         // floormod(e_off - halo - n_head, period) + pbias, or -1: use TransferMap::blk (64-bit)
+};
+
+__device__ __forceinline__ void small_divmod(int x, int d, int* q, int* r) {   // x >= 0, d >= 1
+    if (d == 1) { *q = x; *r = 0; }
+    else if (d == 2) { *q = x >> 1; *r = x & 1; }
+    else { *q = x / d; *r = x - *q * d; }
+}
+
+// transfer-block index of global fine element c = (window thread tc of this CTA), see TransferMap::blk
+__device__ __forceinline__ int64_t win_blk(const TransferMap& tm, const WinIdx& w, int64_t c, int tc) {
+    if (tm.period == 0 || w.pmod0 < 0) return tm.blk(c);
+    if (c < tm.n_head) return c;
+    if (c >= tm.n_fine - tm.n_tail) return tm.n_head + tm.period + (c - (tm.n_fine - tm.n_tail));
+    int q, r;
+    small_divmod(w.pmod0 + tc, tm.period, &q, &r);
+    return tm.n_head + r;
+}
+
+// Programmatic dependent launch (PDL): every fused kernel first lets its successor in the stream start
+// launching, issues the loads that do not depend on earlier kernels (the level's operator - most of its
+// bytes), and only then waits for the preceding kernels to complete.  The successor's CTAs fill the SMs
+// that the last wave of this grid leaves idle, and the launch latency of the small levels disappears.
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_fused(void (*kern)(KArgs...), unsigned grid, unsigned block, size_t smem,
+                                cudaStream_t st, bool pdl, Args... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(grid, 1, 1);
+    cfg.blockDim = dim3(block, 1, 1);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = pdl ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);
+}
+
 #ifndef FUSED_B
 #define FUSED_B 128  // window (threads) per CTA of f_down / f_up
 #endif
 #ifndef FUSED_MINB
 #define FUSED_MINB 3   // __launch_bounds__ min CTAs per SM for f_down / f_up
 #endif
-#define TAIL_B 1024    // threads (= max elements of the first tail level) of f_tail
+#define TAIL_B 512     // threads (= max elements of the first tail level) of f_tail
 
 // ---- small helpers ---------------------------------------------------------------------------------
 template <int M>
@@ -395,17 +445,20 @@ __global__ void FUSED_BOUNDS(M)
 f_down(const double* __restrict__ mat, int ilo, int iup, const double* __restrict__ b,
        const double* __restrict__ xin, double* __restrict__ xout, const double* __restrict__ P0,
        const double* __restrict__ P1, TransferMap tm, double* __restrict__ rc, int64_t n, double alpha,
-       int nsweep, int zero_guess, int halo, int out, Slab sl) {
+       int nsweep, int zero_guess, WinIdx wi, Slab sl) {
     __shared__ Exchange<M, B> ex;
     __shared__ double rs[M][B + 8];
     __shared__ double ds[DIAG ? M : M * M][B];
+    pdl_launch_dependents();
     const int t = threadIdx.x;
+    const int halo = wi.halo, out = wi.out;
     const int64_t e = (int64_t)blockIdx.x * out - halo + t;     // local element index (ghosts < 0, >= n)
     const bool active = e >= -(int64_t)sl.gl && e < n + sl.gr;
     exch_init<M, B>(ex);
     RegOp<M, ST> A;
     double bb[M], xc[M], xl[M], xr[M];
-    load_blocks<M, B, ST, DIAG>(mat, e, active, A, ds);
+    load_blocks<M, B, ST, DIAG>(mat, e, active, A, ds);         // operator: independent of earlier kernels
+    pdl_wait();                                                  // b, x and everything written below are not
     if (active) {
         load_vec<M>(b + e * M, bb);
         if (zero_guess) {
@@ -440,28 +493,30 @@ f_down(const double* __restrict__ mat, int ilo, int iup, const double* __restric
     __syncthreads();
     const int64_t eg = e + sl.e_off;                            // global element index
     if (mine && eg < tm.n_fine) {
-        const int64_t q = eg + tm.shift;
-        if (q % tm.ratio == 0) {
-            const int64_t Kc = q / tm.ratio + tm.base;          // eg == tm.first(Kc)
+        int kdiv, kmod;                                         // (eg + shift) = ratio * (.. + kdiv) + kmod
+        small_divmod(wi.qmod0 + t, tm.ratio, &kdiv, &kmod);
+        if (kmod == 0) {
+            const int64_t Kc = (int64_t)blockIdx.x * wi.opr + wi.qdiv0 + kdiv + tm.base;   // eg == tm.first(Kc)
             const int64_t Kl = Kc - sl.c_off;                   // local coarse element index
             if (Kc >= 0 && Kc < tm.n_coarse && Kl >= 0 && Kl < sl.nc) {
                 double acc[MC];
 #pragma unroll
                 for (int j = 0; j < MC; ++j) acc[j] = 0.0;
-                if (P1) {
-                    for (int64_t c = tm.first(Kc - 1); c < eg; ++c) {
-                        const double* P = P1 + tm.blk(c) * (M * MC);
-                        const int w = t + (int)(c - eg);
+                if (P1) {                                       // children of Kc - 1: [eg - ratio, eg), clamped
+                    const int k0 = eg >= tm.ratio ? -tm.ratio : -(int)eg;
+                    for (int k = k0; k < 0; ++k) {
+                        const double* P = P1 + win_blk(tm, wi, eg + k, t + k) * (M * MC);
+                        const int w = t + k;
 #pragma unroll
                         for (int j = 0; j < MC; ++j)
 #pragma unroll
                             for (int i = 0; i < M; ++i) acc[j] = fma(P[j * M + i], rs[i][w], acc[j]);
                     }
                 }
-                const int64_t c1 = tm.first(Kc + 1);
-                for (int64_t c = eg; c < c1; ++c) {
-                    const double* P = P0 + tm.blk(c) * (M * MC);
-                    const int w = t + (int)(c - eg);
+                const int k1 = eg + tm.ratio <= tm.n_fine ? tm.ratio : (int)(tm.n_fine - eg);   // own children
+                for (int k = 0; k < k1; ++k) {
+                    const double* P = P0 + win_blk(tm, wi, eg + k, t + k) * (M * MC);
+                    const int w = t + k;
 #pragma unroll
                     for (int j = 0; j < MC; ++j)
 #pragma unroll
@@ -480,23 +535,29 @@ __global__ void FUSED_BOUNDS(M)
 f_up(const double* __restrict__ mat, int ilo, int iup, const double* __restrict__ b,
      const double* __restrict__ xin, double* __restrict__ xout, const double* __restrict__ P0,
      const double* __restrict__ P1, TransferMap tm, const double* __restrict__ xcoarse, int64_t n,
-     double alpha, int nsweep, int halo, int out, double* __restrict__ partial, Slab sl) {
+     double alpha, int nsweep, WinIdx wi, double* __restrict__ partial, Slab sl) {
     __shared__ Exchange<M, B> ex;
     __shared__ double ds[DIAG ? M : M * M][B];
+    pdl_launch_dependents();
     const int t = threadIdx.x;
+    const int halo = wi.halo, out = wi.out;
     const int64_t e = (int64_t)blockIdx.x * out - halo + t;
     const bool active = e >= -(int64_t)sl.gl && e < n + sl.gr;
     exch_init<M, B>(ex);
     RegOp<M, ST> A;
     double bb[M], xc[M], xl[M], xr[M];
-    load_blocks<M, B, ST, DIAG>(mat, e, active, A, ds);
+    load_blocks<M, B, ST, DIAG>(mat, e, active, A, ds);         // operator: independent of earlier kernels
+    pdl_wait();
     if (active) {
         load_vec<M>(b + e * M, bb);
         load_vec<M>(xin + e * M, xc);
         // x += P0 x_c[parent] (+ P1 x_c[parent + 1])   (same operation order as g_prolong)
         const int64_t eg = e + sl.e_off;
-        const int64_t pb = tm.blk(eg) * (M * MC);
-        const double* c0 = xcoarse + (tm.par(eg) - sl.c_off) * MC;
+        const int64_t pb = win_blk(tm, wi, eg, t) * (M * MC);
+        int kdiv, kmod;
+        small_divmod(wi.qmod0 + t, tm.ratio, &kdiv, &kmod);
+        const int64_t par = (int64_t)blockIdx.x * wi.opr + wi.qdiv0 + kdiv + tm.base;   // == tm.par(eg)
+        const double* c0 = xcoarse + (par - sl.c_off) * MC;
         double y[M];
 #pragma unroll
         for (int i = 0; i < M; ++i) y[i] = 0.0;
@@ -591,43 +652,63 @@ f_residual_restrict(const double* __restrict__ mat, int K, int ilo, int iup, con
 }
 
 // ---- single-CTA coarse tail ----------------------------------------------------------------------------
-// The sub-V-cycle of the coarse levels (every level with at most TAIL_B elements, all with the same
-// block size M, block smoother, single-parent closed-form transfers) in ONE CTA: one thread per
-// element, operator blocks in registers per leg, iterates exchanged through shared memory, the coarse
-// right-hand side / correction handed from level to level through shared memory.  Replaces two
-// launches per level (each a few microseconds of latency for a few hundred bytes of work) by one
-// launch for the whole tail.  Arithmetic per element is that of f_down / f_up / g_coarse_solve.
+// The sub-V-cycle of the coarse levels (at most TAIL_B elements each, one block size M, block
+// smoothers, single-parent closed-form transfers) in ONE CTA that works entirely out of shared memory:
+//   * at entry every tail level's operator tiles (and transfer blocks) are copied global -> shared with
+//     cp.async - BEFORE the programmatic-dependency wait, so under PDL this prefetch overlaps the last
+//     f_down of the levels above;
+//   * one thread per element; per leg the element's blocks go shared -> registers, iterates are
+//     exchanged through shared memory, the right-hand sides and pre-smoothed iterates of all tail
+//     levels stay in shared memory between the down and the up leg;
+//   * the only dependent global traffic is the first level's right-hand side in and its iterate out.
+// It replaces two launches per level (each a few microseconds of latency for a few hundred bytes of
+// work) by one launch.  Arithmetic per element is that of f_down / f_up / g_coarse_solve, so the
+// results are bit-identical to the per-level kernels.
+#define TAIL_MAXL 16
 struct TailLevel {
     MatDesc md;
     const double* mat;
     int64_t n;
-    double* x;          // iterate buffer 0 of the level (element 0)
-    double* b;          // right-hand side
+    double* x;          // iterate buffer 0 of the level (element 0); written for the first tail level only
+    double* b;          // right-hand side; read for the first tail level only
     TransferMap tm;     // transfer to the next tail level (unused on the last one)
     const double* P0;
+    int op_off, op_len; // this level's tiles inside the shared operator area (doubles)
+    int vec_off;        // this level's vectors inside the shared b / x areas (doubles)
+    int p_off, p_len;   // this level's transfer blocks inside the shared P area (doubles)
 };
 
-struct TailSmem {
-    template <int M>
-    struct Layout {
-        Exchange<M, TAIL_B> ex;
-        double rs[M][TAIL_B + 8];
-        double ds[M * M][TAIL_B];
-        double cs[M * TAIL_B];   // coarse rhs on the way down, coarse correction on the way up
-        double cw[2 * 32];       // block-Thomas work space
-    };
+// shared-memory carve-up of f_tail (in doubles, after the descriptors)
+struct TailPlan {
+    int n_desc, ex, rs, cw, ops, bvec, xvec, pblk, total;   // offsets; total = size in doubles
 };
+inline TailPlan tail_plan(int m, int op_total, int vec_total, int p_total) {
+    TailPlan p;
+    int o = 0;
+    p.n_desc = o; o += (int)((TAIL_MAXL * sizeof(TailLevel) + 7) / 8);
+    p.ex = o; o += 2 * m * (TAIL_B + 2);
+    p.rs = o; o += m * (TAIL_B + 8);
+    p.cw = o; o += 64;
+    o = (o + 1) & ~1;                                   // 16-byte alignment for cp.async
+    p.ops = o; o += op_total;
+    p.pblk = o; o += (p_total + 1) & ~1;
+    p.bvec = o; o += vec_total;
+    p.xvec = o; o += vec_total;
+    p.total = o;
+    return p;
+}
+
+__device__ __forceinline__ void cp_async16(double* smem_dst, const double* gmem_src) {
+    const unsigned sa = (unsigned)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(sa), "l"(gmem_src) : "memory");
+}
 
 // Dense register copy of the element's operator whatever the level's structure class (entries that
-// the class does not store are exact zeros, so the dense chains give identical results).
+// the class does not store are exact zeros, so the dense chains give identical results).  T points at
+// the element's lane of its (shared-memory) tile.
 template <int M>
-__device__ __forceinline__ void tail_load(const TailLevel& L, int t, bool active, RegOp<M, 0>& A,
-                                          double (*ds)[TAIL_B]) {
-    const MatDesc& d = L.md;
+__device__ __forceinline__ void tail_load(const MatDesc& d, const double* T, bool active, RegOp<M, 0>& A) {
     if (active) {
-        const double* T = L.mat + (t >> 5) * (int64_t)d.K * AMG1D_TILE + (t & 31);
-#pragma unroll
-        for (int k = 0; k < M * M; ++k) ds[k][t] = T[(d.o_dv + k) * AMG1D_TILE];
 #pragma unroll
         for (int k = 0; k < M * M; ++k) A.di[k] = T[(d.o_di + k) * AMG1D_TILE];
         if (d.st == AMG1D_ST_DENSE) {
@@ -649,88 +730,127 @@ __device__ __forceinline__ void tail_load(const TailLevel& L, int t, bool active
         }
     } else {
 #pragma unroll
-        for (int k = 0; k < M * M; ++k) { ds[k][t] = 0.0; A.lo[k] = 0.0; A.di[k] = 0.0; A.up[k] = 0.0; }
+        for (int k = 0; k < M * M; ++k) { A.lo[k] = 0.0; A.di[k] = 0.0; A.up[k] = 0.0; }
     }
+}
+
+// one damped block-Jacobi sweep with Dinv read from the element's shared tile (inactive threads: x stays 0)
+template <int M>
+__device__ __forceinline__ void tail_sweep(const RegOp<M, 0>& A, const double* dcol, bool active,
+                                           const double (&bb)[M], const double (&xl)[M], double (&xc)[M],
+                                           const double (&xr)[M], double alpha, bool zero_guess) {
+    if (active) reg_sweep<M, 0, false, AMG1D_TILE>(A, 0, 0, dcol, bb, xl, xc, xr, alpha, zero_guess);
 }
 
 template <int M>
 __global__ void __launch_bounds__(TAIL_B, 1)
 f_tail(const TailLevel* __restrict__ lv, int nl, const double* __restrict__ fac, int nPre, int nPost,
-       double alpha) {
-    extern __shared__ __align__(16) unsigned char tail_smem[];
-    using SM = TailSmem::Layout<M>;
-    SM& sm = *reinterpret_cast<SM*>(tail_smem);
+       double alpha, TailPlan pl) {
+    extern __shared__ __align__(16) double tsm[];
+    pdl_launch_dependents();
     const int t = threadIdx.x;
-    exch_init<M, TAIL_B>(sm.ex);
+    TailLevel* sd = reinterpret_cast<TailLevel*>(tsm + pl.n_desc);
+    Exchange<M, TAIL_B>& ex = *reinterpret_cast<Exchange<M, TAIL_B>*>(tsm + pl.ex);
+    double (*rs)[TAIL_B + 8] = reinterpret_cast<double (*)[TAIL_B + 8]>(tsm + pl.rs);
+    double* cw = tsm + pl.cw;
+    double* ops = tsm + pl.ops;
+    double* pblk = tsm + pl.pblk;
+    double* bvec = tsm + pl.bvec;
+    double* xvec = tsm + pl.xvec;
+    // descriptors, then every level's operator tiles and transfer blocks: read-only data, fetched before
+    // the dependency wait
+    for (int i = t; i < (int)(nl * sizeof(TailLevel) / 8); i += TAIL_B)
+        (tsm + pl.n_desc)[i] = reinterpret_cast<const double*>(lv)[i];
+    exch_init<M, TAIL_B>(ex);
+    __syncthreads();
+    for (int l = 0; l < nl; ++l) {
+        const TailLevel& L = sd[l];
+        for (int i = 2 * t; i < L.op_len; i += 2 * TAIL_B) cp_async16(ops + L.op_off + i, L.mat + i);
+        for (int i = t; i < L.p_len; i += TAIL_B) cp_async8(pblk + L.p_off + i, L.P0 + i);
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+    pdl_wait();
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
     __syncthreads();
     RegOp<M, 0> A;
     double bb[M], xc[M], xl[M], xr[M];
     int buf = 0;
     // ---- down: zero guess, nPre sweeps, residual, restriction ----
     for (int l = 0; l < nl - 1; ++l) {
-        const TailLevel& L = lv[l];
+        const TailLevel& L = sd[l];
         const bool active = t < L.n;
-        tail_load<M>(L, t, active, A, sm.ds);
+        const double* T = ops + L.op_off + (t >> 5) * (L.md.K * AMG1D_TILE) + (t & 31);
+        const double* dcol = T + L.md.o_dv * AMG1D_TILE;
+        double* bl = bvec + L.vec_off;
+        tail_load<M>(L.md, T, active, A);
 #pragma unroll
         for (int i = 0; i < M; ++i) {
-            bb[i] = active ? (l == 0 ? L.b[t * M + i] : sm.cs[t * M + i]) : 0.0;
+            bb[i] = active ? (l == 0 ? L.b[t * M + i] : bl[t * M + i]) : 0.0;
             xc[i] = 0.0;
+        }
+        if (l == 0 && active) {
+#pragma unroll
+            for (int i = 0; i < M; ++i) bl[t * M + i] = bb[i];       // kept for the up leg
         }
         for (int s = 0; s < nPre; ++s) {
             if (s > 0) {
-                exchange<M, TAIL_B, 0>(sm.ex, buf, 0, 0, xc, xl, xr);
+                exchange<M, TAIL_B, 0>(ex, buf, 0, 0, xc, xl, xr);
                 buf ^= 1;
             }
-            reg_sweep<M, 0, false, TAIL_B>(A, 0, 0, &sm.ds[0][t], bb, xl, xc, xr, alpha, s == 0);
+            tail_sweep<M>(A, dcol, active, bb, xl, xc, xr, alpha, s == 0);
         }
-        if (active) store_vec<M>(L.x + t * M, xc);
-        exchange<M, TAIL_B, 0>(sm.ex, buf, 0, 0, xc, xl, xr);
+        if (active) {
+#pragma unroll
+            for (int i = 0; i < M; ++i) xvec[L.vec_off + t * M + i] = xc[i];
+        }
+        exchange<M, TAIL_B, 0>(ex, buf, 0, 0, xc, xl, xr);
         buf ^= 1;
         double r[M];
         reg_residual<M, 0>(A, 0, 0, bb, xl, xc, xr, r);
 #pragma unroll
-        for (int i = 0; i < M; ++i) sm.rs[i][t] = r[i];
-        __syncthreads();                                   // rs complete; every read of cs is done
+        for (int i = 0; i < M; ++i) rs[i][t] = r[i];
+        __syncthreads();
         const int ratio = L.tm.ratio;
         if (active && (t % ratio) == 0) {
             double acc[M];
 #pragma unroll
             for (int j = 0; j < M; ++j) acc[j] = 0.0;
             for (int c = 0; c < ratio && t + c < L.n; ++c) {
-                const double* P = L.P0 + L.tm.blk(t + c) * (M * M);
+                const double* P = pblk + L.p_off + L.tm.blk(t + c) * (M * M);
 #pragma unroll
                 for (int j = 0; j < M; ++j)
 #pragma unroll
-                    for (int i = 0; i < M; ++i) acc[j] = fma(P[j * M + i], sm.rs[i][t + c], acc[j]);
+                    for (int i = 0; i < M; ++i) acc[j] = fma(P[j * M + i], rs[i][t + c], acc[j]);
             }
-            const int Kc = t / ratio;
-            double* bc = lv[l + 1].b;
+            double* bc = bvec + sd[l + 1].vec_off + (t / ratio) * M;
 #pragma unroll
-            for (int j = 0; j < M; ++j) { bc[Kc * M + j] = acc[j]; sm.cs[Kc * M + j] = acc[j]; }
+            for (int j = 0; j < M; ++j) bc[j] = acc[j];
         }
         __syncthreads();
     }
     // ---- coarsest level: block-Thomas substitution by one warp ----
     {
-        const TailLevel& L = lv[nl - 1];
-        if (t < 32) coarse_solve_warp(fac, M, L.n, L.b, L.x, sm.cw, sm.cw + 32);
-        __syncthreads();
-        for (int64_t i = t; i < L.n * M; i += TAIL_B) sm.cs[i] = L.x[i];
+        const TailLevel& L = sd[nl - 1];
+        if (t < 32) coarse_solve_warp(fac, M, L.n, bvec + L.vec_off, xvec + L.vec_off, cw, cw + 32);
         __syncthreads();
     }
     // ---- up: prolongation + correction, nPost sweeps ----
     for (int l = nl - 2; l >= 0; --l) {
-        const TailLevel& L = lv[l];
+        const TailLevel& L = sd[l];
         const bool active = t < L.n;
-        tail_load<M>(L, t, active, A, sm.ds);
+        const double* T = ops + L.op_off + (t >> 5) * (L.md.K * AMG1D_TILE) + (t & 31);
+        const double* dcol = T + L.md.o_dv * AMG1D_TILE;
+        tail_load<M>(L.md, T, active, A);
         if (active) {
-            load_vec<M>(L.b + t * M, bb);
-            load_vec<M>(L.x + t * M, xc);
-            const double* P = L.P0 + L.tm.blk(t) * (M * M);
-            const double* c0 = sm.cs + (t / L.tm.ratio) * M;
+            const double* P = pblk + L.p_off + L.tm.blk(t) * (M * M);
+            const double* c0 = xvec + sd[l + 1].vec_off + (t / L.tm.ratio) * M;
             double y[M];
 #pragma unroll
-            for (int i = 0; i < M; ++i) y[i] = 0.0;
+            for (int i = 0; i < M; ++i) {
+                bb[i] = bvec[L.vec_off + t * M + i];
+                xc[i] = xvec[L.vec_off + t * M + i];
+                y[i] = 0.0;
+            }
 #pragma unroll
             for (int j = 0; j < M; ++j) {
                 const double cj = c0[j];
@@ -744,15 +864,14 @@ f_tail(const TailLevel* __restrict__ lv, int nl, const double* __restrict__ fac,
             for (int i = 0; i < M; ++i) { bb[i] = 0.0; xc[i] = 0.0; }
         }
         for (int s = 0; s < nPost; ++s) {
-            exchange<M, TAIL_B, 0>(sm.ex, buf, 0, 0, xc, xl, xr);
+            exchange<M, TAIL_B, 0>(ex, buf, 0, 0, xc, xl, xr);
             buf ^= 1;
-            reg_sweep<M, 0, false, TAIL_B>(A, 0, 0, &sm.ds[0][t], bb, xl, xc, xr, alpha, false);
+            tail_sweep<M>(A, dcol, active, bb, xl, xc, xr, alpha, false);
         }
-        __syncthreads();                                   // every read of cs is done
         if (active) {
-            store_vec<M>(L.x + t * M, xc);
 #pragma unroll
-            for (int i = 0; i < M; ++i) sm.cs[t * M + i] = xc[i];
+            for (int i = 0; i < M; ++i) xvec[L.vec_off + t * M + i] = xc[i];
+            if (l == 0) store_vec<M>(L.x + t * M, xc);
         }
         __syncthreads();
     }
@@ -816,10 +935,24 @@ inline bool fused_resnorm(const MatDesc& d, const double* mat, const double* b, 
 
 inline int fused_key(int m, int mc, int st, int diag) { return ((m * 16 + mc) * 4 + st) * 2 + (diag ? 1 : 0); }
 
-// halo and elements emitted per CTA for a leg of nsweep sweeps
-inline void fused_window(int nsweep, int ratio, bool two_parent, int* halo, int* out) {
-    *halo = nsweep + 1 + (two_parent ? ratio : 0);
-    *out = ((FUSED_B - 2 * *halo) / ratio) * ratio;
+// halo, elements emitted per CTA and the 32-bit index constants for a leg of nsweep sweeps
+inline int64_t floordiv64(int64_t a, int64_t b) { int64_t q = a / b; return (a % b != 0 && ((a < 0) != (b < 0))) ? q - 1 : q; }
+inline WinIdx fused_window(int nsweep, const TransferMap& tm, bool wide, const Slab& sl) {
+    WinIdx w;
+    w.halo = nsweep + 1 + (wide ? tm.ratio : 0);
+    w.out = ((FUSED_B - 2 * w.halo) / tm.ratio) * tm.ratio;
+    if (w.out < 1) w.out = 0;
+    w.opr = w.out / tm.ratio;
+    const int64_t q0 = sl.e_off + tm.shift - w.halo;
+    w.qdiv0 = floordiv64(q0, tm.ratio);
+    w.qmod0 = (int)(q0 - w.qdiv0 * tm.ratio);
+    w.pmod0 = -1;
+    if (tm.period > 0 && w.out % tm.period == 0) {
+        const int64_t p0 = sl.e_off - w.halo - tm.n_head;
+        const int64_t pm = p0 - floordiv64(p0, tm.period) * tm.period;            // floormod
+        w.pmod0 = (int)pm + ((tm.ratio + tm.period - 1) / tm.period) * tm.period; // bias: thread offsets >= -ratio
+    }
+    return w;
 }
 
 // tm must be a closed-form map (parent == cp == nullptr); P1 != nullptr selects the two-parent form.
@@ -828,18 +961,15 @@ inline void fused_window(int nsweep, int ratio, bool two_parent, int* halo, int*
 inline bool fused_down(const MatDesc& d, int mc, const TransferMap& tm, int nsweep, bool zero,
                        const double* mat, const double* b, const double* xin, double* xout,
                        const double* P0, const double* P1, double* rc, int64_t n, int64_t n_cover,
-                       double alpha, const Slab& sl, cudaStream_t st) {
-    int halo, out;
-    fused_window(nsweep, tm.ratio, P1 != nullptr || tm.shift != 0 || tm.base != 0, &halo, &out);
-    if (out < tm.ratio || out < FUSED_B / 2 || !fast_tier_ok(d)) return false;
-    const unsigned grid = (unsigned)((n_cover + out - 1) / out);
+                       double alpha, const Slab& sl, cudaStream_t st, bool pdl) {
+    const WinIdx w = fused_window(nsweep, tm, P1 != nullptr || tm.shift != 0 || tm.base != 0, sl);
+    if (w.out < tm.ratio || w.out < FUSED_B / 2 || !fast_tier_ok(d)) return false;
+    const unsigned grid = (unsigned)((n_cover + w.out - 1) / w.out);
     switch (fused_key(d.m, mc, d.st, d.diag)) {
 #define X(MM, MCC, SS, DG)                                                                               \
     case ((MM * 16 + MCC) * 4 + SS) * 2 + (DG ? 1 : 0):                                                  \
-        f_down<MM, MCC, FUSED_B, SS, DG><<<grid, FUSED_B, 0, st>>>(mat, d.ilo, d.iup, b, xin, xout, P0, P1, \
-                                                                    tm, rc, n, alpha, nsweep, zero ? 1 : 0, \
-                                                                    halo, out, sl);                      \
-        return true;
+        return launch_fused(f_down<MM, MCC, FUSED_B, SS, DG>, grid, FUSED_B, 0, st, pdl, mat, d.ilo, d.iup, b, \
+                            xin, xout, P0, P1, tm, rc, n, alpha, nsweep, zero ? 1 : 0, w, sl) == cudaSuccess;
         FUSED_COMBOS(X)
 #undef X
         default: return false;
@@ -849,20 +979,17 @@ inline bool fused_down(const MatDesc& d, int mc, const TransferMap& tm, int nswe
 inline bool fused_up(const MatDesc& d, int mc, const TransferMap& tm, int nsweep, const double* mat,
                      const double* b, const double* xin, double* xout, const double* P0,
                      const double* P1, const double* xcoarse, int64_t n, double alpha, double* partial,
-                     int64_t partial_cap, int* nblocks, const Slab& sl, cudaStream_t st) {
-    int halo, out;
-    fused_window(nsweep, tm.ratio, false, &halo, &out);
-    if (out < tm.ratio || out < FUSED_B / 2 || !fast_tier_ok(d)) return false;
-    const int64_t grid = (n + out - 1) / out;
+                     int64_t partial_cap, int* nblocks, const Slab& sl, cudaStream_t st, bool pdl) {
+    const WinIdx w = fused_window(nsweep, tm, false, sl);
+    if (w.out < tm.ratio || w.out < FUSED_B / 2 || !fast_tier_ok(d)) return false;
+    const int64_t grid = (n + w.out - 1) / w.out;
     if (partial && grid > partial_cap) return false;
     if (nblocks) *nblocks = (int)grid;
     switch (fused_key(d.m, mc, d.st, d.diag)) {
 #define X(MM, MCC, SS, DG)                                                                               \
     case ((MM * 16 + MCC) * 4 + SS) * 2 + (DG ? 1 : 0):                                                  \
-        f_up<MM, MCC, FUSED_B, SS, DG><<<(unsigned)grid, FUSED_B, 0, st>>>(mat, d.ilo, d.iup, b, xin, xout, \
-                                                                            P0, P1, tm, xcoarse, n, alpha, \
-                                                                            nsweep, halo, out, partial, sl); \
-        return true;
+        return launch_fused(f_up<MM, MCC, FUSED_B, SS, DG>, (unsigned)grid, FUSED_B, 0, st, pdl, mat, d.ilo, \
+                            d.iup, b, xin, xout, P0, P1, tm, xcoarse, n, alpha, nsweep, w, partial, sl) == cudaSuccess;
         FUSED_COMBOS(X)
 #undef X
         default: return false;
@@ -894,34 +1021,28 @@ inline bool fused_residual_restrict(const MatDesc& d, int mc, const TransferMap&
 
 // Block sizes with a single-CTA tail kernel.
 inline bool tail_supported(int m) { return m == 1 || m == 2; }
+#define TAIL_SMEM_MAX (227 * 1024)
 
 template <int M>
-inline cudaError_t tail_configure_t() {
-    return cudaFuncSetAttribute(f_tail<M>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                (int)sizeof(TailSmem::Layout<M>));
+inline cudaError_t tail_configure_t(size_t smem) {
+    return cudaFuncSetAttribute(f_tail<M>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
 }
 
-// once per device context, before the first launch (amg1d_finalize)
-inline cudaError_t tail_configure(int m) {
+// once per device context and tail shape, before the first launch (amg1d_finalize)
+inline cudaError_t tail_configure(int m, size_t smem) {
     switch (m) {
-        case 1: return tail_configure_t<1>();
-        case 2: return tail_configure_t<2>();
+        case 1: return tail_configure_t<1>(smem);
+        case 2: return tail_configure_t<2>(smem);
         default: return cudaErrorInvalidValue;
     }
 }
 
-template <int M>
-inline cudaError_t tail_launch_t(const TailLevel* lv, int nl, const double* fac, int nPre, int nPost,
-                                 double alpha, cudaStream_t st) {
-    f_tail<M><<<1, TAIL_B, sizeof(TailSmem::Layout<M>), st>>>(lv, nl, fac, nPre, nPost, alpha);
-    return cudaGetLastError();
-}
-
 inline cudaError_t tail_launch(int m, const TailLevel* lv, int nl, const double* fac, int nPre, int nPost,
-                               double alpha, cudaStream_t st) {
+                               double alpha, const TailPlan& pl, cudaStream_t st, bool pdl) {
+    const size_t smem = (size_t)pl.total * 8;
     switch (m) {
-        case 1: return tail_launch_t<1>(lv, nl, fac, nPre, nPost, alpha, st);
-        case 2: return tail_launch_t<2>(lv, nl, fac, nPre, nPost, alpha, st);
+        case 1: return launch_fused(f_tail<1>, 1, TAIL_B, smem, st, pdl, lv, nl, fac, nPre, nPost, alpha, pl);
+        case 2: return launch_fused(f_tail<2>, 1, TAIL_B, smem, st, pdl, lv, nl, fac, nPre, nPost, alpha, pl);
         default: return cudaErrorInvalidValue;
     }
 }

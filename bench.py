@@ -268,6 +268,9 @@ def run_gpu(args):
     dev = U.upload(device=local, stream=stream, dist=dist_arg)
     dev.synchronize()
     t_setup = time.perf_counter() - t_setup
+    for kv in args.opt:
+        k, v = kv.split("=")
+        dev.set_option(k, int(v))
     N0 = dev.info("local_dofs")                   # DOFs (slots) of this rank's slab of the fine level
     N0_all = U.levels[0].n * U.levels[0].m        # whole fine level
     upd = U.dof_updates_per_cycle()               # whole job
@@ -371,8 +374,15 @@ def run_gpu(args):
     barrier()
     t_solve = max_over_ranks(time.perf_counter() - t0)
     nb = dev.dev_rhs_norm()
-    solve = {"iters": it.value, "seconds_e2e": t_solve, "final_relative_residual": float(res[it.value - 1] / nb),
+    rel = float(res[it.value - 1] / nb)
+    solve = {"iters": it.value, "seconds_e2e": t_solve, "final_relative_residual": rel, "converged": rel < 1e-10,
              "call": "amg1d_solve (multigrid(H, x0, b, 100, 1e-10)), host b in / host x out"}
+    if not solve["converged"]:
+        # CG-first hierarchy at 2^26 elements: cond(A) ~ n^2 = 4.5e15 ~ 1 / eps; the Galerkin coarse
+        # operators lose their smoothest modes to rounding and the cycle stops contracting below ~1e-7
+        # (same history in the generic tier; converges in 16 cycles at 2^25 - see DESIGN.md)
+        solve["note"] = ("not converged to 1e-10: FP64 conditioning limit of this problem size "
+                         "(cond ~ n^2 ~ 1/eps); throughput figures are unaffected")
 
     # ---- CPU baseline beside it (oracle port, bounded sample) ----------------------------------------
     cpu = None
@@ -396,7 +406,7 @@ def run_gpu(args):
                    if dev.info("device_bytes") > 2 ** 29 else "working set comparable to L2; no flush",
                    "structure_classes": [dev.info(f"structure:{l}") for l in range(min(4, len(U.levels)))],
                    "tile_rows": [U.tile_rows(l) for l in range(min(4, len(U.levels)))],
-                   "tail_start": dev.info("tail_start"),
+                   "tail_start": dev.info("tail_start"), "options": args.opt,
                    "device_bytes": dev.info("device_bytes"), "setup_s": t_setup, "rhs_assembly_s": t_rhs,
                    "residual_after_timed_steps": res_after},
         "roofline": roofline, "cpu_baseline": cpu, "clocks": clocks, "e2e": e2e,
@@ -419,6 +429,8 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="T", choices=sorted(WORKLOADS))
     ap.add_argument("--no-cpu", action="store_true", help="skip the CPU baseline leg")
+    ap.add_argument("--opt", action="append", default=[], metavar="KEY=VALUE",
+                    help="amg1d_set_option after the upload (A/B experiments, e.g. --opt pdl=0)")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "b200":
         args.warmup = 3

@@ -66,6 +66,11 @@ def test_properties_at_baseline_sizes(log2n):
     assert np.array_equal(dev.vcycle(x0, b), x1)
     dev.set_option("coarse_cta_elems", 1024)
     assert dev.info("structure:0") == 1 and dev.info("tile_rows:0") == 40      # 4 + 16 + 4 + 16 doubles
+    # every level above the tail runs as exactly one fused kernel per leg (a silent fall-back to the
+    # streaming kernels would show up here as 4-5 launches per level)
+    dev.dev_vcycle(with_residual_norm=True)
+    dev.synchronize()
+    assert dev.info("launches_per_cycle") <= 2 * dev.info("tail_start") + 1 + 3
     # both kernel tiers give bit-identical iterates (generic tier only at 2^20: it is ~4x slower)
     if log2n <= 20:
         dev.set_option("fused", 0)
@@ -161,6 +166,7 @@ def test_c4_shape_at_scale():
     assert it <= 20 and np.all(np.diff(res) < 0) and res[-1] < 1e-10 * np.linalg.norm(b)
     x1 = dev.vcycle(np.zeros(len(b)), b)
     assert np.array_equal(dev.vcycle(np.zeros(len(b)), 2.0 * b), 2.0 * x1)
+    assert dev.info("launches_per_cycle") <= 2 * dev.info("tail_start") + 1      # CG levels fused too
     dev.set_option("fused", 0)
     assert np.array_equal(dev.vcycle(np.zeros(len(b)), b), x1)       # generic tier, same bits
     dev.close()
