@@ -16,22 +16,35 @@ import dist_emulation as emu                              # noqa: E402
 
 def main():
     out, n = sys.argv[1], int(sys.argv[2])
+    kind = sys.argv[3] if len(sys.argv) > 3 else "dg"
     dist.init_process_group("gloo")
     rank, world = dist.get_rank(), dist.get_world_size()
     nlev = int(round(math.log2(n)))
-    U = uniform.UniformDgHierarchy(n, [3, 1], [2] * nlev, xin=0.0, xout=float(n), CDir=1000.0)
     w = 2.0 * math.pi / 64.0
-    b = U.rhs(lambda x: w * w * np.cos(w * x), [0.0, math.cos(w * n)])
+    func, vals = (lambda x: w * w * np.cos(w * x)), [0.0, math.cos(w * n)]
     nloc = n // world
+    if kind == "cg":      # BASELINE C4 shape: slabs of vertex groups, closing group on the last rank
+        U = uniform.UniformCgHierarchy(n, [3, 1], [1], [2] * nlev, xin=0.0, xout=float(n), CDir=1000.0)
+        b = U.rhs(func, vals)
+        lo, hi = rank * nloc, (rank + 1) * nloc + (1 if rank == world - 1 else 0)
+        b_loc = U.rhs(func, vals, group_range=(lo, hi))
+        gd = 4 + 1
+    else:
+        U = uniform.UniformDgHierarchy(n, [3, 1], [2] * nlev, xin=0.0, xout=float(n), CDir=1000.0)
+        b = U.rhs(func, vals)
+        lo, hi = rank * nloc, (rank + 1) * nloc
+        b_loc = U.rhs(func, vals, elem_range=(lo, hi))
+        gd = 4
+    m0 = U.levels[0].m
     # each rank assembles only its own slab of the right-hand side
-    b_loc = U.rhs(lambda x: w * w * np.cos(w * x), [0.0, math.cos(w * n)],
-                  elem_range=(rank * nloc, (rank + 1) * nloc))
-    assert np.array_equal(b_loc, b[rank * nloc * 4:(rank + 1) * nloc * 4])
+    assert np.array_equal(b_loc, b[lo * m0:hi * m0])
     rng = np.random.default_rng(3)
     x0 = rng.standard_normal(len(b))
+    if kind == "cg":
+        x0.reshape(-1, m0)[n, 1:] = 0.0                   # padding slots of the closing group
     res = {}
     for key, (nPre, nPost) in {"33": (3, 3), "12": (1, 2), "03": (0, 3)}.items():
-        res[key] = emu.vcycle(U, x0, b, rank, world, nPre=nPre, nPost=nPost)
+        res[key] = emu.vcycle(U, x0, b, rank, world, nPre=nPre, nPost=nPost, gd=gd)
     parts = [None] * world
     dist.gather_object(res, parts if rank == 0 else None, dst=0)
     if rank == 0:

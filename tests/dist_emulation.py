@@ -9,7 +9,7 @@ import numpy as np
 import torch
 import torch.distributed as dist
 
-from agglomerationmultigrid1d_b200.slabs import plan_slabs
+from agglomerationmultigrid1d_b200.slabs import plan_slabs, slab_size, slab_start
 
 
 class Comm:
@@ -56,12 +56,41 @@ def residual(ops, b, x):
                 + np.einsum("eij,ej->ei", up, xr))
 
 
+def transfer_of(U, l):
+    """(parent, P0, P1) of transfer l with explicit global arrays: fine element e receives
+    P0[e] x_c[parent[e]] + P1[e] x_c[parent[e] + 1]  (P1 None for single-parent transfers)."""
+    if hasattr(U, "cg_orders"):
+        return U.transfer_blocks(l)
+    P, ratio = U.transfers[l]
+    e = np.arange(U.levels[l].n)
+    return e // ratio, P[e % ratio], None
+
+
+def level_ratios(U):
+    if hasattr(U, "cg_orders"):
+        return [t["ratio"] for t in U.cg_transfers] + [r for (_, r) in U.transfers]
+    return [r for (_, r) in U.transfers]
+
+
+def smoother_inverse(U, l, di):
+    """Block Jacobi (DG-type levels) or point Jacobi (CG levels) as explicit inverse blocks."""
+    if getattr(U.levels[l], "is_cg", False):
+        d = np.zeros_like(di)
+        idx = np.arange(di.shape[1])
+        d[:, idx, idx] = 1.0 / di[:, idx, idx]
+        return d
+    return np.linalg.inv(di)
+
+
 def vcycle(U, x0_glob, b_glob, rank, world, nPre=3, nPost=3, alpha=2.0 / 3.0, shard_min=16, gd=4):
-    """Returns this rank's owned slab of x after one V-cycle (the whole vector when world == 1)."""
+    """Returns this rank's owned slab of x after one V-cycle (the whole vector when world == 1).
+    Works for DG-first hierarchies (single-parent transfers, slabs of elements) and CG-first ones
+    (two-parent transfers across the slab edges, slabs of vertex groups with the closing group on the
+    last rank); gd must be max(nPre, nPost) + 1 (+ the ratio of the two-parent transfers)."""
     comm = Comm(rank, world)
     nL = len(U.levels)
     sizes = [lv.n for lv in U.levels]
-    ratios = [r for (_, r) in U.transfers]
+    ratios = level_ratios(U)
     plan, g = plan_slabs(sizes, ratios, rank, world, shard_min=shard_min, ghost_depth=gd)
     ops, b, x = [None] * nL, [None] * nL, [None] * nL
     for l, sl in enumerate(plan):
@@ -71,7 +100,7 @@ def vcycle(U, x0_glob, b_glob, rank, world, nPre=3, nPost=3, alpha=2.0 / 3.0, sh
         lo, di, up = U.level_blocks(l)
         a, e = sl.start - sl.gl, sl.start + sl.n + sl.gr
         if sl.present:
-            ops[l] = (lo[a:e], di[a:e], up[a:e], np.linalg.inv(di[a:e]))
+            ops[l] = (lo[a:e], di[a:e], up[a:e], smoother_inverse(U, l, di[a:e]))
         b[l] = np.zeros((e - a, m))
         x[l] = np.zeros((e - a, m))
     own = lambda l: slice(plan[l].gl, plan[l].gl + plan[l].n)             # noqa: E731
@@ -83,7 +112,7 @@ def vcycle(U, x0_glob, b_glob, rank, world, nPre=3, nPost=3, alpha=2.0 / 3.0, sh
         halo(comm, b[0], s0.n, gd)
     # proxy slab of the gather level on ranks > 0
     if world > 1 and rank > 0:
-        ng = sizes[g] // world
+        ng = slab_size(sizes[g], world, rank)
         mg = U.levels[g].m
         b[g] = np.zeros((ng, mg))
         x[g] = np.zeros((gd + ng + (gd if rank < world - 1 else 0), mg))
@@ -92,7 +121,7 @@ def vcycle(U, x0_glob, b_glob, rank, world, nPre=3, nPost=3, alpha=2.0 / 3.0, sh
         sl = plan[l]
         if not sl.present:
             break
-        P, ratio = U.transfers[l]
+        parent, P0, P1 = transfer_of(U, l)
         zero = l > 0
         if sl.sharded and not zero:
             halo(comm, x[l], sl.n, gd)
@@ -101,11 +130,20 @@ def vcycle(U, x0_glob, b_glob, rank, world, nPre=3, nPost=3, alpha=2.0 / 3.0, sh
             xx = sweep(ops[l], b[l], xx, alpha, zero and s == 0)
         r = residual(ops[l], b[l], xx)
         x[l][own(l)] = xx[own(l)]
-        ro = r[own(l)]
-        eg = sl.start + np.arange(sl.n)
-        t = np.einsum("eij,ei->ej", P[eg % ratio], ro)
-        rc = t.reshape(sl.n // ratio, ratio, -1).sum(axis=1) if ratio > 1 else t
+        # restriction into this rank's coarse elements, from the slab extended by its ghosts (stale
+        # values near the ghost edge included, exactly what the kernel's window would read)
         nxt = plan[l + 1]
+        c_lo = slab_start(sizes[l + 1], world, rank) if sl.sharded else 0
+        c_n = slab_size(sizes[l + 1], world, rank) if sl.sharded else sizes[l + 1]
+        eg = (sl.start - sl.gl) + np.arange(r.shape[0])
+        rc = np.zeros((c_n, U.levels[l + 1].m))
+        for P, off in ((P0, 0), (P1, 1)):
+            if P is None:
+                continue
+            t = np.einsum("eij,ei->ej", P[eg], r)
+            k = parent[eg] + off - c_lo
+            ok = (k >= 0) & (k < c_n)
+            np.add.at(rc, k[ok], t[ok])
         if sl.sharded:
             halo(comm, x[l], sl.n, gd)
             if nxt.sharded:
@@ -135,25 +173,29 @@ def vcycle(U, x0_glob, b_glob, rank, world, nPre=3, nPost=3, alpha=2.0 / 3.0, sh
         sl, nxt = plan[l], plan[l + 1]
         if not sl.present:
             continue
-        P, ratio = U.transfers[l]
+        parent, P0, P1 = transfer_of(U, l)
         if sl.sharded and not nxt.sharded:                  # scatter rank 0 -> slabs (+ ghosts)
-            ng = sizes[l + 1] // world
             if rank == 0:
-                objs = [x[l + 1][max(0, r * ng - gd):(r + 1) * ng + (gd if r < world - 1 else 0)]
-                        for r in range(world)]
+                objs = []
+                for r_ in range(world):
+                    c0, cn = slab_start(sizes[l + 1], world, r_), slab_size(sizes[l + 1], world, r_)
+                    objs.append(x[l + 1][max(0, c0 - gd):c0 + cn + (gd if r_ < world - 1 else 0)])
             else:
                 objs = None
             got = [None]
             dist.scatter_object_list(got, objs, src=0)
-            xc, c_first = (x[l + 1], 0) if rank == 0 else (got[0], rank * ng - gd)
+            xc, c_first = (x[l + 1], 0) if rank == 0 else (got[0], slab_start(sizes[l + 1], world, rank) - gd)
         else:
             xc, c_first = x[l + 1], nxt.start - nxt.gl
         a = sl.start - sl.gl
         eg = a + np.arange(x[l].shape[0])
-        par = eg // ratio - c_first
-        ok = (par >= 0) & (par < xc.shape[0])
         xx = x[l].copy()
-        xx[ok] = xx[ok] + np.einsum("eij,ej->ei", P[eg[ok] % ratio], xc[par[ok]])
+        for P, off in ((P0, 0), (P1, 1)):
+            if P is None:
+                continue
+            par = parent[eg] + off - c_first
+            ok = (par >= 0) & (par < xc.shape[0])
+            xx[ok] = xx[ok] + np.einsum("eij,ej->ei", P[eg[ok]], xc[par[ok]])
         for s in range(nPost):
             xx = sweep(ops[l], b[l], xx, alpha, False)
         x[l][own(l)] = xx[own(l)]
