@@ -18,7 +18,7 @@ from .interpolation import (cg_cg_interpolation, dg_dg_interpolation, dg_cg_inte
                             aggdg_aggdg_interpolation, aggdg_dg_interpolation, aggdg_cg_interpolation)
 from .smoother import AbstractSmoother, JacobiSmoother, BlockJacobi, cg_smoother, dg_smoother
 from .mesh_hierarchy import MeshHierarchy, dg_flux_operators
-from .solvers import (multigrid_v_cycle, multigrid, ldiv, iterative_smoother_solve, apply_smoother)
+from .solvers import (multigrid_v_cycle, multigrid, ldiv, pcg, iterative_smoother_solve, apply_smoother)
 from .device import DeviceHierarchy
 from ._capi import Amg1dError
 

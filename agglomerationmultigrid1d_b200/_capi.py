@@ -38,6 +38,9 @@ PROTOTYPES = {
     "amg1d_vcycle": (C.c_int, [_h, _pd, _pd, C.c_int, C.c_int, C.c_double]),
     "amg1d_solve": (C.c_int, [_h, _pd, _pd, C.c_int, C.c_double, C.c_int, C.c_int, C.c_double,
                               C.POINTER(C.c_int), _pd, _pd, _pd]),
+    "amg1d_ldiv": (C.c_int, [_h, _pd, _pd, C.c_int, C.c_int, C.c_double]),
+    "amg1d_pcg": (C.c_int, [_h, _pd, _pd, C.c_int, C.c_double, C.c_int, C.c_int, C.c_double,
+                            C.POINTER(C.c_int), _pd]),
     "amg1d_apply_smoother": (C.c_int, [_h, C.c_int, _pd, _pd, C.c_int64, C.c_double]),
     "amg1d_smoother_solve": (C.c_int, [_h, C.c_int, _pd, _pd, C.c_int, C.c_double, C.c_double,
                                        C.POINTER(C.c_int), _pd, _pd, _pd]),

@@ -109,11 +109,19 @@ struct amg1d {
     int tail_start = -1;
     TailLevel* d_tail = nullptr;
     TailPlan tail_plan_ = {};
-    // graph cache
-    cudaGraphExec_t gexec = nullptr;
-    int g_pre = -1, g_post = -1, g_norm = -1;
-    double g_alpha = 0.0;
+    // graph cache: a few instantiated V-cycle graphs keyed by (nPre, nPost, alpha, norm, zero guess)
+    struct GraphEntry {
+        cudaGraphExec_t exec = nullptr;
+        int pre = -1, post = -1, norm = -1, zero0 = -1;
+        double alpha = 0.0;
+        int64_t launches = 0;
+        uint64_t stamp = 0;
+    };
+    GraphEntry graphs[4];
+    uint64_t graph_clock = 0;
     int64_t launches_per_cycle = 0;
+    // conjugate gradients (amg1d_pcg): solution, search direction, A p - allocated at the first call
+    DVec cg_x, cg_p, cg_ap;
     int64_t launch_counter = 0;
     int64_t device_bytes = 0;
     // per-kernel event profiling (option "profile"): one (start, stop) pair per launch of a leg
@@ -461,6 +469,53 @@ int op_resnorm(amg1d* h, int l, int slot) {
     return op_norm(h, h->scratch.p, nullptr, lv.n * lv.m, slot);
 }
 
+// d_scal[slot] = sum partial[0..np) (no square root), summed over the ranks in the sharded case
+int op_sum_partials(amg1d* h, int64_t np, int slot) {
+    const double* src = h->partial;
+    if (np > 8192) {
+        double* stage2 = h->partial + h->partial_cap;
+        k_sum_partial<<<256, AMG1D_RED_THREADS, 0, h->stream>>>(h->partial, np, stage2);
+        h->launch_counter++;
+        src = stage2;
+        np = 256;
+    }
+    k_reduce_final<<<1, AMG1D_RED_THREADS, 0, h->stream>>>(src, (int)np, h->d_scal, slot, 0);
+    h->launch_counter++;
+    LAUNCH_CHECK();
+#ifdef AMG1D_WITH_NCCL
+    if (h->nranks > 1) {
+        NCK(g_nccl.AllReduce(h->d_scal + slot, h->d_scal + slot, 1, ncclDouble, ncclSum, h->comm, h->stream));
+        h->launch_counter++;
+    }
+#endif
+    return AMG1D_OK;
+}
+
+// slot <- a . c over the owned entries
+int op_dot(amg1d* h, const double* a, const double* c, int64_t n, int slot) {
+    int nb = (int)std::min<int64_t>(AMG1D_RED_BLOCKS, (n + AMG1D_RED_THREADS - 1) / AMG1D_RED_THREADS);
+    if (nb < 1) nb = 1;
+    k_dot_partial<<<nb, AMG1D_RED_THREADS, 0, h->stream>>>(a, c, n, h->partial);
+    h->launch_counter++;
+    LAUNCH_CHECK();
+    return op_sum_partials(h, nb, slot);
+}
+
+// y = A x on level l (x must carry valid ghost elements), slot <- x . y when slot >= 0
+int op_matvec_dot(amg1d* h, int l, double* x, double* y, int slot) {
+    Level& lv = h->L[l];
+    if (lv.sharded) RET(op_halo(h, x, lv.n, lv.m));
+    int nb = 0;
+    if (h->opt_fused && fused_matvec_dot(lv.md, lv.mat, x, y, lv.n, slot >= 0 ? h->partial : nullptr,
+                                         h->partial_cap, &nb, h->stream)) {
+        h->launch_counter++;
+        LAUNCH_CHECK();
+        return slot >= 0 ? op_sum_partials(h, nb, slot) : AMG1D_OK;
+    }
+    RET(op_apply(h, l, nullptr, x, y, 0));
+    return slot >= 0 ? op_dot(h, x, y, lv.n * lv.m, slot) : AMG1D_OK;
+}
+
 int prof_mark(amg1d* h, int level, int leg) {
     if (!h->opt_profile) return AMG1D_OK;
     if (h->prof.size() < (size_t)h->n_levels * 2) h->prof.resize((size_t)h->n_levels * 2);
@@ -473,11 +528,11 @@ int prof_mark(amg1d* h, int level, int leg) {
 
 // ---- the V-cycle (src/solvers.jl:19-50) ------------------------------------------------------------
 // Down leg of level l: nPre sweeps (zero guess on l > 0), residual, restriction into level l+1's rhs.
-int leg_down(amg1d* h, int l, int nPre, double alpha) {
+int leg_down(amg1d* h, int l, int nPre, double alpha, bool zero0) {
     Level& lv = h->L[l];
     Transfer& t = h->T[l];
     Level& lc = h->L[l + 1];
-    const bool zero = l > 0;
+    const bool zero = l > 0 || zero0;         // zero0: level 0 starts from a zero guess too (ldiv!, PCG)
     if (zero) lv.cur = 0;
     RET(prof_mark(h, l, 0));
     if (lv.sharded && !zero) RET(op_halo(h, lv.x[lv.cur].p, lv.n, lv.m));   // ghosts of the incoming iterate
@@ -551,7 +606,7 @@ int leg_up(amg1d* h, int l, int nPost, double alpha, bool fuse_norm, bool* norm_
     return prof_mark(h, l, 1);
 }
 
-int enqueue_vcycle(amg1d* h, int nPre, int nPost, double alpha, bool want_norm) {
+int enqueue_vcycle(amg1d* h, int nPre, int nPost, double alpha, bool want_norm, bool zero0) {
     const int nl = h->n_levels;
     const int g = h->gather_level;          // -1 on a single GPU: every level is local
     bool norm_done = false;
@@ -569,7 +624,7 @@ int enqueue_vcycle(amg1d* h, int nPre, int nPost, double alpha, bool want_norm) 
     for (int l = 0; l < nl - 1 && l < ts; ++l) {
         Level& lv = h->L[l];
         if (!lv.present) break;                       // ranks > 0 stop at the gather level
-        RET(leg_down(h, l, nPre, alpha));
+        RET(leg_down(h, l, nPre, alpha, zero0));
         if (lv.sharded) {
             Level& lc = h->L[l + 1];
             RET(op_halo(h, lv.x[lv.cur].p, lv.n, lv.m));              // pre-smoothed iterate, for the up leg
@@ -586,7 +641,7 @@ int enqueue_vcycle(amg1d* h, int nPre, int nPost, double alpha, bool want_norm) 
         h->launch_counter++;
     } else if (h->L[nl - 1].present) {
         Level& lv = h->L[nl - 1];
-        if (nl > 1) lv.cur = 0;
+        if (nl > 1 || zero0) lv.cur = 0;
         RET(op_coarse(h, lv.b.p, lv.x[lv.cur].p));   // single level: x = A \ b overwrites x
     }
     // ---- up ----
@@ -608,42 +663,52 @@ int enqueue_vcycle(amg1d* h, int nPre, int nPost, double alpha, bool want_norm) 
     return AMG1D_OK;
 }
 
-int run_vcycle(amg1d* h, int nPre, int nPost, double alpha, bool want_norm) {
+int run_vcycle(amg1d* h, int nPre, int nPost, double alpha, bool want_norm, bool zero0 = false) {
     if (nPre < 0 || nPost < 0) return fail(h, AMG1D_ERR_ARG, "nPre and nPost must be >= 0");
     if (!h->opt_graph || h->opt_profile) {
         const int64_t c0 = h->launch_counter;
-        RET(enqueue_vcycle(h, nPre, nPost, alpha, want_norm));
+        RET(enqueue_vcycle(h, nPre, nPost, alpha, want_norm, zero0));
         h->launches_per_cycle = h->launch_counter - c0;
         h->norm_valid = want_norm;
         return AMG1D_OK;
     }
-    if (!h->gexec || h->g_pre != nPre || h->g_post != nPost || h->g_alpha != alpha ||
-        h->g_norm != (int)want_norm) {
-        if (h->gexec) { cudaGraphExecDestroy(h->gexec); h->gexec = nullptr; }
+    amg1d::GraphEntry* ge = nullptr;
+    for (auto& g : h->graphs)
+        if (g.exec && g.pre == nPre && g.post == nPost && g.alpha == alpha && g.norm == (int)want_norm &&
+            g.zero0 == (int)zero0)
+            ge = &g;
+    if (!ge) {
+        ge = &h->graphs[0];                               // free slot, else the least recently used one
+        for (auto& g : h->graphs) if (!g.exec) { ge = &g; break; } else if (g.stamp < ge->stamp) ge = &g;
+        if (ge->exec) { cudaGraphExecDestroy(ge->exec); ge->exec = nullptr; }
         if (h->L[0].cur != 0) return fail(h, AMG1D_ERR_STATE, "internal: level-0 buffer parity");
         cudaGraph_t g = nullptr;
         const int64_t c0 = h->launch_counter;
         CK(cudaStreamBeginCapture(h->stream, cudaStreamCaptureModeThreadLocal));
-        int rc = enqueue_vcycle(h, nPre, nPost, alpha, want_norm);
+        int rc = enqueue_vcycle(h, nPre, nPost, alpha, want_norm, zero0);
         cudaError_t ce = cudaStreamEndCapture(h->stream, &g);
         if (rc != AMG1D_OK) { if (g) cudaGraphDestroy(g); return rc; }
         if (ce != cudaSuccess) return fail(h, AMG1D_ERR_CUDA, "graph capture failed: %s", cudaGetErrorString(ce));
-        h->launches_per_cycle = h->launch_counter - c0;
+        ge->launches = h->launch_counter - c0;
         h->launch_counter = c0;
-        ce = cudaGraphInstantiate(&h->gexec, g, 0);
+        ce = cudaGraphInstantiate(&ge->exec, g, 0);
         cudaGraphDestroy(g);
-        if (ce != cudaSuccess) return fail(h, AMG1D_ERR_CUDA, "graph instantiate failed: %s", cudaGetErrorString(ce));
-        h->g_pre = nPre; h->g_post = nPost; h->g_alpha = alpha; h->g_norm = (int)want_norm;
+        if (ce != cudaSuccess) { ge->exec = nullptr; return fail(h, AMG1D_ERR_CUDA, "graph instantiate failed: %s", cudaGetErrorString(ce)); }
+        ge->pre = nPre; ge->post = nPost; ge->alpha = alpha; ge->norm = (int)want_norm; ge->zero0 = (int)zero0;
     }
-    CK(cudaGraphLaunch(h->gexec, h->stream));
-    h->launch_counter += h->launches_per_cycle;
+    ge->stamp = ++h->graph_clock;
+    CK(cudaGraphLaunch(ge->exec, h->stream));
+    h->launches_per_cycle = ge->launches;
+    h->launch_counter += ge->launches;
     h->norm_valid = want_norm;
     return AMG1D_OK;
 }
 
 void invalidate_graph(amg1d* h) {
-    if (h->gexec) { cudaGraphExecDestroy(h->gexec); h->gexec = nullptr; }
-    h->g_pre = h->g_post = h->g_norm = -1;
+    for (auto& g : h->graphs) {
+        if (g.exec) cudaGraphExecDestroy(g.exec);
+        g = amg1d::GraphEntry();
+    }
     h->norm_valid = false;
 }
 
@@ -986,7 +1051,8 @@ int amg1d_destroy(amg1d_t* h) {
     if (!h) return AMG1D_OK;
     cudaSetDevice(h->device);
     cudaStreamSynchronize(h->stream);
-    if (h->gexec) cudaGraphExecDestroy(h->gexec);
+    for (auto& g : h->graphs) if (g.exec) cudaGraphExecDestroy(g.exec);
+    vec_free(h->cg_x); vec_free(h->cg_p); vec_free(h->cg_ap);
     for (auto& pr : h->prof) for (auto ev : pr.ev) cudaEventDestroy(ev);
     for (auto& lv : h->L) {
         if (lv.mat_alloc) cudaFree(lv.mat_alloc);
@@ -1434,6 +1500,80 @@ int amg1d_solve(amg1d_t* h, double* x, const double* b, int maxiter, double tol,
     RET(rc);
     *iters = it;
     return to_host(h, 0, l0.x[l0.cur].p, x);
+}
+
+int amg1d_ldiv(amg1d_t* h, double* y, const double* b, int nPre, int nPost, double alpha) {
+    RET(check_ready(h));
+    if (!y || !b) return fail(h, AMG1D_ERR_ARG, "null vector");
+    Level& l0 = h->L[0];
+    h->norm_valid = false;
+    RET(to_device(h, 0, b, l0.b.p));
+    if (l0.sharded) RET(op_halo(h, l0.b.p, l0.n, l0.m));
+    l0.cur = 0;
+    RET(run_vcycle(h, nPre, nPost, alpha, false, true));      // zero guess: x0 is neither uploaded nor read
+    return to_host(h, 0, l0.x[l0.cur].p, y);
+}
+
+int amg1d_pcg(amg1d_t* h, double* x, const double* b, int maxiter, double tol, int nPre, int nPost,
+              double alpha, int* iters, double* res) {
+    RET(check_ready(h));
+    if (!x || !b || !res || !iters) return fail(h, AMG1D_ERR_ARG, "null argument");
+    if (maxiter < 0) return fail(h, AMG1D_ERR_ARG, "maxiter must be >= 0");
+    Level& l0 = h->L[0];
+    const int64_t N = l0.n * l0.m;
+    if (!h->cg_x.raw) {
+        RET(vec_alloc(h, h->cg_x, l0.n, l0.m));
+        RET(vec_alloc(h, h->cg_p, l0.n, l0.m));
+        RET(vec_alloc(h, h->cg_ap, l0.n, l0.m));
+    }
+    h->norm_valid = false;
+    double* X = h->cg_x.p;
+    double* P = h->cg_p.p;
+    double* AP = h->cg_ap.p;
+    double* R = l0.b.p;                       // the residual lives in the level's rhs buffer: it IS the
+                                              // right-hand side of every preconditioner application
+    RET(to_device(h, 0, b, R));
+    RET(to_device(h, 0, x, X));
+    RET(op_norm(h, R, nullptr, N, CG_NB));                       // ||b||
+    // r = b - A x0
+    RET(op_matvec_dot(h, 0, X, AP, -1));
+    {
+        int nb = (int)std::min<int64_t>(AMG1D_RED_BLOCKS, (N + AMG1D_RED_THREADS - 1) / AMG1D_RED_THREADS);
+        k_axpy<<<nb, AMG1D_RED_THREADS, 0, h->stream>>>(R, AP, N, -1.0);
+        h->launch_counter++;
+        LAUNCH_CHECK();
+    }
+    int it = 0, rc = AMG1D_OK;
+    const int nbv = (int)std::max<int64_t>(1, std::min<int64_t>(AMG1D_RED_BLOCKS, (N + AMG1D_RED_THREADS - 1) / AMG1D_RED_THREADS));
+    for (int i = 0; i < maxiter; ++i) {
+        // z = M^-1 r: one V-cycle from a zero guess with rhs r (already in place); z = level-0 iterate
+        if (l0.sharded) { rc = op_halo(h, R, l0.n, l0.m); if (rc) break; }
+        l0.cur = 0;
+        rc = run_vcycle(h, nPre, nPost, alpha, false, true);
+        if (rc) break;
+        double* Z = l0.x[l0.cur].p;
+        rc = op_dot(h, R, Z, N, i == 0 ? CG_RZ : CG_RZ_NEW);
+        if (rc) break;
+        if (i > 0) { k_cg_beta<<<1, 1, 0, h->stream>>>(h->d_scal); h->launch_counter++; }
+        k_cg_direction<<<nbv, AMG1D_RED_THREADS, 0, h->stream>>>(P, Z, N, h->d_scal, i == 0 ? 1 : 0);
+        h->launch_counter++;
+        rc = op_matvec_dot(h, 0, P, AP, CG_PAP);
+        if (rc) break;
+        k_cg_alpha<<<1, 1, 0, h->stream>>>(h->d_scal);
+        k_cg_update<<<nbv, AMG1D_RED_THREADS, 0, h->stream>>>(X, R, P, AP, N, h->d_scal, h->partial);
+        h->launch_counter += 2;
+        { cudaError_t e_ = cudaGetLastError(); if (e_ != cudaSuccess) { rc = fail(h, AMG1D_ERR_CUDA, "pcg kernels: %s", cudaGetErrorString(e_)); break; } }
+        rc = op_reduce_partials(h, nbv, CG_RES);                 // ||r||_2
+        if (rc) break;
+        rc = read_scalars(h, 3);
+        if (rc) break;
+        res[i] = h->h_scal[CG_RES];
+        it = i + 1;
+        if (!(res[i] >= tol * h->h_scal[CG_NB])) break;          // also stops on NaN
+    }
+    RET(rc);
+    *iters = it;
+    return to_host(h, 0, X, x);
 }
 
 int amg1d_apply_smoother(amg1d_t* h, int level, double* Y, const double* B, int64_t n_rhs,

@@ -257,6 +257,30 @@ __global__ void __launch_bounds__(256) f_resnorm(const double* __restrict__ mat,
     if (threadIdx.x == 0) partial[blockIdx.x] = s;
 }
 
+// y = A x and partial[blockIdx] = sum over the block's elements of x . y   (the p' A p of conjugate
+// gradients fused into the product; partial may be null)
+template <int M, int ST>
+__global__ void __launch_bounds__(256) f_matvec_dot(const double* __restrict__ mat, int K, int ilo, int iup,
+                                                    const double* __restrict__ x, double* __restrict__ y,
+                                                    int64_t n, double* __restrict__ partial) {
+    const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    double s = 0.0;
+    if (e < n) {
+        const double* T = mat + (e >> 5) * (int64_t)K * AMG1D_TILE + (e & 31);
+        double xl[M], xc[M], xr[M], yy[M];
+        load_vec<M>(x + e * M, xc);
+        load_neighbours<M, ST>(x, e, ilo, iup, xl, xr);
+        stream_Ax<M, ST>(T, ilo, iup, xl, xc, xr, yy);
+        store_vec<M>(y + e * M, yy);
+#pragma unroll
+        for (int i = 0; i < M; ++i) s = fma(xc[i], yy[i], s);
+    }
+    if (partial) {
+        s = block_sum(s);
+        if (threadIdx.x == 0) partial[blockIdx.x] = s;
+    }
+}
+
 // ---- register-resident multi-sweep kernels -----------------------------------------------------------
 // Shared-memory exchange buffers, structure-of-arrays so that neighbouring threads hit neighbouring
 // banks: xs[buf][i][slot], slot = thread + 1, slots 0 and B+1 stay zero.
@@ -914,6 +938,24 @@ inline bool fused_resnorm(const MatDesc& d, const double* mat, const double* b, 
 #define Y(MM, SS)                                                                                       \
     case MM * 4 + SS:                                                                                   \
         f_resnorm<MM, SS><<<(unsigned)grid, 256, 0, st>>>(mat, d.K, d.ilo, d.iup, b, x, n, partial);    \
+        return true;
+#define X(MM) Y(MM, 0) Y(MM, 1) Y(MM, 2)
+        FUSED_FOR_M(X)
+#undef X
+#undef Y
+        default: return false;
+    }
+}
+
+inline bool fused_matvec_dot(const MatDesc& d, const double* mat, const double* x, double* y, int64_t n,
+                             double* partial, int64_t partial_cap, int* nblocks, cudaStream_t st) {
+    const int64_t grid = (n + 255) / 256;
+    if (grid > partial_cap || !fast_tier_ok(d)) return false;
+    *nblocks = (int)grid;
+    switch (d.m * 4 + d.st) {
+#define Y(MM, SS)                                                                                       \
+    case MM * 4 + SS:                                                                                   \
+        f_matvec_dot<MM, SS><<<(unsigned)grid, 256, 0, st>>>(mat, d.K, d.ilo, d.iup, x, y, n, partial); \
         return true;
 #define X(MM) Y(MM, 0) Y(MM, 1) Y(MM, 2)
         FUSED_FOR_M(X)

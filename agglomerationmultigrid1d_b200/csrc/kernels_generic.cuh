@@ -260,6 +260,58 @@ __global__ void k_sqdiff_partial(const double* __restrict__ a, const double* __r
     if (threadIdx.x == 0) partial[blockIdx.x] = s;
 }
 
+// partial[b] = sum over a grid-stride slice of a[i] * c[i]
+__global__ void k_dot_partial(const double* __restrict__ a, const double* __restrict__ c, int64_t n,
+                              double* __restrict__ partial) {
+    double s = 0.0;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n;
+         i += (int64_t)gridDim.x * blockDim.x)
+        s = fma(a[i], c[i], s);
+    s = block_sum(s);
+    if (threadIdx.x == 0) partial[blockIdx.x] = s;
+}
+
+// ---- conjugate gradients (amg1d_pcg): scalars live in the device scalar array ------------------------
+enum { CG_RES = 0, CG_NB = 2, CG_RZ = 3, CG_PAP = 4, CG_ALPHA = 5, CG_BETA = 6, CG_RZ_NEW = 7 };
+
+// y += a x
+__global__ void k_axpy(double* __restrict__ y, const double* __restrict__ x, int64_t n, double a) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n;
+         i += (int64_t)gridDim.x * blockDim.x)
+        y[i] = fma(a, x[i], y[i]);
+}
+
+// alpha = rz / pAp
+__global__ void k_cg_alpha(double* s) { s[CG_ALPHA] = s[CG_RZ] / s[CG_PAP]; }
+// beta = rz_new / rz; rz = rz_new
+__global__ void k_cg_beta(double* s) { s[CG_BETA] = s[CG_RZ_NEW] / s[CG_RZ]; s[CG_RZ] = s[CG_RZ_NEW]; }
+
+// x += alpha p;  r -= alpha Ap;  partial[b] = sum r[i]^2 over the block's slice
+__global__ void k_cg_update(double* __restrict__ x, double* __restrict__ r, const double* __restrict__ p,
+                            const double* __restrict__ Ap, int64_t n, const double* __restrict__ s,
+                            double* __restrict__ partial) {
+    const double alpha = s[CG_ALPHA];
+    double acc = 0.0;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n;
+         i += (int64_t)gridDim.x * blockDim.x) {
+        x[i] = fma(alpha, p[i], x[i]);
+        const double ri = fma(-alpha, Ap[i], r[i]);
+        r[i] = ri;
+        acc = fma(ri, ri, acc);
+    }
+    acc = block_sum(acc);
+    if (threadIdx.x == 0) partial[blockIdx.x] = acc;
+}
+
+// p = z + beta p   (first = 1: p = z)
+__global__ void k_cg_direction(double* __restrict__ p, const double* __restrict__ z, int64_t n,
+                               const double* __restrict__ s, int first) {
+    const double beta = first ? 0.0 : s[CG_BETA];
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n;
+         i += (int64_t)gridDim.x * blockDim.x)
+        p[i] = first ? z[i] : fma(beta, p[i], z[i]);
+}
+
 // second-stage partial sums for long partial arrays: out[b] = sum of a fixed grid-stride slice
 __global__ void k_sum_partial(const double* __restrict__ partial, int64_t np, double* __restrict__ out) {
     double s = 0.0;

@@ -106,6 +106,23 @@ class DeviceHierarchy:
                                        capi.dptr(ue)))
         return x, it.value, res[:it.value].copy(), err[:it.value].copy()
 
+    def ldiv(self, b, nPre=3, nPost=3, alpha=2.0 / 3.0):
+        b = capi.f64(b)
+        self._check_len(0, b)
+        y = np.zeros_like(b)
+        self._ck(self._lib.amg1d_ldiv(self._h, capi.dptr(y), capi.dptr(b), nPre, nPost, alpha))
+        return y
+
+    def pcg(self, x0, b, maxiter, tol, nPre=3, nPost=3, alpha=2.0 / 3.0):
+        x = np.array(x0, dtype=np.float64, order="C", copy=True)
+        b = capi.f64(b)
+        self._check_len(0, x, b)
+        res = np.zeros(max(maxiter, 1))
+        it = C.c_int(0)
+        self._ck(self._lib.amg1d_pcg(self._h, capi.dptr(x), capi.dptr(b), maxiter, tol, nPre, nPost, alpha,
+                                     C.byref(it), capi.dptr(res)))
+        return x, it.value, res[:it.value].copy()
+
     def apply_smoother(self, level, B, alpha=1.0):
         B = np.asarray(B, dtype=np.float64)
         vec = B.ndim == 1

@@ -5,6 +5,7 @@ libamg1d.so (the GPU).  There is no CPU implementation behind them.
 
     multigrid_v_cycle(H, x0, b; nPre=3, nPost=3, alpha=2/3) -> x            src/solvers.jl:19-50
     ldiv(H, b) -> b overwritten / ldiv(y, H, b) -> y overwritten            src/solvers.jl:63-92
+    pcg(H, x0, b, maxiter, tol) -> (x, iter, res)      CG with ldiv! as preconditioner (the hook's purpose)
     multigrid(H, x0, b, maxiter, tol) -> (x, iter, res, err)                src/solvers.jl:116-139
     iterative_smoother_solve(A, smoother, x0, b; maxiter, tol, alpha)       src/solvers.jl:189-213
     apply_smoother(S, B; alpha) -> alpha * S^-1 B                           src/smoother.jl:52-81
@@ -37,9 +38,16 @@ def ldiv(*args):
         out, H, b = args
     else:
         raise TypeError("ldiv(H, b) or ldiv(y, H, b)")
-    u0 = np.zeros(H.mStiffness[0].shape[0])
-    out[:] = multigrid_v_cycle(H, u0, b)
+    out[:] = _device_of(H).ldiv(b)          # zero guess inside the library: no x0 upload, first sweep skips A
     return None
+
+
+def pcg(H, x0, b, maxiter, tol, nPre=3, nPost=3, alpha=2.0 / 3.0):
+    """Conjugate gradients preconditioned with ``ldiv!(z, H, r)`` - the use the reference's ``ldiv!``
+    methods are written for (src/solvers.jl:63-92: MeshHierarchy as the ``Pl`` of a Krylov solver); the
+    reference itself ships no driver.  Returns (x, iter, res) with res[i] = ||r_i||_2 and the stop rule of
+    ``multigrid`` (res < tol ||b||)."""
+    return _device_of(H).pcg(x0, b, maxiter, tol, nPre=nPre, nPost=nPost, alpha=alpha)
 
 
 def _host_direct_solve(A, b):

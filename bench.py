@@ -389,6 +389,31 @@ def run_gpu(args):
         solve["note"] = ("not converged to 1e-10: FP64 conditioning limit of this problem size "
                          "(cond ~ n^2 ~ 1/eps); throughput figures are unaffected")
 
+    # ---- the same solve with CG, one V-cycle (ldiv!(z, H, r)) as the preconditioner ------------------
+    xh[:] = 0.0
+    res2 = np.zeros(100)
+    it2 = C.c_int(0)
+    barrier()
+    t0 = time.perf_counter()
+    capi.check(dev._h, lib.amg1d_pcg(dev._h, capi.dptr(xh), capi.dptr(bh), 100, 1e-10, 3, 3, 2.0 / 3.0,
+                                      C.byref(it2), capi.dptr(res2)))
+    barrier()
+    t_pcg = max_over_ranks(time.perf_counter() - t0)
+    rel2 = float(res2[max(it2.value, 1) - 1] / nb)
+    solve["pcg"] = {"iters": it2.value, "seconds_e2e": t_pcg, "final_relative_residual": rel2,
+                    "converged": rel2 < 1e-10,
+                    "call": "amg1d_pcg (CG preconditioned with ldiv!(z, H, r)), host b in / host x out"}
+    # ---- ldiv!(y, H, b): one V-cycle from zero, only b travels up ----------------------------------------
+    capi.check(dev._h, lib.amg1d_ldiv(dev._h, capi.dptr(xh), capi.dptr(bh), 3, 3, 2.0 / 3.0))
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        capi.check(dev._h, lib.amg1d_ldiv(dev._h, capi.dptr(xh), capi.dptr(bh), 3, 3, 2.0 / 3.0))
+    barrier()
+    t_ldiv = max_over_ranks(time.perf_counter() - t0) / e2e_steps
+    e2e["ldiv"] = {"value": upd / t_ldiv, "ms_per_step": t_ldiv * 1e3, "h2d_bytes_per_step": N0_all * 8,
+                   "d2h_bytes_per_step": N0_all * 8, "call": "amg1d_ldiv (ldiv!(y, H, b)) with pinned host b, y"}
+
     # ---- CPU baseline beside it (oracle port, bounded sample) ----------------------------------------
     cpu = None
     if not args.no_cpu and world == 1:

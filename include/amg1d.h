@@ -117,6 +117,20 @@ int amg1d_solve(amg1d_t* h, double* x, const double* b, int maxiter, double tol,
                 int nPost, double alpha, int* iters, double* res, double* err,
                 const double* u_exact);
 
+/* ldiv!(y, H, b) / ldiv!(H, b) - src/solvers.jl:63-92: one V-cycle from a ZERO guess, y <- result (y may
+ * alias b).  Unlike amg1d_vcycle no initial guess is uploaded, and the first pre-smoothing sweep of
+ * the finest level skips the operator (x = alpha Dinv b), exactly as the levels below always do. */
+int amg1d_ldiv(amg1d_t* h, double* y, const double* b, int nPre, int nPost, double alpha);
+
+/* Conjugate gradients on the finest level, preconditioned with ldiv!(z, H, r) - what the reference's
+ * ldiv! methods exist for (src/solvers.jl:63-92 make MeshHierarchy usable as `Pl` of a Krylov solver
+ * such as IterativeSolvers.cg; the reference ships no driver for it).  Textbook PCG: z = M^-1 r,
+ * beta = r.z / (r.z)_old, p = z + beta p, alpha = r.z / p.Ap, x += alpha p, r -= alpha Ap; res[i] =
+ * ||r_i||_2 of the recurrence residual; stops when res[i] < tol * ||b||_2 (the rule of multigrid()).
+ * x: in x0, out x; res: maxiter doubles.  The V-cycle with nPre == nPost is a symmetric operator. */
+int amg1d_pcg(amg1d_t* h, double* x, const double* b, int maxiter, double tol, int nPre, int nPost,
+              double alpha, int* iters, double* res);
+
 /* apply_smoother(S, B; alpha) - src/smoother.jl:52-58, :69-81.  Y = alpha * S^-1 * B, B and Y are
  * n_dof_host x n_rhs column-major (the scripts also pass matrices, tests/dg_smoother_test.jl:105). */
 int amg1d_apply_smoother(amg1d_t* h, int level, double* Y, const double* B, int64_t n_rhs,
@@ -153,12 +167,20 @@ void* amg1d_dev_ptr(amg1d_t* h, int level, int which);             /* raw device
 
 /* ---- options and introspection ------------------------------------------------------------------
  * amg1d_set_option keys: "fused" (1 = fused multi-sweep kernels where available, default 1),
- * "graph" (1 = replay the V-cycle as a CUDA graph, default 1), "coarse_cta_elems" (levels with at
- * most this many elements run inside the single-CTA coarse kernel, default 1024), "profile" (see
- * amg1d_get_profile; setting it clears earlier samples). */
+ * "graph" (1 = replay the V-cycle as a CUDA graph, default 1), "pdl" (1 = programmatic dependent
+ * launch between the fused kernels, default 1), "coarse_cta_elems" (levels with at most this many
+ * elements - capped at 512 - run inside the single-CTA coarse kernel; 0 disables it; default 1024),
+ * "profile" (see amg1d_get_profile; setting it clears earlier samples); before the first level is
+ * set: "compress" (1 = store only the structurally non-zero column / row of the off-diagonal blocks
+ * where every element of the level has that structure, default 1), "shard_min" (elements per rank
+ * below which a level is gathered to rank 0, default 8192), "ghost_depth" (ghost elements per slab
+ * edge, default 4 = max(nPre, nPost) + 1; CG levels with two-parent transfers need + ratio). */
 int amg1d_set_option(amg1d_t* h, const char* key, int64_t value);
-int64_t amg1d_get_info(amg1d_t* h, const char* key); /* "kernel_launches", "dof_updates_per_cycle",
-                                                        "bytes_per_cycle", "device_bytes", "n_levels" */
+int64_t amg1d_get_info(amg1d_t* h, const char* key); /* "kernel_launches", "launches_per_cycle",
+                                                        "device_bytes", "n_levels", "local_elements",
+                                                        "local_dofs", "gather_level", "tail_start",
+                                                        "ghost_depth", "structure:<level>",
+                                                        "tile_rows:<level>", ... (-1: unknown key) */
 
 /* With option "profile" = 1 every V-cycle runs un-graphed and brackets each level's down leg (leg 0:
  * pre-smoothing + residual + restriction) and up leg (leg 1: prolongation + post-smoothing) with CUDA

@@ -46,6 +46,35 @@ def ldiv(H, b):
     return multigrid_v_cycle(H, np.zeros(H.mStiffness[0].shape[0]), b)
 
 
+def pcg(H, x0, b, maxiter, tol, nPre=3, nPost=3, alpha=2.0 / 3.0):
+    """Conjugate gradients with M^-1 r = ldiv!(z, H, r) (one V-cycle from zero, src/solvers.jl:84-92).
+    The reference only provides the ldiv! hook; the Krylov driver a user would pair it with is
+    IterativeSolvers.cg (third-party, not vendored, version unpinned) - this is the textbook
+    preconditioned CG it implements (Hestenes-Stiefel recurrences, residual by recurrence).
+    Returns (x, iter, res), res[i] = ||r_i||_2; stop rule of ``multigrid``: res < tol ||b||."""
+    A = H.mStiffness[0]
+    b = np.asarray(b, dtype=np.float64)
+    x = np.array(x0, dtype=np.float64, copy=True)
+    r = b - A @ x
+    nb = np.linalg.norm(b, 2)
+    res = []
+    p = None
+    rz = 0.0
+    for i in range(maxiter):
+        z = multigrid_v_cycle(H, np.zeros(len(b)), r, nPre=nPre, nPost=nPost, alpha=alpha)
+        rz_new = float(r @ z)
+        p = z.copy() if i == 0 else z + (rz_new / rz) * p
+        rz = rz_new
+        Ap = A @ p
+        a = rz / float(p @ Ap)
+        x = x + a * p
+        r = r - a * Ap
+        res.append(np.linalg.norm(r, 2))
+        if not res[-1] >= tol * nb:
+            break
+    return x, len(res), np.array(res)
+
+
 def multigrid(H, x0, b, maxiter, tol, u_exact=None):
     """Returns (x, iter, res, err).  ``multigrid`` always uses the V-cycle defaults
     nPre = nPost = 3, alpha = 2/3 (src/solvers.jl:125)."""

@@ -120,6 +120,35 @@ def test_ldiv(case):
     b2 = bp.copy()
     aggmg.ldiv(Hp, b2)
     assert np.array_equal(b2, y)
+    # ldiv! starts from zero inside the library (no x0 upload, level 0 skips A in its first sweep):
+    # the same bits as the V-cycle called with an explicit zero guess
+    assert np.array_equal(y, aggmg.multigrid_v_cycle(Hp, np.zeros(len(bp)), bp))
+
+
+def test_pcg_with_vcycle_preconditioner(case):
+    """CG with ldiv!(z, H, r) as preconditioner (src/solvers.jl:84-92 is that hook): same iteration
+    count as the CPU restatement, residual histories within 1e-8 relative (dot products are summed in
+    another order), solution within the problem's conditioning; and fewer iterations than multigrid()."""
+    name, Ho, bo, Hp, bp = case
+    x_or, it_or, res_or = osolv.pcg(Ho, np.zeros(len(bo)), bo, 100, 1e-10)
+    x, it, res = aggmg.pcg(Hp, np.zeros(len(bp)), bp, 100, 1e-10)
+    floor = rounding_floor(Ho, x_or)
+    with dense_coarse_solver():
+        _, it_d, res_d = osolv.pcg(Ho, np.zeros(len(bo)), bo, 100, 1e-10)
+    assert abs(it - it_or) <= (0 if it_d == it_or else 1), (name, it, it_or, it_d)
+    k = min(it, it_or, it_d)
+    noise = 20 * np.abs(res_d[:k] - res_or[:k])
+    assert np.all(np.abs(res[:k] - res_or[:k]) <= np.maximum(np.maximum(1e-8 * res_or[:k], floor), noise)), (res, res_or)
+    assert res[-1] < 1e-10 * np.linalg.norm(bp)
+    assert np.abs(x - x_or).max() <= 1e-8 * np.abs(x_or).max()
+    _, it_mg, _, _ = aggmg.multigrid(Hp, np.zeros(len(bp)), bp, 100, 1e-10, with_error=False)
+    assert it <= it_mg
+    # non-zero initial guess, other smoothing parameters
+    rng = np.random.default_rng(4)
+    x0 = rng.standard_normal(len(bp)) * np.abs(x_or).max()
+    x2, it2, res2 = aggmg.pcg(Hp, x0, bp, 100, 1e-9, nPre=2, nPost=2, alpha=0.6)
+    xo2, ito2, reso2 = osolv.pcg(Ho, x0, bo, 100, 1e-9, nPre=2, nPost=2, alpha=0.6)
+    assert abs(it2 - ito2) <= 1 and np.abs(x2 - xo2).max() <= 1e-7 * np.abs(xo2).max()
 
 
 def test_multigrid_histories(case):
