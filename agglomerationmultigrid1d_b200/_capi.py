@@ -49,6 +49,7 @@ PROTOTYPES = {
     "amg1d_restrict": (C.c_int, [_h, C.c_int, _pd, _pd]),
     "amg1d_prolong": (C.c_int, [_h, C.c_int, _pd, _pd]),
     "amg1d_coarse_solve": (C.c_int, [_h, _pd, _pd]),
+    "amg1d_direct_solve": (C.c_int, [_h, C.c_int, _pd, _pd]),
     "amg1d_dev_set_problem": (C.c_int, [_h, _pd, _pd]),
     "amg1d_dev_fill_rhs_random": (C.c_int, [_h, C.c_uint64]),
     "amg1d_dev_vcycle": (C.c_int, [_h, C.c_int, C.c_int, C.c_double, C.c_int]),

@@ -21,6 +21,7 @@
 #include "../../include/amg1d.h"
 #include "kernels_generic.cuh"
 #include "kernels_fused.cuh"
+#include "direct_bcr.cuh"
 
 #define AMG1D_VERSION 100
 #define PAD_FRONT 64  // doubles in front of element 0 (ghost elements live at the end of them)
@@ -120,6 +121,10 @@ struct amg1d {
     GraphEntry graphs[4];
     uint64_t graph_clock = 0;
     int64_t launches_per_cycle = 0;
+    // block-cyclic-reduction direct solvers: coarsest level (when it has more than AMG1D_BCR_MIN
+    // elements) and, built on demand, any level asked for through amg1d_direct_solve
+    BcrSolver coarse_bcr;
+    std::vector<BcrSolver> direct;
     // conjugate gradients (amg1d_pcg): solution, search direction, A p - allocated at the first call
     DVec cg_x, cg_p, cg_ap;
     int64_t launch_counter = 0;
@@ -415,6 +420,10 @@ int op_prolong(amg1d* h, int l, const double* xc, double* xf, int add) {
 
 int op_coarse(amg1d* h, const double* b, double* x) {
     Level& lv = h->L[h->n_levels - 1];
+    if (h->coarse_bcr.ready()) {             // parallel cyclic reduction (direct_bcr.cuh)
+        CK(h->coarse_bcr.solve(b, x, h->stream, &h->launch_counter));
+        return AMG1D_OK;
+    }
     g_coarse_solve<<<1, 32, 2 * lv.m * sizeof(double), h->stream>>>(h->coarse_fac, lv.m, lv.n, b, x);
     h->launch_counter++;
     LAUNCH_CHECK();
@@ -798,12 +807,26 @@ void matmul_cm(const double* A, const double* B, double* C, int m) {  // C = A B
         }
 }
 
+int bcr_factor(amg1d* h, BcrSolver& S, int level) {
+    Level& lv = h->L[level];
+    if (lv.m > AMG1D_BCR_MAXM) return fail(h, AMG1D_ERR_UNSUPPORTED, "block size %d too large for the direct solver", lv.m);
+    bool singular = false;
+    const cudaError_t e = S.factor(lv.mat, lv.md, lv.n, h->stream, &singular);
+    if (e != cudaSuccess) {
+        S.release();
+        return fail(h, e == cudaErrorMemoryAllocation ? AMG1D_ERR_NOMEM : AMG1D_ERR_CUDA,
+                    "direct solver factorisation of level %d failed: %s", level, cudaGetErrorString(e));
+    }
+    if (singular) { S.release(); return fail(h, AMG1D_ERR_ARG, "level %d is singular (cyclic reduction hit a singular block)", level); }
+    h->device_bytes += S.bytes;
+    return AMG1D_OK;
+}
+
 int factor_coarsest(amg1d* h) {
     Level& lv = h->L[h->n_levels - 1];
+    if (lv.n > AMG1D_BCR_MIN) return bcr_factor(h, h->coarse_bcr, h->n_levels - 1);
     if (lv.h_di.empty())
-        return fail(h, AMG1D_ERR_UNSUPPORTED,
-                    "coarsest level has %lld elements: too large for the block-Thomas direct solve "
-                    "(limit 65536); add coarser levels", (long long)lv.n);
+        return fail(h, AMG1D_ERR_STATE, "internal: host copy of the coarsest level is missing");
     const int m = lv.m, mm = m * m;
     std::vector<double> fac((size_t)lv.n * 3 * mm, 0.0), S(mm), tmp(mm), Sinv_prev(mm);
     for (int64_t k = 0; k < lv.n; ++k) {
@@ -835,7 +858,7 @@ int build_tail(amg1d* h) {
     h->tail_start = -1;
     if (h->d_tail) { cudaFree(h->d_tail); h->d_tail = nullptr; }
     const int nl = h->n_levels;
-    if (nl < 3 || h->opt_coarse_cta < 1 || !h->L[nl - 1].present) return AMG1D_OK;
+    if (nl < 3 || h->opt_coarse_cta < 1 || !h->L[nl - 1].present || h->coarse_bcr.ready()) return AMG1D_OK;
     const int m = h->L[nl - 1].m;
     if (!tail_supported(m)) return AMG1D_OK;
     const int64_t cap = std::min<int64_t>(h->opt_coarse_cta, TAIL_B);
@@ -1072,6 +1095,8 @@ int amg1d_destroy(amg1d_t* h) {
     if (h->h_scal) cudaFreeHost(h->h_scal);
     if (h->coarse_fac) cudaFree(h->coarse_fac);
     if (h->d_tail) cudaFree(h->d_tail);
+    h->coarse_bcr.release();
+    for (auto& S : h->direct) S.release();
 #ifdef AMG1D_WITH_NCCL
     if (h->comm) g_nccl.CommDestroy(h->comm);
 #endif
@@ -1133,7 +1158,7 @@ int amg1d_set_level(amg1d_t* h, int level, int64_t n_elem, int m, const double* 
     }
     cudaFree(d_lo); cudaFree(d_di); cudaFree(d_up); cudaFree(d_dv);
     RET(rc);
-    if (n_elem <= 65536 && !lv.sharded) {
+    if (n_elem <= AMG1D_BCR_MIN && !lv.sharded) {   // host copy for the block-Thomas factorisation
         lv.h_lo.assign(A_lo, A_lo + (size_t)n_elem * mm);
         lv.h_di.assign(A_di, A_di + (size_t)n_elem * mm);
         lv.h_up.assign(A_up, A_up + (size_t)n_elem * mm);
@@ -1177,7 +1202,7 @@ int amg1d_set_level_pattern(amg1d_t* h, int level, int64_t n_elem, int m, int n_
     if (e == cudaSuccess) e = cudaGetLastError();
     cudaFree(d_lo); cudaFree(d_di); cudaFree(d_up); cudaFree(d_dv);
     if (e != cudaSuccess) return fail(h, AMG1D_ERR_CUDA, "pattern fill failed: %s", cudaGetErrorString(e));
-    if (n_elem <= 65536 && !lv.sharded) {
+    if (n_elem <= AMG1D_BCR_MIN && !lv.sharded) {   // host copy for the block-Thomas factorisation
         lv.h_lo.resize((size_t)n_elem * mm); lv.h_di.resize((size_t)n_elem * mm); lv.h_up.resize((size_t)n_elem * mm);
         for (int64_t el = 0; el < n_elem; ++el) {
             int64_t s = el < n_head ? el : (el >= n_elem - n_tail ? n_head + 1 + (el - (n_elem - n_tail)) : n_head);
@@ -1703,6 +1728,22 @@ int amg1d_coarse_solve(amg1d_t* h, double* x, const double* b) {
     RET(to_device(h, l, b, bin));
     RET(op_coarse(h, bin, h->scratch.p));
     return to_host(h, l, h->scratch.p, x);
+}
+
+int amg1d_direct_solve(amg1d_t* h, int level, double* x, const double* b) {
+    RET(check_ready(h));
+    if (h->nranks > 1) return fail(h, AMG1D_ERR_UNSUPPORTED, "per-level host operations are single-GPU only");
+    if (!valid_level(h, level)) return fail(h, AMG1D_ERR_ARG, "level %d out of range", level);
+    if (!x || !b) return fail(h, AMG1D_ERR_ARG, "null vector");
+    Level& lv = h->L[level];
+    if (h->direct.size() < (size_t)h->n_levels) h->direct.resize((size_t)h->n_levels);
+    BcrSolver& S = h->direct[(size_t)level];
+    if (!S.ready()) RET(bcr_factor(h, S, level));
+    invalidate_graph(h);
+    double* bin = lv.x[1 - lv.cur].p;            // free ping-pong buffer as input staging
+    RET(to_device(h, level, b, bin));
+    CK(S.solve(bin, h->scratch.p, h->stream, &h->launch_counter));
+    return to_host(h, level, h->scratch.p, x);
 }
 
 int amg1d_set_option(amg1d_t* h, const char* key, int64_t value) {

@@ -183,6 +183,13 @@ class DeviceHierarchy:
         self._ck(self._lib.amg1d_coarse_solve(self._h, capi.dptr(x), capi.dptr(b)))
         return x
 
+    def direct_solve(self, level, b):
+        """x = mStiffness[level] \\ b by block cyclic reduction on the GPU (any level, any size)."""
+        b = capi.f64(b); self._check_len(level, b)
+        x = np.zeros_like(b)
+        self._ck(self._lib.amg1d_direct_solve(self._h, level, capi.dptr(x), capi.dptr(b)))
+        return x
+
     # ---- device-resident path -----------------------------------------------------------------
     def dev_set_problem(self, x0, b):
         x0 = capi.f64(x0) if x0 is not None else None

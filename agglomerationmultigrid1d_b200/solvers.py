@@ -19,6 +19,9 @@ from .device import DeviceHierarchy
 from .smoother import AbstractSmoother, smoother_inverse
 
 
+DEVICE_DIRECT_ABOVE = 1 << 18      # DOFs above which u_exact = A \\ b is computed on the GPU
+
+
 def _device_of(H):
     if H.device is None:
         raise RuntimeError("MeshHierarchy was built with upload=False; call H.upload() first")
@@ -67,7 +70,12 @@ def multigrid(H, x0, b, maxiter, tol, u_exact=None, with_error=True):
     if maxiter <= 0:
         return np.zeros(len(x0)), 0, np.zeros(0), np.zeros(0)
     if u_exact is None and with_error:
-        u_exact = _host_direct_solve(H.mStiffness[0], b)
+        # src/solvers.jl:120: u_exact = A \\ b.  Small systems: the host's sparse LU, as the reference does;
+        # large ones: block cyclic reduction on the GPU (amg1d_direct_solve)
+        if len(b) <= DEVICE_DIRECT_ABOVE:
+            u_exact = _host_direct_solve(H.mStiffness[0], b)
+        else:
+            u_exact = _device_of(H).direct_solve(0, b)
     return _device_of(H).solve(x0, b, maxiter, tol, u_exact=u_exact)
 
 

@@ -152,6 +152,13 @@ int amg1d_restrict(amg1d_t* h, int level, double* rc, const double* rf);
 int amg1d_prolong(amg1d_t* h, int level, double* xf, const double* xc);
 int amg1d_coarse_solve(amg1d_t* h, double* x, const double* b);
 
+/* x = mStiffness[l] \ b for ANY level: the sparse direct solves the reference uses for error histories
+ * (u_exact = A \ b, src/solvers.jl:120, :194) and for the coarsest level (:39).  Block cyclic reduction
+ * on the GPU; the level is factorised at the first call (about 10 n m^2 doubles of device memory) and
+ * the factors are kept.  The coarsest level of the V-cycle itself is solved the same way when it has
+ * more than 64 elements (a serial block-Thomas kernel below that). */
+int amg1d_direct_solve(amg1d_t* h, int level, double* x, const double* b);
+
 /* ---- device-resident path (no host copies; what bench.py times as `value`) -------------------- */
 int amg1d_dev_set_problem(amg1d_t* h, const double* x0, const double* b); /* host -> device, x0 NULL = 0 */
 int amg1d_dev_fill_rhs_random(amg1d_t* h, uint64_t seed);          /* b[i] ~ U(-1,1) on the device, x = 0 */

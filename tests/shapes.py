@@ -35,6 +35,9 @@ SHAPES = {
     "C3_dg4_agg": dict(n=32, dg_orders=[4, 2, 1], agg_factors=[2] * 5),
     "C4_cg3_dg1_agg": dict(n=32, cg_orders=[3, 1], dg_orders=[1], agg_factors=[2] * 5),
     "dg_p0_agg0": dict(n=16, dg_orders=[1], agg_factors=[2, 2], pAgg=0),
+    # coarsest levels with more than 64 elements: solved by block cyclic reduction on the GPU
+    "bcr_dg_cg_n128": dict(n=128, cg_orders=[4, 2, 1], dg_orders=[0]),       # literal dg_cg_heirarchy: size-n coarse solve
+    "bcr_dg3_agg_n512": dict(n=512, dg_orders=[3, 1], agg_factors=[2]),     # coarsest: 256 agglomerated elements
     "factor3_n24": dict(n=24, dg_orders=[2, 1], agg_factors=[3, 2, 2, 2]),
 }
 

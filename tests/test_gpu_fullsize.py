@@ -170,3 +170,29 @@ def test_c4_shape_at_scale():
     dev.set_option("fused", 0)
     assert np.array_equal(dev.vcycle(np.zeros(len(b)), b), x1)       # generic tier, same bits
     dev.close()
+
+
+def test_direct_solver_at_scale():
+    """Block cyclic reduction at sizes no host direct solver is asked to do here:
+    A \\ b on the finest DG p=3 level of 2^20 elements (4 M unknowns), and the literal dg_cg_heirarchy
+    shape (CG 3 -> 1 -> DG 0, src/mesh_heirarchy.jl:57-74) at 2^22 elements, whose coarsest level is a
+    2^22-unknown tridiagonal system solved exactly inside every V-cycle."""
+    n = 2 ** 20
+    U, dev = _build(20)
+    func, vals = _problem(n)
+    b = U.rhs(func, vals)
+    x = dev.direct_solve(0, b)
+    r = dev.residual(0, x, b)
+    assert np.linalg.norm(r) <= 1e-6 * np.linalg.norm(b)        # cond ~ 1e12 at this size: backward stable
+    xm, it, res, _ = dev.solve(np.zeros(len(b)), b, 100, 1e-10)
+    assert np.abs(x - xm).max() <= 1e-5 * np.abs(xm).max()
+    dev.close()
+    n = 2 ** 22
+    w = 2.0 * math.pi / 64.0
+    U = uniform.UniformCgHierarchy(n, [3, 1], [0], [], xin=0.0, xout=float(n), CDir=1000.0)
+    dev = U.upload()
+    assert dev.info("n_levels") == 3 and dev.info("tail_start") < 0
+    b = U.rhs(lambda x: w * w * np.cos(w * x), [0.0, math.cos(w * n)])
+    x, it, res, _ = dev.solve(np.zeros(len(b)), b, 100, 1e-10)
+    assert it <= 25 and res[-1] < 1e-10 * np.linalg.norm(b) and np.all(np.diff(res) < 0)
+    dev.close()

@@ -74,6 +74,14 @@ def test_level_operations(case):
             xc = rng.standard_normal(L.shape[1])
             assert np.abs(dev.restrict(l, x) - L.T @ x).max() <= 1e-13 * abs(L).sum(axis=0).max() * np.abs(x).max()
             assert np.abs(dev.prolong(l, xc) - L @ xc).max() <= 1e-13 * abs(L).sum(axis=1).max() * np.abs(xc).max()
+    # A_l \\ b on every level: block cyclic reduction (amg1d_direct_solve) against the sparse direct solve
+    for l in range(nL):
+        A = Ho.mStiffness[l]
+        b = rng.standard_normal(A.shape[0])
+        x_or = osolv._direct_solve(A, b)
+        x_d = np.linalg.solve(sp.csc_matrix(A).toarray(), b)
+        noise = np.abs(x_d - x_or).max() / np.abs(x_or).max()
+        assert np.abs(dev.direct_solve(l, b) - x_or).max() <= max(1e-10, 20 * noise) * np.abs(x_or).max(), l
     A = Ho.mStiffness[-1]
     b = rng.standard_normal(A.shape[0])
     x_or = osolv._direct_solve(A, b)
