@@ -16,7 +16,8 @@ from .agglomerated_dg_mesh import (AgglomeratedDgMesh1, AgglomeratedDgMeshN, agg
                                    uniform_agglomeration)
 from .interpolation import (cg_cg_interpolation, dg_dg_interpolation, dg_cg_interpolation,
                             aggdg_aggdg_interpolation, aggdg_dg_interpolation, aggdg_cg_interpolation)
-from .smoother import AbstractSmoother, JacobiSmoother, BlockJacobi, cg_smoother, dg_smoother
+from .smoother import (AbstractSmoother, JacobiSmoother, BlockJacobi, AdditiveSchwarzSmoother,
+                       HybridSchwarzSmoother, cg_smoother, dg_smoother)
 from .mesh_hierarchy import MeshHierarchy, dg_flux_operators
 from .solvers import (multigrid_v_cycle, multigrid, ldiv, pcg, iterative_smoother_solve, apply_smoother)
 from .device import DeviceHierarchy

@@ -52,6 +52,12 @@ struct Level {
     int K = 0;           // == md.K
     MatDesc md = {};     // structure class and tile-row offsets (layout.cuh)
     int64_t base_n = 0;  // sharded: elements per rank (the last rank also holds n_glob % nranks)
+    // optional block-tridiagonal smoother operator S (overlapping Schwarz smoothers of CG levels,
+    // src/smoother.jl:1-46): z = S r instead of z = Dinv r; stored like a level operator
+    bool smooth_tri = false;
+    double* smat_alloc = nullptr;
+    double* smat = nullptr;
+    MatDesc smd = {};
     int64_t n_host = 0;  // reference vector length
     double* mat = nullptr;
     int64_t* perm = nullptr;  // device, n*m entries, or null
@@ -373,9 +379,21 @@ int op_allreduce_norm(amg1d* h, int) { return fail(h, AMG1D_ERR_UNSUPPORTED, "bu
 #endif
 
 // ---- elementary enqueued operations ---------------------------------------------------------------
+int op_apply(amg1d* h, int l, const double* b, const double* x, double* out, int mode);
+
 int op_sweep(amg1d* h, int l, const double* b, const double* xin, double* xout, double alpha,
              int zero_guess) {
     Level& lv = h->L[l];
+    if (lv.smooth_tri) {
+        // r = b - A x into the scratch vector (its ghost elements stay zero), then x + alpha S r
+        if (zero_guess) CK(cudaMemcpyAsync(h->scratch.p, b, (size_t)lv.n * lv.m * 8, cudaMemcpyDeviceToDevice, h->stream));
+        else RET(op_apply(h, l, b, xin, h->scratch.p, 1));
+        g_apply_tri_smoother<<<ggrid(lv.n, lv.m), gblock(lv.m), 0, h->stream>>>(
+            lv.smat, lv.smd, h->scratch.p, zero_guess ? nullptr : xin, xout, lv.n, alpha);
+        h->launch_counter++;
+        LAUNCH_CHECK();
+        return AMG1D_OK;
+    }
     if (h->opt_fused && fused_sweep(lv.md, lv.mat, b, xin, xout, lv.n, alpha, zero_guess, h->stream)) {
         h->launch_counter++;
         LAUNCH_CHECK();
@@ -546,7 +564,7 @@ int leg_down(amg1d* h, int l, int nPre, double alpha, bool zero0) {
     RET(prof_mark(h, l, 0));
     if (lv.sharded && !zero) RET(op_halo(h, lv.x[lv.cur].p, lv.n, lv.m));   // ghosts of the incoming iterate
     // fused: nPre sweeps + residual + restriction in one pass over the operator
-    if (h->opt_fused && t.fusable) {
+    if (h->opt_fused && t.fusable && !lv.smooth_tri) {
         const int ob = zero ? 0 : 1 - lv.cur;
         if (fused_down(lv.md, t.mc, make_map_closed(t), nPre, zero, lv.mat, lv.b.p, lv.x[lv.cur].p,
                        lv.x[ob].p, t.P0, t.P1, lc.b.p, lv.n, lv.n + (lv.gr ? t.cover_extra : 0), alpha,
@@ -588,7 +606,7 @@ int leg_up(amg1d* h, int l, int nPost, double alpha, bool fuse_norm, bool* norm_
     Transfer& t = h->T[l];
     Level& lc = h->L[l + 1];
     RET(prof_mark(h, l, 1));
-    if (h->opt_fused && t.fusable) {
+    if (h->opt_fused && t.fusable && !lv.smooth_tri) {
         int nb = 0;
         if (fused_up(lv.md, t.mc, make_map_closed(t), nPost, lv.mat, lv.b.p, lv.x[lv.cur].p,
                      lv.x[1 - lv.cur].p, t.P0, t.P1, lc.x[lc.cur].p, lv.n, alpha,
@@ -870,7 +888,7 @@ int build_tail(amg1d* h) {
         int p_len = 0;
         if (l < nl - 1) {
             const Transfer& t = h->T[l];
-            if (lv.diag || !t.single_parent_uniform || t.P1) break;
+            if (lv.diag || lv.smooth_tri || !t.single_parent_uniform || t.P1) break;
             p_len = (int)(t.nblk * m * m);
         }
         const int op_len = (int)(amg1d_tiles(lv.n) * lv.K * AMG1D_TILE);
@@ -1079,6 +1097,7 @@ int amg1d_destroy(amg1d_t* h) {
     for (auto& pr : h->prof) for (auto ev : pr.ev) cudaEventDestroy(ev);
     for (auto& lv : h->L) {
         if (lv.mat_alloc) cudaFree(lv.mat_alloc);
+        if (lv.smat_alloc) cudaFree(lv.smat_alloc);
         if (lv.perm) cudaFree(lv.perm);
         vec_free(lv.x[0]); vec_free(lv.x[1]); vec_free(lv.b);
     }
@@ -1212,6 +1231,51 @@ int amg1d_set_level_pattern(amg1d_t* h, int level, int64_t n_elem, int m, int n_
         }
     }
     lv.set = true;
+    return AMG1D_OK;
+}
+
+int amg1d_set_level_smoother(amg1d_t* h, int level, const double* S_lo, const double* S_di,
+                             const double* S_up) {
+    if (!h) return AMG1D_ERR_ARG;
+    if (!valid_level(h, level)) return fail(h, AMG1D_ERR_ARG, "level %d out of range", level);
+    if (h->finalized) return fail(h, AMG1D_ERR_STATE, "hierarchy already finalized");
+    if (!S_lo || !S_di || !S_up) return fail(h, AMG1D_ERR_ARG, "null smoother array");
+    Level& lv = h->L[level];
+    if (!lv.set) return fail(h, AMG1D_ERR_STATE, "level %d must be set before its smoother operator", level);
+    if (lv.sharded || h->nranks > 1) return fail(h, AMG1D_ERR_UNSUPPORTED, "block-tridiagonal smoothers are single-GPU only");
+    if (lv.smooth_tri) return fail(h, AMG1D_ERR_STATE, "level %d already has a smoother operator", level);
+    CK(cudaSetDevice(h->device));
+    const int m = lv.m, mm = m * m;
+    const int64_t n = lv.n;
+    int st = 0, ilo = 0, iup = 0;
+    if (h->opt_compress) detect_structure(S_lo, S_up, n, m, &st, &ilo, &iup);
+    lv.smd = amg1d_desc(m, 1, st, ilo, iup);            // the "Dinv" rows of this tile are unused (zeros)
+    const int64_t bytes = (amg1d_tiles(n) + 1) * (int64_t)lv.smd.K * AMG1D_TILE * 8;
+    RET(dev_alloc(h, (void**)&lv.smat_alloc, bytes));
+    CK(cudaMemsetAsync(lv.smat_alloc, 0, (size_t)bytes, h->stream));
+    lv.smat = lv.smat_alloc + (int64_t)lv.smd.K * AMG1D_TILE;
+    double *d_lo, *d_di, *d_up, *d_dv;
+    const int64_t c = std::min<int64_t>(1 << 18, (n + 31) / 32 * 32);
+    CK(cudaMalloc(&d_lo, (size_t)c * mm * 8));
+    CK(cudaMalloc(&d_di, (size_t)c * mm * 8));
+    CK(cudaMalloc(&d_up, (size_t)c * mm * 8));
+    CK(cudaMalloc(&d_dv, (size_t)c * m * 8));
+    cudaMemsetAsync(d_dv, 0, (size_t)c * m * 8, h->stream);
+    int rc = AMG1D_OK;
+    for (int64_t e0 = 0; e0 < n && rc == AMG1D_OK; e0 += c) {
+        const int64_t cnt = std::min<int64_t>(c, n - e0);
+        cudaMemcpyAsync(d_lo, S_lo + e0 * mm, (size_t)cnt * mm * 8, cudaMemcpyHostToDevice, h->stream);
+        cudaMemcpyAsync(d_di, S_di + e0 * mm, (size_t)cnt * mm * 8, cudaMemcpyHostToDevice, h->stream);
+        cudaMemcpyAsync(d_up, S_up + e0 * mm, (size_t)cnt * mm * 8, cudaMemcpyHostToDevice, h->stream);
+        const int64_t total = amg1d_tiles(cnt) * (int64_t)lv.smd.K * AMG1D_TILE;
+        k_repack<<<(unsigned)((total + 255) / 256), 256, 0, h->stream>>>(d_lo, d_di, d_up, d_dv, lv.smd, e0, cnt, lv.smat);
+        cudaError_t e = cudaStreamSynchronize(h->stream);
+        if (e == cudaSuccess) e = cudaGetLastError();
+        if (e != cudaSuccess) rc = fail(h, AMG1D_ERR_CUDA, "smoother upload failed: %s", cudaGetErrorString(e));
+    }
+    cudaFree(d_lo); cudaFree(d_di); cudaFree(d_up); cudaFree(d_dv);
+    RET(rc);
+    lv.smooth_tri = true;
     return AMG1D_OK;
 }
 
@@ -1611,6 +1675,10 @@ int amg1d_apply_smoother(amg1d_t* h, int level, double* Y, const double* B, int6
     double* in = lv.x[1 - lv.cur].p;  // free ping-pong buffer as input staging
     for (int64_t c = 0; c < n_rhs; ++c) {
         RET(to_device(h, level, B + c * lv.n_host, in));
+        if (lv.smooth_tri)
+            g_apply_tri_smoother<<<ggrid(lv.n, lv.m), gblock(lv.m), 0, h->stream>>>(
+                lv.smat, lv.smd, in, nullptr, h->scratch.p, lv.n, alpha);
+        else
         g_apply_smoother<<<ggrid(lv.n, lv.m), gblock(lv.m), 0, h->stream>>>(
             lv.mat, lv.md, in, h->scratch.p, lv.n, alpha);
         LAUNCH_CHECK();

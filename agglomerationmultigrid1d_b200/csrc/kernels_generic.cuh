@@ -129,6 +129,23 @@ __global__ void g_apply_smoother(const double* __restrict__ mat, MatDesc d,
     Y[e * m + i] = __dmul_rn(alpha, g_row_Dinv(T, d, i, B + e * m, 1));
 }
 
+// xout = x + alpha * (S r) for a block-tridiagonal smoother operator S stored like a level operator
+// (overlapping Schwarz smoothers, src/smoother.jl:1-46); x == nullptr: xout = alpha * (S r), which is
+// apply_smoother itself.  r must carry zero (or valid) ghost elements.
+__global__ void g_apply_tri_smoother(const double* __restrict__ smat, MatDesc d, const double* __restrict__ r,
+                                     const double* __restrict__ x, double* __restrict__ xout, int64_t n,
+                                     double alpha) {
+    const int m = d.m;
+    const int lane = threadIdx.x, i = threadIdx.y, tz = threadIdx.z;
+    const int64_t tile = (int64_t)blockIdx.x * blockDim.z + tz;
+    const int64_t e = tile * AMG1D_TILE + lane;
+    if (e >= n) return;
+    const double* T = smat + tile * (int64_t)d.K * AMG1D_TILE + lane;
+    const double z = g_row_Ax(T, d, i, r + (e - 1) * m, r + e * m, r + (e + 1) * m);
+    const double az = __dmul_rn(alpha, z);
+    xout[e * m + i] = x ? __dadd_rn(x[e * m + i], az) : az;
+}
+
 // rc[Kc] = sum_{parent(e) = Kc-1} P1[e]' rf[e] + sum_{parent(e) = Kc} P0[e]' rf[e]
 // one thread per (coarse element, coarse row); P blocks are m_f x m_c column-major.
 __global__ void g_restrict(TransferMap tm, int mf, int mc, const double* __restrict__ P0,

@@ -56,6 +56,12 @@ class DeviceHierarchy:
                                            capi.dptr(a_up), capi.dptr(dinv), int(dinv_is_diagonal),
                                            capi.iptr(perm), int(n_dof)))
 
+    def set_level_smoother(self, level, s_lo, s_di, s_up):
+        """Block-tridiagonal smoother operator of a level (Schwarz smoothers); (n, m, m) arrays in (e, i, j) order."""
+        a_lo, a_di, a_up = blk.to_abi(s_lo), blk.to_abi(s_di), blk.to_abi(s_up)
+        self._ck(self._lib.amg1d_set_level_smoother(self._h, level, capi.dptr(a_lo), capi.dptr(a_di),
+                                                    capi.dptr(a_up)))
+
     def set_level_pattern(self, level, n_elem, lo, di, up, dinv, dinv_is_diagonal, n_head, n_tail):
         m = di.shape[1]
         self.n_dof[level] = int(n_elem) * m

@@ -12,14 +12,10 @@ libamg1d.so (the GPU).  There is no CPU implementation behind them.
 """
 import numpy as np
 import scipy.sparse as sp
-import scipy.sparse.linalg as spla
 
 from . import blocks as blk
 from .device import DeviceHierarchy
-from .smoother import AbstractSmoother, smoother_inverse
-
-
-DEVICE_DIRECT_ABOVE = 1 << 18      # DOFs above which u_exact = A \\ b is computed on the GPU
+from .smoother import AbstractSmoother, AdditiveSchwarzSmoother, schwarz_tridiag_blocks, smoother_inverse
 
 
 def _device_of(H):
@@ -53,29 +49,16 @@ def pcg(H, x0, b, maxiter, tol, nPre=3, nPost=3, alpha=2.0 / 3.0):
     return _device_of(H).pcg(x0, b, maxiter, tol, nPre=nPre, nPost=nPost, alpha=alpha)
 
 
-def _host_direct_solve(A, b):
-    """u_exact = A \\ b for the *error history only* (src/solvers.jl:120).  This is set-up-side
-    bookkeeping the reference does with SuiteSparse; it is not part of the iteration."""
-    A = sp.csc_matrix(A)
-    if A.shape[0] == 1:
-        return np.asarray(b, dtype=np.float64) / A[0, 0]
-    return spla.spsolve(A, np.asarray(b, dtype=np.float64))
-
-
 def multigrid(H, x0, b, maxiter, tol, u_exact=None, with_error=True):
     """Always cycles with nPre = nPost = 3, alpha = 2/3 like the reference (src/solvers.jl:125).
-    ``err`` needs u_exact = A \\ b; pass ``with_error=False`` to skip that host solve at large n
-    (err is then filled with NaN)."""
+    ``err`` needs u_exact = A \\ b (GPU direct solve, ~10 n m^2 doubles of factors); pass
+    ``with_error=False`` to skip it (err is then filled with NaN)."""
     b = np.asarray(b, dtype=np.float64)
     if maxiter <= 0:
         return np.zeros(len(x0)), 0, np.zeros(0), np.zeros(0)
     if u_exact is None and with_error:
-        # src/solvers.jl:120: u_exact = A \\ b.  Small systems: the host's sparse LU, as the reference does;
-        # large ones: block cyclic reduction on the GPU (amg1d_direct_solve)
-        if len(b) <= DEVICE_DIRECT_ABOVE:
-            u_exact = _host_direct_solve(H.mStiffness[0], b)
-        else:
-            u_exact = _device_of(H).direct_solve(0, b)
+        # src/solvers.jl:120: u_exact = A \\ b - block cyclic reduction on the GPU (amg1d_direct_solve)
+        u_exact = _device_of(H).direct_solve(0, b)
     return _device_of(H).solve(x0, b, maxiter, tol, u_exact=u_exact)
 
 
@@ -90,6 +73,8 @@ def _single_level(A, smoother):
     dinv, is_diag = smoother_inverse(smoother, slots)
     dev = DeviceHierarchy(1)
     dev.set_level_blocks(0, lo, di, up, dinv, is_diag, slots, A.shape[0])
+    if isinstance(smoother, AdditiveSchwarzSmoother):       # also HybridSchwarzSmoother
+        dev.set_level_smoother(0, *schwarz_tridiag_blocks(smoother, slots))
     dev.finalize()
     smoother._device = dev
     smoother._device_A = A
@@ -116,7 +101,7 @@ def iterative_smoother_solve(A, smoother, x0, b, maxiter=1000, tol=1e-6, alpha=1
     b = np.asarray(b, dtype=np.float64)
     if maxiter <= 0:
         return np.zeros(len(x0)), 0, np.zeros(0), np.zeros(0)
-    if u_exact is None and with_error:
-        u_exact = _host_direct_solve(A, b)
     dev = _single_level(A, smoother)
+    if u_exact is None and with_error:
+        u_exact = dev.direct_solve(0, b)          # src/solvers.jl:194, on the GPU
     return dev.smoother_solve(0, x0, b, maxiter=maxiter, tol=tol, alpha=alpha, u_exact=u_exact)

@@ -72,6 +72,15 @@ int amg1d_set_level(amg1d_t* h, int level, int64_t n_elem, int m, const double* 
                     const double* A_di, const double* A_up, const double* Dinv,
                     int dinv_is_diagonal, const int64_t* perm, int64_t n_dof_host);
 
+/* Replaces the smoother of a level that has been set by a block-TRIDIAGONAL smoother operator S:
+ * z = S r with S r[e] = S_lo[e] r[e-1] + S_di[e] r[e] + S_up[e] r[e+1] (blocks as in amg1d_set_level).
+ * This is the form the overlapping Schwarz smoothers of CG levels take in the [vertex_k, interior_k]
+ * grouping (AdditiveSchwarzSmoother / HybridSchwarzSmoother, src/smoother.jl:1-46, built by
+ * cg_smoother(:addSchwarz / :hybridSchwarz), :104-135): an element's local solve touches its own group
+ * and the first slot of the next one.  Such levels smooth with the generic (unfused) kernels. */
+int amg1d_set_level_smoother(amg1d_t* h, int level, const double* S_lo, const double* S_di,
+                             const double* S_up);
+
 /* Same operator given as a translation-invariant pattern (uniform meshes at 2^20..2^26 elements,
  * where per-element host arrays would be tens of GB): the first n_head and last n_tail elements are
  * explicit, every element in between repeats the single `interior` block set.  Arrays hold

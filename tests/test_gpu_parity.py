@@ -175,8 +175,12 @@ def test_multigrid_histories(case):
     tol = np.maximum(np.maximum(REL * res_or, floor), noise)
     assert np.all(np.abs(res - res_or) <= tol), (name, res, res_or, floor)
     assert np.abs(x - x_or).max() <= 1e-9 * np.abs(x_or).max()
-    # error history against the direct solve (both sides use their own A \ b)
-    assert np.all(np.abs(err - err_or) <= np.maximum(1e-8 * err_or, 1e-9 * np.linalg.norm(x_or)))
+    # error history against the direct solve (both sides use their own A \ b: SuperLU in the oracle, block
+    # cyclic reduction on the GPU; the two u_exact differ by the conditioning noise of the problem, measured
+    # as before by SuperLU vs dense LAPACK on the CPU)
+    A0 = sp.csc_matrix(Ho.mStiffness[0])
+    du = np.linalg.norm(np.linalg.solve(A0.toarray(), bo) - osolv._direct_solve(A0, bo))
+    assert np.all(np.abs(err - err_or) <= np.maximum(np.maximum(1e-8 * err_or, 1e-9 * np.linalg.norm(x_or)), 20 * du))
 
 
 def test_fused_and_generic_tiers_agree(case):
