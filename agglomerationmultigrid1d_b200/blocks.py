@@ -44,9 +44,10 @@ def is_identity_slots(slots):
     return bool(np.array_equal(slots.ravel(), np.arange(slots.size)))
 
 
-def csc_to_blocks(A, slots):
+def csc_to_blocks(A, slots, pad_identity=True):
     """Block-tridiagonal blocks (lo, di, up), each (n_elem, m, m) in (e, i, j) order.
-    Raises if A has an entry outside the block-tridiagonal band.  Padding rows get a unit diagonal."""
+    Raises if A has an entry outside the block-tridiagonal band.  Padding rows get a unit diagonal
+    (level operators; not the flux operators G, D, C)."""
     A = sp.coo_matrix(A)
     ne, m = slots.shape
     elem_of, local_of = slot_lookup(slots, A.shape[0])
@@ -59,8 +60,9 @@ def csc_to_blocks(A, slots):
     for k, off in enumerate((-1, 0, 1)):
         sel = (d == off)
         np.add.at(out[k], (er[sel], local_of[A.row[sel]], local_of[A.col[sel]]), A.data[sel])
-    pe, pi = np.nonzero(slots < 0)
-    out[1][pe, pi, pi] = 1.0
+    if pad_identity:
+        pe, pi = np.nonzero(slots < 0)
+        out[1][pe, pi, pi] = 1.0
     return out[0], out[1], out[2]
 
 

@@ -22,6 +22,7 @@
 #include "kernels_generic.cuh"
 #include "kernels_fused.cuh"
 #include "direct_bcr.cuh"
+#include "device_setup.cuh"
 
 #define AMG1D_VERSION 100
 #define PAD_FRONT 64  // doubles in front of element 0 (ghost elements live at the end of them)
@@ -54,6 +55,9 @@ struct Level {
     int64_t base_n = 0;  // sharded: elements per rank (the last rank also holds n_glob % nranks)
     // optional block-tridiagonal smoother operator S (overlapping Schwarz smoothers of CG levels,
     // src/smoother.jl:1-46): z = S r instead of z = Dinv r; stored like a level operator
+    // flux operators G, D, C of the level as element-block arrays on the device (lo, di, up each), kept
+    // between amg1d_set_level_flux / amg1d_coarsen_level and amg1d_finalize (device-side set-up)
+    double* flux[9] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
     bool smooth_tri = false;
     double* smat_alloc = nullptr;
     double* smat = nullptr;
@@ -1012,6 +1016,88 @@ int alloc_level_common(amg1d* h, int level, int64_t n_elem, int m, int diag, con
     return AMG1D_OK;
 }
 
+void free_flux(amg1d* h, Level& lv) {
+    for (double*& p : lv.flux)
+        if (p) { cudaFree(p); p = nullptr; h->device_bytes -= lv.n * lv.m * lv.m * 8; }
+}
+
+// Device-side set-up of one level from its flux operators (device_setup.cuh): A = C - D M^-1 G, block-
+// Jacobi inverses, structure detection, tile layout.  flux: 9 element-block device arrays; d_minv: n
+// blocks (or one when mi_const).  The level is installed exactly as amg1d_set_level would.
+int install_from_flux(amg1d* h, int level, int64_t n, int m, double* const* flux, const double* d_minv,
+                      int mi_const) {
+    const int mm = m * m;
+    double *dA[3] = {nullptr, nullptr, nullptr}, *dDinv = nullptr, *dband = nullptr;
+    int *dmask = nullptr, *dflag = nullptr;
+    auto cleanup = [&]() {
+        for (double* p : dA) if (p) cudaFree(p);
+        if (dDinv) cudaFree(dDinv);
+        if (dband) cudaFree(dband);
+        if (dmask) cudaFree(dmask);
+        if (dflag) cudaFree(dflag);
+    };
+#define CKC(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { cleanup(); \
+        return fail(h, e_ == cudaErrorMemoryAllocation ? AMG1D_ERR_NOMEM : AMG1D_ERR_CUDA, "%s failed: %s", #call, cudaGetErrorString(e_)); } } while (0)
+    for (auto& p : dA) CKC(cudaMalloc((void**)&p, (size_t)n * mm * 8));
+    CKC(cudaMalloc((void**)&dDinv, (size_t)n * mm * 8));
+    CKC(cudaMalloc((void**)&dband, 2 * 8));
+    CKC(cudaMalloc((void**)&dmask, 4 * m * sizeof(int)));
+    CKC(cudaMalloc((void**)&dflag, sizeof(int)));
+    cudaMemsetAsync(dband, 0, 16, h->stream);
+    cudaMemsetAsync(dmask, 0, 4 * m * sizeof(int), h->stream);
+    cudaMemsetAsync(dflag, 0, sizeof(int), h->stream);
+    const unsigned grid = (unsigned)((n * mm + 127) / 128);
+    k_flux_operator<<<grid, 128, 0, h->stream>>>(flux[0], flux[1], flux[2], flux[3], flux[4], flux[5], flux[6],
+                                                  flux[7], flux[8], d_minv, mi_const, n, m, dA[0], dA[1], dA[2],
+                                                  dband);
+    CKC(cudaMemcpyAsync(dDinv, dA[1], (size_t)n * mm * 8, cudaMemcpyDeviceToDevice, h->stream));
+    k_bcr_invert_odd<<<(unsigned)((n + 31) / 32), 32, 0, h->stream>>>(dDinv, m, n, 0, 1, dflag);
+    k_structure_masks<<<grid, 128, 0, h->stream>>>(dA[0], dA[2], n, m, dmask);
+    double band[2] = {0.0, 0.0};
+    int flag = 0;
+    std::vector<int> mask(4 * (size_t)m, 0);
+    CKC(cudaMemcpyAsync(band, dband, 16, cudaMemcpyDeviceToHost, h->stream));
+    CKC(cudaMemcpyAsync(&flag, dflag, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+    CKC(cudaMemcpyAsync(mask.data(), dmask, 4 * m * sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+    CKC(cudaStreamSynchronize(h->stream));
+    CKC(cudaGetLastError());
+    if (flag) { cleanup(); return fail(h, AMG1D_ERR_ARG, "level %d: singular diagonal block", level); }
+    if (band[0] > 1e-11 * band[1]) {
+        cleanup();
+        return fail(h, AMG1D_ERR_ARG, "level %d: C - D M^-1 G is not block tridiagonal (outer band %.3e vs "
+                    "diagonal %.3e)", level, band[0], band[1]);
+    }
+    int st = AMG1D_ST_DENSE, ilo = 0, iup = 0;
+    if (h->opt_compress && m >= 2) {
+        auto single = [m](const int* mk, int* idx) {
+            int cnt = 0;
+            *idx = 0;
+            for (int q = 0; q < m; ++q) if (mk[q]) { ++cnt; *idx = q; }
+            return cnt <= 1;
+        };
+        int a, b;
+        if (single(&mask[0], &a) && single(&mask[3 * m], &b)) { st = AMG1D_ST_COLROW; ilo = a; iup = b; }
+        else if (single(&mask[m], &a) && single(&mask[2 * m], &b)) { st = AMG1D_ST_ROWCOL; ilo = a; iup = b; }
+    }
+    int rc = alloc_level_common(h, level, n, m, 0, nullptr, n * m, st, ilo, iup);
+    if (rc != AMG1D_OK) { cleanup(); return rc; }
+    Level& lv = h->L[level];
+    const int64_t total = amg1d_tiles(n) * (int64_t)lv.K * AMG1D_TILE;
+    k_repack<<<(unsigned)((total + 255) / 256), 256, 0, h->stream>>>(dA[0], dA[1], dA[2], dDinv, lv.md, 0, n, lv.mat);
+    if (n <= AMG1D_BCR_MIN) {                      // host copy for the block-Thomas factorisation
+        lv.h_lo.resize((size_t)n * mm); lv.h_di.resize((size_t)n * mm); lv.h_up.resize((size_t)n * mm);
+        CKC(cudaMemcpyAsync(lv.h_lo.data(), dA[0], (size_t)n * mm * 8, cudaMemcpyDeviceToHost, h->stream));
+        CKC(cudaMemcpyAsync(lv.h_di.data(), dA[1], (size_t)n * mm * 8, cudaMemcpyDeviceToHost, h->stream));
+        CKC(cudaMemcpyAsync(lv.h_up.data(), dA[2], (size_t)n * mm * 8, cudaMemcpyDeviceToHost, h->stream));
+    }
+    CKC(cudaStreamSynchronize(h->stream));
+    CKC(cudaGetLastError());
+#undef CKC
+    cleanup();
+    lv.set = true;
+    return AMG1D_OK;
+}
+
 }  // namespace
 
 // =====================================================================================================
@@ -1098,6 +1184,7 @@ int amg1d_destroy(amg1d_t* h) {
     for (auto& lv : h->L) {
         if (lv.mat_alloc) cudaFree(lv.mat_alloc);
         if (lv.smat_alloc) cudaFree(lv.smat_alloc);
+        free_flux(h, lv);
         if (lv.perm) cudaFree(lv.perm);
         vec_free(lv.x[0]); vec_free(lv.x[1]); vec_free(lv.b);
     }
@@ -1276,6 +1363,97 @@ int amg1d_set_level_smoother(amg1d_t* h, int level, const double* S_lo, const do
     cudaFree(d_lo); cudaFree(d_di); cudaFree(d_up); cudaFree(d_dv);
     RET(rc);
     lv.smooth_tri = true;
+    return AMG1D_OK;
+}
+
+static int upload_blocks(amg1d* h, double** dst, const double* src, int64_t count) {
+    CK(cudaMalloc((void**)dst, (size_t)std::max<int64_t>(count, 1) * 8));
+    CK(cudaMemcpyAsync(*dst, src, (size_t)count * 8, cudaMemcpyHostToDevice, h->stream));
+    return AMG1D_OK;
+}
+
+int amg1d_set_level_flux(amg1d_t* h, int level, int64_t n_elem, int m, const double* G_lo,
+                         const double* G_di, const double* G_up, const double* D_lo, const double* D_di,
+                         const double* D_up, const double* C_lo, const double* C_di, const double* C_up,
+                         const double* Minv, int minv_is_constant) {
+    if (!h) return AMG1D_ERR_ARG;
+    const double* src[9] = {G_lo, G_di, G_up, D_lo, D_di, D_up, C_lo, C_di, C_up};
+    for (const double* p : src) if (!p) return fail(h, AMG1D_ERR_ARG, "null flux operator array");
+    if (!Minv) return fail(h, AMG1D_ERR_ARG, "null mass-matrix inverse");
+    if (!valid_level(h, level)) return fail(h, AMG1D_ERR_ARG, "level %d out of range", level);
+    if (h->finalized) return fail(h, AMG1D_ERR_STATE, "hierarchy already finalized");
+    if (h->nranks > 1) return fail(h, AMG1D_ERR_UNSUPPORTED, "device-side set-up is single-GPU only");
+    if (n_elem < 1 || m < 1 || m > AMG1D_BCR_MAXM) return fail(h, AMG1D_ERR_ARG, "need n_elem >= 1 and 1 <= m <= 32");
+    Level& lv = h->L[level];
+    if (lv.set) return fail(h, AMG1D_ERR_STATE, "level %d already set", level);
+    CK(cudaSetDevice(h->device));
+    const int64_t cnt = n_elem * m * m;
+    for (int k = 0; k < 9; ++k) {
+        RET(upload_blocks(h, &lv.flux[k], src[k], cnt));
+        h->device_bytes += cnt * 8;
+    }
+    double* d_minv = nullptr;
+    RET(upload_blocks(h, &d_minv, Minv, minv_is_constant ? (int64_t)m * m : cnt));
+    lv.n = n_elem; lv.m = m;                       // for free_flux if the installation fails
+    const int rc = install_from_flux(h, level, n_elem, m, lv.flux, d_minv, minv_is_constant);
+    cudaFree(d_minv);
+    return rc;
+}
+
+int amg1d_coarsen_level(amg1d_t* h, int level, const double* Minv_coarse, int minv_is_constant) {
+    if (!h) return AMG1D_ERR_ARG;
+    if (level < 0 || level >= h->n_levels - 1) return fail(h, AMG1D_ERR_ARG, "level %d has no coarser level", level);
+    if (h->finalized) return fail(h, AMG1D_ERR_STATE, "hierarchy already finalized");
+    if (!Minv_coarse) return fail(h, AMG1D_ERR_ARG, "null mass-matrix inverse");
+    Level& lf = h->L[level];
+    Level& lc = h->L[level + 1];
+    Transfer& t = h->T[level];
+    if (!lf.set || !lf.flux[0]) return fail(h, AMG1D_ERR_STATE, "level %d has no flux operators (amg1d_set_level_flux / amg1d_coarsen_level)", level);
+    if (!t.set) return fail(h, AMG1D_ERR_STATE, "transfer %d must be set before amg1d_coarsen_level", level);
+    if (lc.set) return fail(h, AMG1D_ERR_STATE, "level %d already set", level + 1);
+    if (!t.single_parent_uniform)
+        return fail(h, AMG1D_ERR_UNSUPPORTED, "device-side coarsening needs a single-parent transfer with parent[e] = e / ratio");
+    if (t.n_fine != lf.n || t.mf != lf.m) return fail(h, AMG1D_ERR_ARG, "transfer %d does not match level %d", level, level);
+    CK(cudaSetDevice(h->device));
+    const int mc = t.mc;
+    const int64_t nc = t.n_coarse, cnt = nc * mc * mc;
+    lc.n = nc; lc.m = mc;
+    for (int k = 0; k < 9; ++k) {
+        CK(cudaMalloc((void**)&lc.flux[k], (size_t)cnt * 8));
+        h->device_bytes += cnt * 8;
+    }
+    const TransferMap tm = make_map_closed(t);
+    const unsigned grid = (unsigned)((cnt + 127) / 128);
+    for (int k = 0; k < 3; ++k)
+        k_galerkin_tri<<<grid, 128, 0, h->stream>>>(lf.flux[3 * k], lf.flux[3 * k + 1], lf.flux[3 * k + 2], t.P0, tm,
+                                                     t.mf, mc, lc.flux[3 * k], lc.flux[3 * k + 1], lc.flux[3 * k + 2]);
+    LAUNCH_CHECK();
+    double* d_minv = nullptr;
+    RET(upload_blocks(h, &d_minv, Minv_coarse, minv_is_constant ? (int64_t)mc * mc : cnt));
+    const int rc = install_from_flux(h, level + 1, nc, mc, lc.flux, d_minv, minv_is_constant);
+    cudaFree(d_minv);
+    return rc;
+}
+
+int amg1d_get_level(amg1d_t* h, int level, double* A_lo, double* A_di, double* A_up, double* Dinv) {
+    if (!h) return AMG1D_ERR_ARG;
+    if (!valid_level(h, level) || !h->L[level].set) return fail(h, AMG1D_ERR_ARG, "level %d is not set", level);
+    if (h->nranks > 1) return fail(h, AMG1D_ERR_UNSUPPORTED, "per-level host operations are single-GPU only");
+    if (!A_lo || !A_di || !A_up || !Dinv) return fail(h, AMG1D_ERR_ARG, "null output array");
+    Level& lv = h->L[level];
+    CK(cudaSetDevice(h->device));
+    const int64_t cnt = lv.n * lv.m * lv.m, dcnt = lv.n * (lv.diag ? lv.m : lv.m * lv.m);
+    double *d[3] = {nullptr, nullptr, nullptr}, *dv = nullptr;
+    for (auto& p : d) CK(cudaMalloc((void**)&p, (size_t)cnt * 8));
+    CK(cudaMalloc((void**)&dv, (size_t)dcnt * 8));
+    k_bcr_extract<<<(unsigned)((cnt + 255) / 256), 256, 0, h->stream>>>(lv.mat, lv.md, lv.n, d[0], d[1], d[2]);
+    k_extract_dinv<<<(unsigned)((dcnt + 255) / 256), 256, 0, h->stream>>>(lv.mat, lv.md, lv.n, dv);
+    double* out[3] = {A_lo, A_di, A_up};
+    for (int k = 0; k < 3; ++k) CK(cudaMemcpyAsync(out[k], d[k], (size_t)cnt * 8, cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaMemcpyAsync(Dinv, dv, (size_t)dcnt * 8, cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    for (auto p : d) cudaFree(p);
+    cudaFree(dv);
     return AMG1D_OK;
 }
 
@@ -1467,6 +1645,7 @@ int amg1d_finalize(amg1d_t* h) {
     CK(cudaMallocHost(&h->h_scal, 64 * 8));
     if (h->L[h->n_levels - 1].present) RET(factor_coarsest(h));
     RET(build_tail(h));
+    for (auto& lv : h->L) free_flux(h, lv);
     CK(cudaStreamSynchronize(h->stream));
     h->finalized = true;
     return AMG1D_OK;

@@ -1,0 +1,144 @@
+// Device-side set-up of the DG-type level chain: what the reference does on the host in
+//   src/mesh_heirarchy.jl:75-106, :160-176   G, D, C  <-  L' (G, D, C) L  (Galerkin products, sparse)
+//                                            A = C - D (M \ G)            (block-diagonal mass matrix)
+//   src/smoother.jl:154-164                  block-Jacobi blocks A[el, el] and their factorisation
+// in element-block form on the GPU.  G, D, C are block tridiagonal in the element grouping, the
+// transfers of the DG-type chain (dg_dg, aggdg_dg, aggdg_aggdg) are element local with a single parent,
+// so every product is a small dense computation per (coarse) element:
+//
+//   Xc_di[K] = sum_{e in ch(K)} P[e]' ( X_di[e] P[e] + [e-1 in ch(K)] X_lo[e] P[e-1] + [e+1 in ch(K)] X_up[e] P[e+1] )
+//   Xc_lo[K] = P[e0]' X_lo[e0] P[e0-1]        e0 = first child of K (e0 - 1 = last child of K - 1)
+//   Xc_up[K] = P[e1]' X_up[e1] P[e1+1]        e1 = last child of K
+//
+//   A_di[e] = C_di[e] - ( D_lo[e] Mi[e-1] G_up[e-1] + D_di[e] Mi[e] G_di[e] + D_up[e] Mi[e+1] G_lo[e+1] )
+//   A_lo[e] = C_lo[e] - ( D_lo[e] Mi[e-1] G_di[e-1] + D_di[e] Mi[e] G_lo[e] )
+//   A_up[e] = C_up[e] - ( D_di[e] Mi[e] G_up[e]     + D_up[e] Mi[e+1] G_di[e+1] )
+// with Mi = M^-1 per element.  The product D M^-1 G is block PENTA-diagonal in general; the reference's
+// one-sided fluxes make its outer bands vanish (every level operator is block tridiagonal),
+// which the kernel verifies instead of assuming (band_max reports the largest outer-band entry).
+// All arrays here are plain element-block arrays (n blocks of m x m, column-major); k_repack then
+// brings the result into the tile layout of the solver kernels.
+#pragma once
+#include <cuda_runtime.h>
+
+#include <cstdint>
+
+#include "kernels_generic.cuh"
+#include "layout.cuh"
+
+// entry (i, j) of  P[ea]' X P[eb]  for X = X[e] (m_f x m_f), P blocks m_f x m_c column-major
+__device__ __forceinline__ double ds_ptxp(const double* Pa, const double* X, const double* Pb, int mf,
+                                          int i, int j) {
+    double s = 0.0;
+    for (int b = 0; b < mf; ++b) {
+        double t = 0.0;
+        for (int a = 0; a < mf; ++a) t = fma(Pa[i * mf + a], X[b * mf + a], t);   // (P' X)(i, b)
+        s = fma(t, Pb[j * mf + b], s);
+    }
+    return s;
+}
+
+// one thread per (coarse element K, column j, row i); single-parent transfers only
+__global__ void k_galerkin_tri(const double* __restrict__ lo, const double* __restrict__ di,
+                               const double* __restrict__ up, const double* __restrict__ P, TransferMap tm,
+                               int mf, int mc, double* __restrict__ lo_c, double* __restrict__ di_c,
+                               double* __restrict__ up_c) {
+    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int mmc = mc * mc, mmf = mf * mf, bs = mf * mc;
+    if (t >= tm.n_coarse * mmc) return;
+    const int64_t K = t / mmc;
+    const int q = (int)(t % mmc);
+    const int j = q / mc, i = q % mc;
+    const int64_t c0 = tm.first(K), c1 = tm.first(K + 1);
+    double d = 0.0, l = 0.0, u = 0.0;
+    for (int64_t e = c0; e < c1; ++e) {
+        const double* Pe = P + tm.blk(e) * bs;
+        d += ds_ptxp(Pe, di + e * mmf, Pe, mf, i, j);
+        if (e > c0) d += ds_ptxp(Pe, lo + e * mmf, P + tm.blk(e - 1) * bs, mf, i, j);
+        if (e < c1 - 1) d += ds_ptxp(Pe, up + e * mmf, P + tm.blk(e + 1) * bs, mf, i, j);
+    }
+    if (c1 > c0) {
+        if (c0 > 0) l = ds_ptxp(P + tm.blk(c0) * bs, lo + c0 * mmf, P + tm.blk(c0 - 1) * bs, mf, i, j);
+        if (c1 < tm.n_fine) u = ds_ptxp(P + tm.blk(c1 - 1) * bs, up + (c1 - 1) * mmf, P + tm.blk(c1) * bs, mf, i, j);
+    }
+    di_c[t] = d;
+    lo_c[t] = l;
+    up_c[t] = u;
+}
+
+// entry (i, j) of  D Mi G  (all m x m column-major)
+__device__ __forceinline__ double ds_dmg(const double* D, const double* Mi, const double* G, int m, int i, int j) {
+    double s = 0.0;
+    for (int b = 0; b < m; ++b) {
+        double t = 0.0;
+        for (int a = 0; a < m; ++a) t = fma(D[a * m + i], Mi[b * m + a], t);       // (D Mi)(i, b)
+        s = fma(t, G[j * m + b], s);
+    }
+    return s;
+}
+
+__device__ __forceinline__ void atomic_max_nonneg(double* addr, double v) {
+    // non-negative doubles order like their bit patterns
+    atomicMax(reinterpret_cast<unsigned long long*>(addr), (unsigned long long)__double_as_longlong(v));
+}
+
+// A = C - D M^-1 G, tridiagonal part; band_max[0] <- max |outer-band entry|.  One thread per (e, j, i).
+// Mi: n blocks, or one block for every element when mi_const != 0.
+__global__ void k_flux_operator(const double* __restrict__ Glo, const double* __restrict__ Gdi,
+                                const double* __restrict__ Gup, const double* __restrict__ Dlo,
+                                const double* __restrict__ Ddi, const double* __restrict__ Dup,
+                                const double* __restrict__ Clo, const double* __restrict__ Cdi,
+                                const double* __restrict__ Cup, const double* __restrict__ Mi, int mi_const,
+                                int64_t n, int m, double* __restrict__ Alo, double* __restrict__ Adi,
+                                double* __restrict__ Aup, double* __restrict__ band_max) {
+    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int mm = m * m;
+    if (t >= n * mm) return;
+    const int64_t e = t / mm;
+    const int q = (int)(t % mm);
+    const int j = q / m, i = q % m;
+    auto mi = [&](int64_t k) { return Mi + (mi_const ? 0 : k * mm); };
+    const bool hl = e > 0, hr = e < n - 1;
+    double d = ds_dmg(Ddi + e * mm, mi(e), Gdi + e * mm, m, i, j);
+    double l = ds_dmg(Ddi + e * mm, mi(e), Glo + e * mm, m, i, j);
+    double u = ds_dmg(Ddi + e * mm, mi(e), Gup + e * mm, m, i, j);
+    double band = 0.0;
+    if (hl) {
+        d += ds_dmg(Dlo + e * mm, mi(e - 1), Gup + (e - 1) * mm, m, i, j);
+        l += ds_dmg(Dlo + e * mm, mi(e - 1), Gdi + (e - 1) * mm, m, i, j);
+        band = fmax(band, fabs(ds_dmg(Dlo + e * mm, mi(e - 1), Glo + (e - 1) * mm, m, i, j)));
+    }
+    if (hr) {
+        d += ds_dmg(Dup + e * mm, mi(e + 1), Glo + (e + 1) * mm, m, i, j);
+        u += ds_dmg(Dup + e * mm, mi(e + 1), Gdi + (e + 1) * mm, m, i, j);
+        band = fmax(band, fabs(ds_dmg(Dup + e * mm, mi(e + 1), Gup + (e + 1) * mm, m, i, j)));
+    }
+    Adi[t] = Cdi[t] - d;
+    Alo[t] = hl ? Clo[t] - l : 0.0;
+    Aup[t] = hr ? Cup[t] - u : 0.0;
+    if (band > 0.0) atomic_max_nonneg(band_max, band);
+    atomic_max_nonneg(band_max + 1, fabs(Adi[t]));
+}
+
+// Union sparsity masks of the off-diagonal blocks: masks[0..m) columns of lo, [m..2m) rows of lo,
+// [2m..3m) columns of up, [3m..4m) rows of up.
+__global__ void k_structure_masks(const double* __restrict__ lo, const double* __restrict__ up, int64_t n,
+                                  int m, int* __restrict__ masks) {
+    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int mm = m * m;
+    if (t >= n * mm) return;
+    const int q = (int)(t % mm);
+    const int j = q / m, i = q % m;
+    if (lo[t] != 0.0) { masks[j] = 1; masks[m + i] = 1; }
+    if (up[t] != 0.0) { masks[2 * m + j] = 1; masks[3 * m + i] = 1; }
+}
+
+// Dinv rows of a level's tiles -> element-block array (n blocks of m*m, or n * m for a diagonal smoother)
+__global__ void k_extract_dinv(const double* __restrict__ mat, MatDesc d, int64_t n, double* __restrict__ dinv) {
+    const int dsz = d.diag ? d.m : d.m * d.m;
+    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n * dsz) return;
+    const int64_t e = t / dsz;
+    const int q = (int)(t % dsz);
+    dinv[t] = mat[(e >> 5) * (int64_t)d.K * AMG1D_TILE + (int64_t)(d.o_dv + q) * AMG1D_TILE + (e & 31)];
+}

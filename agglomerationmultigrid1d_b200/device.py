@@ -56,6 +56,32 @@ class DeviceHierarchy:
                                            capi.dptr(a_up), capi.dptr(dinv), int(dinv_is_diagonal),
                                            capi.iptr(perm), int(n_dof)))
 
+    def set_level_flux(self, level, G, D, C, minv):
+        """Device-side set-up of a level from its flux operators: G, D, C are (lo, di, up) triples of
+        (n, m, m) blocks in (e, i, j) order, minv the (n, m, m) inverse mass blocks (or one (m, m) block)."""
+        n, m = G[1].shape[0], G[1].shape[1]
+        arrs = [blk.to_abi(a) for X in (G, D, C) for a in X]
+        const = minv.ndim == 2
+        mi = blk.to_abi(minv[None] if const else minv)
+        self.n_dof[level] = n * m
+        self._ck(self._lib.amg1d_set_level_flux(self._h, level, n, m, *[capi.dptr(a) for a in arrs],
+                                                capi.dptr(mi), int(const)))
+
+    def coarsen_level(self, level, minv_coarse, n_coarse):
+        """level + 1 <- Galerkin coarsening of level on the GPU (transfer `level` must be set)."""
+        const = minv_coarse.ndim == 2
+        mi = blk.to_abi(minv_coarse[None] if const else minv_coarse)
+        self.n_dof[level + 1] = int(n_coarse) * mi.shape[1]
+        self._ck(self._lib.amg1d_coarsen_level(self._h, level, capi.dptr(mi), int(const)))
+
+    def get_level(self, level, n, m, diag=False):
+        """(lo, di, up) as (n, m, m) blocks in (e, i, j) order and Dinv ((n, m, m), or (n, m) if diag)."""
+        out = [np.zeros((n, m, m)) for _ in range(3)]
+        dinv = np.zeros((n, m) if diag else (n, m, m))
+        self._ck(self._lib.amg1d_get_level(self._h, level, *[capi.dptr(a) for a in out], capi.dptr(dinv)))
+        tr = lambda a: np.ascontiguousarray(np.transpose(a, (0, 2, 1)))      # noqa: E731  ABI is column-major
+        return tr(out[0]), tr(out[1]), tr(out[2]), (dinv if diag else tr(dinv))
+
     def set_level_smoother(self, level, s_lo, s_di, s_up):
         """Block-tridiagonal smoother operator of a level (Schwarz smoothers); (n, m, m) arrays in (e, i, j) order."""
         a_lo, a_di, a_up = blk.to_abi(s_lo), blk.to_abi(s_di), blk.to_abi(s_up)

@@ -47,14 +47,23 @@ class MeshHierarchy:
     mSmoothers, mInterpolation, mBdConds; plus ``device`` (the uploaded hierarchy)."""
 
     def __init__(self, mMeshes, *args, nCG=None, nDG=None, nAgg=0, CDir=1.0, device=0, upload=True,
-                 stream=None):
+                 stream=None, device_setup=False):
+        """device_setup=True (DG-first constructor only): the host assembles level 0's flux operators and
+        the element-local transfers; the Galerkin products, A = C - D (M \\ G) and the smoother blocks of
+        every level are computed on the GPU.  mStiffness[k], k > 0, then stay None on the
+        host; ``level_blocks(k)`` downloads them."""
         self.mMeshes = list(mMeshes)
+        self.device_setup = bool(device_setup)
         if len(args) == 3:                      # (mesh, mBdConds, A): CG-first constructor
             mesh, mBdConds, A = args
             self._build_cg_first(mesh, mBdConds, A, 1 if nCG is None else nCG,
                                  0 if nDG is None else nDG, nAgg, CDir)
         elif len(args) == 5:                    # (mBdConds, A, G, D, C): DG-first constructor
             mBdConds, A, G, D, C = args
+            if self.device_setup:
+                self._build_dg_first_on_device(mBdConds, A, G, D, C, 1 if nDG is None else nDG, nAgg,
+                                               device, stream)
+                return
             self._build_dg_first(mBdConds, A, G, D, C, 1 if nDG is None else nDG, nAgg)
         else:
             raise TypeError("MeshHierarchy(mMeshes, mesh, mBdConds, A; ...) or "
@@ -136,6 +145,50 @@ class MeshHierarchy:
             Gs[k], Ds[k], Cs[k] = _galerkin(L, Gs[k - 1]), _galerkin(L, Ds[k - 1]), _galerkin(L, Cs[k - 1])
             S[k], Sm[k] = _dg_level(M[k], Gs[k], Ds[k], Cs[k])
         self._set(S, Gs, Ds, Cs, Sm, I, mBdConds)
+
+    # ---- the same chain with the Galerkin products on the GPU ------------------------
+    def _build_dg_first_on_device(self, mBdConds, A, G, D, C, nDG, nAgg, device, stream):
+        from .smoother import DeviceBlockJacobi
+        import numpy as np
+        M = self.mMeshes
+        if nDG <= 0:
+            raise ValueError("At least one DG mesh required.")
+        if len(M) != nDG + nAgg:
+            raise ValueError("Length of vector of meshes does not match inputed number of DG and "
+                             "agglomerated meshes.")
+        nL = nDG + nAgg
+        slots = [blk.level_slots(m) for m in M]
+        if not all(blk.is_identity_slots(s) for s in slots):
+            raise ValueError("device-side set-up needs DG-type levels (element-major DOF numbering)")
+        dev = DeviceHierarchy(nL, device=device, stream=stream)
+        minv = lambda mesh: np.linalg.inv(mesh.mMassMatrix.mBlocks)          # noqa: E731
+        flux = [blk.csc_to_blocks(sp.csc_matrix(X), slots[0], pad_identity=False) for X in (G, D, C)]
+        dev.set_level_flux(0, flux[0], flux[1], flux[2], minv(M[0]))
+        I = [None] * (nL - 1)
+        for k in range(1, nL):
+            if k < nDG:
+                I[k - 1] = dg_dg_interpolation(M[k], M[k - 1])
+            elif k == nDG:
+                I[k - 1] = aggdg_dg_interpolation(M[k], M[k - 1])
+            else:
+                I[k - 1] = aggdg_aggdg_interpolation(M[k], M[k - 1], M[nDG - 1])
+            parent, P0, P1 = blk.transfer_to_blocks(I[k - 1], slots[k - 1], slots[k])
+            dev.set_transfer_blocks(k - 1, parent, P0, P1)
+            dev.coarsen_level(k - 1, minv(M[k]), slots[k].shape[0])
+        dev.finalize()
+        S = [sp.csc_matrix(A)] + [None] * (nL - 1)
+        Sm = [DeviceBlockJacobi(dev, l) for l in range(nL)]
+        none = [None] * nL
+        self._set(S, [sp.csc_matrix(G)] + none[1:], [sp.csc_matrix(D)] + none[1:],
+                  [sp.csc_matrix(C)] + none[1:], Sm, I, mBdConds)
+        self.device = dev
+        self.mSlots = slots
+
+    def level_blocks(self, l):
+        """(lo, di, up, dinv) of level l as the device holds them (downloads; any set-up path)."""
+        n, m = self.mSlots[l].shape
+        from .smoother import JacobiSmoother
+        return self.device.get_level(l, n, m, diag=isinstance(self.mSmoothers[l], JacobiSmoother))
 
     def _set(self, S, Gs, Ds, Cs, Sm, I, mBdConds):
         self.mStiffness, self.mGradient, self.mDivergence, self.mC = S, Gs, Ds, Cs

@@ -44,6 +44,16 @@ class BlockJacobi(AbstractSmoother):
         self._slots = slots
 
 
+class DeviceBlockJacobi(AbstractSmoother):
+    """Block-Jacobi smoother of a level whose blocks were extracted and inverted on the GPU
+    (MeshHierarchy(..., device_setup=True)); it exists only as (device hierarchy, level)."""
+
+    def __init__(self, dev, level):
+        self._owner = (dev, level)
+        self._A = None
+        self._slots = None
+
+
 class AdditiveSchwarzSmoother(AbstractSmoother):
     """mBlocks: (n, p+1, p+1) element matrices A[el.mNodesInd, el.mNodesInd] (the reference keeps their
     LU factors); mBlockInds (p+1, n) = el.mNodesInd columns (left vertex, right vertex, interior nodes)."""

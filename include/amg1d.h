@@ -72,6 +72,32 @@ int amg1d_set_level(amg1d_t* h, int level, int64_t n_elem, int m, const double* 
                     const double* A_di, const double* A_up, const double* Dinv,
                     int dinv_is_diagonal, const int64_t* perm, int64_t n_dof_host);
 
+/* ---- device-side set-up of the DG-type level chain -------------------------------------
+ * Instead of mStiffness[l] and its smoother, the host hands over what the assembly produces - the flux
+ * operators G, D, C of the level (block tridiagonal in the element grouping, blocks as in
+ * amg1d_set_level) and the inverse element mass matrices Minv (n_elem*m*m, or ONE m*m block for all
+ * elements with minv_is_constant = 1) - and the library forms, on the GPU,
+ *     A = C - D M^-1 G                       (src/mesh_heirarchy.jl:85-86, :100-101, :172-173)
+ * and the block-Jacobi inverses of its diagonal blocks (src/smoother.jl:154-164).  The level is then set
+ * exactly as after amg1d_set_level with a block smoother.  The flux operators stay on the device until
+ * amg1d_finalize so that amg1d_coarsen_level can project them. */
+int amg1d_set_level_flux(amg1d_t* h, int level, int64_t n_elem, int m, const double* G_lo,
+                         const double* G_di, const double* G_up, const double* D_lo, const double* D_di,
+                         const double* D_up, const double* C_lo, const double* C_di, const double* C_up,
+                         const double* Minv, int minv_is_constant);
+
+/* Galerkin coarsening on the GPU: level + 1 <- level.  Needs the flux operators of `level` (from
+ * amg1d_set_level_flux or an earlier amg1d_coarsen_level) and transfer `level` (single parent,
+ * parent[e] = e / ratio: dg_dg / aggdg_dg / aggdg_aggdg).  Computes G, D, C <- L' (G, D, C) L
+ * (src/mesh_heirarchy.jl:75-84, :89-99, :160-171), then A and the smoother of level + 1 as above with the
+ * coarse elements' inverse mass matrices Minv_coarse. */
+int amg1d_coarsen_level(amg1d_t* h, int level, const double* Minv_coarse, int minv_is_constant);
+
+/* Download of a level as the element-block arrays of amg1d_set_level (A_lo, A_di, A_up: n_elem*m*m each;
+ * Dinv: n_elem*m*m or n_elem*m) - for checking device-side set-up and for scripts that inspect
+ * H.mStiffness[k] of a level the host never assembled. */
+int amg1d_get_level(amg1d_t* h, int level, double* A_lo, double* A_di, double* A_up, double* Dinv);
+
 /* Replaces the smoother of a level that has been set by a block-TRIDIAGONAL smoother operator S:
  * z = S r with S r[e] = S_lo[e] r[e-1] + S_di[e] r[e] + S_up[e] r[e+1] (blocks as in amg1d_set_level).
  * This is the form the overlapping Schwarz smoothers of CG levels take in the [vertex_k, interior_k]

@@ -60,7 +60,7 @@ def build_oracle(n, cg_orders=(), dg_orders=(), agg_factors=(), pAgg=1, unit_h=F
 
 
 def build_package(n, cg_orders=(), dg_orders=(), agg_factors=(), pAgg=1, unit_h=False, upload=True,
-                  bc_kinds=("neu", "dir")):
+                  bc_kinds=("neu", "dir"), device_setup=False):
     """The product's host path, written the way the reference scripts are."""
     pr = _problem(unit_h, n)
     xin, xout, CDir = pr["xin"], pr["xout"], pr["CDir"]
@@ -90,5 +90,6 @@ def build_package(n, cg_orders=(), dg_orders=(), agg_factors=(), pAgg=1, unit_h=
         A = (C - D @ meshes[0].mMassMatrixLU.solve(G)).tocsc()
         f, r = aggmg.dg_flux_rhs(meshes[0], mesh, pr["func"], bdCond, CDir)
         b = f - D @ meshes[0].mMassMatrixLU.solve(r)
-        H = aggmg.MeshHierarchy(meshes, bdConds, A, G, D, C, nDG=nDG, nAgg=nAgg, upload=upload)
+        H = aggmg.MeshHierarchy(meshes, bdConds, A, G, D, C, nDG=nDG, nAgg=nAgg, upload=upload,
+                                device_setup=device_setup)
     return H, np.zeros(len(b)), b

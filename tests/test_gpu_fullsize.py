@@ -196,3 +196,48 @@ def test_direct_solver_at_scale():
     x, it, res, _ = dev.solve(np.zeros(len(b)), b, 100, 1e-10)
     assert it <= 25 and res[-1] < 1e-10 * np.linalg.norm(b) and np.all(np.diff(res) < 0)
     dev.close()
+
+
+def test_device_side_setup_nonuniform_mesh():
+    """Device-side set-up on a graded, non-uniform mesh of 2^14 elements - the case the
+    uniform-mesh pattern path cannot take: every level's blocks against the host's sparse algebra, and the
+    solve converges at the usual rate."""
+    import time
+    import agglomerationmultigrid1d_b200 as aggmg
+    n = 2 ** 14
+    rng = np.random.default_rng(0)
+    hs = 0.5 + rng.random(n)                                   # element sizes within a factor of 3
+    x = np.concatenate([[0.0], np.cumsum(hs)])
+    xout = float(x[-1])
+    mesh = aggmg.Mesh(x)
+    w = 2.0 * math.pi / 64.0
+    bd = aggmg.set_boundary(mesh, 0.0, xout, [("neu", 0.0), ("dir", math.cos(w * xout))])
+    meshes = [aggmg.DgMesh(mesh, 3), aggmg.DgMesh(mesh, 1)]
+    cur = n
+    for i in range(10):
+        agg = [[2 * j, 2 * j + 1] for j in range(cur // 2)]
+        cur //= 2
+        meshes.append(aggmg.AgglomeratedDgMesh1(1, agg, mesh, meshes[1]) if i == 0
+                      else aggmg.AgglomeratedDgMeshN(1, agg, meshes[-1], meshes[1]))
+    G, D, C = aggmg.dg_flux_operators(meshes[0], mesh, bd, 1000.0)
+    A = (C - D @ meshes[0].mMassMatrixLU.solve(G)).tocsc()
+    f, r = aggmg.dg_flux_rhs(meshes[0], mesh, lambda t: w * w * np.cos(w * t), bd, 1000.0)
+    b = f - D @ meshes[0].mMassMatrixLU.solve(r)
+    t0 = time.perf_counter()
+    Hh = aggmg.MeshHierarchy(meshes, [bd] * len(meshes), A, G, D, C, nDG=2, nAgg=10)
+    t_host = time.perf_counter() - t0
+    t0 = time.perf_counter()
+    Hd = aggmg.MeshHierarchy(meshes, [bd] * len(meshes), A, G, D, C, nDG=2, nAgg=10, device_setup=True)
+    t_dev = time.perf_counter() - t0
+    print(f"set-up of 12 levels, 2^14 non-uniform elements: host {t_host:.2f} s, device-side {t_dev:.2f} s")
+    for l in range(len(meshes)):
+        got, ref = Hd.level_blocks(l), Hh.level_blocks(l)
+        scale = np.abs(ref[1]).max()
+        assert all(np.abs(g - r_).max() <= 1e-12 * scale for g, r_ in zip(got[:3], ref[:3])), l
+    xh, ith, resh, _ = aggmg.multigrid(Hh, np.zeros(len(b)), b, 100, 1e-10, with_error=False)
+    xd, itd, resd, _ = aggmg.multigrid(Hd, np.zeros(len(b)), b, 100, 1e-10, with_error=False)
+    assert itd == ith and ith <= 20 and resd[-1] < 1e-10 * np.linalg.norm(b)
+    assert np.allclose(resd, resh, rtol=1e-8, atol=1e-13 * np.linalg.norm(b))
+    assert np.abs(xd - xh).max() <= 1e-9 * np.abs(xh).max()
+    Hh.device.close()
+    Hd.device.close()

@@ -309,3 +309,39 @@ def test_error_behaviour(lib):
     assert lib.amg1d_destroy(h) == capi.OK
     with pytest.raises(ValueError):
         build_package(8, dg_orders=[2, 1], agg_factors=[2], pAgg=2, upload=False)   # p in {0,1} only
+
+
+@pytest.mark.parametrize("name", ["dg_heirarchy", "C2_dg3_agg", "C3_dg4_agg", "dg_p0_agg0", "factor3_n24",
+                                  "bcr_dg3_agg_n512"])
+def test_device_side_setup(name):
+    """Galerkin products L'(G, D, C)L, A = C - D (M \\ G) and the block-Jacobi inverses on the
+    GPU (amg1d_set_level_flux / amg1d_coarsen_level) against the host's sparse algebra: every level's
+    blocks to 1e-12, same structure classes, and the V-cycle histories against the oracle."""
+    kw = SHAPES[name]
+    Ho, x0, bo, _ = build_oracle(**kw)
+    Hh, _, bp = build_package(**kw)                                   # host set-up, uploaded
+    Hd, _, _ = build_package(**kw, device_setup=True)                 # device set-up
+    try:
+        nL = len(Ho.mMeshes)
+        for l in range(nL):
+            got = Hd.level_blocks(l)
+            ref = Hh.level_blocks(l)
+            scale = np.abs(ref[1]).max()
+            for g, r_, what in zip(got[:3], ref[:3], ("lo", "di", "up")):
+                assert np.abs(g - r_).max() <= 1e-12 * scale, (l, what)
+            assert np.abs(got[3] - ref[3]).max() <= 1e-10 * np.abs(ref[3]).max(), l
+            assert Hd.device.info(f"structure:{l}") == Hh.device.info(f"structure:{l}"), l
+        x_or, it_or, res_or, _ = osolv.multigrid(Ho, np.zeros(len(bo)), bo, 100, 1e-10)
+        x, it, res, _ = aggmg.multigrid(Hd, np.zeros(len(bp)), bp, 100, 1e-10, with_error=False)
+        assert it == it_or
+        floor = rounding_floor(Ho, x_or)
+        assert np.all(np.abs(res - res_or) <= np.maximum(1e-9 * res_or, floor)), (res, res_or)
+        assert np.abs(x - x_or).max() <= 1e-9 * np.abs(x_or).max()
+        # the smoothers of device-built levels answer apply_smoother like any other
+        l = nL - 1
+        r = np.random.default_rng(0).standard_normal(Ho.mStiffness[l].shape[0])
+        y_or = osm.apply_smoother(Ho.mSmoothers[l], r, alpha=0.5)
+        assert np.abs(aggmg.apply_smoother(Hd.mSmoothers[l], r, alpha=0.5) - y_or).max() <= 1e-10 * np.abs(y_or).max()
+    finally:
+        Hh.device.close()
+        Hd.device.close()
