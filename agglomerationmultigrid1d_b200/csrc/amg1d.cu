@@ -309,17 +309,25 @@ Slab make_slab(amg1d* h, int l) {
     } while (0)
 
 // Exchange ghost_depth edge elements of a slab vector with both neighbour ranks.
-// v points at local element 0; n = owned elements; m = block size.
-int op_halo(amg1d* h, double* v, int64_t n, int m) {
-    const int64_t cnt = (int64_t)h->ghost_depth * m;
+// v points at local element 0; n = owned elements; m = block size.  A second vector (v2 != nullptr)
+// travels in the same NCCL group: one communication kernel instead of two (the exchanges are latency
+// bound: 4 x m doubles each way).
+int op_halo(amg1d* h, double* v, int64_t n, int m, double* v2 = nullptr, int64_t n2 = 0, int m2 = 0) {
     NCK(g_nccl.GroupStart());
-    if (h->rank > 0) {
-        NCK(g_nccl.Send(v, cnt, ncclDouble, h->rank - 1, h->comm, h->stream));
-        NCK(g_nccl.Recv(v - cnt, cnt, ncclDouble, h->rank - 1, h->comm, h->stream));
-    }
-    if (h->rank < h->nranks - 1) {
-        NCK(g_nccl.Send(v + (n - h->ghost_depth) * m, cnt, ncclDouble, h->rank + 1, h->comm, h->stream));
-        NCK(g_nccl.Recv(v + n * m, cnt, ncclDouble, h->rank + 1, h->comm, h->stream));
+    for (int k = 0; k < 2; ++k) {
+        double* p = k == 0 ? v : v2;
+        if (!p) continue;
+        const int64_t nn = k == 0 ? n : n2;
+        const int mm = k == 0 ? m : m2;
+        const int64_t cnt = (int64_t)h->ghost_depth * mm;
+        if (h->rank > 0) {
+            NCK(g_nccl.Send(p, cnt, ncclDouble, h->rank - 1, h->comm, h->stream));
+            NCK(g_nccl.Recv(p - cnt, cnt, ncclDouble, h->rank - 1, h->comm, h->stream));
+        }
+        if (h->rank < h->nranks - 1) {
+            NCK(g_nccl.Send(p + (nn - h->ghost_depth) * mm, cnt, ncclDouble, h->rank + 1, h->comm, h->stream));
+            NCK(g_nccl.Recv(p + nn * mm, cnt, ncclDouble, h->rank + 1, h->comm, h->stream));
+        }
     }
     NCK(g_nccl.GroupEnd());
     h->launch_counter++;
@@ -376,7 +384,7 @@ int op_allreduce_norm(amg1d* h, int slot) {
     return AMG1D_OK;
 }
 #else
-int op_halo(amg1d* h, double*, int64_t, int) { return fail(h, AMG1D_ERR_UNSUPPORTED, "built without NCCL"); }
+int op_halo(amg1d* h, double*, int64_t, int, double* = nullptr, int64_t = 0, int = 0) { return fail(h, AMG1D_ERR_UNSUPPORTED, "built without NCCL"); }
 int op_gather_rhs(amg1d* h, int) { return fail(h, AMG1D_ERR_UNSUPPORTED, "built without NCCL"); }
 int op_scatter_sol(amg1d* h, int) { return fail(h, AMG1D_ERR_UNSUPPORTED, "built without NCCL"); }
 int op_allreduce_norm(amg1d* h, int) { return fail(h, AMG1D_ERR_UNSUPPORTED, "built without NCCL"); }
@@ -658,9 +666,12 @@ int enqueue_vcycle(amg1d* h, int nPre, int nPost, double alpha, bool want_norm, 
         RET(leg_down(h, l, nPre, alpha, zero0));
         if (lv.sharded) {
             Level& lc = h->L[l + 1];
-            RET(op_halo(h, lv.x[lv.cur].p, lv.n, lv.m));              // pre-smoothed iterate, for the up leg
-            if (lc.sharded) RET(op_halo(h, lc.b.p, lc.n, lc.m));      // coarse rhs ghosts
-            else RET(op_gather_rhs(h, l + 1));                        // slabs -> rank 0
+            // ghosts of the pre-smoothed iterate (for the up leg) and of the coarse rhs, in one exchange
+            if (lc.sharded) RET(op_halo(h, lv.x[lv.cur].p, lv.n, lv.m, lc.b.p, lc.n, lc.m));
+            else {
+                RET(op_halo(h, lv.x[lv.cur].p, lv.n, lv.m));
+                RET(op_gather_rhs(h, l + 1));                         // slabs -> rank 0
+            }
         }
     }
     // ---- coarse tail in one CTA, or just the coarsest level: exact solve (src/solvers.jl:39) ----

@@ -270,7 +270,8 @@ def run_gpu(args):
     pr = problem(n)
     t_setup = time.perf_counter()
     U = build_hierarchy(args.workload, n)
-    dev = U.upload(device=local, stream=stream, dist=dist_arg)
+    pre = {kv.split("=")[0]: int(kv.split("=")[1]) for kv in args.pre_opt}
+    dev = U.upload(device=local, stream=stream, dist=dist_arg, options=pre or None)
     dev.synchronize()
     t_setup = time.perf_counter() - t_setup
     for kv in args.opt:
@@ -439,7 +440,8 @@ def run_gpu(args):
                    if dev.info("device_bytes") > 2 ** 29 else "working set comparable to L2; no flush",
                    "structure_classes": [dev.info(f"structure:{l}") for l in range(min(4, len(U.levels)))],
                    "tile_rows": [U.tile_rows(l) for l in range(min(4, len(U.levels)))],
-                   "tail_start": dev.info("tail_start"), "options": args.opt,
+                   "tail_start": dev.info("tail_start"), "options": args.opt + args.pre_opt,
+                   "gather_level": dev.info("gather_level"),
                    "device_bytes": dev.info("device_bytes"), "setup_s": t_setup, "rhs_assembly_s": t_rhs,
                    "residual_after_timed_steps": res_after},
         "roofline": roofline, "cpu_baseline": cpu, "clocks": clocks, "e2e": e2e,
@@ -462,6 +464,8 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="T", choices=sorted(WORKLOADS))
     ap.add_argument("--no-cpu", action="store_true", help="skip the CPU baseline leg")
+    ap.add_argument("--pre-opt", action="append", default=[], metavar="KEY=VALUE",
+                    help="amg1d_set_option before the first level is set (e.g. --pre-opt shard_min=65536)")
     ap.add_argument("--opt", action="append", default=[], metavar="KEY=VALUE",
                     help="amg1d_set_option after the upload (A/B experiments, e.g. --opt pdl=0)")
     args = ap.parse_args()
