@@ -452,9 +452,15 @@ __device__ __forceinline__ void load_blocks(const double* __restrict__ mat, int6
 // Resident CTAs per SM the register allocation aims for.  Dense 4x4 blocks keep 48 operator doubles in
 // registers (164 registers, 3 CTAs of 128 threads); the compressed structure classes keep 24 and fit 5
 // CTAs (<= 102 registers, no spills), which is what hides the compute phase of one CTA behind the load
-// phase of the others (measured on B200, T level 0: 5.0 -> 4.5 ms per leg).
+// phase of the others (measured on B200, T level 0: 5.0 -> 4.5 ms per leg; 6 CTAs spill and lose).  The
+// 2x2 and 1x1 kernels are capped at 64 registers for 8 CTAs/SM.
+#ifndef FUSED_MINB_SMALL
+#define FUSED_MINB_SMALL 8   // m <= 2: <= 64 registers, no spills; measured best of 3 / 8 / 10 / 12 (T: -4 %)
+#endif
 constexpr int fused_min_blocks(int m, int st) {
-    return m >= 5 ? (st != AMG1D_ST_DENSE ? 3 : 2) : (m == 4 && st != AMG1D_ST_DENSE ? (FUSED_MINB > 5 ? FUSED_MINB : 5) : FUSED_MINB);
+    return m >= 5 ? (st != AMG1D_ST_DENSE ? 3 : 2)
+         : m == 4 ? (st != AMG1D_ST_DENSE ? 5 : 3)
+         : m <= 2 ? FUSED_MINB_SMALL : FUSED_MINB;
 }
 #define FUSED_BOUNDS(M) __launch_bounds__(B, fused_min_blocks(M, ST))
 
