@@ -38,6 +38,16 @@ struct DVec {
     int64_t len = 0;      // n * m
 };
 
+// Scratch device allocation that is released on every exit path of an upload / download routine.
+struct DevBuf {
+    double* p = nullptr;
+    ~DevBuf() { if (p) cudaFree(p); }
+    cudaError_t alloc(int64_t doubles) { return cudaMalloc((void**)&p, (size_t)(doubles > 0 ? doubles : 1) * 8); }
+    DevBuf() = default;
+    DevBuf(const DevBuf&) = delete;
+    DevBuf& operator=(const DevBuf&) = delete;
+};
+
 struct Level {
     bool set = false;
     int64_t n = 0;       // elements held by this rank (== n_glob unless the level is sharded)
@@ -578,9 +588,12 @@ int leg_down(amg1d* h, int l, int nPre, double alpha, bool zero0) {
     // fused: nPre sweeps + residual + restriction in one pass over the operator
     if (h->opt_fused && t.fusable && !lv.smooth_tri) {
         const int ob = zero ? 0 : 1 - lv.cur;
-        if (fused_down(lv.md, t.mc, make_map_closed(t), nPre, zero, lv.mat, lv.b.p, lv.x[lv.cur].p,
-                       lv.x[ob].p, t.P0, t.P1, lc.b.p, lv.n, lv.n + (lv.gr ? t.cover_extra : 0), alpha,
-                       make_slab(h, l), h->stream, h->opt_pdl != 0)) {
+        cudaError_t le = cudaSuccess;
+        const int fr = fused_down(lv.md, t.mc, make_map_closed(t), nPre, zero, lv.mat, lv.b.p, lv.x[lv.cur].p,
+                                  lv.x[ob].p, t.P0, t.P1, lc.b.p, lv.n, lv.n + (lv.gr ? t.cover_extra : 0),
+                                  alpha, make_slab(h, l), h->stream, h->opt_pdl != 0, &le);
+        if (fr == FUSED_ERR) return fail(h, AMG1D_ERR_CUDA, "f_down launch failed on level %d: %s", l, cudaGetErrorString(le));
+        if (fr == FUSED_OK) {
             lv.cur = ob;
             h->launch_counter++;
             LAUNCH_CHECK();
@@ -620,10 +633,13 @@ int leg_up(amg1d* h, int l, int nPost, double alpha, bool fuse_norm, bool* norm_
     RET(prof_mark(h, l, 1));
     if (h->opt_fused && t.fusable && !lv.smooth_tri) {
         int nb = 0;
-        if (fused_up(lv.md, t.mc, make_map_closed(t), nPost, lv.mat, lv.b.p, lv.x[lv.cur].p,
-                     lv.x[1 - lv.cur].p, t.P0, t.P1, lc.x[lc.cur].p, lv.n, alpha,
-                     fuse_norm ? h->partial : nullptr, h->partial_cap, &nb, make_slab(h, l),
-                     h->stream, h->opt_pdl != 0)) {
+        cudaError_t le = cudaSuccess;
+        const int fr = fused_up(lv.md, t.mc, make_map_closed(t), nPost, lv.mat, lv.b.p, lv.x[lv.cur].p,
+                                lv.x[1 - lv.cur].p, t.P0, t.P1, lc.x[lc.cur].p, lv.n, alpha,
+                                fuse_norm ? h->partial : nullptr, h->partial_cap, &nb, make_slab(h, l),
+                                h->stream, h->opt_pdl != 0, &le);
+        if (fr == FUSED_ERR) return fail(h, AMG1D_ERR_CUDA, "f_up launch failed on level %d: %s", l, cudaGetErrorString(le));
+        if (fr == FUSED_OK) {
             lv.cur = 1 - lv.cur;
             h->launch_counter++;
             LAUNCH_CHECK();
@@ -1242,11 +1258,12 @@ int amg1d_set_level(amg1d_t* h, int level, int64_t n_elem, int m, const double* 
     const int64_t g0 = lv.start - lv.gl, g1 = lv.start + lv.n + lv.gr;
     const int64_t chunk = 1 << 18;  // elements per staging chunk (multiple of 32)
     const int64_t c = std::min(chunk, (lv.n + lv.gr + 63) / 32 * 32);
-    double *d_lo, *d_di, *d_up, *d_dv;
-    CK(cudaMalloc(&d_lo, (size_t)c * mm * 8));
-    CK(cudaMalloc(&d_di, (size_t)c * mm * 8));
-    CK(cudaMalloc(&d_up, (size_t)c * mm * 8));
-    CK(cudaMalloc(&d_dv, (size_t)c * dsz * 8));
+    DevBuf b_lo, b_di, b_up, b_dv;
+    CK(b_lo.alloc(c * mm));
+    CK(b_di.alloc(c * mm));
+    CK(b_up.alloc(c * mm));
+    CK(b_dv.alloc(c * dsz));
+    double *d_lo = b_lo.p, *d_di = b_di.p, *d_up = b_up.p, *d_dv = b_dv.p;
     int rc = AMG1D_OK;
     // chunks are aligned to tiles of the local storage; the first one starts at local element -32 when
     // the slab has left ghosts (those tiles are zero-filled outside [g0, g1))
@@ -1273,7 +1290,6 @@ int amg1d_set_level(amg1d_t* h, int level, int64_t n_elem, int m, const double* 
         if (e == cudaSuccess) e = cudaGetLastError();
         if (e != cudaSuccess) rc = fail(h, AMG1D_ERR_CUDA, "level upload failed: %s", cudaGetErrorString(e));
     }
-    cudaFree(d_lo); cudaFree(d_di); cudaFree(d_up); cudaFree(d_dv);
     RET(rc);
     if (n_elem <= AMG1D_BCR_MIN && !lv.sharded) {   // host copy for the block-Thomas factorisation
         lv.h_lo.assign(A_lo, A_lo + (size_t)n_elem * mm);
@@ -1300,11 +1316,12 @@ int amg1d_set_level_pattern(amg1d_t* h, int level, int64_t n_elem, int m, int n_
     Level& lv = h->L[level];
     const int dsz = lv.diag ? m : mm;
     if (!lv.present) { lv.set = true; return AMG1D_OK; }
-    double *d_lo, *d_di, *d_up, *d_dv;
-    CK(cudaMalloc(&d_lo, (size_t)nb * mm * 8));
-    CK(cudaMalloc(&d_di, (size_t)nb * mm * 8));
-    CK(cudaMalloc(&d_up, (size_t)nb * mm * 8));
-    CK(cudaMalloc(&d_dv, (size_t)nb * dsz * 8));
+    DevBuf b_lo, b_di, b_up, b_dv;
+    CK(b_lo.alloc((int64_t)nb * mm));
+    CK(b_di.alloc((int64_t)nb * mm));
+    CK(b_up.alloc((int64_t)nb * mm));
+    CK(b_dv.alloc((int64_t)nb * dsz));
+    double *d_lo = b_lo.p, *d_di = b_di.p, *d_up = b_up.p, *d_dv = b_dv.p;
     cudaMemcpyAsync(d_lo, A_lo, (size_t)nb * mm * 8, cudaMemcpyHostToDevice, h->stream);
     cudaMemcpyAsync(d_di, A_di, (size_t)nb * mm * 8, cudaMemcpyHostToDevice, h->stream);
     cudaMemcpyAsync(d_up, A_up, (size_t)nb * mm * 8, cudaMemcpyHostToDevice, h->stream);
@@ -1317,7 +1334,6 @@ int amg1d_set_level_pattern(amg1d_t* h, int level, int64_t n_elem, int m, int n_
         lv.n + lv.gr, ntiles, lv.mat_alloc);
     cudaError_t e = cudaStreamSynchronize(h->stream);
     if (e == cudaSuccess) e = cudaGetLastError();
-    cudaFree(d_lo); cudaFree(d_di); cudaFree(d_up); cudaFree(d_dv);
     if (e != cudaSuccess) return fail(h, AMG1D_ERR_CUDA, "pattern fill failed: %s", cudaGetErrorString(e));
     if (n_elem <= AMG1D_BCR_MIN && !lv.sharded) {   // host copy for the block-Thomas factorisation
         lv.h_lo.resize((size_t)n_elem * mm); lv.h_di.resize((size_t)n_elem * mm); lv.h_up.resize((size_t)n_elem * mm);
@@ -1352,12 +1368,13 @@ int amg1d_set_level_smoother(amg1d_t* h, int level, const double* S_lo, const do
     RET(dev_alloc(h, (void**)&lv.smat_alloc, bytes));
     CK(cudaMemsetAsync(lv.smat_alloc, 0, (size_t)bytes, h->stream));
     lv.smat = lv.smat_alloc + (int64_t)lv.smd.K * AMG1D_TILE;
-    double *d_lo, *d_di, *d_up, *d_dv;
     const int64_t c = std::min<int64_t>(1 << 18, (n + 31) / 32 * 32);
-    CK(cudaMalloc(&d_lo, (size_t)c * mm * 8));
-    CK(cudaMalloc(&d_di, (size_t)c * mm * 8));
-    CK(cudaMalloc(&d_up, (size_t)c * mm * 8));
-    CK(cudaMalloc(&d_dv, (size_t)c * m * 8));
+    DevBuf b_lo, b_di, b_up, b_dv;
+    CK(b_lo.alloc(c * mm));
+    CK(b_di.alloc(c * mm));
+    CK(b_up.alloc(c * mm));
+    CK(b_dv.alloc(c * m));
+    double *d_lo = b_lo.p, *d_di = b_di.p, *d_up = b_up.p, *d_dv = b_dv.p;
     cudaMemsetAsync(d_dv, 0, (size_t)c * m * 8, h->stream);
     int rc = AMG1D_OK;
     for (int64_t e0 = 0; e0 < n && rc == AMG1D_OK; e0 += c) {
@@ -1371,7 +1388,6 @@ int amg1d_set_level_smoother(amg1d_t* h, int level, const double* S_lo, const do
         if (e == cudaSuccess) e = cudaGetLastError();
         if (e != cudaSuccess) rc = fail(h, AMG1D_ERR_CUDA, "smoother upload failed: %s", cudaGetErrorString(e));
     }
-    cudaFree(d_lo); cudaFree(d_di); cudaFree(d_up); cudaFree(d_dv);
     RET(rc);
     lv.smooth_tri = true;
     return AMG1D_OK;
@@ -1398,17 +1414,16 @@ int amg1d_set_level_flux(amg1d_t* h, int level, int64_t n_elem, int m, const dou
     Level& lv = h->L[level];
     if (lv.set) return fail(h, AMG1D_ERR_STATE, "level %d already set", level);
     CK(cudaSetDevice(h->device));
+    free_flux(h, lv);                              // left over from an earlier, failed attempt
     const int64_t cnt = n_elem * m * m;
     for (int k = 0; k < 9; ++k) {
         RET(upload_blocks(h, &lv.flux[k], src[k], cnt));
         h->device_bytes += cnt * 8;
     }
-    double* d_minv = nullptr;
-    RET(upload_blocks(h, &d_minv, Minv, minv_is_constant ? (int64_t)m * m : cnt));
+    DevBuf minv;
+    RET(upload_blocks(h, &minv.p, Minv, minv_is_constant ? (int64_t)m * m : cnt));
     lv.n = n_elem; lv.m = m;                       // for free_flux if the installation fails
-    const int rc = install_from_flux(h, level, n_elem, m, lv.flux, d_minv, minv_is_constant);
-    cudaFree(d_minv);
-    return rc;
+    return install_from_flux(h, level, n_elem, m, lv.flux, minv.p, minv_is_constant);
 }
 
 int amg1d_coarsen_level(amg1d_t* h, int level, const double* Minv_coarse, int minv_is_constant) {
@@ -1428,6 +1443,7 @@ int amg1d_coarsen_level(amg1d_t* h, int level, const double* Minv_coarse, int mi
     CK(cudaSetDevice(h->device));
     const int mc = t.mc;
     const int64_t nc = t.n_coarse, cnt = nc * mc * mc;
+    free_flux(h, lc);
     lc.n = nc; lc.m = mc;
     for (int k = 0; k < 9; ++k) {
         CK(cudaMalloc((void**)&lc.flux[k], (size_t)cnt * 8));
@@ -1439,11 +1455,9 @@ int amg1d_coarsen_level(amg1d_t* h, int level, const double* Minv_coarse, int mi
         k_galerkin_tri<<<grid, 128, 0, h->stream>>>(lf.flux[3 * k], lf.flux[3 * k + 1], lf.flux[3 * k + 2], t.P0, tm,
                                                      t.mf, mc, lc.flux[3 * k], lc.flux[3 * k + 1], lc.flux[3 * k + 2]);
     LAUNCH_CHECK();
-    double* d_minv = nullptr;
-    RET(upload_blocks(h, &d_minv, Minv_coarse, minv_is_constant ? (int64_t)mc * mc : cnt));
-    const int rc = install_from_flux(h, level + 1, nc, mc, lc.flux, d_minv, minv_is_constant);
-    cudaFree(d_minv);
-    return rc;
+    DevBuf minv;
+    RET(upload_blocks(h, &minv.p, Minv_coarse, minv_is_constant ? (int64_t)mc * mc : cnt));
+    return install_from_flux(h, level + 1, nc, mc, lc.flux, minv.p, minv_is_constant);
 }
 
 int amg1d_get_level(amg1d_t* h, int level, double* A_lo, double* A_di, double* A_up, double* Dinv) {
@@ -1454,17 +1468,16 @@ int amg1d_get_level(amg1d_t* h, int level, double* A_lo, double* A_di, double* A
     Level& lv = h->L[level];
     CK(cudaSetDevice(h->device));
     const int64_t cnt = lv.n * lv.m * lv.m, dcnt = lv.n * (lv.diag ? lv.m : lv.m * lv.m);
-    double *d[3] = {nullptr, nullptr, nullptr}, *dv = nullptr;
-    for (auto& p : d) CK(cudaMalloc((void**)&p, (size_t)cnt * 8));
-    CK(cudaMalloc((void**)&dv, (size_t)dcnt * 8));
-    k_bcr_extract<<<(unsigned)((cnt + 255) / 256), 256, 0, h->stream>>>(lv.mat, lv.md, lv.n, d[0], d[1], d[2]);
-    k_extract_dinv<<<(unsigned)((dcnt + 255) / 256), 256, 0, h->stream>>>(lv.mat, lv.md, lv.n, dv);
+    DevBuf d[3], dv;
+    for (auto& b : d) CK(b.alloc(cnt));
+    CK(dv.alloc(dcnt));
+    k_bcr_extract<<<(unsigned)((cnt + 255) / 256), 256, 0, h->stream>>>(lv.mat, lv.md, lv.n, d[0].p, d[1].p, d[2].p);
+    k_extract_dinv<<<(unsigned)((dcnt + 255) / 256), 256, 0, h->stream>>>(lv.mat, lv.md, lv.n, dv.p);
+    LAUNCH_CHECK();
     double* out[3] = {A_lo, A_di, A_up};
-    for (int k = 0; k < 3; ++k) CK(cudaMemcpyAsync(out[k], d[k], (size_t)cnt * 8, cudaMemcpyDeviceToHost, h->stream));
-    CK(cudaMemcpyAsync(Dinv, dv, (size_t)dcnt * 8, cudaMemcpyDeviceToHost, h->stream));
+    for (int k = 0; k < 3; ++k) CK(cudaMemcpyAsync(out[k], d[k].p, (size_t)cnt * 8, cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaMemcpyAsync(Dinv, dv.p, (size_t)dcnt * 8, cudaMemcpyDeviceToHost, h->stream));
     CK(cudaStreamSynchronize(h->stream));
-    for (auto p : d) cudaFree(p);
-    cudaFree(dv);
     return AMG1D_OK;
 }
 
@@ -1752,12 +1765,12 @@ int amg1d_solve(amg1d_t* h, double* x, const double* b, int maxiter, double tol,
     if (maxiter < 0) return fail(h, AMG1D_ERR_ARG, "maxiter must be >= 0");
     Level& l0 = h->L[0];
     RET(amg1d_dev_set_problem(h, x, b));
+    DevBuf exact;
     double* d_exact = nullptr;
     if (err && u_exact) {
-        // u_exact lives in the scratch-free second buffer of a dedicated allocation
-        CK(cudaMalloc(&d_exact, (size_t)(l0.x[0].len + 8) * 8));
-        int rc = to_device(h, 0, u_exact, d_exact);
-        if (rc != AMG1D_OK) { cudaFree(d_exact); return rc; }
+        CK(exact.alloc(l0.x[0].len + 8));
+        d_exact = exact.p;
+        RET(to_device(h, 0, u_exact, d_exact));
     }
     int rc = op_norm(h, l0.b.p, nullptr, l0.b.len, 2);
     int it = 0;
@@ -1775,7 +1788,6 @@ int amg1d_solve(amg1d_t* h, double* x, const double* b, int maxiter, double tol,
         it = i + 1;
         if (res[i] < tol * h->h_scal[2]) break;
     }
-    if (d_exact) cudaFree(d_exact);
     RET(rc);
     *iters = it;
     return to_host(h, 0, l0.x[l0.cur].p, x);
@@ -1888,11 +1900,12 @@ int amg1d_smoother_solve(amg1d_t* h, int level, double* x, const double* b, int 
     lv.cur = 0;
     RET(to_device(h, level, b, lv.b.p));
     RET(to_device(h, level, x, lv.x[0].p));
+    DevBuf exact;
     double* d_exact = nullptr;
     if (err && u_exact) {
-        CK(cudaMalloc(&d_exact, (size_t)(lv.x[0].len + 8) * 8));
-        int rc = to_device(h, level, u_exact, d_exact);
-        if (rc != AMG1D_OK) { cudaFree(d_exact); return rc; }
+        CK(exact.alloc(lv.x[0].len + 8));
+        d_exact = exact.p;
+        RET(to_device(h, level, u_exact, d_exact));
     }
     int rc = op_norm(h, lv.b.p, nullptr, lv.b.len, 2);
     int it = 0;
@@ -1913,7 +1926,6 @@ int amg1d_smoother_solve(amg1d_t* h, int level, double* x, const double* b, int 
         it = i + 1;
         if (res[i] < tol * h->h_scal[2]) break;
     }
-    if (d_exact) cudaFree(d_exact);
     RET(rc);
     *iters = it;
     rc = to_host(h, level, lv.x[lv.cur].p, x);

@@ -1006,41 +1006,49 @@ inline WinIdx fused_window(int nsweep, const TransferMap& tm, bool wide, const S
 // tm must be a closed-form map (parent == cp == nullptr); P1 != nullptr selects the two-parent form.
 // n_cover: local elements whose coarse parents this rank may have to gather (n, or n + ratio when the
 // right slab neighbour's first children contribute to this rank's last coarse element).
-inline bool fused_down(const MatDesc& d, int mc, const TransferMap& tm, int nsweep, bool zero,
+// Return value of fused_down / fused_up: FUSED_NA = no such kernel (the caller takes the streaming /
+// generic path), FUSED_OK = launched, FUSED_ERR = the launch itself failed (*err holds the CUDA error;
+// never silently papered over by a fall-back).
+enum { FUSED_NA = 0, FUSED_OK = 1, FUSED_ERR = -1 };
+
+inline int fused_down(const MatDesc& d, int mc, const TransferMap& tm, int nsweep, bool zero,
                        const double* mat, const double* b, const double* xin, double* xout,
                        const double* P0, const double* P1, double* rc, int64_t n, int64_t n_cover,
-                       double alpha, const Slab& sl, cudaStream_t st, bool pdl) {
+                       double alpha, const Slab& sl, cudaStream_t st, bool pdl, cudaError_t* err) {
     const WinIdx w = fused_window(nsweep, tm, P1 != nullptr || tm.shift != 0 || tm.base != 0, sl);
-    if (w.out < tm.ratio || w.out < FUSED_B / 2 || !fast_tier_ok(d)) return false;
+    if (w.out < tm.ratio || w.out < FUSED_B / 2 || !fast_tier_ok(d)) return FUSED_NA;
     const unsigned grid = (unsigned)((n_cover + w.out - 1) / w.out);
     switch (fused_key(d.m, mc, d.st, d.diag)) {
 #define X(MM, MCC, SS, DG)                                                                               \
     case ((MM * 16 + MCC) * 4 + SS) * 2 + (DG ? 1 : 0):                                                  \
-        return launch_fused(f_down<MM, MCC, FUSED_B, SS, DG>, grid, FUSED_B, 0, st, pdl, mat, d.ilo, d.iup, b, \
-                            xin, xout, P0, P1, tm, rc, n, alpha, nsweep, zero ? 1 : 0, w, sl) == cudaSuccess;
+        *err = launch_fused(f_down<MM, MCC, FUSED_B, SS, DG>, grid, FUSED_B, 0, st, pdl, mat, d.ilo, d.iup, b, \
+                            xin, xout, P0, P1, tm, rc, n, alpha, nsweep, zero ? 1 : 0, w, sl);           \
+        return *err == cudaSuccess ? FUSED_OK : FUSED_ERR;
         FUSED_COMBOS(X)
 #undef X
-        default: return false;
+        default: return FUSED_NA;
     }
 }
 
-inline bool fused_up(const MatDesc& d, int mc, const TransferMap& tm, int nsweep, const double* mat,
+inline int fused_up(const MatDesc& d, int mc, const TransferMap& tm, int nsweep, const double* mat,
                      const double* b, const double* xin, double* xout, const double* P0,
                      const double* P1, const double* xcoarse, int64_t n, double alpha, double* partial,
-                     int64_t partial_cap, int* nblocks, const Slab& sl, cudaStream_t st, bool pdl) {
+                     int64_t partial_cap, int* nblocks, const Slab& sl, cudaStream_t st, bool pdl,
+                     cudaError_t* err) {
     const WinIdx w = fused_window(nsweep, tm, false, sl);
-    if (w.out < tm.ratio || w.out < FUSED_B / 2 || !fast_tier_ok(d)) return false;
+    if (w.out < tm.ratio || w.out < FUSED_B / 2 || !fast_tier_ok(d)) return FUSED_NA;
     const int64_t grid = (n + w.out - 1) / w.out;
-    if (partial && grid > partial_cap) return false;
+    if (partial && grid > partial_cap) return FUSED_NA;
     if (nblocks) *nblocks = (int)grid;
     switch (fused_key(d.m, mc, d.st, d.diag)) {
 #define X(MM, MCC, SS, DG)                                                                               \
     case ((MM * 16 + MCC) * 4 + SS) * 2 + (DG ? 1 : 0):                                                  \
-        return launch_fused(f_up<MM, MCC, FUSED_B, SS, DG>, (unsigned)grid, FUSED_B, 0, st, pdl, mat, d.ilo, \
-                            d.iup, b, xin, xout, P0, P1, tm, xcoarse, n, alpha, nsweep, w, partial, sl) == cudaSuccess;
+        *err = launch_fused(f_up<MM, MCC, FUSED_B, SS, DG>, (unsigned)grid, FUSED_B, 0, st, pdl, mat, d.ilo, \
+                            d.iup, b, xin, xout, P0, P1, tm, xcoarse, n, alpha, nsweep, w, partial, sl);  \
+        return *err == cudaSuccess ? FUSED_OK : FUSED_ERR;
         FUSED_COMBOS(X)
 #undef X
-        default: return false;
+        default: return FUSED_NA;
     }
 }
 

@@ -345,3 +345,48 @@ def test_device_side_setup(name):
     finally:
         Hh.device.close()
         Hd.device.close()
+
+
+def test_error_behaviour_of_the_wider_api(lib):
+    """Call-order and argument errors of the set-up extensions come back as status codes with a message."""
+    import ctypes as C
+    from agglomerationmultigrid1d_b200 import _capi as capi
+    h = C.c_void_p()
+    assert lib.amg1d_create(C.byref(h), 2, 0, None) == capi.OK
+    z4, one4, eye = np.zeros(4), np.ones(4), np.array([1.0, 0.0, 0.0, 1.0])
+    p = capi.dptr
+    # smoother operator before its level / coarsening without flux operators / download of an unset level
+    assert lib.amg1d_set_level_smoother(h, 0, p(z4), p(eye), p(z4)) == capi.ERR_STATE
+    assert lib.amg1d_coarsen_level(h, 0, p(eye), 1) == capi.ERR_STATE
+    assert b"flux" in lib.amg1d_last_error(h)
+    assert lib.amg1d_get_level(h, 0, p(z4), p(z4), p(z4), p(z4)) == capi.ERR_ARG
+    assert lib.amg1d_coarsen_level(h, 1, p(eye), 1) == capi.ERR_ARG          # no coarser level
+    # a singular mass-free level: C - D M^-1 G with C = 0, D = 0 has singular diagonal blocks
+    assert lib.amg1d_set_level_flux(h, 0, 1, 2, p(z4), p(z4), p(z4), p(z4), p(z4), p(z4), p(z4), p(z4), p(z4),
+                                    p(eye), 1) == capi.ERR_ARG
+    assert b"singular" in lib.amg1d_last_error(h)
+    assert lib.amg1d_set_level_flux(h, 0, 1, 2, p(z4), p(z4), p(z4), p(z4), p(z4), p(z4), p(z4), p(eye), p(z4),
+                                    None, 1) == capi.ERR_ARG                  # null Minv
+    assert lib.amg1d_destroy(h) == capi.OK
+    # unfinalized handle: solver entry points refuse
+    assert lib.amg1d_create(C.byref(h), 1, 0, None) == capi.OK
+    x = np.zeros(2)
+    it = C.c_int(0)
+    assert lib.amg1d_pcg(h, p(x), p(x), 5, 1e-8, 3, 3, 0.5, C.byref(it), p(x)) == capi.ERR_STATE
+    assert lib.amg1d_ldiv(h, p(x), p(x), 3, 3, 0.5) == capi.ERR_STATE
+    assert lib.amg1d_direct_solve(h, 0, p(x), p(x)) == capi.ERR_STATE
+    # a singular level is reported by the direct solver, not returned as garbage
+    assert lib.amg1d_set_level(h, 0, 1, 2, p(z4), p(np.array([1.0, 1.0, 1.0, 1.0])), p(z4), p(eye), 0, None, 2) == capi.OK
+    assert lib.amg1d_finalize(h) == capi.ERR_ARG and b"singular" in lib.amg1d_last_error(h)
+    assert lib.amg1d_destroy(h) == capi.OK
+    # unknown option, negative sweeps
+    Hp, _, bp = build_package(**SHAPES["C2_dg3_agg"])
+    try:
+        with pytest.raises(aggmg.Amg1dError):
+            Hp.device.set_option("no_such_option", 1)
+        with pytest.raises(aggmg.Amg1dError):
+            Hp.device.vcycle(np.zeros(len(bp)), bp, nPre=-1)
+        with pytest.raises(ValueError):
+            Hp.device.pcg(np.zeros(3), bp, 10, 1e-8)                          # DimensionMismatch
+    finally:
+        Hp.device.close()
