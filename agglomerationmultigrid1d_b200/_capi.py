@@ -32,6 +32,7 @@ PROTOTYPES = {
     "amg1d_set_level_flux": (C.c_int, [_h, C.c_int, C.c_int64, C.c_int, _pd, _pd, _pd, _pd, _pd, _pd, _pd,
                                        _pd, _pd, _pd, C.c_int]),
     "amg1d_coarsen_level": (C.c_int, [_h, C.c_int, _pd, C.c_int]),
+    "amg1d_coarsen_level_galerkin": (C.c_int, [_h, C.c_int, C.c_int64, C.c_int, _pi64, C.c_int64]),
     "amg1d_get_level": (C.c_int, [_h, C.c_int, _pd, _pd, _pd, _pd]),
     "amg1d_set_level_smoother": (C.c_int, [_h, C.c_int, _pd, _pd, _pd]),
     "amg1d_set_level_pattern": (C.c_int, [_h, C.c_int, C.c_int64, C.c_int, C.c_int, C.c_int, _pd,

@@ -21,6 +21,7 @@
 #include "../../include/amg1d.h"
 #include "kernels_generic.cuh"
 #include "kernels_fused.cuh"
+#include "kernels_rows.cuh"
 #include "direct_bcr.cuh"
 #include "device_setup.cuh"
 
@@ -126,6 +127,7 @@ struct amg1d {
     int64_t opt_coarse_cta = 1024;
     int opt_compress = 1;         // drop structural zeros of the off-diagonal blocks (layout.cuh)
     int opt_pdl = 1;              // programmatic dependent launch between the fused kernels
+    int opt_rows = 64;            // window of the row-per-thread fused legs (kernels_rows.cuh): 32, 64; 0 = off
     // single-CTA coarse tail (f_tail): levels [tail_start, n_levels)
     int tail_start = -1;
     TailLevel* d_tail = nullptr;
@@ -589,9 +591,13 @@ int leg_down(amg1d* h, int l, int nPre, double alpha, bool zero0) {
     if (h->opt_fused && t.fusable && !lv.smooth_tri) {
         const int ob = zero ? 0 : 1 - lv.cur;
         cudaError_t le = cudaSuccess;
-        const int fr = fused_down(lv.md, t.mc, make_map_closed(t), nPre, zero, lv.mat, lv.b.p, lv.x[lv.cur].p,
-                                  lv.x[ob].p, t.P0, t.P1, lc.b.p, lv.n, lv.n + (lv.gr ? t.cover_extra : 0),
-                                  alpha, make_slab(h, l), h->stream, h->opt_pdl != 0, &le);
+        int fr = fused_down(lv.md, t.mc, make_map_closed(t), nPre, zero, lv.mat, lv.b.p, lv.x[lv.cur].p,
+                            lv.x[ob].p, t.P0, t.P1, lc.b.p, lv.n, lv.n + (lv.gr ? t.cover_extra : 0),
+                            alpha, make_slab(h, l), h->stream, h->opt_pdl != 0, &le);
+        if (fr == FUSED_NA && h->opt_rows)      // large blocks: one thread per block row
+            fr = rows_down(lv.md, t.mc, make_map_closed(t), nPre, zero, lv.mat, lv.b.p, lv.x[lv.cur].p,
+                           lv.x[ob].p, t.P0, t.P1, lc.b.p, lv.n, lv.n + (lv.gr ? t.cover_extra : 0), alpha,
+                           make_slab(h, l), h->opt_rows, h->stream, h->opt_pdl != 0, &le);
         if (fr == FUSED_ERR) return fail(h, AMG1D_ERR_CUDA, "f_down launch failed on level %d: %s", l, cudaGetErrorString(le));
         if (fr == FUSED_OK) {
             lv.cur = ob;
@@ -603,7 +609,7 @@ int leg_down(amg1d* h, int l, int nPre, double alpha, bool zero0) {
     }
     if (lv.sharded)
         return fail(h, AMG1D_ERR_UNSUPPORTED, "level %d: sharded levels need the fused kernels "
-                    "(block size <= 5, closed-form transfer, option fused = 1)", l);
+                    "(a block size / transfer with a fused leg, closed-form transfer, option fused = 1)", l);
     if (zero && nPre == 0) CK(cudaMemsetAsync(lv.x[0].p, 0, (size_t)lv.x[0].len * 8, h->stream));
     for (int s = 0; s < nPre; ++s) {
         if (zero && s == 0) {
@@ -634,10 +640,15 @@ int leg_up(amg1d* h, int l, int nPost, double alpha, bool fuse_norm, bool* norm_
     if (h->opt_fused && t.fusable && !lv.smooth_tri) {
         int nb = 0;
         cudaError_t le = cudaSuccess;
-        const int fr = fused_up(lv.md, t.mc, make_map_closed(t), nPost, lv.mat, lv.b.p, lv.x[lv.cur].p,
-                                lv.x[1 - lv.cur].p, t.P0, t.P1, lc.x[lc.cur].p, lv.n, alpha,
-                                fuse_norm ? h->partial : nullptr, h->partial_cap, &nb, make_slab(h, l),
-                                h->stream, h->opt_pdl != 0, &le);
+        int fr = fused_up(lv.md, t.mc, make_map_closed(t), nPost, lv.mat, lv.b.p, lv.x[lv.cur].p,
+                          lv.x[1 - lv.cur].p, t.P0, t.P1, lc.x[lc.cur].p, lv.n, alpha,
+                          fuse_norm ? h->partial : nullptr, h->partial_cap, &nb, make_slab(h, l),
+                          h->stream, h->opt_pdl != 0, &le);
+        if (fr == FUSED_NA && h->opt_rows)
+            fr = rows_up(lv.md, t.mc, make_map_closed(t), nPost, lv.mat, lv.b.p, lv.x[lv.cur].p,
+                         lv.x[1 - lv.cur].p, t.P0, t.P1, lc.x[lc.cur].p, lv.n, alpha,
+                         fuse_norm ? h->partial : nullptr, h->partial_cap, &nb, make_slab(h, l), h->opt_rows,
+                         h->stream, h->opt_pdl != 0, &le);
         if (fr == FUSED_ERR) return fail(h, AMG1D_ERR_CUDA, "f_up launch failed on level %d: %s", l, cudaGetErrorString(le));
         if (fr == FUSED_OK) {
             lv.cur = 1 - lv.cur;
@@ -1048,52 +1059,27 @@ void free_flux(amg1d* h, Level& lv) {
         if (p) { cudaFree(p); p = nullptr; h->device_bytes -= lv.n * lv.m * lv.m * 8; }
 }
 
-// Device-side set-up of one level from its flux operators (device_setup.cuh): A = C - D M^-1 G, block-
-// Jacobi inverses, structure detection, tile layout.  flux: 9 element-block device arrays; d_minv: n
-// blocks (or one when mi_const).  The level is installed exactly as amg1d_set_level would.
-int install_from_flux(amg1d* h, int level, int64_t n, int m, double* const* flux, const double* d_minv,
-                      int mi_const) {
+// Installs a level whose operator blocks A_lo / A_di / A_up already sit on the device as element-block
+// arrays dA[0..2] (n blocks of m x m): smoother inverses (block-Jacobi inverses of the diagonal blocks,
+// src/smoother.jl:154-164, or the reciprocal diagonal, :92-98), structure detection, tile layout - the
+// state amg1d_set_level leaves.  perm / n_dof_host as in amg1d_set_level; padding slots of a regrouped
+// level get the identity on the diagonal.  dA[1] is modified (padding) and stays owned by the caller.
+int install_from_blocks(amg1d* h, int level, int64_t n, int m, double* const* dA, int diag,
+                        const int64_t* perm, int64_t n_dof_host) {
     const int mm = m * m;
-    double *dA[3] = {nullptr, nullptr, nullptr}, *dDinv = nullptr, *dband = nullptr;
-    int *dmask = nullptr, *dflag = nullptr;
-    auto cleanup = [&]() {
-        for (double* p : dA) if (p) cudaFree(p);
-        if (dDinv) cudaFree(dDinv);
-        if (dband) cudaFree(dband);
-        if (dmask) cudaFree(dmask);
-        if (dflag) cudaFree(dflag);
-    };
-#define CKC(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { cleanup(); \
-        return fail(h, e_ == cudaErrorMemoryAllocation ? AMG1D_ERR_NOMEM : AMG1D_ERR_CUDA, "%s failed: %s", #call, cudaGetErrorString(e_)); } } while (0)
-    for (auto& p : dA) CKC(cudaMalloc((void**)&p, (size_t)n * mm * 8));
-    CKC(cudaMalloc((void**)&dDinv, (size_t)n * mm * 8));
-    CKC(cudaMalloc((void**)&dband, 2 * 8));
-    CKC(cudaMalloc((void**)&dmask, 4 * m * sizeof(int)));
-    CKC(cudaMalloc((void**)&dflag, sizeof(int)));
-    cudaMemsetAsync(dband, 0, 16, h->stream);
-    cudaMemsetAsync(dmask, 0, 4 * m * sizeof(int), h->stream);
-    cudaMemsetAsync(dflag, 0, sizeof(int), h->stream);
+    const int dsz = diag ? m : mm;
+    DevBuf dDinv, dints;                           // dints: 4 m structure masks + 1 singular flag (ints)
+    CK(dDinv.alloc((int64_t)n * dsz));
+    CK(dints.alloc(2 * m + 1));
+    int* dmask = reinterpret_cast<int*>(dints.p);
+    int* dflag = dmask + 4 * m;
+    CK(cudaMemsetAsync(dints.p, 0, (size_t)(2 * m + 1) * 8, h->stream));
     const unsigned grid = (unsigned)((n * mm + 127) / 128);
-    k_flux_operator<<<grid, 128, 0, h->stream>>>(flux[0], flux[1], flux[2], flux[3], flux[4], flux[5], flux[6],
-                                                  flux[7], flux[8], d_minv, mi_const, n, m, dA[0], dA[1], dA[2],
-                                                  dband);
-    CKC(cudaMemcpyAsync(dDinv, dA[1], (size_t)n * mm * 8, cudaMemcpyDeviceToDevice, h->stream));
-    k_bcr_invert_odd<<<(unsigned)((n + 31) / 32), 32, 0, h->stream>>>(dDinv, m, n, 0, 1, dflag);
     k_structure_masks<<<grid, 128, 0, h->stream>>>(dA[0], dA[2], n, m, dmask);
-    double band[2] = {0.0, 0.0};
-    int flag = 0;
     std::vector<int> mask(4 * (size_t)m, 0);
-    CKC(cudaMemcpyAsync(band, dband, 16, cudaMemcpyDeviceToHost, h->stream));
-    CKC(cudaMemcpyAsync(&flag, dflag, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
-    CKC(cudaMemcpyAsync(mask.data(), dmask, 4 * m * sizeof(int), cudaMemcpyDeviceToHost, h->stream));
-    CKC(cudaStreamSynchronize(h->stream));
-    CKC(cudaGetLastError());
-    if (flag) { cleanup(); return fail(h, AMG1D_ERR_ARG, "level %d: singular diagonal block", level); }
-    if (band[0] > 1e-11 * band[1]) {
-        cleanup();
-        return fail(h, AMG1D_ERR_ARG, "level %d: C - D M^-1 G is not block tridiagonal (outer band %.3e vs "
-                    "diagonal %.3e)", level, band[0], band[1]);
-    }
+    CK(cudaMemcpyAsync(mask.data(), dmask, 4 * m * sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    CK(cudaGetLastError());
     int st = AMG1D_ST_DENSE, ilo = 0, iup = 0;
     if (h->opt_compress && m >= 2) {
         auto single = [m](const int* mk, int* idx) {
@@ -1106,23 +1092,65 @@ int install_from_flux(amg1d* h, int level, int64_t n, int m, double* const* flux
         if (single(&mask[0], &a) && single(&mask[3 * m], &b)) { st = AMG1D_ST_COLROW; ilo = a; iup = b; }
         else if (single(&mask[m], &a) && single(&mask[2 * m], &b)) { st = AMG1D_ST_ROWCOL; ilo = a; iup = b; }
     }
-    int rc = alloc_level_common(h, level, n, m, 0, nullptr, n * m, st, ilo, iup);
-    if (rc != AMG1D_OK) { cleanup(); return rc; }
+    RET(alloc_level_common(h, level, n, m, diag, perm, n_dof_host, st, ilo, iup));
     Level& lv = h->L[level];
+    auto undo = [&]() {                            // the level stays unset: release what alloc_level_common took
+        if (lv.mat_alloc) { cudaFree(lv.mat_alloc); lv.mat_alloc = nullptr; lv.mat = nullptr; h->device_bytes -= lv.mat_bytes; }
+        if (lv.perm) { cudaFree(lv.perm); lv.perm = nullptr; h->device_bytes -= n * m * 8; }
+    };
+#define CKU(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { undo(); \
+        return fail(h, e_ == cudaErrorMemoryAllocation ? AMG1D_ERR_NOMEM : AMG1D_ERR_CUDA, "%s failed: %s", #call, cudaGetErrorString(e_)); } } while (0)
+    const unsigned gs = (unsigned)((n * m + 127) / 128);
+    if (lv.perm) k_pad_identity<<<gs, 128, 0, h->stream>>>(dA[1], lv.perm, n, m);
+    if (diag) {
+        k_diag_reciprocal<<<gs, 128, 0, h->stream>>>(dA[1], n, m, dDinv.p, dflag);
+    } else {
+        CKU(cudaMemcpyAsync(dDinv.p, dA[1], (size_t)n * mm * 8, cudaMemcpyDeviceToDevice, h->stream));
+        k_bcr_invert_odd<<<(unsigned)((n + 31) / 32), 32, 0, h->stream>>>(dDinv.p, m, n, 0, 1, dflag);
+    }
+    int flag = 0;
+    CKU(cudaMemcpyAsync(&flag, dflag, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+    CKU(cudaStreamSynchronize(h->stream));
+    CKU(cudaGetLastError());
+    if (flag) { undo(); return fail(h, AMG1D_ERR_ARG, "level %d: singular diagonal block", level); }
     const int64_t total = amg1d_tiles(n) * (int64_t)lv.K * AMG1D_TILE;
-    k_repack<<<(unsigned)((total + 255) / 256), 256, 0, h->stream>>>(dA[0], dA[1], dA[2], dDinv, lv.md, 0, n, lv.mat);
+    k_repack<<<(unsigned)((total + 255) / 256), 256, 0, h->stream>>>(dA[0], dA[1], dA[2], dDinv.p, lv.md, 0, n, lv.mat);
     if (n <= AMG1D_BCR_MIN) {                      // host copy for the block-Thomas factorisation
         lv.h_lo.resize((size_t)n * mm); lv.h_di.resize((size_t)n * mm); lv.h_up.resize((size_t)n * mm);
-        CKC(cudaMemcpyAsync(lv.h_lo.data(), dA[0], (size_t)n * mm * 8, cudaMemcpyDeviceToHost, h->stream));
-        CKC(cudaMemcpyAsync(lv.h_di.data(), dA[1], (size_t)n * mm * 8, cudaMemcpyDeviceToHost, h->stream));
-        CKC(cudaMemcpyAsync(lv.h_up.data(), dA[2], (size_t)n * mm * 8, cudaMemcpyDeviceToHost, h->stream));
+        CKU(cudaMemcpyAsync(lv.h_lo.data(), dA[0], (size_t)n * mm * 8, cudaMemcpyDeviceToHost, h->stream));
+        CKU(cudaMemcpyAsync(lv.h_di.data(), dA[1], (size_t)n * mm * 8, cudaMemcpyDeviceToHost, h->stream));
+        CKU(cudaMemcpyAsync(lv.h_up.data(), dA[2], (size_t)n * mm * 8, cudaMemcpyDeviceToHost, h->stream));
     }
-    CKC(cudaStreamSynchronize(h->stream));
-    CKC(cudaGetLastError());
-#undef CKC
-    cleanup();
+    CKU(cudaStreamSynchronize(h->stream));
+    CKU(cudaGetLastError());
+#undef CKU
     lv.set = true;
     return AMG1D_OK;
+}
+
+// Device-side set-up of one level from its flux operators (device_setup.cuh): A = C - D M^-1 G, then
+// install_from_blocks with a block smoother.  flux: 9 element-block device arrays; d_minv: n blocks (or
+// one when mi_const).
+int install_from_flux(amg1d* h, int level, int64_t n, int m, double* const* flux, const double* d_minv,
+                      int mi_const) {
+    const int mm = m * m;
+    DevBuf A[3], dband;
+    for (auto& b : A) CK(b.alloc((int64_t)n * mm));
+    CK(dband.alloc(2));
+    CK(cudaMemsetAsync(dband.p, 0, 16, h->stream));
+    const unsigned grid = (unsigned)((n * mm + 127) / 128);
+    k_flux_operator<<<grid, 128, 0, h->stream>>>(flux[0], flux[1], flux[2], flux[3], flux[4], flux[5], flux[6],
+                                                  flux[7], flux[8], d_minv, mi_const, n, m, A[0].p, A[1].p, A[2].p,
+                                                  dband.p);
+    double band[2] = {0.0, 0.0};
+    CK(cudaMemcpyAsync(band, dband.p, 16, cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    CK(cudaGetLastError());
+    if (band[0] > 1e-11 * band[1])
+        return fail(h, AMG1D_ERR_ARG, "level %d: C - D M^-1 G is not block tridiagonal (outer band %.3e vs "
+                    "diagonal %.3e)", level, band[0], band[1]);
+    double* dA[3] = {A[0].p, A[1].p, A[2].p};
+    return install_from_blocks(h, level, n, m, dA, 0, nullptr, n * m);
 }
 
 }  // namespace
@@ -1460,6 +1488,67 @@ int amg1d_coarsen_level(amg1d_t* h, int level, const double* Minv_coarse, int mi
     return install_from_flux(h, level + 1, nc, mc, lc.flux, minv.p, minv_is_constant);
 }
 
+int amg1d_coarsen_level_galerkin(amg1d_t* h, int level, int64_t n_coarse_elem, int dinv_is_diagonal,
+                                 const int64_t* perm_coarse, int64_t n_dof_host_coarse) {
+    if (!h) return AMG1D_ERR_ARG;
+    if (level < 0 || level >= h->n_levels - 1) return fail(h, AMG1D_ERR_ARG, "level %d has no coarser level", level);
+    if (h->finalized) return fail(h, AMG1D_ERR_STATE, "hierarchy already finalized");
+    if (h->nranks > 1) return fail(h, AMG1D_ERR_UNSUPPORTED, "device-side set-up is single-GPU only");
+    Level& lf = h->L[level];
+    Level& lc = h->L[level + 1];
+    Transfer& t = h->T[level];
+    if (!lf.set) return fail(h, AMG1D_ERR_STATE, "level %d must be set before amg1d_coarsen_level_galerkin", level);
+    if (!t.set) return fail(h, AMG1D_ERR_STATE, "transfer %d must be set before amg1d_coarsen_level_galerkin", level);
+    if (lc.set) return fail(h, AMG1D_ERR_STATE, "level %d already set", level + 1);
+    if (lf.smooth_tri) return fail(h, AMG1D_ERR_UNSUPPORTED, "level %d carries a tridiagonal smoother operator", level);
+    if (t.n_fine != lf.n || t.mf != lf.m) return fail(h, AMG1D_ERR_ARG, "transfer %d does not match level %d", level, level);
+    const int mc = t.mc, mf = t.mf;
+    const int64_t nc = n_coarse_elem;
+    if (mc > AMG1D_BCR_MAXM) return fail(h, AMG1D_ERR_ARG, "coarse block size %d too large", mc);
+    if (nc < t.n_coarse || nc > t.n_coarse + (t.P1 ? 1 : 0))
+        return fail(h, AMG1D_ERR_ARG, "transfer %d reaches coarse element %lld but n_coarse_elem is %lld", level,
+                    (long long)t.n_coarse - 1, (long long)nc);
+    CK(cudaSetDevice(h->device));
+    // fine operator as element-block arrays, coarse result, child pointers of an explicit parent map
+    DevBuf F[3], C[3], dband, dcp;
+    const int64_t fcnt = lf.n * mf * mf, ccnt = nc * mc * mc;
+    for (auto& b : F) CK(b.alloc(fcnt));
+    for (auto& b : C) CK(b.alloc(ccnt));
+    CK(dband.alloc(2));
+    CK(cudaMemsetAsync(dband.p, 0, 16, h->stream));
+    k_bcr_extract<<<(unsigned)((fcnt + 255) / 256), 256, 0, h->stream>>>(lf.mat, lf.md, lf.n, F[0].p, F[1].p, F[2].p);
+    TransferMap tm = make_map(t);
+    tm.n_coarse = nc;
+    tm.cp = nullptr;
+    if (!t.closed) {
+        if (t.h_parent.size() != (size_t)t.n_fine) return fail(h, AMG1D_ERR_STATE, "transfer %d has no parent map", level);
+        std::vector<int64_t> cp((size_t)nc + 2);
+        int64_t e = 0;
+        for (int64_t q = 0; q < nc + 2; ++q) {
+            while (e < t.n_fine && t.h_parent[(size_t)e] < q - 1) ++e;
+            cp[(size_t)q] = e;
+        }
+        CK(dcp.alloc((int64_t)cp.size()));
+        CK(cudaMemcpyAsync(dcp.p, cp.data(), cp.size() * 8, cudaMemcpyHostToDevice, h->stream));
+        CK(cudaStreamSynchronize(h->stream));         // cp is a local vector
+        tm.cp = reinterpret_cast<const int64_t*>(dcp.p);
+    } else {
+        tm.parent = nullptr;
+    }
+    k_galerkin_general<<<(unsigned)((ccnt + 127) / 128), 128, 0, h->stream>>>(F[0].p, F[1].p, F[2].p, t.P0, t.P1, tm, mf,
+                                                                               mc, nc, C[0].p, C[1].p, C[2].p, dband.p);
+    double band[2] = {0.0, 0.0};
+    CK(cudaMemcpyAsync(band, dband.p, 16, cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    CK(cudaGetLastError());
+    if (band[0] > 1e-11 * band[1])
+        return fail(h, AMG1D_ERR_ARG, "level %d: L' A L is not block tridiagonal (outer band %.3e vs diagonal %.3e)",
+                    level + 1, band[0], band[1]);
+    double* dA[3] = {C[0].p, C[1].p, C[2].p};
+    return install_from_blocks(h, level + 1, nc, mc, dA, dinv_is_diagonal, perm_coarse,
+                               perm_coarse ? n_dof_host_coarse : nc * mc);
+}
+
 int amg1d_get_level(amg1d_t* h, int level, double* A_lo, double* A_di, double* A_up, double* Dinv) {
     if (!h) return AMG1D_ERR_ARG;
     if (!valid_level(h, level) || !h->L[level].set) return fail(h, AMG1D_ERR_ARG, "level %d is not set", level);
@@ -1661,7 +1750,7 @@ int amg1d_finalize(amg1d_t* h) {
         RET(vec_alloc(h, lv.b, lv.n, lv.m));
         if (lv.present) RET(vec_alloc(h, lv.x[1], lv.n, lv.m));
         maxlen = std::max(maxlen, lv.n * lv.m);
-        h->partial_cap = std::max<int64_t>(h->partial_cap, lv.n / (FUSED_B / 2) + 16);
+        h->partial_cap = std::max<int64_t>(h->partial_cap, lv.n / (lv.m > 5 ? 16 : FUSED_B / 2) + 16);
     }
     RET(vec_alloc(h, h->scratch, maxlen, 1));
     RET(dev_alloc(h, (void**)&h->partial, (h->partial_cap + 256) * 8));
@@ -1669,6 +1758,15 @@ int amg1d_finalize(amg1d_t* h) {
     CK(cudaMallocHost(&h->h_scal, 64 * 8));
     if (h->L[h->n_levels - 1].present) RET(factor_coarsest(h));
     RET(build_tail(h));
+    // the row-per-thread legs of the large-block levels use > 48 KB of dynamic shared memory
+    for (int l = 0; l + 1 < h->n_levels; ++l) {
+        const Level& lv = h->L[l];
+        if (!lv.present || !h->T[l].fusable) continue;
+        bool have = false;
+        cudaError_t e = rows_configure(lv.md, h->T[l].mc, &have);
+        if (e != cudaSuccess)
+            return fail(h, AMG1D_ERR_CUDA, "r_down / r_up configuration failed on level %d: %s", l, cudaGetErrorString(e));
+    }
     for (auto& lv : h->L) free_flux(h, lv);
     CK(cudaStreamSynchronize(h->stream));
     h->finalized = true;
@@ -2022,6 +2120,10 @@ int amg1d_set_option(amg1d_t* h, const char* key, int64_t value) {
     if (!strcmp(key, "fused")) h->opt_fused = (int)value;
     else if (!strcmp(key, "graph")) h->opt_graph = (int)value;
     else if (!strcmp(key, "pdl")) h->opt_pdl = (int)value;
+    else if (!strcmp(key, "rows_window")) {
+        if (value != 0 && !rows_window_ok((int)value)) return fail(h, AMG1D_ERR_ARG, "rows_window must be 0, 32 or 64");
+        h->opt_rows = (int)value;
+    }
     else if (!strcmp(key, "coarse_cta_elems")) {
         h->opt_coarse_cta = value;
         if (h->finalized) { CK(cudaSetDevice(h->device)); CK(cudaStreamSynchronize(h->stream)); RET(build_tail(h)); }
@@ -2056,6 +2158,7 @@ int64_t amg1d_get_info(amg1d_t* h, const char* key) {
     if (!strcmp(key, "gather_level")) return h->gather_level;
     if (!strcmp(key, "tail_start")) return h->tail_start;
     if (!strcmp(key, "ghost_depth")) return h->ghost_depth;
+    if (!strcmp(key, "rows_window")) return h->opt_rows;
     if (!strncmp(key, "structure:", 10)) {          // "structure:<level>" -> structure class (layout.cuh)
         const int l = atoi(key + 10);
         return valid_level(h, l) && h->L[l].set ? h->L[l].md.st : -1;

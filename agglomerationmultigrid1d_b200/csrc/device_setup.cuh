@@ -38,6 +38,11 @@ __device__ __forceinline__ double ds_ptxp(const double* Pa, const double* X, con
     return s;
 }
 
+__device__ __forceinline__ void atomic_max_nonneg(double* addr, double v) {
+    // non-negative doubles order like their bit patterns
+    atomicMax(reinterpret_cast<unsigned long long*>(addr), (unsigned long long)__double_as_longlong(v));
+}
+
 // one thread per (coarse element K, column j, row i); single-parent transfers only
 __global__ void k_galerkin_tri(const double* __restrict__ lo, const double* __restrict__ di,
                                const double* __restrict__ up, const double* __restrict__ P, TransferMap tm,
@@ -66,6 +71,81 @@ __global__ void k_galerkin_tri(const double* __restrict__ lo, const double* __re
     up_c[t] = u;
 }
 
+// Galerkin product of the stiffness matrix itself, A_c = L' A L, for any element-local transfer: one
+// parent (L[e, par(e)] = P0[e]) or two (additionally L[e, par(e) + 1] = P1[e]: cg_cg / dg_cg / aggdg_cg,
+// where the nodes of a fine group interpolate from the coarse group of their element and from the
+// vertex that opens the next one).  This is the CG loop of the reference's first constructor,
+// mStiffness[i] = L' mStiffness[i-1] L (src/mesh_heirarchy.jl:52-60), in element-block form:
+//
+//   A_c[K, J] = sum over fine e with L[e, K] != 0, f in {e-1, e, e+1} with L[f, J] != 0 of
+//               L[e, K]' A[e, f] L[f, J]
+//
+// One thread per (coarse element K, column j, row i) accumulates J = K-1, K, K+1; contributions to any
+// other J (the product of two-parent transfers is block PENTA-diagonal in general; the reference's
+// nodal interpolation makes the outer bands vanish) go to band_max[0] and are checked by the host.
+// band_max[1] <- max |diagonal-block entry|.
+__global__ void k_galerkin_general(const double* __restrict__ lo, const double* __restrict__ di,
+                                   const double* __restrict__ up, const double* __restrict__ P0,
+                                   const double* __restrict__ P1, TransferMap tm, int mf, int mc, int64_t nc,
+                                   double* __restrict__ lo_c, double* __restrict__ di_c,
+                                   double* __restrict__ up_c, double* __restrict__ band_max) {
+    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int mmc = mc * mc, mmf = mf * mf, bs = mf * mc;
+    if (t >= nc * mmc) return;
+    const int64_t K = t / mmc;
+    const int q = (int)(t % mmc);
+    const int j = q / mc, i = q % mc;
+    const int64_t e0 = P1 ? tm.first(K - 1) : tm.first(K), e1 = tm.first(K + 1);
+    double d = 0.0, l = 0.0, u = 0.0, band = 0.0;
+    for (int64_t e = e0; e < e1; ++e) {
+        const double* Pe = (tm.par(e) == K ? P0 : P1) + tm.blk(e) * bs;        // L[e, K]
+        for (int s = -1; s <= 1; ++s) {
+            const int64_t f = e + s;
+            if (f < 0 || f >= tm.n_fine) continue;
+            const double* X = (s < 0 ? lo : (s == 0 ? di : up)) + e * mmf;     // A[e, f]
+            const int64_t pf = tm.par(f);
+            for (int two = 0; two < (P1 ? 2 : 1); ++two) {
+                const int64_t J = pf + two;                                    // L[f, J]
+                const double v = ds_ptxp(Pe, X, (two ? P1 : P0) + tm.blk(f) * bs, mf, i, j);
+                if (J == K) d += v;
+                else if (J == K - 1) l += v;
+                else if (J == K + 1 && J < nc) u += v;
+                else band = fmax(band, fabs(v));
+            }
+        }
+    }
+    di_c[t] = d;
+    lo_c[t] = K > 0 ? l : 0.0;
+    up_c[t] = K < nc - 1 ? u : 0.0;
+    if (K == 0 && l != 0.0) band = fmax(band, fabs(l));
+    if (band > 0.0) atomic_max_nonneg(band_max, band);
+    atomic_max_nonneg(band_max + 1, fabs(d));
+}
+
+// padding slots of a regrouped (CG) level, perm[slot] < 0: identity on the diagonal, as the host's
+// block extraction does (blocks.csc_to_blocks)
+__global__ void k_pad_identity(double* __restrict__ di, const int64_t* __restrict__ perm, int64_t n, int m) {
+    const int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= n * m) return;
+    if (perm[s] < 0) {
+        const int64_t e = s / m;
+        const int i = (int)(s % m);
+        di[e * m * m + i * m + i] = 1.0;
+    }
+}
+
+// point-Jacobi smoother (src/smoother.jl:92-98): dinv[e*m + i] = 1 / A_di[e](i, i)
+__global__ void k_diag_reciprocal(const double* __restrict__ di, int64_t n, int m, double* __restrict__ dinv,
+                                  int* __restrict__ flag) {
+    const int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= n * m) return;
+    const int64_t e = s / m;
+    const int i = (int)(s % m);
+    const double a = di[e * m * m + i * m + i];
+    if (a == 0.0) { flag[0] = 1; dinv[s] = 0.0; return; }
+    dinv[s] = 1.0 / a;
+}
+
 // entry (i, j) of  D Mi G  (all m x m column-major)
 __device__ __forceinline__ double ds_dmg(const double* D, const double* Mi, const double* G, int m, int i, int j) {
     double s = 0.0;
@@ -77,10 +157,6 @@ __device__ __forceinline__ double ds_dmg(const double* D, const double* Mi, cons
     return s;
 }
 
-__device__ __forceinline__ void atomic_max_nonneg(double* addr, double v) {
-    // non-negative doubles order like their bit patterns
-    atomicMax(reinterpret_cast<unsigned long long*>(addr), (unsigned long long)__double_as_longlong(v));
-}
 
 // A = C - D M^-1 G, tridiagonal part; band_max[0] <- max |outer-band entry|.  One thread per (e, j, i).
 // Mi: n blocks, or one block for every element when mi_const != 0.

@@ -985,10 +985,10 @@ inline int fused_key(int m, int mc, int st, int diag) { return ((m * 16 + mc) * 
 
 // halo, elements emitted per CTA and the 32-bit index constants for a leg of nsweep sweeps
 inline int64_t floordiv64(int64_t a, int64_t b) { int64_t q = a / b; return (a % b != 0 && ((a < 0) != (b < 0))) ? q - 1 : q; }
-inline WinIdx fused_window(int nsweep, const TransferMap& tm, bool wide, const Slab& sl) {
+inline WinIdx fused_window(int nsweep, const TransferMap& tm, bool wide, const Slab& sl, int window = FUSED_B) {
     WinIdx w;
     w.halo = nsweep + 1 + (wide ? tm.ratio : 0);
-    w.out = ((FUSED_B - 2 * w.halo) / tm.ratio) * tm.ratio;
+    w.out = ((window - 2 * w.halo) / tm.ratio) * tm.ratio;
     if (w.out < 1) w.out = 0;
     w.opr = w.out / tm.ratio;
     const int64_t q0 = sl.e_off + tm.shift - w.halo;

@@ -74,6 +74,16 @@ class DeviceHierarchy:
         self.n_dof[level + 1] = int(n_coarse) * mi.shape[1]
         self._ck(self._lib.amg1d_coarsen_level(self._h, level, capi.dptr(mi), int(const)))
 
+    def coarsen_level_galerkin(self, level, slots_coarse, n_dof_coarse, dinv_is_diagonal=True):
+        """level + 1 <- L' A L of level's stiffness matrix on the GPU (one- or two-parent transfer `level`
+        must be set): the CG loop of the reference's first constructor.  slots_coarse: the coarse
+        level's (element block, row) -> host DOF map (blocks.level_slots)."""
+        perm = None if blk.is_identity_slots(slots_coarse) else capi.i64(slots_coarse.ravel())
+        self.n_dof[level + 1] = int(n_dof_coarse)
+        self._ck(self._lib.amg1d_coarsen_level_galerkin(self._h, level, int(slots_coarse.shape[0]),
+                                                        int(dinv_is_diagonal), capi.iptr(perm),
+                                                        int(n_dof_coarse)))
+
     def get_level(self, level, n, m, diag=False):
         """(lo, di, up) as (n, m, m) blocks in (e, i, j) order and Dinv ((n, m, m), or (n, m) if diag)."""
         out = [np.zeros((n, m, m)) for _ in range(3)]

@@ -48,14 +48,19 @@ class MeshHierarchy:
 
     def __init__(self, mMeshes, *args, nCG=None, nDG=None, nAgg=0, CDir=1.0, device=0, upload=True,
                  stream=None, device_setup=False):
-        """device_setup=True (DG-first constructor only): the host assembles level 0's flux operators and
-        the element-local transfers; the Galerkin products, A = C - D (M \\ G) and the smoother blocks of
-        every level are computed on the GPU.  mStiffness[k], k > 0, then stay None on the
-        host; ``level_blocks(k)`` downloads them."""
+        """device_setup=True: the host assembles what the reference assembles from the mesh (level 0's
+        operator, the flux operators of the first DG-type level, the element-local transfers); every
+        Galerkin product - L' A L of the CG levels, L' (G, D, C) L of the DG-type levels -, A = C - D (M \\ G)
+        and the smoothers of every level are computed on the GPU.  mStiffness[k], k > 0, then
+        stay None on the host; ``level_blocks(k)`` downloads them."""
         self.mMeshes = list(mMeshes)
         self.device_setup = bool(device_setup)
         if len(args) == 3:                      # (mesh, mBdConds, A): CG-first constructor
             mesh, mBdConds, A = args
+            if self.device_setup:
+                self._build_cg_first_on_device(mesh, mBdConds, A, 1 if nCG is None else nCG,
+                                               0 if nDG is None else nDG, nAgg, CDir, device, stream)
+                return
             self._build_cg_first(mesh, mBdConds, A, 1 if nCG is None else nCG,
                                  0 if nDG is None else nDG, nAgg, CDir)
         elif len(args) == 5:                    # (mBdConds, A, G, D, C): DG-first constructor
@@ -181,6 +186,70 @@ class MeshHierarchy:
         none = [None] * nL
         self._set(S, [sp.csc_matrix(G)] + none[1:], [sp.csc_matrix(D)] + none[1:],
                   [sp.csc_matrix(C)] + none[1:], Sm, I, mBdConds)
+        self.device = dev
+        self.mSlots = slots
+
+    # ---- the CG-first chain with every product on the GPU ------------------------------
+    def _build_cg_first_on_device(self, mesh, mBdConds, A, nCG, nDG, nAgg, CDir, device, stream):
+        """src/mesh_heirarchy.jl:30-138 with mStiffness[i] = L' mStiffness[i-1] L of the CG levels
+        (amg1d_coarsen_level_galerkin, two-parent cg_cg transfers) and the DG-type chain underneath
+        (amg1d_set_level_flux on its first level, amg1d_coarsen_level below) formed on the device."""
+        from .smoother import DeviceBlockJacobi, DeviceJacobi
+        import numpy as np
+        M = self.mMeshes
+        if nCG <= 0:
+            raise ValueError("At least one CG mesh required.")
+        if len(M) != nCG + nDG + nAgg:
+            raise ValueError("Length of vector of meshes does not match inputed number of CG, DG, "
+                             "and agglomerated meshes.")
+        nL = nCG + nDG + nAgg
+        slots = [blk.level_slots(m) for m in M]
+        dev = DeviceHierarchy(nL, device=device, stream=stream)
+        S0 = sp.csc_matrix(A)
+        Sm = [None] * nL
+        Sm[0] = cg_smoother(M[0], S0, "jac")
+        lo, di, up = blk.csc_to_blocks(S0, slots[0])
+        dinv, is_diag = smoother_inverse(Sm[0], slots[0])
+        dev.set_level_blocks(0, lo, di, up, dinv, is_diag, slots[0], S0.shape[0])
+        Sm[0]._owner = (dev, 0)
+        I = [None] * (nL - 1)
+
+        def transfer(k, L):
+            I[k] = L
+            parent, P0, P1 = blk.transfer_to_blocks(L, slots[k], slots[k + 1])
+            dev.set_transfer_blocks(k, parent, P0, P1)
+
+        for i in range(1, nCG):
+            transfer(i - 1, cg_cg_interpolation(M[i], M[i - 1]))
+            dev.coarsen_level_galerkin(i - 1, slots[i], M[i].mNumNodes, dinv_is_diagonal=True)
+            Sm[i] = DeviceJacobi(dev, i, slots[i], M[i].mNumNodes)
+        minv = lambda m: np.linalg.inv(m.mMassMatrix.mBlocks)                # noqa: E731
+        G = D = C = None
+        if nDG + nAgg >= 1:
+            if nDG >= 1:
+                transfer(nCG - 1, dg_cg_interpolation(M[nCG], M[nCG - 1], mesh, 1))
+                G, D, C = dg_flux_operators(M[nCG], mesh, mBdConds[nCG], CDir)
+            else:
+                transfer(nCG - 1, aggdg_cg_interpolation(M[nCG], M[nCG - 1], mesh, 1))
+                G, D, C = dg_flux_operators(M[nCG], M[nCG - 1], mBdConds[nCG], CDir)
+            flux = [blk.csc_to_blocks(sp.csc_matrix(X), slots[nCG], pad_identity=False) for X in (G, D, C)]
+            dev.set_level_flux(nCG, flux[0], flux[1], flux[2], minv(M[nCG]))
+            for k in range(nCG + 1, nL):
+                if k < nCG + nDG:
+                    L = dg_dg_interpolation(M[k], M[k - 1])
+                elif k == nCG + nDG:
+                    L = aggdg_dg_interpolation(M[k], M[k - 1])
+                else:
+                    L = aggdg_aggdg_interpolation(M[k], M[k - 1], M[nCG + nDG - 1] if nDG else M[nCG - 1])
+                transfer(k - 1, L)
+                dev.coarsen_level(k - 1, minv(M[k]), slots[k].shape[0])
+            for k in range(nCG, nL):
+                Sm[k] = DeviceBlockJacobi(dev, k)
+        dev.finalize()
+        nD = nDG + nAgg
+        none = [None] * max(nD, 1)
+        first = lambda X: ([sp.csc_matrix(X)] + none[1:nD]) if nD else []    # noqa: E731
+        self._set([S0] + [None] * (nL - 1), first(G), first(D), first(C), Sm, I, mBdConds)
         self.device = dev
         self.mSlots = slots
 

@@ -54,6 +54,30 @@ class DeviceBlockJacobi(AbstractSmoother):
         self._slots = None
 
 
+class DeviceJacobi(JacobiSmoother):
+    """Point-Jacobi smoother of a level whose operator is a Galerkin product formed on the GPU
+    (MeshHierarchy(..., device_setup=True), CG levels); mJac is downloaded on first use."""
+
+    def __init__(self, dev, level, slots, n_dof):
+        self._owner = (dev, level)
+        self._A = None
+        self._slots = slots
+        self._n_dof = int(n_dof)
+        self._jac = None
+
+    @property
+    def mJac(self):
+        if self._jac is None:
+            dev, level = self._owner
+            ne, m = self._slots.shape
+            _, di, _, _ = dev.get_level(level, ne, m, diag=True)
+            d = np.einsum("eii->ei", di)
+            self._jac = np.zeros(self._n_dof)
+            valid = self._slots >= 0
+            self._jac[self._slots[valid]] = d[valid]
+        return self._jac
+
+
 class AdditiveSchwarzSmoother(AbstractSmoother):
     """mBlocks: (n, p+1, p+1) element matrices A[el.mNodesInd, el.mNodesInd] (the reference keeps their
     LU factors); mBlockInds (p+1, n) = el.mNodesInd columns (left vertex, right vertex, interior nodes)."""

@@ -7,7 +7,7 @@ plus the convergence check ||A x - b||_2 that ``multigrid`` performs after every
 resident in HBM; `e2e` = the same metric through the reference-facing call
 ``multigrid_v_cycle(H, x0, b)`` (amg1d_vcycle) with pinned HOST vectors, copies inside the timing.
 
-  python bench.py [--gpus N] [--steps K] [--warmup W] [--workload T|C2|C3|C4|C5|S] [--impl reference]
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--workload T|C2|C3|C4|C5|P8|S] [--impl reference]
 """
 import argparse
 import json
@@ -37,6 +37,9 @@ WORKLOADS = {
     "C4": (26, [3, 1], [1], "CG p=3 -> CG 1 -> DG 1 -> factor-2 agglomeration, 2^26 elements (dg_cg_heirarchy shape, 29 levels)"),
     "C5": (24, [], [3, 1], "DG p=3, 2^24 elements per GPU, full hierarchy"),
     "S": (14, [], [3, 1], "DG p=3, 2^14 elements (smoke-sized)"),
+    # the order the reference's own hierarchy scripts start from (tests/dg_heirarchy_test.jl: p = 8, 4, 2, 1):
+    # 9x9 element blocks on level 0, handled by the row-per-thread fused legs (csrc/kernels_rows.cuh)
+    "P8": (23, [], [8, 4, 2, 1], "DG p=8, 2^23 elements, DG 8->4->2->1 then factor-2 agglomeration (27 levels)"),
 }
 
 
@@ -323,7 +326,8 @@ def run_gpu(args):
     # f_up at level 0 (prolongation + 3 sweeps + ||b - A x||^2), this rank's slab: the level's stored
     # operator once (tile_rows doubles per element for its structure class), b, x in, x out, coarse x
     bytes_up = U.bytes_per_leg_fused(0, down=False) // world
-    kern = (f"f_up<{m},{mc},128,st={st0},{'point' if getattr(lv0, 'is_cg', False) else 'block'}-Jacobi> level 0 "
+    kname = "f_up<%d,%d,128" % (m, mc) if m <= 5 else "r_up<%d,%d,%d" % (m, mc, dev.info("rows_window"))
+    kern = (f"{kname},st={st0},{'point' if getattr(lv0, 'is_cg', False) else 'block'}-Jacobi> level 0 "
             f"(prolong + 3 sweeps + ||b-Ax||^2; {U.tile_rows(0)} + {3 * m} doubles per element)")
     t_k = legs["L0_up"]
     achieved = bytes_up / (t_k * 1e-3) / 1e9

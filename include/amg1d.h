@@ -93,6 +93,20 @@ int amg1d_set_level_flux(amg1d_t* h, int level, int64_t n_elem, int m, const dou
  * coarse elements' inverse mass matrices Minv_coarse. */
 int amg1d_coarsen_level(amg1d_t* h, int level, const double* Minv_coarse, int minv_is_constant);
 
+/* Galerkin coarsening of the stiffness matrix itself on the GPU: level + 1 <- level,
+ *     mStiffness[level + 1] = L' mStiffness[level] L
+ * - the CG loop of the reference's first constructor (src/mesh_heirarchy.jl:52-60, cg_cg_interpolation)
+ * and any other level whose operator is the plain triple product.  `level` must be set (by any of the
+ * set / coarsen calls), transfer `level` may have one parent or two (P1: cg_cg / dg_cg / aggdg_cg) and
+ * an explicit or a closed-form parent map.  The library verifies that the product is block tridiagonal
+ * in the coarse grouping (AMG1D_ERR_ARG otherwise) and builds the smoother of the coarse level from its
+ * diagonal: reciprocals (dinv_is_diagonal = 1: JacobiSmoother, cg_smoother(:jac), src/smoother.jl:92-98)
+ * or block inverses (0: BlockJacobi, :154-164).  n_coarse_elem: element blocks of the coarse level (for
+ * a CG level in [vertex_k, interior_k] grouping: elements + 1); perm_coarse / n_dof_host_coarse as perm /
+ * n_dof_host of amg1d_set_level (padding slots, perm = -1, get the identity). */
+int amg1d_coarsen_level_galerkin(amg1d_t* h, int level, int64_t n_coarse_elem, int dinv_is_diagonal,
+                                 const int64_t* perm_coarse, int64_t n_dof_host_coarse);
+
 /* Download of a level as the element-block arrays of amg1d_set_level (A_lo, A_di, A_up: n_elem*m*m each;
  * Dinv: n_elem*m*m or n_elem*m) - for checking device-side set-up and for scripts that inspect
  * H.mStiffness[k] of a level the host never assembled. */

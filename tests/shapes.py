@@ -84,7 +84,7 @@ def build_package(n, cg_orders=(), dg_orders=(), agg_factors=(), pAgg=1, unit_h=
     if nCG:
         A, b = aggmg.cg_stiffness_and_rhs(meshes[0], mesh, pr["func"], bdCond)
         H = aggmg.MeshHierarchy(meshes, mesh, bdConds, A, nCG=nCG, nDG=nDG, nAgg=nAgg, CDir=CDir,
-                                upload=upload)
+                                upload=upload, device_setup=device_setup)
     else:
         G, D, C = aggmg.dg_flux_operators(meshes[0], mesh, bdCond, CDir)
         A = (C - D @ meshes[0].mMassMatrixLU.solve(G)).tocsc()

@@ -347,6 +347,48 @@ def test_device_side_setup(name):
         Hd.device.close()
 
 
+@pytest.mark.parametrize("name", ["cg_heirarchy", "dg_cg_heirarchy", "full_heirarchy", "C4_cg3_dg1_agg",
+                                  "C1_cg1_agg", "bcr_dg_cg_n128"])
+def test_device_side_setup_cg_first(name):
+    """SURVEY 8f-1 for the CG-first constructor (src/mesh_heirarchy.jl:30-138): mStiffness[i] = L' mStiffness[i-1] L
+    of the CG levels with two-parent cg_cg transfers (amg1d_coarsen_level_galerkin), their point-Jacobi
+    smoothers, and the DG-type chain underneath, all formed on the GPU - against the host's sparse algebra
+    (blocks to 1e-12, same structure classes) and, for the V-cycle, against the host-built hierarchy on the
+    same GPU (which test_multigrid_histories ties to the oracle)."""
+    kw = SHAPES[name]
+    Hh, _, bp = build_package(**kw)
+    Hd, _, _ = build_package(**kw, device_setup=True)
+    try:
+        nL = len(Hh.mMeshes)
+        nCG = len(kw["cg_orders"])
+        for l in range(nL):
+            got = Hd.level_blocks(l)
+            ref = Hh.level_blocks(l)
+            scale = np.abs(ref[1]).max()
+            for g, r_, what in zip(got[:3], ref[:3], ("lo", "di", "up")):
+                assert np.abs(g - r_).max() <= 1e-12 * scale, (l, what)
+            assert np.abs(got[3] - ref[3]).max() <= 1e-10 * np.abs(ref[3]).max(), l
+            assert Hd.device.info(f"structure:{l}") == Hh.device.info(f"structure:{l}"), l
+            assert Hd.device.info(f"tile_rows:{l}") == Hh.device.info(f"tile_rows:{l}"), l
+        x_h, it_h, res_h, _ = aggmg.multigrid(Hh, np.zeros(len(bp)), bp, 60, 1e-10, with_error=False)
+        x_d, it_d, res_d, _ = aggmg.multigrid(Hd, np.zeros(len(bp)), bp, 60, 1e-10, with_error=False)
+        k = min(it_h, it_d)
+        assert abs(it_h - it_d) <= 1                                   # operators differ by rounding only
+        floor = 1e-8 * np.linalg.norm(bp)
+        assert np.all(np.abs(res_d[:k] - res_h[:k]) <= np.maximum(1e-4 * res_h[:k], floor)), (res_d, res_h)
+        # smoothers of device-built CG levels: mJac is the device operator's diagonal
+        for l in range(1, nCG):
+            jac_h, jac_d = Hh.mSmoothers[l].mJac, Hd.mSmoothers[l].mJac
+            assert np.abs(jac_d - jac_h).max() <= 1e-12 * np.abs(jac_h).max(), l
+            r = np.random.default_rng(l).standard_normal(len(jac_h))
+            y_h = aggmg.apply_smoother(Hh.mSmoothers[l], r, alpha=0.5)
+            y_d = aggmg.apply_smoother(Hd.mSmoothers[l], r, alpha=0.5)
+            assert np.abs(y_d - y_h).max() <= 1e-12 * np.abs(y_h).max(), l
+    finally:
+        Hh.device.close()
+        Hd.device.close()
+
+
 def test_error_behaviour_of_the_wider_api(lib):
     """Call-order and argument errors of the set-up extensions come back as status codes with a message."""
     import ctypes as C
