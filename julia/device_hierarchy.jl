@@ -1,41 +1,18 @@
-# INTEGRATION - binding `libamg1d.so` from the reference
+# device_hierarchy.jl - the reference-side binding of libamg1d.so (C ABI: include/amg1d.h).
+#
+# To be included in the reference's module after solvers.jl (src/AgglomerationMultigrid1D.jl):
+#
+#     include( "device_hierarchy.jl" )
+#
+# It keeps the package's entry points - multigrid_v_cycle, multigrid, ldiv!, apply_smoother - and adds
+# methods for `DeviceHierarchy`, the uploaded form of a `MeshHierarchy`; every method is one ccall.
+# Names used from the module: MeshHierarchy, CgMesh, DgMesh, AgglomeratedDgMesh1, AgglomeratedDgMeshN,
+# JacobiSmoother, BlockJacobi, and its aliases `sp` (SparseArrays) and `la` (LinearAlgebra).
+#
+# NOT EXECUTED in this repository's build environment (no Julia there).  It targets exactly the ABI that
+# the tested Python driver uses (agglomerationmultigrid1d_b200/_capi.py, device.py, blocks.py), call for
+# call; INTEGRATION.md maps each reference call (file:line) to its ABI call.
 
-The reference (`mheinz757/AgglomerationMultigrid1D`) is a single Julia module with no FFI.  Its
-boundary for the V-cycle path is Julia dispatch on `MeshHierarchy`, `BlockJacobi`, `JacobiSmoother`
-(`src/mesh_heirarchy.jl:17-28`, `src/smoother.jl:52-81`).  The drop-in keeps those entry points and
-lowers them to the C ABI of `include/amg1d.h`.  Julia is not available in this build environment, so
-the binding below is what a maintainer would add to the reference; it targets exactly the ABI that the
-tested Python driver (`agglomerationmultigrid1d_b200/_capi.py`, `device.py`) uses, call for call, but it
-has **not been executed** here.
-
-## 1. Build
-
-```
-python -c 'import __graft_entry__ as g; g.build()'      # nvcc -gencode arch=compute_100a,code=sm_100a ...
-# -> agglomerationmultigrid1d_b200/libamg1d.so   (C ABI: include/amg1d.h)
-```
-
-## 2. What each reference call becomes
-
-| reference call (file:line) | ABI call |
-|---|---|
-| end of `MeshHierarchy(...)` (`src/mesh_heirarchy.jl:136-137`, `:179-180`) | `amg1d_create`; per level `amg1d_set_level` (blocks of `mStiffness[l]` + inverse smoother blocks); per transfer `amg1d_set_transfer` (blocks of `mInterpolation[l]`); `amg1d_finalize` |
-| the Galerkin loop of the DG-first constructor (`src/mesh_heirarchy.jl:160-176`; optional) | `amg1d_set_level_flux(h, 0, n, m, G.., D.., C.., Minv, 0)`, then per level `amg1d_set_transfer` + `amg1d_coarsen_level(h, k, Minv_{k+1}, 0)`: the products `L'(G,D,C)L`, `A = C - D (M \ G)` and the block-Jacobi factors are computed on the GPU |
-| `multigrid_v_cycle(H, x0, b; nPre, nPost, alpha)` (`src/solvers.jl:19-50`) | `amg1d_vcycle(h, x, b, nPre, nPost, alpha)` |
-| `multigrid(H, x0, b, maxiter, tol)` (`src/solvers.jl:116-139`) | `amg1d_solve(h, x, b, maxiter, tol, 3, 3, 2/3, iters, res, err, u_exact)` |
-| `ldiv!(H, b)` / `ldiv!(y, H, b)` (`src/solvers.jl:63-92`) | `amg1d_ldiv(h, y, b, 3, 3, 2/3)` (zero guess inside the library: no `x0` upload, `y` may alias `b`) |
-| `IterativeSolvers.cg(A, b; Pl = H)` - the use `ldiv!(y, H, b)` exists for; the reference ships no driver | `amg1d_pcg(h, x, b, maxiter, tol, 3, 3, 2/3, iters, res)` (whole Krylov loop on the device, one 24-byte read-back per iteration) |
-| `apply_smoother(S, B; alpha)` (`src/smoother.jl:52-58`, `:69-81`) | `amg1d_apply_smoother(h, level, Y, B, n_rhs, alpha)` |
-| `iterative_smoother_solve(A, S, x0, b; ...)` (`src/solvers.jl:189-213`) | one-level handle + `amg1d_smoother_solve` |
-| `cg_smoother(cgMesh, A, :addSchwarz / :hybridSchwarz)` + `apply_smoother` (`src/smoother.jl:1-46`, `:104-135`) | `amg1d_set_level` + `amg1d_set_level_smoother(h, level, S_lo, S_di, S_up)` (the smoother as a block-tridiagonal operator in the `[vertex_k, interior_k]` grouping; host recipe: `smoother.schwarz_tridiag_blocks`), then `amg1d_apply_smoother` / `amg1d_smoother_solve` |
-| `H.mStiffness[k]*u`, `H.mInterpolation[k]'*r`, `H.mInterpolation[k]*u`, `H.mStiffness[end] \ r` | `amg1d_matvec`, `amg1d_restrict`, `amg1d_prolong`, `amg1d_coarse_solve` |
-| `H.mStiffness[k] \ b` (`u_exact`, `src/solvers.jl:120`, `:194`) | `amg1d_direct_solve(h, k - 1, x, b)` (GPU block cyclic reduction; replaces `uExact = H.mStiffness[1] \ bb` in the binding below at large n) |
-
-## 3. Julia binding (`julia/device_hierarchy.jl` in this repository; to add as `src/device_hierarchy.jl`, included after `solvers.jl`)
-
-The file holds what is shown here plus `transfer_blocks` (the Julia twin of `blocks.transfer_to_blocks`).
-
-```julia
 const libamg1d = "libamg1d.so"     # on LD_LIBRARY_PATH, or an absolute path
 
 mutable struct DeviceHierarchy
@@ -89,6 +66,46 @@ smoother_inverse(S::JacobiSmoother, slots, di) =
       for i in 1:size(slots, 1), e in 1:size(slots, 2)], 1)
 smoother_inverse(S::BlockJacobi, slots, di) =
     (cat([inv(Matrix(b)) for b in S.mBlocks]...; dims = 3), 0)
+
+# (parent, P0, P1) of an interpolation matrix L (src/interpolation.jl) in the groupings `fs` (fine) and
+# `cs` (coarse):  x_f[e] += P0[:, :, e] * x_c[parent[e]] + P1[:, :, e] * x_c[parent[e] + 1].
+# parent is 0-based and non-decreasing; P1 === nothing for single-parent transfers (dg_dg, aggdg_dg,
+# aggdg_aggdg); cg_cg / dg_cg / aggdg_cg rows at shared vertices reach into the next coarse group.
+function transfer_blocks(L::sp.SparseMatrixCSC{Float64,Int64}, fs::Matrix{Int64}, cs::Matrix{Int64})
+    mf, nf = size(fs); mc, nc = size(cs)
+    eF = zeros(Int64, size(L, 1)); lF = zeros(Int64, size(L, 1))
+    eC = zeros(Int64, size(L, 2)); lC = zeros(Int64, size(L, 2))
+    for e in 1:nf, i in 1:mf
+        fs[i, e] > 0 && (eF[fs[i, e]] = e; lF[fs[i, e]] = i)
+    end
+    for e in 1:nc, i in 1:mc
+        cs[i, e] > 0 && (eC[cs[i, e]] = e; lC[cs[i, e]] = i)
+    end
+    rows = sp.rowvals(L); vals = sp.nonzeros(L)
+    pmin = fill(typemax(Int64), nf); pmax = zeros(Int64, nf)
+    for col in 1:size(L, 2), k in sp.nzrange(L, col)
+        vals[k] == 0.0 && continue
+        e = eF[rows[k]]
+        pmin[e] = min(pmin[e], eC[col]); pmax[e] = max(pmax[e], eC[col])
+    end
+    for e in 1:nf                                   # all-zero row blocks inherit the left neighbour's parent
+        if pmax[e] == 0
+            pmin[e] = e > 1 ? pmin[e - 1] : 1
+            pmax[e] = pmin[e]
+        end
+    end
+    all(pmax .- pmin .<= 1) || throw(ArgumentError("a fine element depends on more than two adjacent coarse elements"))
+    issorted(pmin) || throw(ArgumentError("transfer parents are not monotone"))
+    two = any(pmax .> pmin)
+    P0 = zeros(mf, mc, nf); P1 = two ? zeros(mf, mc, nf) : nothing
+    for col in 1:size(L, 2), k in sp.nzrange(L, col)
+        vals[k] == 0.0 && continue
+        e = eF[rows[k]]
+        blk = eC[col] == pmin[e] ? P0 : P1
+        blk[lF[rows[k]], lC[col], e] += vals[k]
+    end
+    return pmin .- 1, P0, P1
+end
 
 function DeviceHierarchy(H::MeshHierarchy; device::Integer = 0)
     nL = length(H.mMeshes)
@@ -167,38 +184,3 @@ function apply_smoother(D::DeviceHierarchy, level::Integer, B::AbstractVecOrMat;
         D.handle, level - 1, Y, Bd, size(Bd, 2), alpha))
     return B isa AbstractVector ? vec(Y) : Y
 end
-```
-
-With this file included, `tests/dg_heirarchy_test.jl` changes in one line -
-`H = aggmg.MeshHierarchy(...)` is followed by `D = aggmg.DeviceHierarchy(H)` and
-`aggmg.multigrid(D, H, x0, b, maxiter, tol)` - and prints the same `iter`, `res`, `err`.
-`tests/test_gpu_parity.py` is that script (and the other three hierarchy scripts) restated in Python
-against the same ABI.
-
-## 4. Python binding (the tested path)
-
-`agglomerationmultigrid1d_b200/_capi.py` declares every prototype of `include/amg1d.h` for ctypes
-(`tests/test_capi_symbols.py` checks the header, the table and the built library against each other);
-`device.py` wraps a handle; `mesh_hierarchy.py` / `solvers.py` mirror the reference API:
-
-```python
-import agglomerationmultigrid1d_b200 as aggmg
-mesh = aggmg.create_uniform_mesh(128, 0.0, 1.0)
-bd = aggmg.set_boundary(mesh, 0.0, 1.0, [("neu", -np.sin(0.0)), ("dir", np.cos(1.0))])
-meshes = [aggmg.DgMesh(mesh, p) for p in (8, 4, 2, 1)]
-G, D, C = aggmg.dg_flux_operators(meshes[0], mesh, bd, 1000.0 * 128)
-A = C - D @ meshes[0].mMassMatrixLU.solve(G)
-f, r = aggmg.dg_flux_rhs(meshes[0], mesh, np.cos, bd, 1000.0 * 128)
-b = f - D @ meshes[0].mMassMatrixLU.solve(r)
-H = aggmg.MeshHierarchy(meshes, [bd] * 4, A, G, D, C, nDG=4)          # uploads to the GPU
-u, it, res, err = aggmg.multigrid(H, 0.0 * b, b, 200, 1e-10)          # tests/dg_heirarchy_test.jl
-```
-
-## 5. Memory ownership, threading, errors
-
-The caller owns every host array; the library copies on upload and owns all device memory through the
-handle; no host pointer is retained after a call returns.  One handle = one CUDA stream; calls on a
-handle are not re-entrant; different handles may be used from different host threads.  Every call
-returns a status (`AMG1D_OK = 0`, `AMG1D_ERR_ARG` for what the reference raises as `ArgumentError`,
-CUDA / NCCL / allocation / state codes otherwise) with text from `amg1d_last_error`; nothing throws or
-exits across the boundary.  Indices are 0-based at the ABI (reference value - 1).

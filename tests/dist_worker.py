@@ -41,13 +41,18 @@ def main():
     def build():
         if kind == "cg":        # BASELINE C4 shape: CG 3 -> 1 -> DG 1 -> agglomerated levels
             return uniform.UniformCgHierarchy(n, [3, 1], [1], [2] * log2n, xin=0.0, xout=float(n), CDir=1000.0)
+        if kind == "cg8":       # the order of the reference's CG scripts: 8 x 8 groups, row-per-thread legs
+            return uniform.UniformCgHierarchy(n, [8, 4, 2, 1], [1], [2] * log2n, xin=0.0, xout=float(n), CDir=1000.0)
+        if kind == "dg8":       # tests/dg_heirarchy_test.jl order: 9 x 9 blocks, row-per-thread legs
+            return uniform.UniformDgHierarchy(n, [8, 4, 2, 1], [2] * log2n, xin=0.0, xout=float(n), CDir=1000.0)
         return uniform.UniformDgHierarchy(n, [3, 1], [2] * log2n, xin=0.0, xout=float(n), CDir=1000.0)
 
     U = build()
     dev = U.upload(device=rank, dist=(rank, world, ids[0]), options={"shard_min": 512})
     nloc = n // world
     m0 = U.levels[0].m
-    if kind == "cg":            # slabs of groups; the last rank also holds the closing vertex group
+    is_cg = kind.startswith("cg")
+    if is_cg:                   # slabs of groups; the last rank also holds the closing vertex group
         lo, hi = rank * nloc, (rank + 1) * nloc + (1 if rank == world - 1 else 0)
         b_loc = U.rhs(func, vals, group_range=(lo, hi))
         n_blocks = n + 1
@@ -62,7 +67,7 @@ def main():
     results["solve"] = (x, it, res)
     rng = np.random.default_rng(5)
     x0_glob = rng.standard_normal(n_blocks * m0)
-    if kind == "cg":
+    if is_cg:
         x0_glob.reshape(n_blocks, m0)[n, 1:] = 0.0               # padding slots of the closing group
     x0_loc = x0_glob[lo * m0:hi * m0]
     for key, (nPre, nPost, alpha) in {"v312": (3, 1, 0.5), "v023": (0, 2, 2.0 / 3.0), "v330": (3, 3, 0.8)}.items():

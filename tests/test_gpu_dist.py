@@ -15,16 +15,17 @@ def _ngpu():
     return torch.cuda.device_count()
 
 
-@pytest.mark.parametrize("kind", ["dg", "cg"])
+@pytest.mark.parametrize("kind", ["dg", "cg", "dg8", "cg8"])
 @pytest.mark.parametrize("world", [2, 4])
 def test_sharded_solve_matches_single_gpu(world, kind, tmp_path):
     """DG-first hierarchy (T / C2 / C5 shape) and CG-first hierarchy (C4 shape: slabs of vertex groups,
-    two-parent transfers across the slab edges): bit-identical to the single-GPU run."""
+    two-parent transfers across the slab edges), and the same two with the p = 8 orders of the reference's
+    scripts (row-per-thread legs, kernels_rows.cuh): bit-identical to the single-GPU run."""
     if _ngpu() < world:
         pytest.skip(f"needs {world} GPUs")
     out = tmp_path / "dist.json"
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}",
-           "--master-addr", "127.0.0.1", "--master-port", str(29500 + world + (10 if kind == "cg" else 0)),
+           "--master-addr", "127.0.0.1", "--master-port", str(29500 + world + 10 * ["dg", "cg", "dg8", "cg8"].index(kind)),
            os.path.join(ROOT, "tests", "dist_worker.py"), str(out), "15", kind]
     r = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]

@@ -421,6 +421,37 @@ def test_error_behaviour_of_the_wider_api(lib):
     assert lib.amg1d_set_level(h, 0, 1, 2, p(z4), p(np.array([1.0, 1.0, 1.0, 1.0])), p(z4), p(eye), 0, None, 2) == capi.OK
     assert lib.amg1d_finalize(h) == capi.ERR_ARG and b"singular" in lib.amg1d_last_error(h)
     assert lib.amg1d_destroy(h) == capi.OK
+    # Galerkin coarsening of the stiffness matrix: call order, shapes, a product that is not block tridiagonal
+    i64 = lambda a: np.ascontiguousarray(a, dtype=np.int64)                   # noqa: E731
+    ip = lambda a: a.ctypes.data_as(C.POINTER(C.c_int64))                     # noqa: E731
+    assert lib.amg1d_create(C.byref(h), 2, 0, None) == capi.OK
+    assert lib.amg1d_coarsen_level_galerkin(h, 0, 2, 1, None, 0) == capi.ERR_STATE       # level 0 not set
+    n = 8
+    lo = np.zeros((n, 1)); lo[1:] = -1.0
+    up = np.zeros((n, 1)); up[:-1] = -1.0
+    di = np.full((n, 1), 2.0)
+    assert lib.amg1d_set_level(h, 0, n, 1, p(lo), p(di), p(up), p(1.0 / di), 1, None, n) == capi.OK
+    assert lib.amg1d_coarsen_level_galerkin(h, 0, 4, 1, None, 0) == capi.ERR_STATE       # transfer not set
+    assert lib.amg1d_coarsen_level_galerkin(h, 1, 4, 1, None, 0) == capi.ERR_ARG         # no coarser level
+    # parents 0 0 1 1 2 2 3 3 with weights in P1 as well: coarse element K then couples to K + 2
+    par = i64(np.arange(n) // 2)
+    ones = np.ones((n, 1))
+    assert lib.amg1d_set_transfer(h, 0, n, 1, 1, ip(par), p(ones), p(ones)) == capi.OK
+    assert lib.amg1d_coarsen_level_galerkin(h, 0, 3, 1, None, 0) == capi.ERR_ARG         # 4 or 5 coarse elements
+    assert lib.amg1d_coarsen_level_galerkin(h, 0, 5, 1, None, 0) == capi.ERR_ARG
+    assert b"not block tridiagonal" in lib.amg1d_last_error(h)
+    assert lib.amg1d_destroy(h) == capi.OK
+    # the same fine level with a single-parent aggregation: L' A L = tridiag(-1, 2, -1) again, diagonal smoother
+    assert lib.amg1d_create(C.byref(h), 2, 0, None) == capi.OK
+    assert lib.amg1d_set_level(h, 0, n, 1, p(lo), p(di), p(up), p(1.0 / di), 1, None, n) == capi.OK
+    assert lib.amg1d_set_transfer(h, 0, n, 1, 1, ip(par), p(ones), None) == capi.OK
+    assert lib.amg1d_coarsen_level_galerkin(h, 0, 4, 1, None, 0) == capi.OK
+    assert lib.amg1d_coarsen_level_galerkin(h, 0, 4, 1, None, 0) == capi.ERR_STATE       # level 1 already set
+    g = [np.zeros((4, 1)) for _ in range(4)]
+    assert lib.amg1d_get_level(h, 1, p(g[0]), p(g[1]), p(g[2]), p(g[3])) == capi.OK
+    assert np.array_equal(g[1].ravel(), [2.0] * 4) and np.array_equal(g[0].ravel(), [0.0, -1.0, -1.0, -1.0])
+    assert np.array_equal(g[2].ravel(), [-1.0, -1.0, -1.0, 0.0]) and np.array_equal(g[3].ravel(), [0.5] * 4)
+    assert lib.amg1d_destroy(h) == capi.OK
     # unknown option, negative sweeps
     Hp, _, bp = build_package(**SHAPES["C2_dg3_agg"])
     try:

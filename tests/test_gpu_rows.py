@@ -58,8 +58,9 @@ def _compare_tiers(dev, b, n_big_levels):
     return launches
 
 
-@pytest.mark.parametrize("orders,n", [((8, 4, 2, 1), 3072), ((8,), 3072), ((7, 3, 1), 1536), ((6, 3, 1), 1536),
-                                      ((5, 2, 1), 1536), ((4,), 3072)])
+# 98304 elements: 1756 (W = 64) / 4096 (W = 32) CTAs per leg
+@pytest.mark.parametrize("orders,n", [((8, 4, 2, 1), 3072), ((8, 4, 2, 1), 98304), ((8,), 3072), ((7, 3, 1), 1536),
+                                      ((7, 3, 1), 98304), ((6, 3, 1), 1536), ((5, 2, 1), 98304), ((4,), 3072)])
 def test_dg_large_blocks_bit_identical(orders, n):
     k = (n & -n).bit_length() - 1                      # n = odd * 2^k: agglomerate down to `odd` elements
     U = uniform.UniformDgHierarchy(n, list(orders), [2] * k, xin=0.0, xout=float(n), CDir=1000.0)
@@ -85,7 +86,8 @@ def test_dg_large_blocks_dense_storage():
         dev.close()
 
 
-@pytest.mark.parametrize("cg,n", [((8, 4, 2, 1), 3072), ((7, 3, 1), 1536), ((6, 3, 1), 1536), ((5, 2, 1), 1536)])
+@pytest.mark.parametrize("cg,n", [((8, 4, 2, 1), 3072), ((8, 4, 2, 1), 98304), ((7, 3, 1), 1536), ((6, 3, 1), 98304),
+                                  ((5, 2, 1), 1536)])
 def test_cg_large_groups_bit_identical(cg, n):
     """CG levels in group form [vertex_k, interior nodes of element k]: m = p, point Jacobi, two-parent
     transfers (cg_cg_interpolation)."""
