@@ -81,6 +81,10 @@ struct Level {
     // host copy of the blocks, kept only for small levels (coarsest-level factorisation)
     std::vector<double> h_lo, h_di, h_up;
     int64_t mat_bytes = 0;
+    // translation-invariant level (amg1d_set_level_pattern): its n_head + 1 + n_tail distinct block sets
+    // as a table tab[set][k] on the device, for the pattern-resident fused legs (PatOp, kernels_fused.cuh)
+    double* pat = nullptr;
+    int pat_head = 0, pat_tail = 0;
 };
 
 struct Transfer {
@@ -128,6 +132,8 @@ struct amg1d {
     int opt_compress = 1;         // drop structural zeros of the off-diagonal blocks (layout.cuh)
     int opt_pdl = 1;              // programmatic dependent launch between the fused kernels
     int opt_rows = 64;            // window of the row-per-thread fused legs (kernels_rows.cuh): 32, 64; 0 = off
+    int opt_rows_rpt = 0;         // block rows per thread of those legs: 1, 2, 3; 0 = auto (rows_rpt() below)
+    int opt_pattern = 0;          // 1: levels given as patterns read their operator from the pattern table
     // single-CTA coarse tail (f_tail): levels [tail_start, n_levels)
     int tail_start = -1;
     TailLevel* d_tail = nullptr;
@@ -292,6 +298,27 @@ const char* load_nccl() {
     return nullptr;
 }
 #endif
+
+// Block rows per thread of the row-per-thread legs on level l.  Measured on B200 (P8, 2^23 elements of 9 x 9
+// blocks, profiles/r01d_*): with the operator streamed from HBM one row per thread (1152 resident threads
+// per SM) is fastest - 3.72 / 3.87 ms per leg against 4.13 / 3.66 ms for three rows; with pattern-resident
+// operators nothing waits for HBM any more and three rows per thread (fewer shared-memory reads per row)
+// win: 3.16 / 2.84 ms against 3.39 / 3.55 ms.
+int rows_rpt(const amg1d* h, int l) {
+    if (h->opt_rows_rpt) return h->opt_rows_rpt;
+    return h->opt_pattern && h->L[l].pat ? 3 : 1;
+}
+
+// pattern-resident operator of level l (option pattern_resident = 1 and the level was given as a pattern)
+PatOp make_pat(const amg1d* h, int l) {
+    const Level& lv = h->L[l];
+    PatOp po;
+    po.tab = h->opt_pattern ? lv.pat : nullptr;
+    po.n_glob = lv.n_glob;
+    po.n_head = lv.pat_head;
+    po.n_tail = lv.pat_tail;
+    return po;
+}
 
 Slab make_slab(amg1d* h, int l) {
     Slab sl;
@@ -591,13 +618,13 @@ int leg_down(amg1d* h, int l, int nPre, double alpha, bool zero0) {
     if (h->opt_fused && t.fusable && !lv.smooth_tri) {
         const int ob = zero ? 0 : 1 - lv.cur;
         cudaError_t le = cudaSuccess;
-        int fr = fused_down(lv.md, t.mc, make_map_closed(t), nPre, zero, lv.mat, lv.b.p, lv.x[lv.cur].p,
+        int fr = fused_down(lv.md, t.mc, make_map_closed(t), nPre, zero, lv.mat, make_pat(h, l), lv.b.p, lv.x[lv.cur].p,
                             lv.x[ob].p, t.P0, t.P1, lc.b.p, lv.n, lv.n + (lv.gr ? t.cover_extra : 0),
                             alpha, make_slab(h, l), h->stream, h->opt_pdl != 0, &le);
         if (fr == FUSED_NA && h->opt_rows)      // large blocks: one thread per block row
-            fr = rows_down(lv.md, t.mc, make_map_closed(t), nPre, zero, lv.mat, lv.b.p, lv.x[lv.cur].p,
+            fr = rows_down(lv.md, t.mc, make_map_closed(t), nPre, zero, lv.mat, make_pat(h, l), lv.b.p, lv.x[lv.cur].p,
                            lv.x[ob].p, t.P0, t.P1, lc.b.p, lv.n, lv.n + (lv.gr ? t.cover_extra : 0), alpha,
-                           make_slab(h, l), h->opt_rows, h->stream, h->opt_pdl != 0, &le);
+                           make_slab(h, l), h->opt_rows, rows_rpt(h, l), h->stream, h->opt_pdl != 0, &le);
         if (fr == FUSED_ERR) return fail(h, AMG1D_ERR_CUDA, "f_down launch failed on level %d: %s", l, cudaGetErrorString(le));
         if (fr == FUSED_OK) {
             lv.cur = ob;
@@ -640,15 +667,15 @@ int leg_up(amg1d* h, int l, int nPost, double alpha, bool fuse_norm, bool* norm_
     if (h->opt_fused && t.fusable && !lv.smooth_tri) {
         int nb = 0;
         cudaError_t le = cudaSuccess;
-        int fr = fused_up(lv.md, t.mc, make_map_closed(t), nPost, lv.mat, lv.b.p, lv.x[lv.cur].p,
+        int fr = fused_up(lv.md, t.mc, make_map_closed(t), nPost, lv.mat, make_pat(h, l), lv.b.p, lv.x[lv.cur].p,
                           lv.x[1 - lv.cur].p, t.P0, t.P1, lc.x[lc.cur].p, lv.n, alpha,
                           fuse_norm ? h->partial : nullptr, h->partial_cap, &nb, make_slab(h, l),
                           h->stream, h->opt_pdl != 0, &le);
         if (fr == FUSED_NA && h->opt_rows)
-            fr = rows_up(lv.md, t.mc, make_map_closed(t), nPost, lv.mat, lv.b.p, lv.x[lv.cur].p,
+            fr = rows_up(lv.md, t.mc, make_map_closed(t), nPost, lv.mat, make_pat(h, l), lv.b.p, lv.x[lv.cur].p,
                          lv.x[1 - lv.cur].p, t.P0, t.P1, lc.x[lc.cur].p, lv.n, alpha,
                          fuse_norm ? h->partial : nullptr, h->partial_cap, &nb, make_slab(h, l), h->opt_rows,
-                         h->stream, h->opt_pdl != 0, &le);
+                         rows_rpt(h, l), h->stream, h->opt_pdl != 0, &le);
         if (fr == FUSED_ERR) return fail(h, AMG1D_ERR_CUDA, "f_up launch failed on level %d: %s", l, cudaGetErrorString(le));
         if (fr == FUSED_OK) {
             lv.cur = 1 - lv.cur;
@@ -1239,6 +1266,7 @@ int amg1d_destroy(amg1d_t* h) {
     for (auto& lv : h->L) {
         if (lv.mat_alloc) cudaFree(lv.mat_alloc);
         if (lv.smat_alloc) cudaFree(lv.smat_alloc);
+        if (lv.pat) cudaFree(lv.pat);
         free_flux(h, lv);
         if (lv.perm) cudaFree(lv.perm);
         vec_free(lv.x[0]); vec_free(lv.x[1]); vec_free(lv.b);
@@ -1363,6 +1391,21 @@ int amg1d_set_level_pattern(amg1d_t* h, int level, int64_t n_elem, int m, int n_
     cudaError_t e = cudaStreamSynchronize(h->stream);
     if (e == cudaSuccess) e = cudaGetLastError();
     if (e != cudaSuccess) return fail(h, AMG1D_ERR_CUDA, "pattern fill failed: %s", cudaGetErrorString(e));
+    {   // the distinct block sets as a table tab[set][k], k = tile row: what the pattern-resident legs read
+        std::vector<double> tab((size_t)nb * lv.K);
+        for (int sidx = 0; sidx < nb; ++sidx)
+            for (int k = 0; k < lv.K; ++k) {
+                int which, idx;
+                amg1d_row_source(lv.md, k, &which, &idx);
+                const double* src = which == 0 ? A_lo + (size_t)sidx * mm : which == 1 ? A_di + (size_t)sidx * mm
+                                  : which == 2 ? A_up + (size_t)sidx * mm : Dinv + (size_t)sidx * dsz;
+                tab[(size_t)sidx * lv.K + k] = src[idx];
+            }
+        RET(dev_alloc(h, (void**)&lv.pat, (int64_t)tab.size() * 8));
+        CK(cudaMemcpy(lv.pat, tab.data(), tab.size() * 8, cudaMemcpyHostToDevice));
+        lv.pat_head = n_head;
+        lv.pat_tail = n_tail;
+    }
     if (n_elem <= AMG1D_BCR_MIN && !lv.sharded) {   // host copy for the block-Thomas factorisation
         lv.h_lo.resize((size_t)n_elem * mm); lv.h_di.resize((size_t)n_elem * mm); lv.h_up.resize((size_t)n_elem * mm);
         for (int64_t el = 0; el < n_elem; ++el) {
@@ -2124,6 +2167,11 @@ int amg1d_set_option(amg1d_t* h, const char* key, int64_t value) {
         if (value != 0 && !rows_window_ok((int)value)) return fail(h, AMG1D_ERR_ARG, "rows_window must be 0, 32 or 64");
         h->opt_rows = (int)value;
     }
+    else if (!strcmp(key, "pattern_resident")) h->opt_pattern = value != 0;
+    else if (!strcmp(key, "rows_per_thread")) {
+        if (value != 0 && !rows_rpt_ok((int)value)) return fail(h, AMG1D_ERR_ARG, "rows_per_thread must be 0 (auto), 1, 2 or 3");
+        h->opt_rows_rpt = (int)value;
+    }
     else if (!strcmp(key, "coarse_cta_elems")) {
         h->opt_coarse_cta = value;
         if (h->finalized) { CK(cudaSetDevice(h->device)); CK(cudaStreamSynchronize(h->stream)); RET(build_tail(h)); }
@@ -2159,6 +2207,12 @@ int64_t amg1d_get_info(amg1d_t* h, const char* key) {
     if (!strcmp(key, "tail_start")) return h->tail_start;
     if (!strcmp(key, "ghost_depth")) return h->ghost_depth;
     if (!strcmp(key, "rows_window")) return h->opt_rows;
+    if (!strcmp(key, "rows_per_thread")) return h->opt_rows_rpt;
+    if (!strcmp(key, "pattern_resident")) return h->opt_pattern;
+    if (!strncmp(key, "pattern:", 8)) {                      // 1: level has a pattern table
+        const int l = atoi(key + 8);
+        return valid_level(h, l) && h->L[l].pat ? 1 : 0;
+    }
     if (!strncmp(key, "structure:", 10)) {          // "structure:<level>" -> structure class (layout.cuh)
         const int l = atoi(key + 10);
         return valid_level(h, l) && h->L[l].set ? h->L[l].md.st : -1;

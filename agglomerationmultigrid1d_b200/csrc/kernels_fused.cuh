@@ -39,6 +39,17 @@ struct Slab {
     int64_t e_off, c_off, nc;
 };
 
+// Translation-invariant level (uniform mesh, amg1d_set_level_pattern) in "pattern-resident" form: the
+// n_head + 1 + n_tail distinct block sets of the level as a small table tab[set][k] (k = tile row of
+// layout.cuh), instead of one stored block set per element.  The fused legs then fetch an element's
+// operator from the table (a few KB, served by L1 as a warp-wide broadcast) and HBM carries only the
+// vectors.  tab == nullptr: the element tiles are streamed (the general per-element layout).
+struct PatOp {
+    const double* tab;
+    int64_t n_glob;        // elements of the whole level (the table is indexed by GLOBAL element)
+    int n_head, n_tail;
+};
+
 // Per-launch constants of a fused leg, computed on the host so that the per-thread index arithmetic
 // (parent element, owner test, transfer-block index) is 32-bit: with out % ratio == 0 the CTA's first
 // thread has (e_global + shift) = ratio * (blockIdx * opr + qdiv0) + qmod0.
@@ -422,23 +433,45 @@ __device__ __forceinline__ void exchange(Exchange<M, B>& ex, int buf, int ilo, i
 
 // A_lo / A_di / A_up go to registers; Dinv (used once per sweep) is copied global -> shared with
 // cp.async, i.e. without register staging, into this thread's own column ds[k][thread].
+template <int M, int B, int ST, bool DIAG, int STRIDE>
+__device__ __forceinline__ void load_blocks_from(const double* __restrict__ T, RegOp<M, ST>& A, double (*ds)[B]) {
+    using S = OpShape<M, ST>;
+    constexpr int ND = DIAG ? M : M * M;
+    const int t = threadIdx.x;
+    if constexpr (STRIDE == 1) {   // pattern table: every lane reads the same address - plain loads broadcast
+#pragma unroll                     // (cp.async with one source address per warp was measured far slower)
+        for (int k = 0; k < ND; ++k) ds[k][t] = T[S::O_DV + k];
+    } else {
+#pragma unroll
+        for (int k = 0; k < ND; ++k) cp_async8(&ds[k][t], T + (S::O_DV + k) * STRIDE);
+    }
+#pragma unroll
+    for (int k = 0; k < S::NO; ++k) A.lo[k] = T[k * STRIDE];
+#pragma unroll
+    for (int k = 0; k < M * M; ++k) A.di[k] = T[(S::O_DI + k) * STRIDE];
+#pragma unroll
+    for (int k = 0; k < S::NO; ++k) A.up[k] = T[(S::O_UP + k) * STRIDE];
+}
+
+// e = local element index (addresses the element tiles), eg = global element index (addresses the
+// pattern table of a translation-invariant level, PatOp)
 template <int M, int B, int ST, bool DIAG>
-__device__ __forceinline__ void load_blocks(const double* __restrict__ mat, int64_t e, bool active,
-                                            RegOp<M, ST>& A, double (*ds)[B]) {
+__device__ __forceinline__ void load_blocks(const double* __restrict__ mat, const PatOp& po, int64_t e,
+                                            int64_t eg, bool active, RegOp<M, ST>& A, double (*ds)[B]) {
     using S = OpShape<M, ST>;
     constexpr int ND = DIAG ? M : M * M;
     constexpr int K = S::O_DV + ND;
     const int t = threadIdx.x;
+    if (po.tab != nullptr) active = active && eg >= 0 && eg < po.n_glob;
     if (active) {
-        const double* T = mat + (e >> 5) * (int64_t)(K * AMG1D_TILE) + (e & 31);
-#pragma unroll
-        for (int k = 0; k < ND; ++k) cp_async8(&ds[k][t], T + (S::O_DV + k) * AMG1D_TILE);
-#pragma unroll
-        for (int k = 0; k < S::NO; ++k) A.lo[k] = T[k * AMG1D_TILE];
-#pragma unroll
-        for (int k = 0; k < M * M; ++k) A.di[k] = T[(S::O_DI + k) * AMG1D_TILE];
-#pragma unroll
-        for (int k = 0; k < S::NO; ++k) A.up[k] = T[(S::O_UP + k) * AMG1D_TILE];
+        if (po.tab != nullptr) {
+            const int64_t s = eg < po.n_head ? eg
+                            : (eg >= po.n_glob - po.n_tail ? po.n_head + 1 + (eg - (po.n_glob - po.n_tail))
+                                                           : po.n_head);
+            load_blocks_from<M, B, ST, DIAG, 1>(po.tab + s * K, A, ds);
+        } else {
+            load_blocks_from<M, B, ST, DIAG, AMG1D_TILE>(mat + (e >> 5) * (int64_t)(K * AMG1D_TILE) + (e & 31), A, ds);
+        }
     } else {
 #pragma unroll
         for (int k = 0; k < ND; ++k) ds[k][t] = 0.0;
@@ -472,7 +505,7 @@ constexpr int fused_min_blocks(int m, int st) {
 //   the P1 blocks of the children of Kc - 1, then the P0 blocks of its own children.
 template <int M, int MC, int B, int ST, bool DIAG>
 __global__ void FUSED_BOUNDS(M)
-f_down(const double* __restrict__ mat, int ilo, int iup, const double* __restrict__ b,
+f_down(const double* __restrict__ mat, PatOp po, int ilo, int iup, const double* __restrict__ b,
        const double* __restrict__ xin, double* __restrict__ xout, const double* __restrict__ P0,
        const double* __restrict__ P1, TransferMap tm, double* __restrict__ rc, int64_t n, double alpha,
        int nsweep, int zero_guess, WinIdx wi, Slab sl) {
@@ -487,7 +520,7 @@ f_down(const double* __restrict__ mat, int ilo, int iup, const double* __restric
     exch_init<M, B>(ex);
     RegOp<M, ST> A;
     double bb[M], xc[M], xl[M], xr[M];
-    load_blocks<M, B, ST, DIAG>(mat, e, active, A, ds);         // operator: independent of earlier kernels
+    load_blocks<M, B, ST, DIAG>(mat, po, e, e + sl.e_off, active, A, ds);         // operator: independent of earlier kernels
     pdl_wait();                                                  // b, x and everything written below are not
     if (active) {
         load_vec<M>(b + e * M, bb);
@@ -562,7 +595,7 @@ f_down(const double* __restrict__ mat, int ilo, int iup, const double* __restric
 // prolongation + correction, nsweep post-smoothing sweeps, optional || b - A x ||^2 partial sums.
 template <int M, int MC, int B, int ST, bool DIAG>
 __global__ void FUSED_BOUNDS(M)
-f_up(const double* __restrict__ mat, int ilo, int iup, const double* __restrict__ b,
+f_up(const double* __restrict__ mat, PatOp po, int ilo, int iup, const double* __restrict__ b,
      const double* __restrict__ xin, double* __restrict__ xout, const double* __restrict__ P0,
      const double* __restrict__ P1, TransferMap tm, const double* __restrict__ xcoarse, int64_t n,
      double alpha, int nsweep, WinIdx wi, double* __restrict__ partial, Slab sl) {
@@ -576,7 +609,7 @@ f_up(const double* __restrict__ mat, int ilo, int iup, const double* __restrict_
     exch_init<M, B>(ex);
     RegOp<M, ST> A;
     double bb[M], xc[M], xl[M], xr[M];
-    load_blocks<M, B, ST, DIAG>(mat, e, active, A, ds);         // operator: independent of earlier kernels
+    load_blocks<M, B, ST, DIAG>(mat, po, e, e + sl.e_off, active, A, ds);         // operator: independent of earlier kernels
     pdl_wait();
     if (active) {
         load_vec<M>(b + e * M, bb);
@@ -1012,7 +1045,7 @@ inline WinIdx fused_window(int nsweep, const TransferMap& tm, bool wide, const S
 enum { FUSED_NA = 0, FUSED_OK = 1, FUSED_ERR = -1 };
 
 inline int fused_down(const MatDesc& d, int mc, const TransferMap& tm, int nsweep, bool zero,
-                       const double* mat, const double* b, const double* xin, double* xout,
+                       const double* mat, const PatOp& po, const double* b, const double* xin, double* xout,
                        const double* P0, const double* P1, double* rc, int64_t n, int64_t n_cover,
                        double alpha, const Slab& sl, cudaStream_t st, bool pdl, cudaError_t* err) {
     const WinIdx w = fused_window(nsweep, tm, P1 != nullptr || tm.shift != 0 || tm.base != 0, sl);
@@ -1021,8 +1054,8 @@ inline int fused_down(const MatDesc& d, int mc, const TransferMap& tm, int nswee
     switch (fused_key(d.m, mc, d.st, d.diag)) {
 #define X(MM, MCC, SS, DG)                                                                               \
     case ((MM * 16 + MCC) * 4 + SS) * 2 + (DG ? 1 : 0):                                                  \
-        *err = launch_fused(f_down<MM, MCC, FUSED_B, SS, DG>, grid, FUSED_B, 0, st, pdl, mat, d.ilo, d.iup, b, \
-                            xin, xout, P0, P1, tm, rc, n, alpha, nsweep, zero ? 1 : 0, w, sl);           \
+        *err = launch_fused(f_down<MM, MCC, FUSED_B, SS, DG>, grid, FUSED_B, 0, st, pdl, mat, po, d.ilo, d.iup, \
+                            b, xin, xout, P0, P1, tm, rc, n, alpha, nsweep, zero ? 1 : 0, w, sl);        \
         return *err == cudaSuccess ? FUSED_OK : FUSED_ERR;
         FUSED_COMBOS(X)
 #undef X
@@ -1031,7 +1064,7 @@ inline int fused_down(const MatDesc& d, int mc, const TransferMap& tm, int nswee
 }
 
 inline int fused_up(const MatDesc& d, int mc, const TransferMap& tm, int nsweep, const double* mat,
-                     const double* b, const double* xin, double* xout, const double* P0,
+                     const PatOp& po, const double* b, const double* xin, double* xout, const double* P0,
                      const double* P1, const double* xcoarse, int64_t n, double alpha, double* partial,
                      int64_t partial_cap, int* nblocks, const Slab& sl, cudaStream_t st, bool pdl,
                      cudaError_t* err) {
@@ -1043,8 +1076,8 @@ inline int fused_up(const MatDesc& d, int mc, const TransferMap& tm, int nsweep,
     switch (fused_key(d.m, mc, d.st, d.diag)) {
 #define X(MM, MCC, SS, DG)                                                                               \
     case ((MM * 16 + MCC) * 4 + SS) * 2 + (DG ? 1 : 0):                                                  \
-        *err = launch_fused(f_up<MM, MCC, FUSED_B, SS, DG>, (unsigned)grid, FUSED_B, 0, st, pdl, mat, d.ilo, \
-                            d.iup, b, xin, xout, P0, P1, tm, xcoarse, n, alpha, nsweep, w, partial, sl);  \
+        *err = launch_fused(f_up<MM, MCC, FUSED_B, SS, DG>, (unsigned)grid, FUSED_B, 0, st, pdl, mat, po,    \
+                            d.ilo, d.iup, b, xin, xout, P0, P1, tm, xcoarse, n, alpha, nsweep, w, partial, sl); \
         return *err == cudaSuccess ? FUSED_OK : FUSED_ERR;
         FUSED_COMBOS(X)
 #undef X

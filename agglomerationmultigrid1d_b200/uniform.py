@@ -344,13 +344,21 @@ class UniformDgHierarchy:
                 return k
         return 4 * self.levels[l].m ** 2
 
+    def streamed_operator_doubles(self, l):
+        """Operator doubles per element a fused leg reads from HBM: tile_rows(l), or 0 when the level's
+        pattern table is used (option pattern_resident: the block sets come from a few KB in L1)."""
+        dev = getattr(self, "device", None)
+        if dev is not None and dev.info("pattern_resident") and dev.info(f"pattern:{l}"):
+            return 0
+        return self.tile_rows(l)
+
     def bytes_per_leg_fused(self, l, down):
         """Algorithmic bytes of one fused leg (f_down / f_up) of level l: the level's operator once
         (tile_rows), b, x in, x out (3 m; the zero-guess down legs of levels > 0 do not read x) and
         the coarse vector (m_c per coarse element); transfer blocks are periodic patterns (L1)."""
         lv, lc = self.levels[l], self.levels[l + 1]
         vec = 2 if (down and l > 0) else 3
-        return 8 * (lv.n * (self.tile_rows(l) + vec * lv.m) + lc.n * lc.m)
+        return 8 * (lv.n * (self.streamed_operator_doubles(l) + vec * lv.m) + lc.n * lc.m)
 
     def bytes_per_cycle_fused(self, with_check=True):
         """Algorithmic bytes of the fused two-kernels-per-level cycle this library runs."""
@@ -620,12 +628,20 @@ class UniformCgHierarchy:
         lv = self.levels[l]
         return 3 * lv.m ** 2 + (lv.m if getattr(lv, "is_cg", False) else lv.m ** 2)
 
+    def streamed_operator_doubles(self, l):
+        """Operator doubles per element a fused leg reads from HBM: tile_rows(l), or 0 when the level's
+        pattern table is used (option pattern_resident: the block sets come from a few KB in L1)."""
+        dev = getattr(self, "device", None)
+        if dev is not None and dev.info("pattern_resident") and dev.info(f"pattern:{l}"):
+            return 0
+        return self.tile_rows(l)
+
     def bytes_per_leg_fused(self, l, down):
         """As UniformDgHierarchy.bytes_per_leg_fused (two-parent transfers read the same coarse
         vector once: neighbouring fine groups share their parents)."""
         lv, lc = self.levels[l], self.levels[l + 1]
         vec = 2 if (down and l > 0) else 3
-        return 8 * (lv.n * (self.tile_rows(l) + vec * lv.m) + lc.n * lc.m)
+        return 8 * (lv.n * (self.streamed_operator_doubles(l) + vec * lv.m) + lc.n * lc.m)
 
     def bytes_per_cycle_fused(self, with_check=True):
         return sum(self.bytes_per_leg_fused(l, True) + self.bytes_per_leg_fused(l, False)

@@ -124,7 +124,11 @@ int amg1d_set_level_smoother(amg1d_t* h, int level, const double* S_lo, const do
 /* Same operator given as a translation-invariant pattern (uniform meshes at 2^20..2^26 elements,
  * where per-element host arrays would be tens of GB): the first n_head and last n_tail elements are
  * explicit, every element in between repeats the single `interior` block set.  Arrays hold
- * n_head + 1 + n_tail blocks in that order.  The device still stores every element's blocks. */
+ * n_head + 1 + n_tail blocks in that order.  The device still stores every element's blocks (the
+ * general layout, which every kernel can read) and keeps the n_head + 1 + n_tail block sets as a small
+ * table next to them; with option "pattern_resident" = 1 the fused legs read the table instead of the
+ * per-element blocks (same numbers, same arithmetic order: bit-identical iterates), so HBM carries
+ * only the vectors. */
 int amg1d_set_level_pattern(amg1d_t* h, int level, int64_t n_elem, int m, int n_head, int n_tail,
                             const double* A_lo, const double* A_di, const double* A_up,
                             const double* Dinv, int dinv_is_diagonal);
@@ -226,7 +230,11 @@ void* amg1d_dev_ptr(amg1d_t* h, int level, int which);             /* raw device
  * "graph" (1 = replay the V-cycle as a CUDA graph, default 1), "pdl" (1 = programmatic dependent
  * launch between the fused kernels, default 1), "coarse_cta_elems" (levels with at most this many
  * elements - capped at 512 - run inside the single-CTA coarse kernel; 0 disables it; default 1024),
- * "profile" (see amg1d_get_profile; setting it clears earlier samples); before the first level is
+ * "profile" (see amg1d_get_profile; setting it clears earlier samples), "pattern_resident" (1 = levels
+ * given by amg1d_set_level_pattern take their operator from the pattern table, default 0),
+ * "rows_window" (elements per CTA of the row-per-thread legs for 5..9-row blocks: 32, 64; 0 = off;
+ * default 64), "rows_per_thread" (block rows per thread of those legs: 1, 2, 3; 0 = auto, default);
+ * before the first level is
  * set: "compress" (1 = store only the structurally non-zero column / row of the off-diagonal blocks
  * where every element of the level has that structure, default 1), "shard_min" (elements per rank
  * below which a level is gathered to rank 0, default 8192), "ghost_depth" (ghost elements per slab
@@ -236,7 +244,9 @@ int64_t amg1d_get_info(amg1d_t* h, const char* key); /* "kernel_launches", "laun
                                                         "device_bytes", "n_levels", "local_elements",
                                                         "local_dofs", "gather_level", "tail_start",
                                                         "ghost_depth", "structure:<level>",
-                                                        "tile_rows:<level>", ... (-1: unknown key) */
+                                                        "tile_rows:<level>", "pattern:<level>" (1 = the
+                                                        level has a pattern table), the option keys,
+                                                        ... (-1: unknown key) */
 
 /* With option "profile" = 1 every V-cycle runs un-graphed and brackets each level's down leg (leg 0:
  * pre-smoothing + residual + restriction) and up leg (leg 1: prolongation + post-smoothing) with CUDA

@@ -15,17 +15,22 @@ def _ngpu():
     return torch.cuda.device_count()
 
 
-@pytest.mark.parametrize("kind", ["dg", "cg", "dg8", "cg8"])
+KINDS = ["dg", "cg", "dg8", "cg8", "dg_pat", "cg_pat", "dg8_pat"]   # *_pat: option pattern_resident = 1
+
+
+@pytest.mark.parametrize("kind", KINDS)
 @pytest.mark.parametrize("world", [2, 4])
 def test_sharded_solve_matches_single_gpu(world, kind, tmp_path):
     """DG-first hierarchy (T / C2 / C5 shape) and CG-first hierarchy (C4 shape: slabs of vertex groups,
     two-parent transfers across the slab edges), and the same two with the p = 8 orders of the reference's
-    scripts (row-per-thread legs, kernels_rows.cuh): bit-identical to the single-GPU run."""
+    scripts (row-per-thread legs, kernels_rows.cuh): bit-identical to the single-GPU run.  The *_pat kinds
+    run the sharded handle with pattern-resident operators (pattern table indexed by the GLOBAL element
+    number) against the single-GPU handle that streams one stored block set per element."""
     if _ngpu() < world:
         pytest.skip(f"needs {world} GPUs")
     out = tmp_path / "dist.json"
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}",
-           "--master-addr", "127.0.0.1", "--master-port", str(29500 + world + 10 * ["dg", "cg", "dg8", "cg8"].index(kind)),
+           "--master-addr", "127.0.0.1", "--master-port", str(29500 + world + 10 * KINDS.index(kind)),
            os.path.join(ROOT, "tests", "dist_worker.py"), str(out), "15", kind]
     r = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]

@@ -3,7 +3,7 @@ hierarchy scripts (DG / CG p = 8 -> m = 9 / 8, tests/dg_heirarchy_test.jl, tests
 and the orders in between.
 
 They must reproduce the generic tier bit for bit (same accumulation order per block row), for both window
-sizes, at element counts that are not a multiple of a CTA's output window, and for sweep counts that
+sizes and 1, 2 or 3 block rows per thread, at element counts that are not a multiple of a CTA's output window, and for sweep counts that
 change the halo.  The oracle comparison of the same shapes is in tests/test_gpu_parity.py (n = 32) and
 tests/test_gpu_fullsize.py::test_cg_pattern_path_matches_oracle (n = 256); here the sizes are large
 enough for several thousand CTAs."""
@@ -15,6 +15,8 @@ import pytest
 from agglomerationmultigrid1d_b200 import uniform
 
 pytestmark = pytest.mark.gpu
+
+ROWS_PER_THREAD_DEFAULT = 0    # amg1d.cu: opt_rows_rpt, 0 = auto (1 streamed, 3 pattern-resident)
 
 
 def _rhs_dg(U, n):
@@ -38,23 +40,25 @@ def _compare_tiers(dev, b, n_big_levels):
     x_ref, it_ref, res_ref, _ = dev.solve(np.zeros(len(b)), b, 40, 1e-10)
     dev.set_option("fused", 1)
     launches = {}
-    for window in (0, 32, 64):
+    for window, rpt in ((0, 1), (32, 1), (64, 1), (32, 2), (64, 2), (32, 3), (64, 3)):
         dev.set_option("rows_window", window)
+        dev.set_option("rows_per_thread", rpt)
         for nPre, nPost, alpha in sweeps:
             got = dev.vcycle(x0, b, nPre=nPre, nPost=nPost, alpha=alpha)
-            assert np.array_equal(got, ref[(nPre, nPost)]), (window, nPre, nPost)
+            assert np.array_equal(got, ref[(nPre, nPost)]), (window, rpt, nPre, nPost)
         x, it, res, _ = dev.solve(np.zeros(len(b)), b, 40, 1e-10)
-        assert it == it_ref and np.array_equal(x, x_ref), window
+        assert it == it_ref and np.array_equal(x, x_ref), (window, rpt)
         # the residual norm is summed in a different order by each tier
-        assert np.allclose(res, res_ref, rtol=1e-9, atol=1e-13 * np.linalg.norm(b)), window
+        assert np.allclose(res, res_ref, rtol=1e-9, atol=1e-13 * np.linalg.norm(b)), (window, rpt)
         dev.dev_set_problem(x0, b)
         dev.dev_vcycle(with_residual_norm=True)
         dev.synchronize()
-        launches[window] = dev.info("launches_per_cycle")
+        launches[(window, rpt)] = dev.info("launches_per_cycle")
     dev.set_option("rows_window", 64)
+    dev.set_option("rows_per_thread", ROWS_PER_THREAD_DEFAULT)
     # one kernel per leg instead of nPre + 1 (down) and nPost + 1 (+ 1 for the norm) streaming passes
-    assert launches[32] == launches[64]
-    assert launches[0] - launches[64] >= 5 * n_big_levels, launches
+    assert len({v for k, v in launches.items() if k[0]}) == 1, launches
+    assert launches[(0, 1)] - launches[(64, 1)] >= 5 * n_big_levels, launches
     return launches
 
 
