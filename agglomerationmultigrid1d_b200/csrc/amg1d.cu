@@ -85,6 +85,7 @@ struct Level {
     // as a table tab[set][k] on the device, for the pattern-resident fused legs (PatOp, kernels_fused.cuh)
     double* pat = nullptr;
     int pat_head = 0, pat_tail = 0;
+    std::vector<double> pat_host;   // host copy of the table (its interior row is the ParamOp of f_down_c / f_up_c)
 };
 
 struct Transfer {
@@ -133,7 +134,8 @@ struct amg1d {
     int opt_pdl = 1;              // programmatic dependent launch between the fused kernels
     int opt_rows = 64;            // window of the row-per-thread fused legs (kernels_rows.cuh): 32, 64; 0 = off
     int opt_rows_rpt = 0;         // block rows per thread of those legs: 1, 2, 3; 0 = auto (rows_rpt() below)
-    int opt_pattern = 0;          // 1: levels given as patterns read their operator from the pattern table
+    int opt_pattern = 0;          // 1: levels given as patterns read their operator from the pattern table;
+                                  // 2: and the interior CTAs of f_down / f_up take it as constant-bank operands
     // single-CTA coarse tail (f_tail): levels [tail_start, n_levels)
     int tail_start = -1;
     TailLevel* d_tail = nullptr;
@@ -317,6 +319,8 @@ PatOp make_pat(const amg1d* h, int l) {
     po.n_glob = lv.n_glob;
     po.n_head = lv.pat_head;
     po.n_tail = lv.pat_tail;
+    po.host_interior = (h->opt_pattern == 2 && lv.pat && !lv.pat_host.empty())
+                           ? lv.pat_host.data() + (size_t)lv.pat_head * lv.K : nullptr;
     return po;
 }
 
@@ -1405,6 +1409,7 @@ int amg1d_set_level_pattern(amg1d_t* h, int level, int64_t n_elem, int m, int n_
         CK(cudaMemcpy(lv.pat, tab.data(), tab.size() * 8, cudaMemcpyHostToDevice));
         lv.pat_head = n_head;
         lv.pat_tail = n_tail;
+        lv.pat_host = std::move(tab);
     }
     if (n_elem <= AMG1D_BCR_MIN && !lv.sharded) {   // host copy for the block-Thomas factorisation
         lv.h_lo.resize((size_t)n_elem * mm); lv.h_di.resize((size_t)n_elem * mm); lv.h_up.resize((size_t)n_elem * mm);
@@ -2167,7 +2172,10 @@ int amg1d_set_option(amg1d_t* h, const char* key, int64_t value) {
         if (value != 0 && !rows_window_ok((int)value)) return fail(h, AMG1D_ERR_ARG, "rows_window must be 0, 32 or 64");
         h->opt_rows = (int)value;
     }
-    else if (!strcmp(key, "pattern_resident")) h->opt_pattern = value != 0;
+    else if (!strcmp(key, "pattern_resident")) {
+        if (value < 0 || value > 2) return fail(h, AMG1D_ERR_ARG, "pattern_resident must be 0, 1 or 2");
+        h->opt_pattern = (int)value;
+    }
     else if (!strcmp(key, "rows_per_thread")) {
         if (value != 0 && !rows_rpt_ok((int)value)) return fail(h, AMG1D_ERR_ARG, "rows_per_thread must be 0 (auto), 1, 2 or 3");
         h->opt_rows_rpt = (int)value;

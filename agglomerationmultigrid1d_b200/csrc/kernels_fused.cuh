@@ -48,6 +48,8 @@ struct PatOp {
     const double* tab;
     int64_t n_glob;        // elements of the whole level (the table is indexed by GLOBAL element)
     int n_head, n_tail;
+    const double* host_interior;   // HOST copy of the interior row tab[n_head][*] (pattern_resident = 2: the
+                                   // launcher passes it by value as ParamOp), else nullptr; unused on the device
 };
 
 // Per-launch constants of a fused leg, computed on the host so that the per-thread index arithmetic
@@ -313,11 +315,22 @@ __device__ __forceinline__ void exch_init(Exchange<M, B>& ex) {
 // The element's A_lo / A_di / A_up in registers (only the stored entries of the structure class).
 template <int M, int ST>
 struct RegOp {
+    static constexpr bool has_dv = false;
     double lo[OpShape<M, ST>::NO], di[M * M], up[OpShape<M, ST>::NO];
 };
 
-template <int M, int ST>
-__device__ __forceinline__ void reg_Ax(const RegOp<M, ST>& A, int ilo, int iup, const double (&xl)[M],
+// One block set (A_lo, A_di, A_up, Dinv in tile-row order = one row of a pattern table) passed BY VALUE as a
+// __grid_constant__ kernel parameter: the entries are constant-bank operands of the FMAs - no loads, no
+// registers, no shared memory for the operator.  Used by f_down_c / f_up_c for the CTAs whose whole window
+// lies in the translation-invariant interior of a level (option pattern_resident = 2).
+template <int M, int ST, bool DIAG>
+struct ParamOp {
+    static constexpr bool has_dv = true;
+    double lo[OpShape<M, ST>::NO], di[M * M], up[OpShape<M, ST>::NO], dv[DIAG ? M : M * M];
+};
+
+template <int M, int ST, class OP>
+__device__ __forceinline__ void reg_Ax(const OP& A, int ilo, int iup, const double (&xl)[M],
                                        const double (&xc)[M], const double (&xr)[M], double (&y)[M]) {
     if constexpr (ST == AMG1D_ST_DENSE) {
 #pragma unroll
@@ -358,8 +371,8 @@ __device__ __forceinline__ void reg_Ax(const RegOp<M, ST>& A, int ilo, int iup, 
 
 // one damped (block-)Jacobi sweep on register-resident blocks; same operation order as g_sweep.
 // Dinv is read from shared memory: dcol points at this thread's column of ds[k][thread], stride DS.
-template <int M, int ST, bool DIAG, int DS>
-__device__ __forceinline__ void reg_sweep(const RegOp<M, ST>& A, int ilo, int iup,
+template <int M, int ST, bool DIAG, int DS, class OP>
+__device__ __forceinline__ void reg_sweep(const OP& A, int ilo, int iup,
                                           const double* __restrict__ dcol, const double (&bb)[M],
                                           const double (&xl)[M], double (&xc)[M], const double (&xr)[M],
                                           double alpha, bool zero_guess) {
@@ -369,13 +382,17 @@ __device__ __forceinline__ void reg_sweep(const RegOp<M, ST>& A, int ilo, int iu
         for (int i = 0; i < M; ++i) r[i] = bb[i] - 0.0;
     } else {
         double y[M];
-        reg_Ax<M, ST>(A, ilo, iup, xl, xc, xr, y);
+        reg_Ax<M, ST, OP>(A, ilo, iup, xl, xc, xr, y);
 #pragma unroll
         for (int i = 0; i < M; ++i) r[i] = bb[i] - y[i];
     }
     if constexpr (DIAG) {
 #pragma unroll
-        for (int i = 0; i < M; ++i) xc[i] = __dadd_rn(xc[i], __dmul_rn(alpha, dcol[i * DS] * r[i]));
+        for (int i = 0; i < M; ++i) {
+            double dvi;
+            if constexpr (OP::has_dv) dvi = A.dv[i]; else dvi = dcol[i * DS];
+            xc[i] = __dadd_rn(xc[i], __dmul_rn(alpha, dvi * r[i]));
+        }
     } else {
         double z[M];
 #pragma unroll
@@ -383,7 +400,11 @@ __device__ __forceinline__ void reg_sweep(const RegOp<M, ST>& A, int ilo, int iu
 #pragma unroll
         for (int j = 0; j < M; ++j)
 #pragma unroll
-            for (int i = 0; i < M; ++i) z[i] = fma(dcol[(j * M + i) * DS], r[j], z[i]);
+            for (int i = 0; i < M; ++i) {
+                double dvk;
+                if constexpr (OP::has_dv) dvk = A.dv[j * M + i]; else dvk = dcol[(j * M + i) * DS];
+                z[i] = fma(dvk, r[j], z[i]);
+            }
 #pragma unroll
         for (int i = 0; i < M; ++i) xc[i] = __dadd_rn(xc[i], __dmul_rn(alpha, z[i]));
     }
@@ -398,13 +419,13 @@ __device__ __forceinline__ void cp_async_commit_wait_all() {
     asm volatile("cp.async.wait_group 0;" ::: "memory");
 }
 
-template <int M, int ST>
-__device__ __forceinline__ void reg_residual(const RegOp<M, ST>& A, int ilo, int iup,
+template <int M, int ST, class OP>
+__device__ __forceinline__ void reg_residual(const OP& A, int ilo, int iup,
                                              const double (&bb)[M], const double (&xl)[M],
                                              const double (&xc)[M], const double (&xr)[M],
                                              double (&r)[M]) {
     double y[M];
-    reg_Ax<M, ST>(A, ilo, iup, xl, xc, xr, y);
+    reg_Ax<M, ST, OP>(A, ilo, iup, xl, xc, xr, y);
 #pragma unroll
     for (int i = 0; i < M; ++i) r[i] = bb[i] - y[i];
 }
@@ -503,24 +524,18 @@ constexpr int fused_min_blocks(int m, int st) {
 //   out = elements emitted per CTA (a multiple of the agglomeration ratio).
 //   Coarse element Kc is gathered by the thread of its first P0-child, in the order of g_restrict:
 //   the P1 blocks of the children of Kc - 1, then the P0 blocks of its own children.
-template <int M, int MC, int B, int ST, bool DIAG>
-__global__ void FUSED_BOUNDS(M)
-f_down(const double* __restrict__ mat, PatOp po, int ilo, int iup, const double* __restrict__ b,
-       const double* __restrict__ xin, double* __restrict__ xout, const double* __restrict__ P0,
-       const double* __restrict__ P1, TransferMap tm, double* __restrict__ rc, int64_t n, double alpha,
-       int nsweep, int zero_guess, WinIdx wi, Slab sl) {
-    __shared__ Exchange<M, B> ex;
-    __shared__ double rs[M][B + 8];
-    __shared__ double ds[DIAG ? M : M * M][B];
-    pdl_launch_dependents();
+// The leg after the operator has been placed (A: RegOp in registers + Dinv column dcol in shared memory, or
+// ParamOp in the constant bank); everything from the dependency wait on.
+template <int M, int MC, int B, int ST, bool DIAG, class OP>
+__device__ __forceinline__ void
+down_leg(const OP& A, const double* __restrict__ dcol, Exchange<M, B>& ex, double (*rs)[B + 8], int64_t e,
+         bool active, int ilo, int iup, const double* __restrict__ b, const double* __restrict__ xin,
+         double* __restrict__ xout, const double* __restrict__ P0, const double* __restrict__ P1,
+         const TransferMap& tm, double* __restrict__ rc, int64_t n, double alpha, int nsweep, int zero_guess,
+         const WinIdx& wi, const Slab& sl) {
     const int t = threadIdx.x;
     const int halo = wi.halo, out = wi.out;
-    const int64_t e = (int64_t)blockIdx.x * out - halo + t;     // local element index (ghosts < 0, >= n)
-    const bool active = e >= -(int64_t)sl.gl && e < n + sl.gr;
-    exch_init<M, B>(ex);
-    RegOp<M, ST> A;
     double bb[M], xc[M], xl[M], xr[M];
-    load_blocks<M, B, ST, DIAG>(mat, po, e, e + sl.e_off, active, A, ds);         // operator: independent of earlier kernels
     pdl_wait();                                                  // b, x and everything written below are not
     if (active) {
         load_vec<M>(b + e * M, bb);
@@ -543,7 +558,7 @@ f_down(const double* __restrict__ mat, PatOp po, int ilo, int iup, const double*
             exchange<M, B, ST>(ex, buf, ilo, iup, xc, xl, xr);
             buf ^= 1;
         }
-        reg_sweep<M, ST, DIAG, B>(A, ilo, iup, &ds[0][t], bb, xl, xc, xr, alpha, zg);
+        reg_sweep<M, ST, DIAG, B>(A, ilo, iup, dcol, bb, xl, xc, xr, alpha, zg);
     }
     const bool mine = t >= halo && t < halo + out;              // this CTA's share of the level (e >= 0)
     if (mine && e < n) store_vec<M>(xout + e * M, xc);
@@ -592,24 +607,75 @@ f_down(const double* __restrict__ mat, PatOp po, int ilo, int iup, const double*
     }
 }
 
-// prolongation + correction, nsweep post-smoothing sweeps, optional || b - A x ||^2 partial sums.
 template <int M, int MC, int B, int ST, bool DIAG>
 __global__ void FUSED_BOUNDS(M)
-f_up(const double* __restrict__ mat, PatOp po, int ilo, int iup, const double* __restrict__ b,
-     const double* __restrict__ xin, double* __restrict__ xout, const double* __restrict__ P0,
-     const double* __restrict__ P1, TransferMap tm, const double* __restrict__ xcoarse, int64_t n,
-     double alpha, int nsweep, WinIdx wi, double* __restrict__ partial, Slab sl) {
+f_down(const double* __restrict__ mat, PatOp po, int ilo, int iup, const double* __restrict__ b,
+       const double* __restrict__ xin, double* __restrict__ xout, const double* __restrict__ P0,
+       const double* __restrict__ P1, TransferMap tm, double* __restrict__ rc, int64_t n, double alpha,
+       int nsweep, int zero_guess, WinIdx wi, Slab sl) {
     __shared__ Exchange<M, B> ex;
+    __shared__ double rs[M][B + 8];
     __shared__ double ds[DIAG ? M : M * M][B];
     pdl_launch_dependents();
     const int t = threadIdx.x;
-    const int halo = wi.halo, out = wi.out;
-    const int64_t e = (int64_t)blockIdx.x * out - halo + t;
+    const int64_t e = (int64_t)blockIdx.x * wi.out - wi.halo + t;     // local element index (ghosts < 0, >= n)
     const bool active = e >= -(int64_t)sl.gl && e < n + sl.gr;
     exch_init<M, B>(ex);
     RegOp<M, ST> A;
-    double bb[M], xc[M], xl[M], xr[M];
     load_blocks<M, B, ST, DIAG>(mat, po, e, e + sl.e_off, active, A, ds);         // operator: independent of earlier kernels
+    down_leg<M, MC, B, ST, DIAG>(A, &ds[0][t], ex, rs, e, active, ilo, iup, b, xin, xout, P0, P1, tm, rc, n, alpha,
+                                 nsweep, zero_guess, wi, sl);
+}
+
+// CTA-uniform test of the constant-operand legs: the whole window of this CTA is active (inside the slab
+// and its ghosts) and lies in the translation-invariant interior of the level, i.e. every thread would
+// fetch row n_head of the pattern table.
+__device__ __forceinline__ bool window_is_interior(const PatOp& po, const WinIdx& wi, const Slab& sl, int64_t n,
+                                                   int B) {
+    const int64_t e0 = (int64_t)blockIdx.x * wi.out - wi.halo;        // local element of thread 0
+    const int64_t g0 = e0 + sl.e_off;                                 // its global number
+    return e0 >= -(int64_t)sl.gl && e0 + B <= n + sl.gr && g0 >= po.n_head && g0 + B <= po.n_glob - po.n_tail;
+}
+
+// f_down with the interior block set of a pattern level as a by-value kernel parameter (ParamOp): interior
+// CTAs run the leg with constant-bank operands, the few CTAs that touch the head / tail block sets, a slab
+// end or the end of the level take the register path of f_down (pattern table, po.tab != nullptr).
+template <int M, int MC, int B, int ST, bool DIAG>
+__global__ void FUSED_BOUNDS(M)
+f_down_c(const __grid_constant__ ParamOp<M, ST, DIAG> pk, PatOp po, int ilo, int iup,
+         const double* __restrict__ b, const double* __restrict__ xin, double* __restrict__ xout,
+         const double* __restrict__ P0, const double* __restrict__ P1, TransferMap tm, double* __restrict__ rc,
+         int64_t n, double alpha, int nsweep, int zero_guess, WinIdx wi, Slab sl) {
+    __shared__ Exchange<M, B> ex;
+    __shared__ double rs[M][B + 8];
+    __shared__ double ds[DIAG ? M : M * M][B];
+    pdl_launch_dependents();
+    const int t = threadIdx.x;
+    const int64_t e = (int64_t)blockIdx.x * wi.out - wi.halo + t;
+    exch_init<M, B>(ex);
+    if (window_is_interior(po, wi, sl, n, B)) {
+        down_leg<M, MC, B, ST, DIAG>(pk, nullptr, ex, rs, e, true, ilo, iup, b, xin, xout, P0, P1, tm, rc, n, alpha,
+                                     nsweep, zero_guess, wi, sl);
+    } else {
+        const bool active = e >= -(int64_t)sl.gl && e < n + sl.gr;
+        RegOp<M, ST> A;
+        load_blocks<M, B, ST, DIAG>(nullptr, po, e, e + sl.e_off, active, A, ds);
+        down_leg<M, MC, B, ST, DIAG>(A, &ds[0][t], ex, rs, e, active, ilo, iup, b, xin, xout, P0, P1, tm, rc, n,
+                                     alpha, nsweep, zero_guess, wi, sl);
+    }
+}
+
+// prolongation + correction, nsweep post-smoothing sweeps, optional || b - A x ||^2 partial sums.
+template <int M, int MC, int B, int ST, bool DIAG, class OP>
+__device__ __forceinline__ void
+up_leg(const OP& A, const double* __restrict__ dcol, Exchange<M, B>& ex, int64_t e, bool active, int ilo, int iup,
+       const double* __restrict__ b, const double* __restrict__ xin, double* __restrict__ xout,
+       const double* __restrict__ P0, const double* __restrict__ P1, const TransferMap& tm,
+       const double* __restrict__ xcoarse, int64_t n, double alpha, int nsweep, const WinIdx& wi,
+       double* __restrict__ partial, const Slab& sl) {
+    const int t = threadIdx.x;
+    const int halo = wi.halo, out = wi.out;
+    double bb[M], xc[M], xl[M], xr[M];
     pdl_wait();
     if (active) {
         load_vec<M>(b + e * M, bb);
@@ -650,7 +716,7 @@ f_up(const double* __restrict__ mat, PatOp po, int ilo, int iup, const double* _
     for (int s = 0; s < nsweep; ++s) {
         exchange<M, B, ST>(ex, buf, ilo, iup, xc, xl, xr);
         buf ^= 1;
-        reg_sweep<M, ST, DIAG, B>(A, ilo, iup, &ds[0][t], bb, xl, xc, xr, alpha, false);
+        reg_sweep<M, ST, DIAG, B>(A, ilo, iup, dcol, bb, xl, xc, xr, alpha, false);
     }
     const bool emit = e < n && t >= halo && t < halo + out;     // e >= 0 for these threads
     if (emit) store_vec<M>(xout + e * M, xc);
@@ -665,6 +731,50 @@ f_up(const double* __restrict__ mat, PatOp po, int ilo, int iup, const double* _
         }
         s2 = block_sum(s2);
         if (t == 0) partial[blockIdx.x] = s2;
+    }
+}
+
+template <int M, int MC, int B, int ST, bool DIAG>
+__global__ void FUSED_BOUNDS(M)
+f_up(const double* __restrict__ mat, PatOp po, int ilo, int iup, const double* __restrict__ b,
+     const double* __restrict__ xin, double* __restrict__ xout, const double* __restrict__ P0,
+     const double* __restrict__ P1, TransferMap tm, const double* __restrict__ xcoarse, int64_t n,
+     double alpha, int nsweep, WinIdx wi, double* __restrict__ partial, Slab sl) {
+    __shared__ Exchange<M, B> ex;
+    __shared__ double ds[DIAG ? M : M * M][B];
+    pdl_launch_dependents();
+    const int t = threadIdx.x;
+    const int64_t e = (int64_t)blockIdx.x * wi.out - wi.halo + t;
+    const bool active = e >= -(int64_t)sl.gl && e < n + sl.gr;
+    exch_init<M, B>(ex);
+    RegOp<M, ST> A;
+    load_blocks<M, B, ST, DIAG>(mat, po, e, e + sl.e_off, active, A, ds);         // operator: independent of earlier kernels
+    up_leg<M, MC, B, ST, DIAG>(A, &ds[0][t], ex, e, active, ilo, iup, b, xin, xout, P0, P1, tm, xcoarse, n, alpha,
+                               nsweep, wi, partial, sl);
+}
+
+// f_up with constant-bank operands for the interior CTAs of a pattern level (see f_down_c)
+template <int M, int MC, int B, int ST, bool DIAG>
+__global__ void FUSED_BOUNDS(M)
+f_up_c(const __grid_constant__ ParamOp<M, ST, DIAG> pk, PatOp po, int ilo, int iup, const double* __restrict__ b,
+       const double* __restrict__ xin, double* __restrict__ xout, const double* __restrict__ P0,
+       const double* __restrict__ P1, TransferMap tm, const double* __restrict__ xcoarse, int64_t n,
+       double alpha, int nsweep, WinIdx wi, double* __restrict__ partial, Slab sl) {
+    __shared__ Exchange<M, B> ex;
+    __shared__ double ds[DIAG ? M : M * M][B];
+    pdl_launch_dependents();
+    const int t = threadIdx.x;
+    const int64_t e = (int64_t)blockIdx.x * wi.out - wi.halo + t;
+    exch_init<M, B>(ex);
+    if (window_is_interior(po, wi, sl, n, B)) {
+        up_leg<M, MC, B, ST, DIAG>(pk, nullptr, ex, e, true, ilo, iup, b, xin, xout, P0, P1, tm, xcoarse, n, alpha,
+                                   nsweep, wi, partial, sl);
+    } else {
+        const bool active = e >= -(int64_t)sl.gl && e < n + sl.gr;
+        RegOp<M, ST> A;
+        load_blocks<M, B, ST, DIAG>(nullptr, po, e, e + sl.e_off, active, A, ds);
+        up_leg<M, MC, B, ST, DIAG>(A, &ds[0][t], ex, e, active, ilo, iup, b, xin, xout, P0, P1, tm, xcoarse, n, alpha,
+                                   nsweep, wi, partial, sl);
     }
 }
 
@@ -1054,6 +1164,12 @@ inline int fused_down(const MatDesc& d, int mc, const TransferMap& tm, int nswee
     switch (fused_key(d.m, mc, d.st, d.diag)) {
 #define X(MM, MCC, SS, DG)                                                                               \
     case ((MM * 16 + MCC) * 4 + SS) * 2 + (DG ? 1 : 0):                                                  \
+        if (po.tab && po.host_interior && sizeof(ParamOp<MM, SS, DG>) == (size_t)d.K * 8) {                                                                \
+            ParamOp<MM, SS, DG> pk;                                                                      \
+            memcpy(&pk, po.host_interior, sizeof(pk));                                                   \
+            *err = launch_fused(f_down_c<MM, MCC, FUSED_B, SS, DG>, grid, FUSED_B, 0, st, pdl, pk, po, d.ilo, \
+                                d.iup, b, xin, xout, P0, P1, tm, rc, n, alpha, nsweep, zero ? 1 : 0, w, sl); \
+        } else                                                                                           \
         *err = launch_fused(f_down<MM, MCC, FUSED_B, SS, DG>, grid, FUSED_B, 0, st, pdl, mat, po, d.ilo, d.iup, \
                             b, xin, xout, P0, P1, tm, rc, n, alpha, nsweep, zero ? 1 : 0, w, sl);        \
         return *err == cudaSuccess ? FUSED_OK : FUSED_ERR;
@@ -1076,6 +1192,12 @@ inline int fused_up(const MatDesc& d, int mc, const TransferMap& tm, int nsweep,
     switch (fused_key(d.m, mc, d.st, d.diag)) {
 #define X(MM, MCC, SS, DG)                                                                               \
     case ((MM * 16 + MCC) * 4 + SS) * 2 + (DG ? 1 : 0):                                                  \
+        if (po.tab && po.host_interior && sizeof(ParamOp<MM, SS, DG>) == (size_t)d.K * 8) {                                                                \
+            ParamOp<MM, SS, DG> pk;                                                                      \
+            memcpy(&pk, po.host_interior, sizeof(pk));                                                   \
+            *err = launch_fused(f_up_c<MM, MCC, FUSED_B, SS, DG>, (unsigned)grid, FUSED_B, 0, st, pdl, pk, po, \
+                                d.ilo, d.iup, b, xin, xout, P0, P1, tm, xcoarse, n, alpha, nsweep, w, partial, sl); \
+        } else                                                                                           \
         *err = launch_fused(f_up<MM, MCC, FUSED_B, SS, DG>, (unsigned)grid, FUSED_B, 0, st, pdl, mat, po,    \
                             d.ilo, d.iup, b, xin, xout, P0, P1, tm, xcoarse, n, alpha, nsweep, w, partial, sl); \
         return *err == cudaSuccess ? FUSED_OK : FUSED_ERR;

@@ -23,8 +23,10 @@ def main():
     out = sys.argv[1]
     log2n = int(sys.argv[2]) if len(sys.argv) > 2 else 15
     kind = sys.argv[3] if len(sys.argv) > 3 else "dg"
-    pattern_resident = kind.endswith("_pat")     # sharded handle reads its operators from the pattern tables
-    kind = kind[:-4] if pattern_resident else kind
+    # *_pat / *_pat2: the sharded handle reads its operators from the pattern tables (option pattern_resident
+    # = 1) / takes the interior block set as constant-bank kernel parameters (= 2)
+    pattern_resident = 2 if kind.endswith("_pat2") else 1 if kind.endswith("_pat") else 0
+    kind = kind[:-5] if pattern_resident == 2 else kind[:-4] if pattern_resident else kind
     dist.init_process_group("gloo")
     rank, world = dist.get_rank(), dist.get_world_size()
     torch.cuda.set_device(rank)
@@ -52,7 +54,7 @@ def main():
     U = build()
     dev = U.upload(device=rank, dist=(rank, world, ids[0]), options={"shard_min": 512})
     if pattern_resident:                          # the single-GPU reference below keeps streaming its operators
-        dev.set_option("pattern_resident", 1)
+        dev.set_option("pattern_resident", pattern_resident)
     nloc = n // world
     m0 = U.levels[0].m
     is_cg = kind.startswith("cg")

@@ -15,7 +15,8 @@ def _ngpu():
     return torch.cuda.device_count()
 
 
-KINDS = ["dg", "cg", "dg8", "cg8", "dg_pat", "cg_pat", "dg8_pat"]   # *_pat: option pattern_resident = 1
+# *_pat: option pattern_resident = 1, *_pat2: = 2 (constant-bank operands in the interior CTAs)
+KINDS = ["dg", "cg", "dg8", "cg8", "dg_pat", "cg_pat", "dg8_pat", "dg_pat2", "cg_pat2"]
 
 
 @pytest.mark.parametrize("kind", KINDS)

@@ -1,4 +1,4 @@
-"""Pattern-resident operators (option pattern_resident = 1, PatOp in csrc/kernels_fused.cuh).
+"""Pattern-resident operators (option pattern_resident = 1 or 2, PatOp / ParamOp in csrc/kernels_fused.cuh).
 
 On a uniform mesh every level is translation invariant: amg1d_set_level_pattern receives n_head + 1 +
 n_tail distinct block sets.  By default the device still stores (and the fused legs stream) one block set
@@ -35,17 +35,23 @@ def _check(U, dev, b):
     dev.dev_vcycle(with_residual_norm=True)
     dev.synchronize()
     launches = dev.info("launches_per_cycle")
-    dev.set_option("pattern_resident", 1)
-    assert dev.info("pattern_resident") == 1
-    for a, c, al in SWEEPS:
-        assert np.array_equal(dev.vcycle(x0, b, nPre=a, nPost=c, alpha=al), ref[(a, c)]), (a, c)
-    x, it, res, _ = dev.solve(np.zeros(len(b)), b, 40, 1e-10)
-    assert it == it_ref and np.array_equal(x, x_ref) and np.array_equal(res, res_ref)
-    assert np.array_equal(dev.ldiv(b), y_ref)
-    dev.dev_set_problem(x0, b)
-    dev.dev_vcycle(with_residual_norm=True)
-    dev.synchronize()
-    assert dev.info("launches_per_cycle") == launches
+    # 1: every thread fetches its block set from the table; 2: the CTAs whose window lies in the interior of
+    # the level take the interior block set as a by-value kernel parameter (constant-bank operands, ParamOp /
+    # f_down_c / f_up_c), the CTAs at the ends of the level keep the table path
+    for mode in (1, 2):
+        dev.set_option("pattern_resident", mode)
+        assert dev.info("pattern_resident") == mode
+        for a, c, al in SWEEPS:
+            assert np.array_equal(dev.vcycle(x0, b, nPre=a, nPost=c, alpha=al), ref[(a, c)]), (mode, a, c)
+        x, it, res, _ = dev.solve(np.zeros(len(b)), b, 40, 1e-10)
+        assert it == it_ref and np.array_equal(x, x_ref) and np.array_equal(res, res_ref), mode
+        assert np.array_equal(dev.ldiv(b), y_ref), mode
+        dev.dev_set_problem(x0, b)
+        dev.dev_vcycle(with_residual_norm=True)
+        dev.synchronize()
+        assert dev.info("launches_per_cycle") == launches
+    with pytest.raises(Exception):
+        dev.set_option("pattern_resident", 3)
     # the streamed-operator byte model drops the operator of every pattern level
     assert U.bytes_per_leg_fused(0, down=False) == 8 * (U.levels[0].n * 3 * U.levels[0].m
                                                          + U.levels[1].n * U.levels[1].m)
