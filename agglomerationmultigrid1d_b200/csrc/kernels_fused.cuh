@@ -517,6 +517,23 @@ constexpr int fused_min_blocks(int m, int st) {
          : m <= 2 ? FUSED_MINB_SMALL : FUSED_MINB;
 }
 #define FUSED_BOUNDS(M) __launch_bounds__(B, fused_min_blocks(M, ST))
+// The constant-operand legs (f_down_c / f_up_c) keep no operator in registers on their interior path, so
+// they can be given more resident CTAs than f_down / f_up; their table path (the few CTAs at the ends of a
+// level) then spills, which costs nothing measurable.  0 = the bounds of f_down / f_up.
+#ifndef FUSED_C_MINB3
+#define FUSED_C_MINB3 8   // C3 level 1 (3 x 3 dense): 0.535 / 0.546 ms per leg at 3 CTAs/SM, 0.369 / 0.364 at 8
+#endif
+#ifndef FUSED_C_MINB4
+#define FUSED_C_MINB4 8   // measured on B200 (T level 0, profiles/r01e_sweep_const.jsonl): 5 CTAs/SM (the bounds
+#endif                    // of f_down / f_up) 2.31 / 2.03 ms per leg, 6: 2.12 / 1.94, 8 (64 registers): 1.99 / 1.92
+#ifndef FUSED_C_MINB5
+#define FUSED_C_MINB5 0   // 5 x 5: the interior path needs the registers (6 CTAs/SM: 1.86 / 1.81 ms against 1.01 / 0.98;
+#endif                    // profiles/r01f_sweep_const.jsonl)
+constexpr int fused_c_min_blocks(int m, int st) {
+    return (m == 3 && FUSED_C_MINB3) ? FUSED_C_MINB3 : (m == 4 && FUSED_C_MINB4) ? FUSED_C_MINB4
+         : (m >= 5 && FUSED_C_MINB5) ? FUSED_C_MINB5 : fused_min_blocks(m, st);
+}
+#define FUSED_C_BOUNDS(M) __launch_bounds__(B, fused_c_min_blocks(M, ST))
 
 // nsweep pre-smoothing sweeps, residual, restriction to the coarse right-hand side.
 //   halo window elements on each side are recomputed (nsweep + 1, plus `ratio` for two-parent
@@ -641,7 +658,7 @@ __device__ __forceinline__ bool window_is_interior(const PatOp& po, const WinIdx
 // CTAs run the leg with constant-bank operands, the few CTAs that touch the head / tail block sets, a slab
 // end or the end of the level take the register path of f_down (pattern table, po.tab != nullptr).
 template <int M, int MC, int B, int ST, bool DIAG>
-__global__ void FUSED_BOUNDS(M)
+__global__ void FUSED_C_BOUNDS(M)
 f_down_c(const __grid_constant__ ParamOp<M, ST, DIAG> pk, PatOp po, int ilo, int iup,
          const double* __restrict__ b, const double* __restrict__ xin, double* __restrict__ xout,
          const double* __restrict__ P0, const double* __restrict__ P1, TransferMap tm, double* __restrict__ rc,
@@ -755,7 +772,7 @@ f_up(const double* __restrict__ mat, PatOp po, int ilo, int iup, const double* _
 
 // f_up with constant-bank operands for the interior CTAs of a pattern level (see f_down_c)
 template <int M, int MC, int B, int ST, bool DIAG>
-__global__ void FUSED_BOUNDS(M)
+__global__ void FUSED_C_BOUNDS(M)
 f_up_c(const __grid_constant__ ParamOp<M, ST, DIAG> pk, PatOp po, int ilo, int iup, const double* __restrict__ b,
        const double* __restrict__ xin, double* __restrict__ xout, const double* __restrict__ P0,
        const double* __restrict__ P1, TransferMap tm, const double* __restrict__ xcoarse, int64_t n,

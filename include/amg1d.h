@@ -126,9 +126,9 @@ int amg1d_set_level_smoother(amg1d_t* h, int level, const double* S_lo, const do
  * explicit, every element in between repeats the single `interior` block set.  Arrays hold
  * n_head + 1 + n_tail blocks in that order.  The device still stores every element's blocks (the
  * general layout, which every kernel can read) and keeps the n_head + 1 + n_tail block sets as a small
- * table next to them; with option "pattern_resident" = 1 the fused legs read the table instead of the
- * per-element blocks (same numbers, same arithmetic order: bit-identical iterates), so HBM carries
- * only the vectors. */
+ * table next to them; with option "pattern_resident" = 1 or 2 the fused legs read the table (2: kernel
+ * parameters in the interior of the level) instead of the per-element blocks (same numbers, same
+ * arithmetic order: bit-identical iterates), so HBM carries only the vectors. */
 int amg1d_set_level_pattern(amg1d_t* h, int level, int64_t n_elem, int m, int n_head, int n_tail,
                             const double* A_lo, const double* A_di, const double* A_up,
                             const double* Dinv, int dinv_is_diagonal);
@@ -231,7 +231,9 @@ void* amg1d_dev_ptr(amg1d_t* h, int level, int which);             /* raw device
  * launch between the fused kernels, default 1), "coarse_cta_elems" (levels with at most this many
  * elements - capped at 512 - run inside the single-CTA coarse kernel; 0 disables it; default 1024),
  * "profile" (see amg1d_get_profile; setting it clears earlier samples), "pattern_resident" (1 = levels
- * given by amg1d_set_level_pattern take their operator from the pattern table, default 0),
+ * given by amg1d_set_level_pattern take their operator from the pattern table; 2 = in addition the CTAs
+ * whose elements all lie in the translation-invariant interior of such a level receive the interior block
+ * set as a kernel parameter and use it as constant operands; default 0; bit-identical results in all modes),
  * "rows_window" (elements per CTA of the row-per-thread legs for 5..9-row blocks: 32, 64; 0 = off;
  * default 64), "rows_per_thread" (block rows per thread of those legs: 1, 2, 3; 0 = auto, default);
  * before the first level is
