@@ -124,6 +124,9 @@ struct amg1d {
     double* partial = nullptr;
     int64_t partial_cap = 0;
     bool norm_valid = false;   // d_scal[0] holds ||b - A x|| of the current level-0 iterate
+    bool dev_problem = true;   // level 0's b / x still hold the device-resident problem (amg1d_dev_set_problem);
+                               // cleared by the calls that stage through them (level-0 residual / smoother
+                               // solve, amg1d_pcg) - the amg1d_dev_* calls then refuse to run on stale data
     double* d_scal = nullptr;  // device scalars
     double* h_scal = nullptr;  // pinned host scalars
     double* coarse_fac = nullptr;
@@ -1008,6 +1011,14 @@ int check_ready(amg1d* h) {
     return AMG1D_OK;
 }
 
+int check_dev_problem(amg1d* h) {
+    RET(check_ready(h));
+    if (!h->dev_problem)
+        return fail(h, AMG1D_ERR_STATE, "the device-resident problem was overwritten by a per-level host operation "
+                    "(amg1d_residual / amg1d_smoother_solve on level 0, amg1d_pcg); call amg1d_dev_set_problem again");
+    return AMG1D_OK;
+}
+
 // Structure class of a level (layout.cuh) from `nb` uploaded off-diagonal block sets.
 void detect_structure(const double* lo, const double* up, int64_t nb, int m, int* st, int* ilo, int* iup) {
     *st = AMG1D_ST_DENSE; *ilo = 0; *iup = 0;
@@ -1029,6 +1040,20 @@ void detect_structure(const double* lo, const double* up, int64_t nb, int m, int
     int a, b;
     if (single(lo_col, &a) && single(up_row, &b)) { *st = AMG1D_ST_COLROW; *ilo = a; *iup = b; return; }
     if (single(lo_row, &a) && single(up_col, &b)) { *st = AMG1D_ST_ROWCOL; *ilo = a; *iup = b; return; }
+}
+
+// A level upload failed after alloc_level_common succeeded: give back what it took (operator tiles,
+// permutation, pattern table, the byte accounting and the gather-level decision) so that the level stays
+// cleanly unset and the same call can be retried.
+void undo_level_alloc(amg1d* h, int level) {
+    Level& lv = h->L[level];
+    if (lv.mat_alloc) { cudaFree(lv.mat_alloc); h->device_bytes -= lv.mat_bytes; }
+    if (lv.perm) { cudaFree(lv.perm); h->device_bytes -= lv.n_glob * lv.m * 8; }
+    if (lv.pat) { cudaFree(lv.pat); h->device_bytes -= (int64_t)lv.pat_host.size() * 8; }
+    lv.mat_alloc = lv.mat = nullptr; lv.perm = nullptr; lv.pat = nullptr; lv.mat_bytes = 0;
+    lv.pat_host.clear(); lv.h_lo.clear(); lv.h_di.clear(); lv.h_up.clear();
+    if (h->gather_level == level) h->gather_level = -1;
+    lv.set = false;
 }
 
 int alloc_level_common(amg1d* h, int level, int64_t n_elem, int m, int diag, const int64_t* perm,
@@ -1068,19 +1093,28 @@ int alloc_level_common(amg1d* h, int level, int64_t n_elem, int m, int diag, con
         if (h->nranks > 1 && h->gather_level < 0) h->gather_level = level;
     }
     lv.n_host = n_dof_host;
+    if (perm)                                     // validated before anything is allocated
+        for (int64_t s = 0; s < n_elem * m; ++s)
+            if (perm[s] < -1 || perm[s] >= n_dof_host) {
+                if (h->gather_level == level) h->gather_level = -1;
+                return fail(h, AMG1D_ERR_ARG, "perm[%lld] out of range", (long long)s);
+            }
     if (!lv.present) return AMG1D_OK;             // ranks > 0 hold nothing of gathered levels
     // one spare tile in front of element 0 (ghost elements have negative local indices)
     lv.mat_bytes = (amg1d_tiles(lv.n + lv.gr) + 1) * (int64_t)lv.K * AMG1D_TILE * 8;
-    RET(dev_alloc(h, (void**)&lv.mat_alloc, lv.mat_bytes));
-    CK(cudaMemsetAsync(lv.mat_alloc, 0, (size_t)lv.K * AMG1D_TILE * 8, h->stream));
+    int rc = dev_alloc(h, (void**)&lv.mat_alloc, lv.mat_bytes);
+    if (rc != AMG1D_OK) { lv.mat_alloc = nullptr; undo_level_alloc(h, level); return rc; }
     lv.mat = lv.mat_alloc + (int64_t)lv.K * AMG1D_TILE;
-    if (perm) {
+    cudaError_t ce = cudaMemsetAsync(lv.mat_alloc, 0, (size_t)lv.K * AMG1D_TILE * 8, h->stream);
+    if (ce == cudaSuccess && perm) {
         const int64_t ns = n_elem * m;
-        for (int64_t s = 0; s < ns; ++s)
-            if (perm[s] < -1 || perm[s] >= n_dof_host)
-                return fail(h, AMG1D_ERR_ARG, "perm[%lld] out of range", (long long)s);
-        RET(dev_alloc(h, (void**)&lv.perm, ns * 8));
-        CK(cudaMemcpy(lv.perm, perm, (size_t)ns * 8, cudaMemcpyHostToDevice));
+        rc = dev_alloc(h, (void**)&lv.perm, ns * 8);
+        if (rc != AMG1D_OK) { lv.perm = nullptr; undo_level_alloc(h, level); return rc; }
+        ce = cudaMemcpy(lv.perm, perm, (size_t)ns * 8, cudaMemcpyHostToDevice);
+    }
+    if (ce != cudaSuccess) {
+        undo_level_alloc(h, level);
+        return fail(h, AMG1D_ERR_CUDA, "level %d allocation failed: %s", level, cudaGetErrorString(ce));
     }
     return AMG1D_OK;
 }
@@ -1125,10 +1159,7 @@ int install_from_blocks(amg1d* h, int level, int64_t n, int m, double* const* dA
     }
     RET(alloc_level_common(h, level, n, m, diag, perm, n_dof_host, st, ilo, iup));
     Level& lv = h->L[level];
-    auto undo = [&]() {                            // the level stays unset: release what alloc_level_common took
-        if (lv.mat_alloc) { cudaFree(lv.mat_alloc); lv.mat_alloc = nullptr; lv.mat = nullptr; h->device_bytes -= lv.mat_bytes; }
-        if (lv.perm) { cudaFree(lv.perm); lv.perm = nullptr; h->device_bytes -= n * m * 8; }
-    };
+    auto undo = [&]() { undo_level_alloc(h, level); };   // the level stays unset
 #define CKU(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { undo(); \
         return fail(h, e_ == cudaErrorMemoryAllocation ? AMG1D_ERR_NOMEM : AMG1D_ERR_CUDA, "%s failed: %s", #call, cudaGetErrorString(e_)); } } while (0)
     const unsigned gs = (unsigned)((n * m + 127) / 128);
@@ -1319,10 +1350,13 @@ int amg1d_set_level(amg1d_t* h, int level, int64_t n_elem, int m, const double* 
     const int64_t chunk = 1 << 18;  // elements per staging chunk (multiple of 32)
     const int64_t c = std::min(chunk, (lv.n + lv.gr + 63) / 32 * 32);
     DevBuf b_lo, b_di, b_up, b_dv;
-    CK(b_lo.alloc(c * mm));
-    CK(b_di.alloc(c * mm));
-    CK(b_up.alloc(c * mm));
-    CK(b_dv.alloc(c * dsz));
+    // from here on a failure must release what alloc_level_common took (undo_level_alloc)
+#define CKU(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { undo_level_alloc(h, level); \
+        return fail(h, e_ == cudaErrorMemoryAllocation ? AMG1D_ERR_NOMEM : AMG1D_ERR_CUDA, "%s failed: %s", #call, cudaGetErrorString(e_)); } } while (0)
+    CKU(b_lo.alloc(c * mm));
+    CKU(b_di.alloc(c * mm));
+    CKU(b_up.alloc(c * mm));
+    CKU(b_dv.alloc(c * dsz));
     double *d_lo = b_lo.p, *d_di = b_di.p, *d_up = b_up.p, *d_dv = b_dv.p;
     int rc = AMG1D_OK;
     // chunks are aligned to tiles of the local storage; the first one starts at local element -32 when
@@ -1333,15 +1367,15 @@ int amg1d_set_level(amg1d_t* h, int level, int64_t n_elem, int m, const double* 
         // global elements of this chunk that exist: [a, b)
         const int64_t a = std::max(g0, lv.start + le0), b = std::min(g1, lv.start + le0 + cnt);
         const int64_t off = a - (lv.start + le0);       // leading elements of the chunk left at zero
-        cudaMemsetAsync(d_lo, 0, (size_t)cnt * mm * 8, h->stream);
-        cudaMemsetAsync(d_di, 0, (size_t)cnt * mm * 8, h->stream);
-        cudaMemsetAsync(d_up, 0, (size_t)cnt * mm * 8, h->stream);
-        cudaMemsetAsync(d_dv, 0, (size_t)cnt * dsz * 8, h->stream);
+        CKU(cudaMemsetAsync(d_lo, 0, (size_t)cnt * mm * 8, h->stream));
+        CKU(cudaMemsetAsync(d_di, 0, (size_t)cnt * mm * 8, h->stream));
+        CKU(cudaMemsetAsync(d_up, 0, (size_t)cnt * mm * 8, h->stream));
+        CKU(cudaMemsetAsync(d_dv, 0, (size_t)cnt * dsz * 8, h->stream));
         if (b > a) {
-            cudaMemcpyAsync(d_lo + off * mm, A_lo + a * mm, (size_t)(b - a) * mm * 8, cudaMemcpyHostToDevice, h->stream);
-            cudaMemcpyAsync(d_di + off * mm, A_di + a * mm, (size_t)(b - a) * mm * 8, cudaMemcpyHostToDevice, h->stream);
-            cudaMemcpyAsync(d_up + off * mm, A_up + a * mm, (size_t)(b - a) * mm * 8, cudaMemcpyHostToDevice, h->stream);
-            cudaMemcpyAsync(d_dv + off * dsz, Dinv + a * dsz, (size_t)(b - a) * dsz * 8, cudaMemcpyHostToDevice, h->stream);
+            CKU(cudaMemcpyAsync(d_lo + off * mm, A_lo + a * mm, (size_t)(b - a) * mm * 8, cudaMemcpyHostToDevice, h->stream));
+            CKU(cudaMemcpyAsync(d_di + off * mm, A_di + a * mm, (size_t)(b - a) * mm * 8, cudaMemcpyHostToDevice, h->stream));
+            CKU(cudaMemcpyAsync(d_up + off * mm, A_up + a * mm, (size_t)(b - a) * mm * 8, cudaMemcpyHostToDevice, h->stream));
+            CKU(cudaMemcpyAsync(d_dv + off * dsz, Dinv + a * dsz, (size_t)(b - a) * dsz * 8, cudaMemcpyHostToDevice, h->stream));
         }
         const int64_t total = amg1d_tiles(cnt) * (int64_t)lv.K * AMG1D_TILE;
         k_repack<<<(unsigned)((total + 255) / 256), 256, 0, h->stream>>>(d_lo, d_di, d_up, d_dv, lv.md,
@@ -1350,7 +1384,7 @@ int amg1d_set_level(amg1d_t* h, int level, int64_t n_elem, int m, const double* 
         if (e == cudaSuccess) e = cudaGetLastError();
         if (e != cudaSuccess) rc = fail(h, AMG1D_ERR_CUDA, "level upload failed: %s", cudaGetErrorString(e));
     }
-    RET(rc);
+    if (rc != AMG1D_OK) { undo_level_alloc(h, level); return rc; }
     if (n_elem <= AMG1D_BCR_MIN && !lv.sharded) {   // host copy for the block-Thomas factorisation
         lv.h_lo.assign(A_lo, A_lo + (size_t)n_elem * mm);
         lv.h_di.assign(A_di, A_di + (size_t)n_elem * mm);
@@ -1377,15 +1411,15 @@ int amg1d_set_level_pattern(amg1d_t* h, int level, int64_t n_elem, int m, int n_
     const int dsz = lv.diag ? m : mm;
     if (!lv.present) { lv.set = true; return AMG1D_OK; }
     DevBuf b_lo, b_di, b_up, b_dv;
-    CK(b_lo.alloc((int64_t)nb * mm));
-    CK(b_di.alloc((int64_t)nb * mm));
-    CK(b_up.alloc((int64_t)nb * mm));
-    CK(b_dv.alloc((int64_t)nb * dsz));
+    CKU(b_lo.alloc((int64_t)nb * mm));
+    CKU(b_di.alloc((int64_t)nb * mm));
+    CKU(b_up.alloc((int64_t)nb * mm));
+    CKU(b_dv.alloc((int64_t)nb * dsz));
     double *d_lo = b_lo.p, *d_di = b_di.p, *d_up = b_up.p, *d_dv = b_dv.p;
-    cudaMemcpyAsync(d_lo, A_lo, (size_t)nb * mm * 8, cudaMemcpyHostToDevice, h->stream);
-    cudaMemcpyAsync(d_di, A_di, (size_t)nb * mm * 8, cudaMemcpyHostToDevice, h->stream);
-    cudaMemcpyAsync(d_up, A_up, (size_t)nb * mm * 8, cudaMemcpyHostToDevice, h->stream);
-    cudaMemcpyAsync(d_dv, Dinv, (size_t)nb * dsz * 8, cudaMemcpyHostToDevice, h->stream);
+    CKU(cudaMemcpyAsync(d_lo, A_lo, (size_t)nb * mm * 8, cudaMemcpyHostToDevice, h->stream));
+    CKU(cudaMemcpyAsync(d_di, A_di, (size_t)nb * mm * 8, cudaMemcpyHostToDevice, h->stream));
+    CKU(cudaMemcpyAsync(d_up, A_up, (size_t)nb * mm * 8, cudaMemcpyHostToDevice, h->stream));
+    CKU(cudaMemcpyAsync(d_dv, Dinv, (size_t)nb * dsz * 8, cudaMemcpyHostToDevice, h->stream));
     // fill every stored tile, including the spare front tile that holds the left ghost elements
     const int64_t ntiles = amg1d_tiles(lv.n + lv.gr) + 1;
     const int64_t total = ntiles * (int64_t)lv.K * AMG1D_TILE;
@@ -1394,7 +1428,7 @@ int amg1d_set_level_pattern(amg1d_t* h, int level, int64_t n_elem, int m, int n_
         lv.n + lv.gr, ntiles, lv.mat_alloc);
     cudaError_t e = cudaStreamSynchronize(h->stream);
     if (e == cudaSuccess) e = cudaGetLastError();
-    if (e != cudaSuccess) return fail(h, AMG1D_ERR_CUDA, "pattern fill failed: %s", cudaGetErrorString(e));
+    if (e != cudaSuccess) { undo_level_alloc(h, level); return fail(h, AMG1D_ERR_CUDA, "pattern fill failed: %s", cudaGetErrorString(e)); }
     {   // the distinct block sets as a table tab[set][k], k = tile row: what the pattern-resident legs read
         std::vector<double> tab((size_t)nb * lv.K);
         for (int sidx = 0; sidx < nb; ++sidx)
@@ -1405,12 +1439,17 @@ int amg1d_set_level_pattern(amg1d_t* h, int level, int64_t n_elem, int m, int n_
                                   : which == 2 ? A_up + (size_t)sidx * mm : Dinv + (size_t)sidx * dsz;
                 tab[(size_t)sidx * lv.K + k] = src[idx];
             }
-        RET(dev_alloc(h, (void**)&lv.pat, (int64_t)tab.size() * 8));
-        CK(cudaMemcpy(lv.pat, tab.data(), tab.size() * 8, cudaMemcpyHostToDevice));
+        lv.pat_host = std::move(tab);                       // (its size is what undo_level_alloc gives back)
+        if (dev_alloc(h, (void**)&lv.pat, (int64_t)lv.pat_host.size() * 8) != AMG1D_OK) {
+            lv.pat = nullptr;
+            undo_level_alloc(h, level);
+            return AMG1D_ERR_NOMEM;
+        }
+        CKU(cudaMemcpy(lv.pat, lv.pat_host.data(), lv.pat_host.size() * 8, cudaMemcpyHostToDevice));
         lv.pat_head = n_head;
         lv.pat_tail = n_tail;
-        lv.pat_host = std::move(tab);
     }
+#undef CKU
     if (n_elem <= AMG1D_BCR_MIN && !lv.sharded) {   // host copy for the block-Thomas factorisation
         lv.h_lo.resize((size_t)n_elem * mm); lv.h_di.resize((size_t)n_elem * mm); lv.h_up.resize((size_t)n_elem * mm);
         for (int64_t el = 0; el < n_elem; ++el) {
@@ -1826,9 +1865,13 @@ int amg1d_dev_set_problem(amg1d_t* h, const double* x0, const double* b) {
     RET(check_ready(h));
     Level& l0 = h->L[0];
     h->norm_valid = false;
+    if (!b && !h->dev_problem)
+        return fail(h, AMG1D_ERR_STATE, "amg1d_dev_set_problem: b == NULL keeps the resident right-hand side, but that "
+                    "was overwritten by a per-level host operation");
     if (b) {
         RET(to_device(h, 0, b, l0.b.p));
         if (l0.sharded) RET(op_halo(h, l0.b.p, l0.n, l0.m));
+        h->dev_problem = true;
     }
     if (l0.cur != 0) l0.cur = 0;
     if (x0) RET(to_device(h, 0, x0, l0.x[0].p));
@@ -1843,6 +1886,7 @@ int amg1d_dev_fill_rhs_random(amg1d_t* h, uint64_t seed) {
     h->norm_valid = false;
     k_fill_random<<<1184, 256, 0, h->stream>>>(l0.b.p, l0.b.len, seed, l0.start * l0.m);
     LAUNCH_CHECK();
+    h->dev_problem = true;
     if (l0.sharded) RET(op_halo(h, l0.b.p, l0.n, l0.m));
     l0.cur = 0;
     CK(cudaMemsetAsync(l0.x[0].p, 0, (size_t)l0.x[0].len * 8, h->stream));
@@ -1850,12 +1894,12 @@ int amg1d_dev_fill_rhs_random(amg1d_t* h, uint64_t seed) {
 }
 
 int amg1d_dev_vcycle(amg1d_t* h, int nPre, int nPost, double alpha, int with_residual_norm) {
-    RET(check_ready(h));
+    RET(check_dev_problem(h));
     return run_vcycle(h, nPre, nPost, alpha, with_residual_norm != 0);
 }
 
 int amg1d_dev_residual_norm(amg1d_t* h, double* res) {
-    RET(check_ready(h));
+    RET(check_dev_problem(h));
     if (!h->norm_valid) RET(op_resnorm(h, 0, 0));
     RET(read_scalars(h, 1));
     if (res) *res = h->h_scal[0];
@@ -1863,10 +1907,11 @@ int amg1d_dev_residual_norm(amg1d_t* h, double* res) {
 }
 
 int amg1d_dev_rhs_norm(amg1d_t* h, double* nb) {
-    RET(check_ready(h));
-    RET(op_norm(h, h->L[0].b.p, nullptr, h->L[0].b.len, 0));
-    RET(read_scalars(h, 1));
-    if (nb) *nb = h->h_scal[0];
+    RET(check_dev_problem(h));
+    // slot 2 (as amg1d_solve): slot 0 caches ||b - A x|| of a norm-fused V-cycle (norm_valid) and must survive
+    RET(op_norm(h, h->L[0].b.p, nullptr, h->L[0].b.len, 2));
+    RET(read_scalars(h, 3));
+    if (nb) *nb = h->h_scal[2];
     return AMG1D_OK;
 }
 
@@ -1964,6 +2009,7 @@ int amg1d_pcg(amg1d_t* h, double* x, const double* b, int maxiter, double tol, i
         RET(vec_alloc(h, h->cg_ap, l0.n, l0.m));
     }
     h->norm_valid = false;
+    h->dev_problem = false;                   // level 0's rhs buffer becomes the CG residual
     double* X = h->cg_x.p;
     double* P = h->cg_p.p;
     double* AP = h->cg_ap.p;
@@ -1982,6 +2028,16 @@ int amg1d_pcg(amg1d_t* h, double* x, const double* b, int maxiter, double tol, i
     }
     int it = 0, rc = AMG1D_OK;
     const int nbv = (int)std::max<int64_t>(1, std::min<int64_t>(AMG1D_RED_BLOCKS, (N + AMG1D_RED_THREADS - 1) / AMG1D_RED_THREADS));
+    // the initial residual is tested first: b = 0 or an x0 that already solves the system returns x0 with
+    // iters = 0 (r.z = p.Ap = 0 would otherwise make the first step 0 / 0)
+    RET(op_norm(h, R, nullptr, N, CG_RES));
+    RET(read_scalars(h, 3));
+    if (!std::isfinite(h->h_scal[CG_RES]) || !std::isfinite(h->h_scal[CG_NB]))
+        return fail(h, AMG1D_ERR_ARG, "amg1d_pcg: non-finite right-hand side or initial guess");
+    if (h->h_scal[CG_NB] == 0.0 || h->h_scal[CG_RES] <= tol * h->h_scal[CG_NB]) {
+        *iters = 0;
+        return to_host(h, 0, X, x);
+    }
     for (int i = 0; i < maxiter; ++i) {
         // z = M^-1 r: one V-cycle from a zero guess with rhs r (already in place); z = level-0 iterate
         if (l0.sharded) { rc = op_halo(h, R, l0.n, l0.m); if (rc) break; }
@@ -2010,6 +2066,9 @@ int amg1d_pcg(amg1d_t* h, double* x, const double* b, int maxiter, double tol, i
     }
     RET(rc);
     *iters = it;
+    if (it > 0 && !std::isfinite(res[it - 1]))                   // never AMG1D_OK with NaNs in the caller's x
+        return fail(h, AMG1D_ERR_ARG, "amg1d_pcg: breakdown at iteration %d (non-finite residual: the operator "
+                    "or the V-cycle preconditioner is not symmetric positive definite)", it);
     return to_host(h, 0, X, x);
 }
 
@@ -2043,6 +2102,7 @@ int amg1d_smoother_solve(amg1d_t* h, int level, double* x, const double* b, int 
     if (!x || !b || !res || !iters) return fail(h, AMG1D_ERR_ARG, "null argument");
     Level& lv = h->L[level];
     invalidate_graph(h);
+    if (level == 0) h->dev_problem = false;    // stages b and x in level 0's own vectors
     lv.cur = 0;
     RET(to_device(h, level, b, lv.b.p));
     RET(to_device(h, level, x, lv.x[0].p));
@@ -2091,8 +2151,11 @@ static int apply_common(amg1d_t* h, int level, double* out, const double* x, con
     invalidate_graph(h);
     double* xin = lv.x[1 - lv.cur].p;
     RET(to_device(h, level, x, xin));
-    double* bin = lv.b.p;  // clobbers the level rhs; the next vcycle / solve re-uploads it
-    if (mode) RET(to_device(h, level, b, bin));
+    double* bin = lv.b.p;  // clobbers the level rhs: amg1d_vcycle / amg1d_solve re-upload it, the device-resident
+    if (mode) {            // problem (level 0) is marked stale so that amg1d_dev_vcycle refuses to use it
+        if (level == 0) h->dev_problem = false;
+        RET(to_device(h, level, b, bin));
+    }
     RET(op_apply(h, level, bin, xin, h->scratch.p, mode));
     return to_host(h, level, h->scratch.p, out);
 }

@@ -299,9 +299,10 @@ __global__ void k_axpy(double* __restrict__ y, const double* __restrict__ x, int
 }
 
 // alpha = rz / pAp
-__global__ void k_cg_alpha(double* s) { s[CG_ALPHA] = s[CG_RZ] / s[CG_PAP]; }
+// (a zero denominator - b = 0, or an exact x0 - gives a zero step instead of 0/0 = NaN)
+__global__ void k_cg_alpha(double* s) { s[CG_ALPHA] = s[CG_PAP] != 0.0 ? s[CG_RZ] / s[CG_PAP] : 0.0; }
 // beta = rz_new / rz; rz = rz_new
-__global__ void k_cg_beta(double* s) { s[CG_BETA] = s[CG_RZ_NEW] / s[CG_RZ]; s[CG_RZ] = s[CG_RZ_NEW]; }
+__global__ void k_cg_beta(double* s) { s[CG_BETA] = s[CG_RZ] != 0.0 ? s[CG_RZ_NEW] / s[CG_RZ] : 0.0; s[CG_RZ] = s[CG_RZ_NEW]; }
 
 // x += alpha p;  r -= alpha Ap;  partial[b] = sum r[i]^2 over the block's slice
 __global__ void k_cg_update(double* __restrict__ x, double* __restrict__ r, const double* __restrict__ p,

@@ -212,7 +212,13 @@ int amg1d_coarse_solve(amg1d_t* h, double* x, const double* b);
  * more than 64 elements (a serial block-Thomas kernel below that). */
 int amg1d_direct_solve(amg1d_t* h, int level, double* x, const double* b);
 
-/* ---- device-resident path (no host copies; what bench.py times as `value`) -------------------- */
+/* ---- device-resident path (no host copies; what bench.py times as `value`) --------------------
+ * The problem (x, b on level 0) stays on the device between calls.  The per-level host operations above
+ * stage their operands in the levels' own vectors: amg1d_residual and amg1d_smoother_solve on level 0 and
+ * amg1d_pcg overwrite the resident right-hand side.  After one of them the amg1d_dev_vcycle /
+ * amg1d_dev_residual_norm / amg1d_dev_rhs_norm calls return AMG1D_ERR_STATE until amg1d_dev_set_problem
+ * (with b != NULL) or amg1d_dev_fill_rhs_random installs a problem again; amg1d_vcycle / amg1d_solve /
+ * amg1d_ldiv upload their own vectors and are not affected. */
 int amg1d_dev_set_problem(amg1d_t* h, const double* x0, const double* b); /* host -> device, x0 NULL = 0 */
 int amg1d_dev_fill_rhs_random(amg1d_t* h, uint64_t seed);          /* b[i] ~ U(-1,1) on the device, x = 0 */
 /* asynchronous on the stream; with_residual_norm = 1 also leaves ||A x - b||_2 of the new iterate on the
