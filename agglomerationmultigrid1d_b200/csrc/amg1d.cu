@@ -70,6 +70,8 @@ struct Level {
     // between amg1d_set_level_flux / amg1d_coarsen_level and amg1d_finalize (device-side set-up)
     double* flux[9] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
     bool smooth_tri = false;
+    bool dv_rec = false;   // the stored Dinv is the device's own Gauss-Jordan inverse of A_di (adopt_device_dinv):
+                           // the fused legs may recompute it in registers instead of streaming it
     double* smat_alloc = nullptr;
     double* smat = nullptr;
     MatDesc smd = {};
@@ -137,6 +139,7 @@ struct amg1d {
     int opt_pdl = 1;              // programmatic dependent launch between the fused kernels
     int opt_rows = 64;            // window of the row-per-thread fused legs (kernels_rows.cuh): 32, 64; 0 = off
     int opt_rows_rpt = 0;         // block rows per thread of those legs: 1, 2, 3; 0 = auto (rows_rpt() below)
+    int opt_dvrec = 1;            // block-Jacobi inverses recomputed inside the fused legs (see adopt_device_dinv)
     int opt_pattern = 0;          // 1: levels given as patterns read their operator from the pattern table;
                                   // 2: and the interior CTAs of f_down / f_up take it as constant-bank operands
     // single-CTA coarse tail (f_tail): levels [tail_start, n_levels)
@@ -627,7 +630,7 @@ int leg_down(amg1d* h, int l, int nPre, double alpha, bool zero0) {
         cudaError_t le = cudaSuccess;
         int fr = fused_down(lv.md, t.mc, make_map_closed(t), nPre, zero, lv.mat, make_pat(h, l), lv.b.p, lv.x[lv.cur].p,
                             lv.x[ob].p, t.P0, t.P1, lc.b.p, lv.n, lv.n + (lv.gr ? t.cover_extra : 0),
-                            alpha, make_slab(h, l), h->stream, h->opt_pdl != 0, &le);
+                            alpha, make_slab(h, l), h->stream, h->opt_pdl != 0, &le, lv.dv_rec && h->opt_dvrec);
         if (fr == FUSED_NA && h->opt_rows)      // large blocks: one thread per block row
             fr = rows_down(lv.md, t.mc, make_map_closed(t), nPre, zero, lv.mat, make_pat(h, l), lv.b.p, lv.x[lv.cur].p,
                            lv.x[ob].p, t.P0, t.P1, lc.b.p, lv.n, lv.n + (lv.gr ? t.cover_extra : 0), alpha,
@@ -677,7 +680,7 @@ int leg_up(amg1d* h, int l, int nPost, double alpha, bool fuse_norm, bool* norm_
         int fr = fused_up(lv.md, t.mc, make_map_closed(t), nPost, lv.mat, make_pat(h, l), lv.b.p, lv.x[lv.cur].p,
                           lv.x[1 - lv.cur].p, t.P0, t.P1, lc.x[lc.cur].p, lv.n, alpha,
                           fuse_norm ? h->partial : nullptr, h->partial_cap, &nb, make_slab(h, l),
-                          h->stream, h->opt_pdl != 0, &le);
+                          h->stream, h->opt_pdl != 0, &le, lv.dv_rec && h->opt_dvrec);
         if (fr == FUSED_NA && h->opt_rows)
             fr = rows_up(lv.md, t.mc, make_map_closed(t), nPost, lv.mat, make_pat(h, l), lv.b.p, lv.x[lv.cur].p,
                          lv.x[1 - lv.cur].p, t.P0, t.P1, lc.x[lc.cur].p, lv.n, alpha,
@@ -1124,6 +1127,42 @@ void free_flux(amg1d* h, Level& lv) {
         if (p) { cudaFree(p); p = nullptr; h->device_bytes -= lv.n * lv.m * lv.m * 8; }
 }
 
+// Option "recompute_dinv" (default on): replace the uploaded block-Jacobi inverses of a level by the device's own
+// pivoted Gauss-Jordan inverse of the stored diagonal blocks - provided the upload agrees with it to 1e-8, i.e.
+// really is inv(A_di) (src/smoother.jl:154-164) and not some other smoother block.  Afterwards every kernel that
+// reads the stored inverse and the fused legs that recompute it in registers (reg_invert; 16 of the 40 stored
+// doubles of a 4 x 4 DG element never leave HBM) produce the same bits.  Point-Jacobi levels keep their diagonal.
+int adopt_device_dinv(amg1d* h, int level) {
+    Level& lv = h->L[level];
+    lv.dv_rec = false;
+    if (!h->opt_dvrec || lv.diag || !lv.present || lv.m > AMG1D_DVREC_MAXM) return AMG1D_OK;
+    DevBuf sc;
+    CK(sc.alloc(2));
+    CK(cudaMemsetAsync(sc.p, 0, 16, h->stream));
+    unsigned long long* d_dev = reinterpret_cast<unsigned long long*>(sc.p);
+    int* d_flag = reinterpret_cast<int*>(sc.p + 1);
+    const int64_t e0 = -(int64_t)lv.gl, e1 = lv.n + lv.gr;
+    const unsigned grid = (unsigned)((e1 - e0 + 127) / 128);
+    k_dinv_recompute<<<grid, 128, 0, h->stream>>>(lv.mat, lv.md, e0, e1, AMG1D_TILE, 0, d_dev, d_flag);
+    double host[2] = {0.0, 0.0};
+    CK(cudaMemcpyAsync(host, sc.p, 16, cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    CK(cudaGetLastError());
+    int flag;
+    memcpy(&flag, &host[1], sizeof flag);
+    if (flag || !(host[0] <= 1e-8)) return AMG1D_OK;          // not the inverse of A_di: keep what was uploaded
+    k_dinv_recompute<<<grid, 128, 0, h->stream>>>(lv.mat, lv.md, e0, e1, AMG1D_TILE, 1, d_dev, d_flag);
+    if (lv.pat) {                                             // the pattern table's Dinv rows as well
+        const int ns = lv.pat_head + 1 + lv.pat_tail;
+        k_dinv_recompute<<<1, 128, 0, h->stream>>>(lv.pat, lv.md, 0, ns, 1, 1, d_dev, d_flag);
+        CK(cudaMemcpyAsync(lv.pat_host.data(), lv.pat, lv.pat_host.size() * 8, cudaMemcpyDeviceToHost, h->stream));
+    }
+    CK(cudaStreamSynchronize(h->stream));
+    CK(cudaGetLastError());
+    lv.dv_rec = true;
+    return AMG1D_OK;
+}
+
 // Installs a level whose operator blocks A_lo / A_di / A_up already sit on the device as element-block
 // arrays dA[0..2] (n blocks of m x m): smoother inverses (block-Jacobi inverses of the diagonal blocks,
 // src/smoother.jl:154-164, or the reciprocal diagonal, :92-98), structure detection, tile layout - the
@@ -1187,7 +1226,7 @@ int install_from_blocks(amg1d* h, int level, int64_t n, int m, double* const* dA
     CKU(cudaGetLastError());
 #undef CKU
     lv.set = true;
-    return AMG1D_OK;
+    return adopt_device_dinv(h, level);
 }
 
 // Device-side set-up of one level from its flux operators (device_setup.cuh): A = C - D M^-1 G, then
@@ -1391,7 +1430,7 @@ int amg1d_set_level(amg1d_t* h, int level, int64_t n_elem, int m, const double* 
         lv.h_up.assign(A_up, A_up + (size_t)n_elem * mm);
     }
     lv.set = true;
-    return AMG1D_OK;
+    return adopt_device_dinv(h, level);
 }
 
 int amg1d_set_level_pattern(amg1d_t* h, int level, int64_t n_elem, int m, int n_head, int n_tail,
@@ -1460,7 +1499,7 @@ int amg1d_set_level_pattern(amg1d_t* h, int level, int64_t n_elem, int m, int n_
         }
     }
     lv.set = true;
-    return AMG1D_OK;
+    return adopt_device_dinv(h, level);
 }
 
 int amg1d_set_level_smoother(amg1d_t* h, int level, const double* S_lo, const double* S_di,
@@ -2239,6 +2278,11 @@ int amg1d_set_option(amg1d_t* h, const char* key, int64_t value) {
         if (value < 0 || value > 2) return fail(h, AMG1D_ERR_ARG, "pattern_resident must be 0, 1 or 2");
         h->opt_pattern = (int)value;
     }
+    else if (!strcmp(key, "recompute_dinv")) {
+        // before the first level: whether uploaded inverses are replaced by the device's own (adopt_device_dinv);
+        // afterwards: whether the fused legs recompute them or stream the stored ones (same bits either way)
+        h->opt_dvrec = value != 0;
+    }
     else if (!strcmp(key, "rows_per_thread")) {
         if (value != 0 && !rows_rpt_ok((int)value)) return fail(h, AMG1D_ERR_ARG, "rows_per_thread must be 0 (auto), 1, 2 or 3");
         h->opt_rows_rpt = (int)value;
@@ -2283,6 +2327,13 @@ int64_t amg1d_get_info(amg1d_t* h, const char* key) {
     if (!strncmp(key, "pattern:", 8)) {                      // 1: level has a pattern table
         const int l = atoi(key + 8);
         return valid_level(h, l) && h->L[l].pat ? 1 : 0;
+    }
+    if (!strcmp(key, "recompute_dinv")) return h->opt_dvrec;
+    if (!strncmp(key, "dinv_recompute:", 15)) {     // 1: the fused legs of this level invert A_di in registers
+        const int l = atoi(key + 15);               //    instead of streaming the stored inverse
+        if (!valid_level(h, l) || !h->L[l].set || !h->L[l].dv_rec || !h->opt_dvrec) return 0;
+        if (h->opt_pattern && h->L[l].pat) return 0;
+        return (h->L[l].m <= 5 && l + 1 < h->n_levels && h->T[l].fusable) ? 1 : 0;
     }
     if (!strncmp(key, "structure:", 10)) {          // "structure:<level>" -> structure class (layout.cuh)
         const int l = atoi(key + 10);

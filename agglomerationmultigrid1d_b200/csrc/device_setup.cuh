@@ -218,3 +218,73 @@ __global__ void k_extract_dinv(const double* __restrict__ mat, MatDesc d, int64_
     const int q = (int)(t % dsz);
     dinv[t] = mat[(e >> 5) * (int64_t)d.K * AMG1D_TILE + (int64_t)(d.o_dv + q) * AMG1D_TILE + (e & 31)];
 }
+
+// ---- device-computed smoother inverses ("recompute_dinv") -------------------------------------------------
+// The block-Jacobi inverse of an element is a function of its diagonal block A_di, which the fused legs hold in
+// registers anyway: they can invert it in-kernel instead of streaming 16 of the 40 stored doubles of a 4 x 4
+// DG element from HBM (kernels_fused.cuh: reg_invert).  For the fused legs and every kernel that READS the
+// stored inverse (generic tier, streaming kernels, single-CTA tail, pattern tables) to stay bit-identical, the
+// stored inverse must be THE SAME Gauss-Jordan result.  This kernel recomputes it per element with the
+// arithmetic of reg_invert (kernels_fused.cuh: partial pivoting by a compare-and-swap chain, same operation order).
+//   mode 0: dev[0] = max over the elements of  max|Dinv_stored - inv(A_di)| / max|inv(A_di)|  (as an ordered
+//           int64 bit pattern, atomicMax), flag[0] |= 1 for a singular block - nothing is written;
+//   mode 1: overwrite the stored Dinv rows with the recomputed inverse.
+// Addressing: element e (e_first <= e < e_end, may be negative: left ghosts) lives at
+// base + (e >> 5) * K * tile_stride + (e & 31) with row stride tile_stride (element tiles: tile_stride = 32);
+// a pattern table tab[set][k] is addressed with tile_stride = 1 and "elements" = its rows: base + e * K.
+#define AMG1D_DVREC_MAXM 9
+__global__ void k_dinv_recompute(double* __restrict__ base, MatDesc d, int64_t e_first, int64_t e_end, int tile_stride,
+                                 int mode, unsigned long long* __restrict__ dev, int* __restrict__ flag) {
+    const int64_t e = e_first + (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= e_end) return;
+    const int m = d.m;
+    double* T = tile_stride == 1 ? base + e * (int64_t)d.K
+                                 : base + (e >> 5) * (int64_t)d.K * AMG1D_TILE + (e & 31);    // e >> 5 floors
+    const int rs = tile_stride == 1 ? 1 : AMG1D_TILE;
+    double A[AMG1D_DVREC_MAXM * AMG1D_DVREC_MAXM];
+    bool sw[AMG1D_DVREC_MAXM][AMG1D_DVREC_MAXM];
+    bool allzero = true;
+    for (int k = 0; k < m * m; ++k) { A[k] = T[(int64_t)(d.o_di + k) * rs]; allzero = allzero && A[k] == 0.0; }
+    if (allzero) return;                          // zero-filled slots outside the level (slab padding)
+    for (int c = 0; c < m; ++c) {
+        for (int r = c + 1; r < m; ++r) {         // compare-and-swap chain: the largest |a(r, c)|, r >= c, ends on the diagonal
+            const bool s = fabs(A[c * m + r]) > fabs(A[c * m + c]);
+            sw[c][r] = s;
+            for (int q = 0; q < m; ++q) {
+                const double x = A[q * m + c], y = A[q * m + r];
+                A[q * m + c] = s ? y : x;
+                A[q * m + r] = s ? x : y;
+            }
+        }
+        if (A[c * m + c] == 0.0) { atomicOr(flag, 1); return; }
+        const double dd = 1.0 / A[c * m + c];
+        A[c * m + c] = 1.0;
+        for (int q = 0; q < m; ++q) A[q * m + c] *= dd;
+        for (int r = 0; r < m; ++r) {
+            if (r == c) continue;
+            const double f = A[c * m + r];
+            A[c * m + r] = 0.0;
+            for (int q = 0; q < m; ++q) A[q * m + r] = fma(-f, A[q * m + c], A[q * m + r]);
+        }
+    }
+    for (int c = m - 1; c >= 0; --c)              // undo the row swaps as column swaps, in reverse order
+        for (int r2 = m - 1; r2 > c; --r2) {
+            const bool s = sw[c][r2];
+            for (int r = 0; r < m; ++r) {
+                const double x = A[c * m + r], y = A[r2 * m + r];
+                A[c * m + r] = s ? y : x;
+                A[r2 * m + r] = s ? x : y;
+            }
+        }
+    if (mode == 0) {
+        double mx = 0.0, df = 0.0;
+        for (int k = 0; k < m * m; ++k) {
+            mx = fmax(mx, fabs(A[k]));
+            df = fmax(df, fabs(A[k] - T[(int64_t)(d.o_dv + k) * rs]));
+        }
+        const double rel = mx > 0.0 ? df / mx : 0.0;
+        atomicMax(dev, (unsigned long long)__double_as_longlong(rel >= 0.0 ? rel : INFINITY));   // NaN -> inf
+    } else {
+        for (int k = 0; k < m * m; ++k) T[(int64_t)(d.o_dv + k) * rs] = A[k];
+    }
+}

@@ -419,6 +419,56 @@ __device__ __forceinline__ void cp_async_commit_wait_all() {
     asm volatile("cp.async.wait_group 0;" ::: "memory");
 }
 
+// In-register inverse of a dense M x M block (column-major: entry (r, c) at a[c * M + r]): Gauss-Jordan with
+// partial pivoting, statement for statement the arithmetic of k_dinv_recompute (device_setup.cuh) so that the
+// result equals the stored inverse bit for bit.  The pivot search is a chain of compare-and-swap steps (row r
+// is swapped up whenever |a(r, c)| exceeds the current pivot candidate, which leaves the largest entry on the
+// diagonal) recorded as booleans: every array index is a compile-time constant and the swaps are selects, so
+// the block never leaves the register file (an integer pivot index made the compiler index local memory).
+template <int M>
+__device__ __forceinline__ void reg_invert(double (&a)[M * M]) {
+    bool sw[M][M];
+#pragma unroll
+    for (int c = 0; c < M; ++c) {
+#pragma unroll
+        for (int r = c + 1; r < M; ++r) {
+            const bool s = fabs(a[c * M + r]) > fabs(a[c * M + c]);
+            sw[c][r] = s;
+#pragma unroll
+            for (int q = 0; q < M; ++q) {
+                const double x = a[q * M + c], y = a[q * M + r];
+                a[q * M + c] = s ? y : x;
+                a[q * M + r] = s ? x : y;
+            }
+        }
+        const double dd = 1.0 / a[c * M + c];
+        a[c * M + c] = 1.0;
+#pragma unroll
+        for (int q = 0; q < M; ++q) a[q * M + c] *= dd;
+#pragma unroll
+        for (int r = 0; r < M; ++r) {
+            if (r == c) continue;
+            const double f = a[c * M + r];
+            a[c * M + r] = 0.0;
+#pragma unroll
+            for (int q = 0; q < M; ++q) a[q * M + r] = fma(-f, a[q * M + c], a[q * M + r]);
+        }
+    }
+#pragma unroll
+    for (int c = M - 1; c >= 0; --c) {            // undo the row swaps as column swaps, in reverse order
+#pragma unroll
+        for (int r2 = M - 1; r2 > c; --r2) {
+            const bool s = sw[c][r2];
+#pragma unroll
+            for (int r = 0; r < M; ++r) {
+                const double x = a[c * M + r], y = a[r2 * M + r];
+                a[c * M + r] = s ? y : x;
+                a[r2 * M + r] = s ? x : y;
+            }
+        }
+    }
+}
+
 template <int M, int ST, class OP>
 __device__ __forceinline__ void reg_residual(const OP& A, int ilo, int iup,
                                              const double (&bb)[M], const double (&xl)[M],
@@ -454,8 +504,11 @@ __device__ __forceinline__ void exchange(Exchange<M, B>& ex, int buf, int ilo, i
 
 // A_lo / A_di / A_up go to registers; Dinv (used once per sweep) is copied global -> shared with
 // cp.async, i.e. without register staging, into this thread's own column ds[k][thread].
+// rec (block smoothers, streamed tiles only): Dinv is NOT loaded - the caller inverts A.di in registers
+// (reg_invert) and puts the result into the same shared-memory column.
 template <int M, int B, int ST, bool DIAG, int STRIDE>
-__device__ __forceinline__ void load_blocks_from(const double* __restrict__ T, RegOp<M, ST>& A, double (*ds)[B]) {
+__device__ __forceinline__ void load_blocks_from(const double* __restrict__ T, RegOp<M, ST>& A, double (*ds)[B],
+                                                 bool rec = false) {
     using S = OpShape<M, ST>;
     constexpr int ND = DIAG ? M : M * M;
     const int t = threadIdx.x;
@@ -463,8 +516,10 @@ __device__ __forceinline__ void load_blocks_from(const double* __restrict__ T, R
 #pragma unroll                     // (cp.async with one source address per warp was measured far slower)
         for (int k = 0; k < ND; ++k) ds[k][t] = T[S::O_DV + k];
     } else {
+        if (!rec) {
 #pragma unroll
-        for (int k = 0; k < ND; ++k) cp_async8(&ds[k][t], T + (S::O_DV + k) * STRIDE);
+            for (int k = 0; k < ND; ++k) cp_async8(&ds[k][t], T + (S::O_DV + k) * STRIDE);
+        }
     }
 #pragma unroll
     for (int k = 0; k < S::NO; ++k) A.lo[k] = T[k * STRIDE];
@@ -478,7 +533,8 @@ __device__ __forceinline__ void load_blocks_from(const double* __restrict__ T, R
 // pattern table of a translation-invariant level, PatOp)
 template <int M, int B, int ST, bool DIAG>
 __device__ __forceinline__ void load_blocks(const double* __restrict__ mat, const PatOp& po, int64_t e,
-                                            int64_t eg, bool active, RegOp<M, ST>& A, double (*ds)[B]) {
+                                            int64_t eg, bool active, RegOp<M, ST>& A, double (*ds)[B],
+                                            bool rec = false) {
     using S = OpShape<M, ST>;
     constexpr int ND = DIAG ? M : M * M;
     constexpr int K = S::O_DV + ND;
@@ -491,7 +547,18 @@ __device__ __forceinline__ void load_blocks(const double* __restrict__ mat, cons
                                                            : po.n_head);
             load_blocks_from<M, B, ST, DIAG, 1>(po.tab + s * K, A, ds);
         } else {
-            load_blocks_from<M, B, ST, DIAG, AMG1D_TILE>(mat + (e >> 5) * (int64_t)(K * AMG1D_TILE) + (e & 31), A, ds);
+            load_blocks_from<M, B, ST, DIAG, AMG1D_TILE>(mat + (e >> 5) * (int64_t)(K * AMG1D_TILE) + (e & 31), A, ds,
+                                                         rec);
+            if constexpr (!DIAG) {
+                if (rec) {                 // Dinv = inv(A_di), in registers, into this thread's shared column
+                    double w[M * M];
+#pragma unroll
+                    for (int k = 0; k < M * M; ++k) w[k] = A.di[k];
+                    reg_invert<M>(w);
+#pragma unroll
+                    for (int k = 0; k < M * M; ++k) ds[k][t] = w[k];
+                }
+            }
         }
     } else {
 #pragma unroll
@@ -629,7 +696,7 @@ __global__ void FUSED_BOUNDS(M)
 f_down(const double* __restrict__ mat, PatOp po, int ilo, int iup, const double* __restrict__ b,
        const double* __restrict__ xin, double* __restrict__ xout, const double* __restrict__ P0,
        const double* __restrict__ P1, TransferMap tm, double* __restrict__ rc, int64_t n, double alpha,
-       int nsweep, int zero_guess, WinIdx wi, Slab sl) {
+       int nsweep, int zero_guess, WinIdx wi, Slab sl, int rec) {
     __shared__ Exchange<M, B> ex;
     __shared__ double rs[M][B + 8];
     __shared__ double ds[DIAG ? M : M * M][B];
@@ -639,7 +706,7 @@ f_down(const double* __restrict__ mat, PatOp po, int ilo, int iup, const double*
     const bool active = e >= -(int64_t)sl.gl && e < n + sl.gr;
     exch_init<M, B>(ex);
     RegOp<M, ST> A;
-    load_blocks<M, B, ST, DIAG>(mat, po, e, e + sl.e_off, active, A, ds);         // operator: independent of earlier kernels
+    load_blocks<M, B, ST, DIAG>(mat, po, e, e + sl.e_off, active, A, ds, rec != 0);   // operator: independent of earlier kernels
     down_leg<M, MC, B, ST, DIAG>(A, &ds[0][t], ex, rs, e, active, ilo, iup, b, xin, xout, P0, P1, tm, rc, n, alpha,
                                  nsweep, zero_guess, wi, sl);
 }
@@ -756,7 +823,7 @@ __global__ void FUSED_BOUNDS(M)
 f_up(const double* __restrict__ mat, PatOp po, int ilo, int iup, const double* __restrict__ b,
      const double* __restrict__ xin, double* __restrict__ xout, const double* __restrict__ P0,
      const double* __restrict__ P1, TransferMap tm, const double* __restrict__ xcoarse, int64_t n,
-     double alpha, int nsweep, WinIdx wi, double* __restrict__ partial, Slab sl) {
+     double alpha, int nsweep, WinIdx wi, double* __restrict__ partial, Slab sl, int rec) {
     __shared__ Exchange<M, B> ex;
     __shared__ double ds[DIAG ? M : M * M][B];
     pdl_launch_dependents();
@@ -765,7 +832,7 @@ f_up(const double* __restrict__ mat, PatOp po, int ilo, int iup, const double* _
     const bool active = e >= -(int64_t)sl.gl && e < n + sl.gr;
     exch_init<M, B>(ex);
     RegOp<M, ST> A;
-    load_blocks<M, B, ST, DIAG>(mat, po, e, e + sl.e_off, active, A, ds);         // operator: independent of earlier kernels
+    load_blocks<M, B, ST, DIAG>(mat, po, e, e + sl.e_off, active, A, ds, rec != 0);   // operator: independent of earlier kernels
     up_leg<M, MC, B, ST, DIAG>(A, &ds[0][t], ex, e, active, ilo, iup, b, xin, xout, P0, P1, tm, xcoarse, n, alpha,
                                nsweep, wi, partial, sl);
 }
@@ -1174,7 +1241,7 @@ enum { FUSED_NA = 0, FUSED_OK = 1, FUSED_ERR = -1 };
 inline int fused_down(const MatDesc& d, int mc, const TransferMap& tm, int nsweep, bool zero,
                        const double* mat, const PatOp& po, const double* b, const double* xin, double* xout,
                        const double* P0, const double* P1, double* rc, int64_t n, int64_t n_cover,
-                       double alpha, const Slab& sl, cudaStream_t st, bool pdl, cudaError_t* err) {
+                       double alpha, const Slab& sl, cudaStream_t st, bool pdl, cudaError_t* err, bool rec = false) {
     const WinIdx w = fused_window(nsweep, tm, P1 != nullptr || tm.shift != 0 || tm.base != 0, sl);
     if (w.out < tm.ratio || w.out < FUSED_B / 2 || !fast_tier_ok(d)) return FUSED_NA;
     const unsigned grid = (unsigned)((n_cover + w.out - 1) / w.out);
@@ -1188,7 +1255,8 @@ inline int fused_down(const MatDesc& d, int mc, const TransferMap& tm, int nswee
                                 d.iup, b, xin, xout, P0, P1, tm, rc, n, alpha, nsweep, zero ? 1 : 0, w, sl); \
         } else                                                                                           \
         *err = launch_fused(f_down<MM, MCC, FUSED_B, SS, DG>, grid, FUSED_B, 0, st, pdl, mat, po, d.ilo, d.iup, \
-                            b, xin, xout, P0, P1, tm, rc, n, alpha, nsweep, zero ? 1 : 0, w, sl);        \
+                            b, xin, xout, P0, P1, tm, rc, n, alpha, nsweep, zero ? 1 : 0, w, sl,         \
+                            (rec && !po.tab && !DG) ? 1 : 0);                                            \
         return *err == cudaSuccess ? FUSED_OK : FUSED_ERR;
         FUSED_COMBOS(X)
 #undef X
@@ -1200,7 +1268,7 @@ inline int fused_up(const MatDesc& d, int mc, const TransferMap& tm, int nsweep,
                      const PatOp& po, const double* b, const double* xin, double* xout, const double* P0,
                      const double* P1, const double* xcoarse, int64_t n, double alpha, double* partial,
                      int64_t partial_cap, int* nblocks, const Slab& sl, cudaStream_t st, bool pdl,
-                     cudaError_t* err) {
+                     cudaError_t* err, bool rec = false) {
     const WinIdx w = fused_window(nsweep, tm, false, sl);
     if (w.out < tm.ratio || w.out < FUSED_B / 2 || !fast_tier_ok(d)) return FUSED_NA;
     const int64_t grid = (n + w.out - 1) / w.out;
@@ -1216,7 +1284,8 @@ inline int fused_up(const MatDesc& d, int mc, const TransferMap& tm, int nsweep,
                                 d.ilo, d.iup, b, xin, xout, P0, P1, tm, xcoarse, n, alpha, nsweep, w, partial, sl); \
         } else                                                                                           \
         *err = launch_fused(f_up<MM, MCC, FUSED_B, SS, DG>, (unsigned)grid, FUSED_B, 0, st, pdl, mat, po,    \
-                            d.ilo, d.iup, b, xin, xout, P0, P1, tm, xcoarse, n, alpha, nsweep, w, partial, sl); \
+                            d.ilo, d.iup, b, xin, xout, P0, P1, tm, xcoarse, n, alpha, nsweep, w, partial, sl, \
+                            (rec && !po.tab && !DG) ? 1 : 0);                                            \
         return *err == cudaSuccess ? FUSED_OK : FUSED_ERR;
         FUSED_COMBOS(X)
 #undef X

@@ -345,11 +345,14 @@ class UniformDgHierarchy:
         return 4 * self.levels[l].m ** 2
 
     def streamed_operator_doubles(self, l):
-        """Operator doubles per element a fused leg reads from HBM: tile_rows(l), or 0 when the level's
-        pattern table is used (option pattern_resident: the block sets come from a few KB in L1)."""
+        """Operator doubles per element a fused leg reads from HBM: tile_rows(l) - minus the m^2 doubles of the
+        block-Jacobi inverse where the leg recomputes it (option recompute_dinv) - or 0 when the level's pattern
+        table is used (option pattern_resident: the block sets come from a few KB in L1)."""
         dev = getattr(self, "device", None)
         if dev is not None and dev.info("pattern_resident") and dev.info(f"pattern:{l}"):
             return 0
+        if dev is not None and dev.info(f"dinv_recompute:{l}") == 1:      # the fused legs invert A_di in registers:
+            return self.tile_rows(l) - self.levels[l].m ** 2            # the stored inverse is not read
         return self.tile_rows(l)
 
     def bytes_per_leg_fused(self, l, down):
@@ -629,11 +632,14 @@ class UniformCgHierarchy:
         return 3 * lv.m ** 2 + (lv.m if getattr(lv, "is_cg", False) else lv.m ** 2)
 
     def streamed_operator_doubles(self, l):
-        """Operator doubles per element a fused leg reads from HBM: tile_rows(l), or 0 when the level's
-        pattern table is used (option pattern_resident: the block sets come from a few KB in L1)."""
+        """Operator doubles per element a fused leg reads from HBM: tile_rows(l) - minus the m^2 doubles of the
+        block-Jacobi inverse where the leg recomputes it (option recompute_dinv) - or 0 when the level's pattern
+        table is used (option pattern_resident: the block sets come from a few KB in L1)."""
         dev = getattr(self, "device", None)
         if dev is not None and dev.info("pattern_resident") and dev.info(f"pattern:{l}"):
             return 0
+        if dev is not None and dev.info(f"dinv_recompute:{l}") == 1:      # the fused legs invert A_di in registers:
+            return self.tile_rows(l) - self.levels[l].m ** 2            # the stored inverse is not read
         return self.tile_rows(l)
 
     def bytes_per_leg_fused(self, l, down):

@@ -242,6 +242,11 @@ void* amg1d_dev_ptr(amg1d_t* h, int level, int which);             /* raw device
  * set as a kernel parameter and use it as constant operands; default 0; bit-identical results in all modes),
  * "rows_window" (elements per CTA of the row-per-thread legs for 5..9-row blocks: 32, 64; 0 = off;
  * default 64), "rows_per_thread" (block rows per thread of those legs: 1, 2, 3; 0 = auto, default);
+ * "recompute_dinv" (default 1.  Set before the first level: the block-Jacobi inverses of a level - when the
+ * uploaded Dinv agrees with inv(A_di) to 1e-8 - are replaced by the device's own pivoted Gauss-Jordan inverse
+ * of the stored diagonal blocks, so that the fused legs can invert A_di in registers instead of streaming the
+ * stored inverse from HBM while every other kernel, which reads the stored inverse, produces the same bits.
+ * Later: 0 makes the fused legs stream the stored inverse again - same results, more bytes);
  * before the first level is
  * set: "compress" (1 = store only the structurally non-zero column / row of the off-diagonal blocks
  * where every element of the level has that structure, default 1), "shard_min" (elements per rank
@@ -252,7 +257,9 @@ int64_t amg1d_get_info(amg1d_t* h, const char* key); /* "kernel_launches", "laun
                                                         "device_bytes", "n_levels", "local_elements",
                                                         "local_dofs", "gather_level", "tail_start",
                                                         "ghost_depth", "structure:<level>",
-                                                        "tile_rows:<level>", "pattern:<level>" (1 = the
+                                                        "tile_rows:<level>", "dinv_recompute:<level>" (1 = the fused
+                                                        legs of the level invert A_di in registers),
+                                                        "pattern:<level>" (1 = the
                                                         level has a pattern table), the option keys,
                                                         ... (-1: unknown key) */
 

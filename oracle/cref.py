@@ -29,6 +29,11 @@ def load():
     lib.ref_destroy.argtypes = [C.c_void_p]
     lib.ref_set_threads.argtypes = [C.c_int]
     lib.ref_set_threads.restype = C.c_int
+    lib.ref_set_level_pattern.argtypes = [C.c_void_p, C.c_int, C.c_int64, C.c_int, C.c_int, C.c_int, _pd, _pd, _pd,
+                                          C.c_int, C.c_int]
+    lib.ref_set_transfer_pattern.argtypes = [C.c_void_p, C.c_int, C.c_int64, C.c_int64, C.c_int, C.c_int, C.c_int,
+                                             C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _pd, _pd, C.c_int]
+    lib.ref_set_coarse_from_pattern.argtypes = [C.c_void_p]
     return lib
 
 
@@ -91,6 +96,87 @@ class CRefHierarchy:
         if self.h:
             self.lib.ref_destroy(self.h)
             self.h = None
+
+
+class CRefPattern(CRefHierarchy):
+    """The same C restatement fed with the block-pattern form of a uniform-mesh hierarchy (vcycle_ref.c header):
+    every level as its distinct block rows, every transfer as its periodic blocks - the very arrays that are
+    uploaded to the GPU - so that the oracle can run at BASELINE's own sizes (2^20 .. 2^26 elements) where
+    global CSR matrices would take tens of GB.  Vectors of CG levels are in the group order of the upload
+    ([vertex k, interior nodes of element k], padded closing group); the row walks still follow the
+    reference's vertex-first DOF numbering (flag vertex_first).
+
+    levels:    list of dict(n, m, n_head, n_tail, lo, di, up, point_jacobi, vertex_first); lo / di / up are
+               (n_head + 1 + n_tail, m, m) arrays in (set, i, j) order
+    transfers: list of dict(ratio, shift, base, period, n_head, n_tail, P0, P1) - parent(e) = (e + shift) //
+               ratio + base, P0 / P1 of shape (n_head + period + n_tail, m_fine, m_coarse), P1 may be None"""
+
+    def __init__(self, levels, transfers):
+        self.lib = load()
+        self.keep = []
+        nL = len(levels)
+        assert len(transfers) == nL - 1
+        self.h = self.lib.ref_create(nL)
+        self.n_dof = [int(lv["n"]) * int(lv["m"]) for lv in levels]
+        for l, lv in enumerate(levels):
+            arrs = [np.ascontiguousarray(lv[k], dtype=np.float64) for k in ("lo", "di", "up")]
+            ns = lv["n_head"] + 1 + lv["n_tail"]
+            assert all(a.shape == (ns, lv["m"], lv["m"]) for a in arrs), (l, [a.shape for a in arrs], ns)
+            self.keep += arrs
+            rc = self.lib.ref_set_level_pattern(self.h, l, int(lv["n"]), int(lv["m"]), int(lv["n_head"]),
+                                                int(lv["n_tail"]), _p(arrs[0], _pd), _p(arrs[1], _pd),
+                                                _p(arrs[2], _pd), int(bool(lv["point_jacobi"])),
+                                                int(bool(lv["vertex_first"])))
+            assert rc == 0, (l, rc)
+        for l, t in enumerate(transfers):
+            P0 = np.ascontiguousarray(t["P0"], dtype=np.float64)
+            P1 = None if t.get("P1") is None else np.ascontiguousarray(t["P1"], dtype=np.float64)
+            nb = t["n_head"] + t["period"] + t["n_tail"]
+            mf, mc = levels[l]["m"], levels[l + 1]["m"]
+            assert P0.shape == (nb, mf, mc) and (P1 is None or P1.shape == P0.shape), (l, P0.shape, nb, mf, mc)
+            self.keep += [P0, P1]
+            rc = self.lib.ref_set_transfer_pattern(
+                self.h, l, int(levels[l]["n"]), int(levels[l + 1]["n"]), mf, mc, int(t["ratio"]), int(t["shift"]),
+                int(t["base"]), int(t["period"]), int(t["n_head"]), int(t["n_tail"]), _p(P0, _pd),
+                None if P1 is None else _p(P1, _pd), int(bool(levels[l + 1]["vertex_first"])))
+            assert rc == 0, (l, rc)
+        assert self.lib.ref_set_coarse_from_pattern(self.h) == 0
+
+    def multigrid(self, x0, b, maxiter, tol, nPre=3, nPost=3, alpha=2.0 / 3.0):
+        """src/solvers.jl:116-139 without the error history: (x, iter, res)."""
+        x = np.array(x0, dtype=np.float64, copy=True)
+        b = np.ascontiguousarray(b, dtype=np.float64)
+        nb = float(np.linalg.norm(b))
+        res = []
+        for _ in range(maxiter):
+            self.lib.ref_vcycle(self.h, _p(x, _pd), _p(b, _pd), nPre, nPost, alpha)
+            res.append(self.lib.ref_residual_norm(self.h, _p(x, _pd), _p(b, _pd)))
+            if res[-1] < tol * nb:
+                break
+        return x, len(res), np.array(res)
+
+
+def pattern_arrays(U):
+    """(levels, transfers) for CRefPattern from a uniform-mesh hierarchy object of the product's host package
+    (duck-typed: ``levels`` with ``n, m, explicit, ops['A']`` and ``is_cg``; ``transfers`` as (P, ratio);
+    ``cg_transfers`` as dicts) - the arrays its ``upload`` hands to amg1d_set_level_pattern /
+    amg1d_set_transfer_pattern, unchanged."""
+    levels = []
+    for lv in U.levels:
+        A = lv.ops["A"]
+        cg = bool(getattr(lv, "is_cg", False))
+        if lv.explicit:
+            lo, di, up = (np.concatenate([a, a[-1:]]) for a in A)    # every block row explicit (+ an unused "interior" one)
+            levels.append(dict(n=lv.n, m=lv.m, n_head=lv.n, n_tail=0, lo=lo, di=di, up=up, point_jacobi=cg,
+                               vertex_first=cg))
+        else:
+            nb = (A.di.shape[0] - 1) // 2
+            levels.append(dict(n=lv.n, m=lv.m, n_head=nb, n_tail=nb, lo=A.lo, di=A.di, up=A.up, point_jacobi=cg,
+                               vertex_first=cg))
+    transfers = [dict(t) for t in getattr(U, "cg_transfers", [])]
+    for P, ratio in U.transfers:
+        transfers.append(dict(ratio=ratio, shift=0, base=0, period=P.shape[0], n_head=0, n_tail=0, P0=P, P1=None))
+    return levels, transfers
 
 
 def _diag_blocks(A, inds):

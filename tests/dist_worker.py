@@ -22,14 +22,26 @@ from agglomerationmultigrid1d_b200 import _capi as capi, uniform   # noqa: E402
 def main():
     out = sys.argv[1]
     log2n = int(sys.argv[2]) if len(sys.argv) > 2 else 15
-    kind = sys.argv[3] if len(sys.argv) > 3 else "dg"
+    kinds = (sys.argv[3] if len(sys.argv) > 3 else "dg").split(",")
+    dist.init_process_group("gloo")
+    rank = dist.get_rank()
+    torch.cuda.set_device(rank)
+    reports = {}
+    for kind in kinds:                      # one rendezvous, one NCCL communicator per kind
+        reports[kind] = run_kind(kind, log2n)
+        dist.barrier()
+    if rank == 0:
+        json.dump(reports, open(out, "w"))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def run_kind(kind, log2n):
     # *_pat / *_pat2: the sharded handle reads its operators from the pattern tables (option pattern_resident
     # = 1) / takes the interior block set as constant-bank kernel parameters (= 2)
     pattern_resident = 2 if kind.endswith("_pat2") else 1 if kind.endswith("_pat") else 0
     kind = kind[:-5] if pattern_resident == 2 else kind[:-4] if pattern_resident else kind
-    dist.init_process_group("gloo")
     rank, world = dist.get_rank(), dist.get_world_size()
-    torch.cuda.set_device(rank)
     lib = capi.load()
     ids = [None]
     if rank == 0:
@@ -100,11 +112,9 @@ def main():
             if not np.array_equal(got, ref):
                 ok = False; msgs.append(f"{key} x max diff {np.abs(got - ref).max():.3e}")
         report.update(ok=ok, msgs=msgs, iters=int(it1), world=world, res_last=float(res1[-1]))
-        json.dump(report, open(out, "w"))
         d1.close()
     dev.close()
-    dist.barrier()
-    dist.destroy_process_group()
+    return report
 
 
 if __name__ == "__main__":
