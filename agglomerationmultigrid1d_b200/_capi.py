@@ -45,6 +45,8 @@ PROTOTYPES = {
     "amg1d_solve": (C.c_int, [_h, _pd, _pd, C.c_int, C.c_double, C.c_int, C.c_int, C.c_double,
                               C.POINTER(C.c_int), _pd, _pd, _pd]),
     "amg1d_ldiv": (C.c_int, [_h, _pd, _pd, C.c_int, C.c_int, C.c_double]),
+    "amg1d_vcycle_batch": (C.c_int, [_h, C.c_int, C.POINTER(_pd), C.POINTER(_pd), C.c_int, C.c_int, C.c_int,
+                                     C.c_double]),
     "amg1d_pcg": (C.c_int, [_h, _pd, _pd, C.c_int, C.c_double, C.c_int, C.c_int, C.c_double,
                             C.POINTER(C.c_int), _pd]),
     "amg1d_apply_smoother": (C.c_int, [_h, C.c_int, _pd, _pd, C.c_int64, C.c_double]),
@@ -58,6 +60,11 @@ PROTOTYPES = {
     "amg1d_direct_solve": (C.c_int, [_h, C.c_int, _pd, _pd]),
     "amg1d_dev_set_problem": (C.c_int, [_h, _pd, _pd]),
     "amg1d_dev_fill_rhs_random": (C.c_int, [_h, C.c_uint64]),
+    "amg1d_dev_assemble_rhs": (C.c_int, [_h, C.c_int, C.c_int, _pd, _pd, C.c_int, C.c_int, _pd, C.c_double,
+                                         C.c_double, _pd, C.c_int, _pi64, _pd, C.POINTER(C.c_int)]),
+    "amg1d_dev_get_rhs": (C.c_int, [_h, _pd]),
+    "amg1d_dev_solve": (C.c_int, [_h, C.c_int, C.c_double, C.c_int, C.c_int, C.c_double, C.POINTER(C.c_int), _pd]),
+    "amg1d_dev_pcg": (C.c_int, [_h, C.c_int, C.c_double, C.c_int, C.c_int, C.c_double, C.POINTER(C.c_int), _pd]),
     "amg1d_dev_vcycle": (C.c_int, [_h, C.c_int, C.c_int, C.c_double, C.c_int]),
     "amg1d_dev_residual_norm": (C.c_int, [_h, _pd]),
     "amg1d_dev_rhs_norm": (C.c_int, [_h, _pd]),

@@ -24,6 +24,7 @@
 #include "kernels_rows.cuh"
 #include "direct_bcr.cuh"
 #include "device_setup.cuh"
+#include "halo_p2p.cuh"
 
 #define AMG1D_VERSION 100
 #define PAD_FRONT 64  // doubles in front of element 0 (ghost elements live at the end of them)
@@ -37,6 +38,7 @@ struct DVec {
     double* raw = nullptr;
     double* p = nullptr;  // element 0
     int64_t len = 0;      // n * m
+    bool in_arena = false;   // carved out of the handle's peer-mapped arena (halo_p2p.cuh): not freed on its own
 };
 
 // Scratch device allocation that is released on every exit path of an upload / download routine.
@@ -70,8 +72,9 @@ struct Level {
     // between amg1d_set_level_flux / amg1d_coarsen_level and amg1d_finalize (device-side set-up)
     double* flux[9] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
     bool smooth_tri = false;
-    bool dv_rec = false;   // the stored Dinv is the device's own Gauss-Jordan inverse of A_di (adopt_device_dinv):
-                           // the fused legs may recompute it in registers instead of streaming it
+    int dv_rec = 0;        // != 0: the stored Dinv is the device's own Gauss-Jordan inverse of A_di (adopt_device_dinv),
+                           // the fused legs may recompute it in registers instead of streaming it; 2: no element
+                           // of the level ever pivots (the legs skip the compare-and-swap chain)
     double* smat_alloc = nullptr;
     double* smat = nullptr;
     MatDesc smd = {};
@@ -139,7 +142,8 @@ struct amg1d {
     int opt_pdl = 1;              // programmatic dependent launch between the fused kernels
     int opt_rows = 64;            // window of the row-per-thread fused legs (kernels_rows.cuh): 32, 64; 0 = off
     int opt_rows_rpt = 0;         // block rows per thread of those legs: 1, 2, 3; 0 = auto (rows_rpt() below)
-    int opt_dvrec = 1;            // block-Jacobi inverses recomputed inside the fused legs (see adopt_device_dinv)
+    int opt_dvrec = 4;            // block-Jacobi inverses recomputed inside the fused legs of levels with blocks of at
+                                  // least this size and at most 4 x 4 (0 = never; see adopt_device_dinv, leg_rec)
     int opt_pattern = 0;          // 1: levels given as patterns read their operator from the pattern table;
                                   // 2: and the interior CTAs of f_down / f_up take it as constant-bank operands
     // single-CTA coarse tail (f_tail): levels [tail_start, n_levels)
@@ -177,6 +181,31 @@ struct amg1d {
 #ifdef AMG1D_WITH_NCCL
     ncclComm_t comm = nullptr;
 #endif
+    // amg1d_vcycle_batch: copy-in / copy-out streams, double-buffered device staging of level-0 vectors, events
+    struct Pipe {
+        cudaStream_t s_in = nullptr, s_out = nullptr;
+        double* st_b[2] = {nullptr, nullptr};
+        double* st_x[2] = {nullptr, nullptr};
+        double* st_o[2] = {nullptr, nullptr};
+        cudaEvent_t ev_in[2] = {nullptr, nullptr}, ev_used[2] = {nullptr, nullptr}, ev_done[2] = {nullptr, nullptr},
+                    ev_out[2] = {nullptr, nullptr};
+        int64_t len = 0;
+    } pipe;
+    // peer-memory halo exchange (halo_p2p.cuh): the vectors of the sharded levels and the receive counters live
+    // in one arena that both slab neighbours map with CUDA IPC
+    int opt_p2p = 1;
+    struct P2P {
+        bool on = false;
+        char* arena = nullptr;
+        int64_t bytes = 0, used = 0;
+        char* peer[2] = {nullptr, nullptr};          // the arenas of rank - 1 / rank + 1, mapped here
+        int n_ch = 0;                                // channels: 2 per sharded level
+        unsigned long long* flags = nullptr;         // [side][channel] receive counters, at the start of the arena
+        unsigned long long* epoch = nullptr;         // V-cycles enqueued so far (device)
+        int* err = nullptr;                          // device: a spin timed out
+        struct Nb { int64_t off[3] = {0, 0, 0}; int64_t n = 0; };   // byte offsets of x[0].p, x[1].p, b.p; owned n
+        std::vector<Nb> nb[2];                       // per level, for the left / right neighbour
+    } p2p;
 };
 
 namespace {
@@ -222,8 +251,22 @@ int vec_alloc(amg1d* h, DVec& v, int64_t n, int m) {
 }
 
 void vec_free(DVec& v) {
-    if (v.raw) cudaFree(v.raw);
+    if (v.raw && !v.in_arena) cudaFree(v.raw);
     v.raw = v.p = nullptr;
+}
+
+inline int64_t arena_round(int64_t bytes) { return (bytes + 255) / 256 * 256; }
+
+// a vector of a sharded level: carved out of the peer-mapped arena (zero-filled at allocation)
+int vec_from_arena(amg1d* h, DVec& v, int64_t n, int m) {
+    v.len = n * m;
+    const int64_t bytes = arena_round((PAD_FRONT + v.len + PAD_BACK) * 8);
+    if (h->p2p.used + bytes > h->p2p.bytes) return fail(h, AMG1D_ERR_STATE, "internal: halo arena overflow");
+    v.raw = reinterpret_cast<double*>(h->p2p.arena + h->p2p.used);
+    v.p = v.raw + PAD_FRONT;
+    v.in_arena = true;
+    h->p2p.used += bytes;
+    return AMG1D_OK;
 }
 
 inline dim3 gblock(int m) {
@@ -281,6 +324,7 @@ struct NcclApi {
     decltype(&ncclSend) Send = nullptr;
     decltype(&ncclRecv) Recv = nullptr;
     decltype(&ncclAllReduce) AllReduce = nullptr;
+    decltype(&ncclAllGather) AllGather = nullptr;
     decltype(&ncclGroupStart) GroupStart = nullptr;
     decltype(&ncclGroupEnd) GroupEnd = nullptr;
     decltype(&ncclGetErrorString) GetErrorString = nullptr;
@@ -299,7 +343,7 @@ const char* load_nccl() {
     if (!g_nccl.field) return "libnccl lacks " name;
     NSYM(GetUniqueId, "ncclGetUniqueId") NSYM(CommInitRank, "ncclCommInitRank")
     NSYM(CommDestroy, "ncclCommDestroy") NSYM(Send, "ncclSend") NSYM(Recv, "ncclRecv")
-    NSYM(AllReduce, "ncclAllReduce") NSYM(GroupStart, "ncclGroupStart") NSYM(GroupEnd, "ncclGroupEnd")
+    NSYM(AllReduce, "ncclAllReduce") NSYM(AllGather, "ncclAllGather") NSYM(GroupStart, "ncclGroupStart") NSYM(GroupEnd, "ncclGroupEnd")
     NSYM(GetErrorString, "ncclGetErrorString")
 #undef NSYM
     g_nccl.lib = lib;
@@ -315,6 +359,13 @@ const char* load_nccl() {
 int rows_rpt(const amg1d* h, int l) {
     if (h->opt_rows_rpt) return h->opt_rows_rpt;
     return h->opt_pattern && h->L[l].pat ? 3 : 1;
+}
+
+// 0: the fused legs of this level stream the stored inverse; 1 / 2: they invert A_di in registers (with / without pivots)
+int leg_rec(const amg1d* h, const Level& lv) {
+    // measured on B200 (profiles/r02c_sweep_dvrec_*.jsonl): 4 x 4 DG blocks gain 4-5 % per leg (T level 0: 4.63 / 4.31
+    // -> 4.43 / 4.12 ms); 5 x 5 blocks lose 10 % (the inversion's registers cost a resident CTA), 2 x 2 lose 5 %
+    return (h->opt_dvrec > 0 && lv.dv_rec && lv.m >= h->opt_dvrec && lv.m <= 4) ? lv.dv_rec : 0;
 }
 
 // pattern-resident operator of level l (option pattern_resident = 1 and the level was given as a pattern)
@@ -432,7 +483,170 @@ int op_allreduce_norm(amg1d* h, int slot) {
     LAUNCH_CHECK();
     return AMG1D_OK;
 }
+
+// ---- peer-memory halo exchange (halo_p2p.cuh) ------------------------------------------------------------
+#define AMG1D_P2P_MAXL 48
+struct P2PXchg {                 // what every rank publishes about its arena
+    cudaIpcMemHandle_t hnd;
+    int32_t ok, n_sharded;
+    int64_t off[AMG1D_P2P_MAXL][3];
+    int64_t n[AMG1D_P2P_MAXL];
+};
+
+// all-gather of a small host struct through NCCL (device staging)
+int nccl_allgather_host(amg1d* h, const void* mine, void* all, size_t bytes) {
+    DevBuf snd, rcv;
+    CK(snd.alloc((int64_t)(bytes + 7) / 8));
+    CK(rcv.alloc((int64_t)(bytes * h->nranks + 7) / 8));
+    CK(cudaMemcpyAsync(snd.p, mine, bytes, cudaMemcpyHostToDevice, h->stream));
+    NCK(g_nccl.AllGather(snd.p, rcv.p, bytes, ncclChar, h->comm, h->stream));
+    CK(cudaMemcpyAsync(all, rcv.p, bytes * h->nranks, cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    return AMG1D_OK;
+}
+
+// one arena for the receive counters and the vectors of every sharded level (amg1d_finalize, before the vectors)
+int p2p_alloc_arena(amg1d* h) {
+    amg1d::P2P& P = h->p2p;
+    int n_sh = 0;
+    int64_t total = 0;
+    for (int l = 0; l < h->n_levels; ++l) {
+        const Level& lv = h->L[l];
+        if (!lv.sharded) continue;
+        ++n_sh;
+        total += 3 * arena_round((PAD_FRONT + lv.n * lv.m + PAD_BACK) * 8);
+    }
+    if (n_sh == 0 || n_sh > AMG1D_P2P_MAXL) return AMG1D_OK;
+    P.n_ch = 2 * n_sh;
+    const int64_t flag_bytes = arena_round((int64_t)2 * P.n_ch * 8);
+    total += flag_bytes;
+    if (cudaMalloc((void**)&P.arena, (size_t)total) != cudaSuccess) { cudaGetLastError(); P.arena = nullptr; return AMG1D_OK; }
+    CK(cudaMemsetAsync(P.arena, 0, (size_t)total, h->stream));
+    h->device_bytes += total;
+    P.bytes = total;
+    P.used = flag_bytes;
+    P.flags = reinterpret_cast<unsigned long long*>(P.arena);
+    return AMG1D_OK;
+}
+
+void p2p_close(amg1d* h) {
+    amg1d::P2P& P = h->p2p;
+    for (int s = 0; s < 2; ++s)
+        if (P.peer[s]) { cudaIpcCloseMemHandle(P.peer[s]); P.peer[s] = nullptr; }
+    P.on = false;
+}
+
+// exchange the arena handles and map both neighbours' arenas; every rank takes the same decision
+int p2p_connect(amg1d* h) {
+    amg1d::P2P& P = h->p2p;
+    if (!P.arena) return AMG1D_OK;
+    P2PXchg mine;
+    memset(&mine, 0, sizeof mine);
+    mine.ok = cudaIpcGetMemHandle(&mine.hnd, P.arena) == cudaSuccess ? 1 : 0;
+    if (!mine.ok) cudaGetLastError();
+    for (int l = 0; l < h->n_levels && l < AMG1D_P2P_MAXL; ++l) {
+        const Level& lv = h->L[l];
+        if (!lv.sharded) continue;
+        ++mine.n_sharded;
+        const DVec* v[3] = {&lv.x[0], &lv.x[1], &lv.b};
+        for (int k = 0; k < 3; ++k) {
+            if (!v[k]->in_arena) mine.ok = 0;
+            mine.off[l][k] = reinterpret_cast<const char*>(v[k]->p) - P.arena;
+        }
+        mine.n[l] = lv.n;
+    }
+    std::vector<P2PXchg> all((size_t)h->nranks);
+    RET(nccl_allgather_host(h, &mine, all.data(), sizeof mine));
+    int good = 1;
+    for (const auto& x : all) good = good && x.ok && x.n_sharded == mine.n_sharded;
+    const int nbr[2] = {h->rank - 1, h->rank + 1};
+    if (good)
+        for (int s = 0; s < 2; ++s) {
+            if (nbr[s] < 0 || nbr[s] >= h->nranks) continue;
+            void* ptr = nullptr;
+            if (cudaIpcOpenMemHandle(&ptr, all[(size_t)nbr[s]].hnd, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) {
+                cudaGetLastError();
+                good = 0;
+                break;
+            }
+            P.peer[s] = static_cast<char*>(ptr);
+            P.nb[s].assign((size_t)h->n_levels, amg1d::P2P::Nb());
+            for (int l = 0; l < h->n_levels && l < AMG1D_P2P_MAXL; ++l) {
+                for (int k = 0; k < 3; ++k) P.nb[s][(size_t)l].off[k] = all[(size_t)nbr[s]].off[l][k];
+                P.nb[s][(size_t)l].n = all[(size_t)nbr[s]].n[l];
+            }
+        }
+    std::vector<int32_t> votes((size_t)h->nranks);
+    const int32_t vote = good;
+    RET(nccl_allgather_host(h, &vote, votes.data(), sizeof vote));
+    for (int32_t v : votes) good = good && v;
+    if (!good) { p2p_close(h); return AMG1D_OK; }            // the NCCL halo path keeps working on the same vectors
+    DevBuf tmp;
+    if (!P.epoch) {
+        RET(dev_alloc(h, (void**)&P.epoch, 64));
+        CK(cudaMemsetAsync(P.epoch, 0, 64, h->stream));
+        P.err = reinterpret_cast<int*>(P.epoch + 4);
+    }
+    P.on = true;
+    return AMG1D_OK;
+}
+
+unsigned long long* p2p_my_flag(amg1d* h, int side, int ch) {
+    const int nbr = side == 0 ? h->rank - 1 : h->rank + 1;
+    return (nbr < 0 || nbr >= h->nranks) ? nullptr : h->p2p.flags + side * h->p2p.n_ch + ch;
+}
+
+// push the edges of level l's vector `vec` (0 / 1: x buffers, 2: b) - and optionally of level l2's vector vec2 - on channel ch
+int op_p2p_push(amg1d* h, int ch, int l, int vec, int l2 = -1, int vec2 = 0) {
+    amg1d::P2P& P = h->p2p;
+    HaloPush a;
+    memset(&a, 0, sizeof a);
+    a.gd = h->ghost_depth;
+    const int lv_[2] = {l, l2}, vc_[2] = {vec, vec2};
+    for (int p = 0; p < 2; ++p) {
+        if (lv_[p] < 0) continue;
+        Level& lv = h->L[lv_[p]];
+        const DVec& v = vc_[p] == 2 ? lv.b : lv.x[vc_[p]];
+        a.src[p] = v.p;
+        a.n[p] = lv.n;
+        a.m[p] = lv.m;
+        if (P.peer[0]) {
+            const amg1d::P2P::Nb& nb = P.nb[0][(size_t)lv_[p]];
+            a.dst_left[p] = reinterpret_cast<double*>(P.peer[0] + nb.off[vc_[p]]) + nb.n * lv.m;
+        }
+        if (P.peer[1]) {
+            const amg1d::P2P::Nb& nb = P.nb[1][(size_t)lv_[p]];
+            a.dst_right[p] = reinterpret_cast<double*>(P.peer[1] + nb.off[vc_[p]]) - (int64_t)a.gd * lv.m;
+        }
+    }
+    // I am the RIGHT neighbour of rank - 1 (its counters of side 1) and the LEFT neighbour of rank + 1 (side 0)
+    if (P.peer[0]) a.flag_left = reinterpret_cast<unsigned long long*>(P.peer[0]) + 1 * P.n_ch + ch;
+    if (P.peer[1]) a.flag_right = reinterpret_cast<unsigned long long*>(P.peer[1]) + 0 * P.n_ch + ch;
+    k_halo_push<<<1, 128, 0, h->stream>>>(a);
+    h->launch_counter++;
+    LAUNCH_CHECK();
+    return AMG1D_OK;
+}
+
+int op_p2p_wait(amg1d* h, int ch) {
+    amg1d::P2P& P = h->p2p;
+    k_halo_wait<<<1, 1, 0, h->stream>>>(p2p_my_flag(h, 0, ch), p2p_my_flag(h, 1, ch), P.epoch, 0ULL, P.err);
+    h->launch_counter++;
+    LAUNCH_CHECK();
+    return AMG1D_OK;
+}
+
+int op_p2p_begin_cycle(amg1d* h) {
+    amg1d::P2P& P = h->p2p;
+    k_epoch_wait<<<1, 1, 0, h->stream>>>(P.epoch, p2p_my_flag(h, 0, 1), p2p_my_flag(h, 1, 1), P.err);   // channel 1 = U_0
+    h->launch_counter++;
+    LAUNCH_CHECK();
+    return AMG1D_OK;
+}
 #else
+int op_p2p_push(amg1d* h, int, int, int, int = -1, int = 0) { return fail(h, AMG1D_ERR_UNSUPPORTED, "built without NCCL"); }
+int op_p2p_wait(amg1d* h, int) { return fail(h, AMG1D_ERR_UNSUPPORTED, "built without NCCL"); }
+int op_p2p_begin_cycle(amg1d* h) { return fail(h, AMG1D_ERR_UNSUPPORTED, "built without NCCL"); }
 int op_halo(amg1d* h, double*, int64_t, int, double* = nullptr, int64_t = 0, int = 0) { return fail(h, AMG1D_ERR_UNSUPPORTED, "built without NCCL"); }
 int op_gather_rhs(amg1d* h, int) { return fail(h, AMG1D_ERR_UNSUPPORTED, "built without NCCL"); }
 int op_scatter_sol(amg1d* h, int) { return fail(h, AMG1D_ERR_UNSUPPORTED, "built without NCCL"); }
@@ -623,14 +837,16 @@ int leg_down(amg1d* h, int l, int nPre, double alpha, bool zero0) {
     const bool zero = l > 0 || zero0;         // zero0: level 0 starts from a zero guess too (ldiv!, PCG)
     if (zero) lv.cur = 0;
     RET(prof_mark(h, l, 0));
-    if (lv.sharded && !zero) RET(op_halo(h, lv.x[lv.cur].p, lv.n, lv.m));   // ghosts of the incoming iterate
+    // ghosts of the incoming iterate (peer-memory mode: they arrived with the last up leg's push, or with
+    // amg1d_dev_set_problem's exchange)
+    if (lv.sharded && !zero && !h->p2p.on) RET(op_halo(h, lv.x[lv.cur].p, lv.n, lv.m));
     // fused: nPre sweeps + residual + restriction in one pass over the operator
     if (h->opt_fused && t.fusable && !lv.smooth_tri) {
         const int ob = zero ? 0 : 1 - lv.cur;
         cudaError_t le = cudaSuccess;
         int fr = fused_down(lv.md, t.mc, make_map_closed(t), nPre, zero, lv.mat, make_pat(h, l), lv.b.p, lv.x[lv.cur].p,
                             lv.x[ob].p, t.P0, t.P1, lc.b.p, lv.n, lv.n + (lv.gr ? t.cover_extra : 0),
-                            alpha, make_slab(h, l), h->stream, h->opt_pdl != 0, &le, lv.dv_rec && h->opt_dvrec);
+                            alpha, make_slab(h, l), h->stream, h->opt_pdl != 0, &le, leg_rec(h, lv));
         if (fr == FUSED_NA && h->opt_rows)      // large blocks: one thread per block row
             fr = rows_down(lv.md, t.mc, make_map_closed(t), nPre, zero, lv.mat, make_pat(h, l), lv.b.p, lv.x[lv.cur].p,
                            lv.x[ob].p, t.P0, t.P1, lc.b.p, lv.n, lv.n + (lv.gr ? t.cover_extra : 0), alpha,
@@ -680,7 +896,7 @@ int leg_up(amg1d* h, int l, int nPost, double alpha, bool fuse_norm, bool* norm_
         int fr = fused_up(lv.md, t.mc, make_map_closed(t), nPost, lv.mat, make_pat(h, l), lv.b.p, lv.x[lv.cur].p,
                           lv.x[1 - lv.cur].p, t.P0, t.P1, lc.x[lc.cur].p, lv.n, alpha,
                           fuse_norm ? h->partial : nullptr, h->partial_cap, &nb, make_slab(h, l),
-                          h->stream, h->opt_pdl != 0, &le, lv.dv_rec && h->opt_dvrec);
+                          h->stream, h->opt_pdl != 0, &le, leg_rec(h, lv));
         if (fr == FUSED_NA && h->opt_rows)
             fr = rows_up(lv.md, t.mc, make_map_closed(t), nPost, lv.mat, make_pat(h, l), lv.b.p, lv.x[lv.cur].p,
                          lv.x[1 - lv.cur].p, t.P0, t.P1, lc.x[lc.cur].p, lv.n, alpha,
@@ -723,6 +939,8 @@ int enqueue_vcycle(amg1d* h, int nPre, int nPost, double alpha, bool want_norm, 
     }
     // levels [ts, nl) run inside the single-CTA tail kernel (rank 0 holds them; ts > gather level)
     const int ts = (h->tail_start > 0 && h->L[h->tail_start].present) ? h->tail_start : nl;
+    const bool p2p = g >= 0 && h->p2p.on;       // slab edges through peer memory (halo_p2p.cuh) instead of NCCL
+    if (p2p) RET(op_p2p_begin_cycle(h));
     // ---- down ----
     for (int l = 0; l < nl - 1 && l < ts; ++l) {
         Level& lv = h->L[l];
@@ -731,7 +949,15 @@ int enqueue_vcycle(amg1d* h, int nPre, int nPost, double alpha, bool want_norm, 
         if (lv.sharded) {
             Level& lc = h->L[l + 1];
             // ghosts of the pre-smoothed iterate (for the up leg) and of the coarse rhs, in one exchange
-            if (lc.sharded) RET(op_halo(h, lv.x[lv.cur].p, lv.n, lv.m, lc.b.p, lc.n, lc.m));
+            if (p2p) {
+                if (lc.sharded) {
+                    RET(op_p2p_push(h, 2 * l, l, lv.cur, l + 1, 2));
+                    RET(op_p2p_wait(h, 2 * l));                       // level l + 1's down leg reads the rhs ghosts
+                } else {
+                    RET(op_p2p_push(h, 2 * l, l, lv.cur));            // (awaited just before this level's up leg)
+                    RET(op_gather_rhs(h, l + 1));                     // slabs -> rank 0
+                }
+            } else if (lc.sharded) RET(op_halo(h, lv.x[lv.cur].p, lv.n, lv.m, lc.b.p, lc.n, lc.m));
             else {
                 RET(op_halo(h, lv.x[lv.cur].p, lv.n, lv.m));
                 RET(op_gather_rhs(h, l + 1));                         // slabs -> rank 0
@@ -755,9 +981,13 @@ int enqueue_vcycle(amg1d* h, int nPre, int nPost, double alpha, bool want_norm, 
         Level& lv = h->L[l];
         Level& lc = h->L[l + 1];
         if (!lv.present) continue;
-        if (lv.sharded && !lc.sharded) RET(op_scatter_sol(h, l + 1));   // rank 0 -> slabs (+ ghosts)
+        if (lv.sharded && !lc.sharded) {
+            RET(op_scatter_sol(h, l + 1));                              // rank 0 -> slabs (+ ghosts)
+            if (p2p) RET(op_p2p_wait(h, 2 * l));                        // this level's pre-smoothed ghosts
+        } else if (p2p && lv.sharded) RET(op_p2p_wait(h, 2 * (l + 1) + 1));   // ghosts of the coarse correction
         RET(leg_up(h, l, nPost, alpha, want_norm && l == 0, &norm_done));
-        if (lv.sharded && l > 0) RET(op_halo(h, lv.x[lv.cur].p, lv.n, lv.m));  // for level l-1's prolongation
+        if (p2p && lv.sharded && l > 0) RET(op_p2p_push(h, 2 * l + 1, l, lv.cur));   // level l - 1's prolongation
+        else if (lv.sharded && l > 0) RET(op_halo(h, lv.x[lv.cur].p, lv.n, lv.m));
     }
     Level& l0 = h->L[0];
     if (l0.cur != 0) {
@@ -765,6 +995,9 @@ int enqueue_vcycle(amg1d* h, int nPre, int nPost, double alpha, bool want_norm, 
                            h->stream));
         l0.cur = 0;
     }
+    // level 0's corrected iterate: the incoming iterate of the next cycle, and the signal that this rank's up
+    // leg no longer reads the ghosts which the neighbours' next down leg overwrites
+    if (p2p && l0.sharded) RET(op_p2p_push(h, 1, 0, 0));
     if (want_norm && !norm_done) RET(op_resnorm(h, 0, 0));
     return AMG1D_OK;
 }
@@ -818,6 +1051,15 @@ void invalidate_graph(amg1d* h) {
     h->norm_valid = false;
 }
 
+int p2p_check(amg1d* h) {                     // after a stream synchronisation: did a peer-memory wait time out?
+    if (!h->p2p.on) return AMG1D_OK;
+    int e = 0;
+    CK(cudaMemcpy(&e, h->p2p.err, sizeof e, cudaMemcpyDeviceToHost));
+    if (e) return fail(h, AMG1D_ERR_NCCL, "peer-memory halo exchange timed out: a neighbour rank did not reach the "
+                       "same V-cycle (crashed or out of step)");
+    return AMG1D_OK;
+}
+
 // ---- host <-> device vector movement (reference ordering <-> device block ordering) --------------
 int ensure_stage(amg1d* h, int64_t len) {
     if (h->stage_len >= len) return AMG1D_OK;
@@ -847,7 +1089,7 @@ int to_host(amg1d* h, int l, const double* dev, double* host) {
     if (!lv.perm) {
         CK(cudaMemcpyAsync(host, dev, (size_t)lv.n_host * 8, cudaMemcpyDeviceToHost, h->stream));
         CK(cudaStreamSynchronize(h->stream));
-        return AMG1D_OK;
+        return p2p_check(h);
     }
     RET(ensure_stage(h, lv.n_host));
     const int64_t ns = lv.n * lv.m;
@@ -861,7 +1103,7 @@ int to_host(amg1d* h, int l, const double* dev, double* host) {
 int read_scalars(amg1d* h, int count) {
     CK(cudaMemcpyAsync(h->h_scal, h->d_scal, sizeof(double) * count, cudaMemcpyDeviceToHost, h->stream));
     CK(cudaStreamSynchronize(h->stream));
-    return AMG1D_OK;
+    return p2p_check(h);
 }
 
 // dense m x m inverse with partial pivoting (Gauss-Jordan), column-major; returns false if singular
@@ -1134,7 +1376,7 @@ void free_flux(amg1d* h, Level& lv) {
 // doubles of a 4 x 4 DG element never leave HBM) produce the same bits.  Point-Jacobi levels keep their diagonal.
 int adopt_device_dinv(amg1d* h, int level) {
     Level& lv = h->L[level];
-    lv.dv_rec = false;
+    lv.dv_rec = 0;
     if (!h->opt_dvrec || lv.diag || !lv.present || lv.m > AMG1D_DVREC_MAXM) return AMG1D_OK;
     DevBuf sc;
     CK(sc.alloc(2));
@@ -1150,7 +1392,7 @@ int adopt_device_dinv(amg1d* h, int level) {
     CK(cudaGetLastError());
     int flag;
     memcpy(&flag, &host[1], sizeof flag);
-    if (flag || !(host[0] <= 1e-8)) return AMG1D_OK;          // not the inverse of A_di: keep what was uploaded
+    if ((flag & 1) || !(host[0] <= 1e-8)) return AMG1D_OK;    // not the inverse of A_di: keep what was uploaded
     k_dinv_recompute<<<grid, 128, 0, h->stream>>>(lv.mat, lv.md, e0, e1, AMG1D_TILE, 1, d_dev, d_flag);
     if (lv.pat) {                                             // the pattern table's Dinv rows as well
         const int ns = lv.pat_head + 1 + lv.pat_tail;
@@ -1159,7 +1401,7 @@ int adopt_device_dinv(amg1d* h, int level) {
     }
     CK(cudaStreamSynchronize(h->stream));
     CK(cudaGetLastError());
-    lv.dv_rec = true;
+    lv.dv_rec = (flag & 2) ? 1 : 2;
     return AMG1D_OK;
 }
 
@@ -1361,8 +1603,20 @@ int amg1d_destroy(amg1d_t* h) {
     h->coarse_bcr.release();
     for (auto& S : h->direct) S.release();
 #ifdef AMG1D_WITH_NCCL
-    if (h->comm) g_nccl.CommDestroy(h->comm);
+    p2p_close(h);
+    if (h->comm) g_nccl.CommDestroy(h->comm);       // (a collective: no neighbour still writes into the arena after it)
 #endif
+    for (int k = 0; k < 2; ++k) {
+        if (h->pipe.st_b[k]) cudaFree(h->pipe.st_b[k]);
+        if (h->pipe.st_x[k]) cudaFree(h->pipe.st_x[k]);
+        if (h->pipe.st_o[k]) cudaFree(h->pipe.st_o[k]);
+        for (cudaEvent_t e : {h->pipe.ev_in[k], h->pipe.ev_used[k], h->pipe.ev_done[k], h->pipe.ev_out[k]})
+            if (e) cudaEventDestroy(e);
+    }
+    if (h->pipe.s_in) cudaStreamDestroy(h->pipe.s_in);
+    if (h->pipe.s_out) cudaStreamDestroy(h->pipe.s_out);
+    if (h->p2p.epoch) cudaFree(h->p2p.epoch);
+    if (h->p2p.arena) cudaFree(h->p2p.arena);
     if (h->own_stream) cudaStreamDestroy(h->stream);
     delete h;
     return AMG1D_OK;
@@ -1869,9 +2123,20 @@ int amg1d_finalize(amg1d_t* h) {
         lg.start = slab_start(lg.n_glob, h->nranks, h->rank);
     }
     h->partial_cap = AMG1D_RED_BLOCKS;
+#ifdef AMG1D_WITH_NCCL
+    if (h->nranks > 1 && h->opt_p2p) RET(p2p_alloc_arena(h));
+#endif
     for (int l = 0; l < h->n_levels; ++l) {
         Level& lv = h->L[l];
         if (!lv.present && !lv.proxy) continue;
+        if (lv.sharded && h->p2p.arena) {             // peer-mapped (halo_p2p.cuh)
+            RET(vec_from_arena(h, lv.x[0], lv.n, lv.m));
+            RET(vec_from_arena(h, lv.b, lv.n, lv.m));
+            RET(vec_from_arena(h, lv.x[1], lv.n, lv.m));
+            maxlen = std::max(maxlen, lv.n * lv.m);
+            h->partial_cap = std::max<int64_t>(h->partial_cap, lv.n / (lv.m > 5 ? 16 : FUSED_B / 2) + 16);
+            continue;
+        }
         RET(vec_alloc(h, lv.x[0], lv.n, lv.m));
         RET(vec_alloc(h, lv.b, lv.n, lv.m));
         if (lv.present) RET(vec_alloc(h, lv.x[1], lv.n, lv.m));
@@ -1895,6 +2160,9 @@ int amg1d_finalize(amg1d_t* h) {
     }
     for (auto& lv : h->L) free_flux(h, lv);
     CK(cudaStreamSynchronize(h->stream));
+#ifdef AMG1D_WITH_NCCL
+    if (h->nranks > 1) RET(p2p_connect(h));           // collective: every rank reaches this point or none does
+#endif
     h->finalized = true;
     return AMG1D_OK;
 }
@@ -1915,6 +2183,9 @@ int amg1d_dev_set_problem(amg1d_t* h, const double* x0, const double* b) {
     if (l0.cur != 0) l0.cur = 0;
     if (x0) RET(to_device(h, 0, x0, l0.x[0].p));
     else CK(cudaMemsetAsync(l0.x[0].p, 0, (size_t)l0.x[0].len * 8, h->stream));
+    // ghosts of the new iterate.  (The two-sided exchange also orders this call after the neighbours' last
+    // peer-memory push of an earlier cycle, which targets the same ghost slots.)
+    if (l0.sharded) RET(op_halo(h, l0.x[0].p, l0.n, l0.m));
     return AMG1D_OK;
 }
 
@@ -1926,9 +2197,105 @@ int amg1d_dev_fill_rhs_random(amg1d_t* h, uint64_t seed) {
     k_fill_random<<<1184, 256, 0, h->stream>>>(l0.b.p, l0.b.len, seed, l0.start * l0.m);
     LAUNCH_CHECK();
     h->dev_problem = true;
-    if (l0.sharded) RET(op_halo(h, l0.b.p, l0.n, l0.m));
     l0.cur = 0;
     CK(cudaMemsetAsync(l0.x[0].p, 0, (size_t)l0.x[0].len * 8, h->stream));
+    if (l0.sharded) RET(op_halo(h, l0.b.p, l0.n, l0.m, l0.x[0].p, l0.n, l0.m));
+    return AMG1D_OK;
+}
+
+int amg1d_dev_assemble_rhs(amg1d_t* h, int kind, int nq, const double* xi, const double* W, int n_basis,
+                           int n_terms, const double* terms, double xin, double xout, const double* vertices,
+                           int n_fix, const int64_t* fix_slot, const double* fix_val, const int* fix_op) {
+    RET(check_ready(h));
+    Level& l0 = h->L[0];
+    if (kind < 0 || kind > 1) return fail(h, AMG1D_ERR_ARG, "kind must be 0 (DG-type level) or 1 (CG level in group form)");
+    if (!xi || !W || !terms || nq < 1 || nq > AMG1D_RHS_MAXQ || n_basis < 1 || n_basis > AMG1D_RHS_MAXM ||
+        n_terms < 1 || n_terms > AMG1D_RHS_MAXT)
+        return fail(h, AMG1D_ERR_ARG, "need 1 <= nq <= %d, 1 <= n_basis <= %d, 1 <= n_terms <= %d", AMG1D_RHS_MAXQ,
+                    AMG1D_RHS_MAXM, AMG1D_RHS_MAXT);
+    if (n_fix < 0 || (n_fix > 0 && (!fix_slot || !fix_val || !fix_op))) return fail(h, AMG1D_ERR_ARG, "bad fix list");
+    if (l0.perm) return fail(h, AMG1D_ERR_UNSUPPORTED, "device right-hand sides need level 0 in device order (no perm): "
+                             "DG-type levels, or CG levels uploaded in group order");
+    if ((kind == 0 && n_basis != l0.m) || (kind == 1 && n_basis != l0.m + 1))
+        return fail(h, AMG1D_ERR_ARG, "n_basis %d does not match level 0 (block size %d)", n_basis, l0.m);
+    for (int t = 0; t < n_terms; ++t) {
+        const double k = terms[5 * t], pw = terms[5 * t + 2];
+        if (!(k == 0.0 || k == 1.0 || k == 2.0 || k == 3.0) || !(pw >= 0.0 && pw <= 16.0 && pw == std::floor(pw)))
+            return fail(h, AMG1D_ERR_ARG, "term %d: kind must be 0 (1), 1 (cos), 2 (sin), 3 (exp); pow an integer in [0, 16]", t);
+    }
+    RhsSpec sp = {};
+    sp.kind = kind; sp.nq = nq; sp.m = n_basis; sp.n_terms = n_terms;
+    for (int q = 0; q < nq; ++q) {
+        sp.xi[q] = xi[q];
+        for (int i = 0; i < n_basis; ++i) sp.W[q * AMG1D_RHS_MAXM + i] = W[q * n_basis + i];
+    }
+    memcpy(sp.terms, terms, sizeof(double) * 5 * n_terms);
+    sp.xin = xin; sp.xout = xout;
+    sp.n_glob = kind == 0 ? l0.n_glob : l0.n_glob - 1;        // CG: n + 1 vertex groups on n elements
+    DevBuf dvert, dfs, dfv, dfo;
+    if (vertices) {
+        CK(dvert.alloc(sp.n_glob + 1));
+        CK(cudaMemcpyAsync(dvert.p, vertices, (size_t)(sp.n_glob + 1) * 8, cudaMemcpyHostToDevice, h->stream));
+    }
+    h->norm_valid = false;
+    // the slab with its ghost elements (their right-hand side feeds the recomputed halo of the fused legs)
+    const int64_t e0 = -(int64_t)l0.gl, e1 = l0.n + l0.gr;
+    CK(cudaMemsetAsync(l0.b.p + e0 * l0.m, 0, (size_t)(e1 - e0) * l0.m * 8, h->stream));
+    k_assemble_rhs<<<(unsigned)((e1 - e0 + 127) / 128), 128, 0, h->stream>>>(sp, dvert.p && vertices ? dvert.p : nullptr,
+                                                                          l0.start, e0, e1, e1 * l0.m, l0.b.p, 0);
+    h->launch_counter++;
+    LAUNCH_CHECK();
+    if (kind == 1 && l0.gl) {
+        // the first ghost group's vertex also receives fe[1] of the element left of it, which no thread of this
+        // rank visits: recompute that one element's contribution
+        k_assemble_rhs<<<1, 1, 0, h->stream>>>(sp, dvert.p && vertices ? dvert.p : nullptr, l0.start, e0 - 1, e0,
+                                               e1 * l0.m, l0.b.p, 1);
+        h->launch_counter++;
+        LAUNCH_CHECK();
+    }
+    if (n_fix) {
+        CK(dfs.alloc(n_fix)); CK(dfv.alloc(n_fix)); CK(dfo.alloc(n_fix));
+        CK(cudaMemcpyAsync(dfs.p, fix_slot, (size_t)n_fix * 8, cudaMemcpyHostToDevice, h->stream));
+        CK(cudaMemcpyAsync(dfv.p, fix_val, (size_t)n_fix * 8, cudaMemcpyHostToDevice, h->stream));
+        CK(cudaMemcpyAsync(dfo.p, fix_op, (size_t)n_fix * sizeof(int), cudaMemcpyHostToDevice, h->stream));
+        k_apply_fixes<<<1, 32, 0, h->stream>>>(l0.b.p, l0.start * l0.m, e0 * l0.m, e1 * l0.m, n_fix,
+                                               reinterpret_cast<const int64_t*>(dfs.p), dfv.p,
+                                               reinterpret_cast<const int*>(dfo.p));
+        h->launch_counter++;
+        LAUNCH_CHECK();
+    }
+    l0.cur = 0;
+    CK(cudaMemsetAsync(l0.x[0].p, 0, (size_t)l0.x[0].len * 8, h->stream));
+    if (l0.sharded) RET(op_halo(h, l0.x[0].p, l0.n, l0.m));      // (zero ghosts; orders this call after earlier pushes)
+    CK(cudaStreamSynchronize(h->stream));         // the staging buffers above are released on return
+    h->dev_problem = true;
+    return AMG1D_OK;
+}
+
+int amg1d_dev_get_rhs(amg1d_t* h, double* b) {
+    RET(check_dev_problem(h));
+    if (!b) return fail(h, AMG1D_ERR_ARG, "null b");
+    return to_host(h, 0, h->L[0].b.p, b);
+}
+
+int amg1d_dev_solve(amg1d_t* h, int maxiter, double tol, int nPre, int nPost, double alpha, int* iters, double* res) {
+    RET(check_dev_problem(h));
+    if (!res || !iters) return fail(h, AMG1D_ERR_ARG, "null argument");
+    if (maxiter < 0) return fail(h, AMG1D_ERR_ARG, "maxiter must be >= 0");
+    Level& l0 = h->L[0];
+    int rc = op_norm(h, l0.b.p, nullptr, l0.b.len, 2);
+    int it = 0;
+    for (int i = 0; i < maxiter && rc == AMG1D_OK; ++i) {
+        rc = run_vcycle(h, nPre, nPost, alpha, true);
+        if (rc != AMG1D_OK) break;
+        rc = read_scalars(h, 3);
+        if (rc != AMG1D_OK) break;
+        res[i] = h->h_scal[0];
+        it = i + 1;
+        if (res[i] < tol * h->h_scal[2]) break;
+    }
+    RET(rc);
+    *iters = it;
     return AMG1D_OK;
 }
 
@@ -1963,7 +2330,7 @@ int amg1d_dev_get_solution(amg1d_t* h, double* x) {
 int amg1d_synchronize(amg1d_t* h) {
     if (!h) return AMG1D_ERR_ARG;
     CK(cudaStreamSynchronize(h->stream));
-    return AMG1D_OK;
+    return p2p_check(h);
 }
 
 void* amg1d_stream(amg1d_t* h) { return h ? (void*)h->stream : nullptr; }
@@ -2035,18 +2402,105 @@ int amg1d_ldiv(amg1d_t* h, double* y, const double* b, int nPre, int nPost, doub
     return to_host(h, 0, l0.x[l0.cur].p, y);
 }
 
-int amg1d_pcg(amg1d_t* h, double* x, const double* b, int maxiter, double tol, int nPre, int nPost,
-              double alpha, int* iters, double* res) {
+// multigrid_v_cycle / ldiv! on `count` independent problems, software-pipelined over PCIe: while problem k runs its
+// V-cycle on the compute stream, problem k + 1 travels host -> device on a copy-in stream and the iterate of
+// problem k - 1 device -> host on a copy-out stream (PCIe is full duplex; with one problem per call the three
+// phases are serial and the call is bound by 3 vector transfers).  Level-0 vectors are staged in two device
+// buffers per direction; every problem runs exactly the kernels of amg1d_vcycle / amg1d_ldiv: same bits.
+int amg1d_vcycle_batch(amg1d_t* h, int count, double* const* x, const double* const* b, int zero_guess, int nPre,
+                       int nPost, double alpha) {
     RET(check_ready(h));
-    if (!x || !b || !res || !iters) return fail(h, AMG1D_ERR_ARG, "null argument");
-    if (maxiter < 0) return fail(h, AMG1D_ERR_ARG, "maxiter must be >= 0");
+    if (count < 0 || (count > 0 && (!x || !b))) return fail(h, AMG1D_ERR_ARG, "bad arguments");
+    for (int k = 0; k < count; ++k)
+        if (!x[k] || !b[k]) return fail(h, AMG1D_ERR_ARG, "null vector %d", k);
+    if (count == 0) return AMG1D_OK;
     Level& l0 = h->L[0];
-    const int64_t N = l0.n * l0.m;
+    amg1d::Pipe& P = h->pipe;
+    if (!P.s_in) {
+        CK(cudaStreamCreateWithFlags(&P.s_in, cudaStreamNonBlocking));
+        CK(cudaStreamCreateWithFlags(&P.s_out, cudaStreamNonBlocking));
+        for (int k = 0; k < 2; ++k) {
+            CK(cudaEventCreateWithFlags(&P.ev_in[k], cudaEventDisableTiming));
+            CK(cudaEventCreateWithFlags(&P.ev_used[k], cudaEventDisableTiming));
+            CK(cudaEventCreateWithFlags(&P.ev_done[k], cudaEventDisableTiming));
+            CK(cudaEventCreateWithFlags(&P.ev_out[k], cudaEventDisableTiming));
+            RET(dev_alloc(h, (void**)&P.st_b[k], l0.n_host * 8));
+            RET(dev_alloc(h, (void**)&P.st_x[k], l0.n_host * 8));
+            RET(dev_alloc(h, (void**)&P.st_o[k], l0.n_host * 8));
+        }
+        P.len = l0.n_host;
+    }
+    h->norm_valid = false;
+    const size_t bytes = (size_t)l0.n_host * 8;
+    const int64_t ns = l0.n * l0.m;
+    const unsigned gp = (unsigned)((ns + 255) / 256);
+    // the compute stream may still be busy with earlier work that the copy streams must not overtake
+    CK(cudaEventRecord(P.ev_used[0], h->stream));
+    CK(cudaStreamWaitEvent(P.s_in, P.ev_used[0], 0));
+    for (int k = 0; k < count; ++k) {
+        const int sl = k & 1;
+        // ---- copy-in stream: stage slot sl is free once problem k - 2 has been moved into the level vectors
+        if (k >= 2) {
+            CK(cudaStreamWaitEvent(P.s_in, P.ev_used[sl], 0));
+            CK(cudaStreamWaitEvent(P.s_in, P.ev_out[sl], 0));    // (a caller may pass problem k - 2's output array again)
+        }
+        CK(cudaMemcpyAsync(P.st_b[sl], b[k], bytes, cudaMemcpyHostToDevice, P.s_in));
+        if (!zero_guess) CK(cudaMemcpyAsync(P.st_x[sl], x[k], bytes, cudaMemcpyHostToDevice, P.s_in));
+        CK(cudaEventRecord(P.ev_in[sl], P.s_in));
+        // ---- compute stream
+        CK(cudaStreamWaitEvent(h->stream, P.ev_in[sl], 0));
+        l0.cur = 0;
+        if (l0.perm) {
+            k_gather_perm<<<gp, 256, 0, h->stream>>>(l0.perm, P.st_b[sl], l0.b.p, ns);
+            if (!zero_guess) k_gather_perm<<<gp, 256, 0, h->stream>>>(l0.perm, P.st_x[sl], l0.x[0].p, ns);
+            LAUNCH_CHECK();
+        } else {
+            CK(cudaMemcpyAsync(l0.b.p, P.st_b[sl], bytes, cudaMemcpyDeviceToDevice, h->stream));
+            if (!zero_guess) CK(cudaMemcpyAsync(l0.x[0].p, P.st_x[sl], bytes, cudaMemcpyDeviceToDevice, h->stream));
+        }
+        CK(cudaEventRecord(P.ev_used[sl], h->stream));
+        if (l0.sharded) {
+            if (zero_guess) RET(op_halo(h, l0.b.p, l0.n, l0.m));
+            else RET(op_halo(h, l0.b.p, l0.n, l0.m, l0.x[0].p, l0.n, l0.m));
+        }
+        RET(run_vcycle(h, nPre, nPost, alpha, false, zero_guess != 0));
+        if (k >= 2) CK(cudaStreamWaitEvent(h->stream, P.ev_out[sl], 0));      // the iterate of problem k - 2 has left
+        if (l0.perm) {
+            k_scatter_perm<<<gp, 256, 0, h->stream>>>(l0.perm, l0.x[l0.cur].p, P.st_o[sl], ns);
+            LAUNCH_CHECK();
+        } else {
+            CK(cudaMemcpyAsync(P.st_o[sl], l0.x[l0.cur].p, bytes, cudaMemcpyDeviceToDevice, h->stream));
+        }
+        CK(cudaEventRecord(P.ev_done[sl], h->stream));
+        // ---- copy-out stream
+        CK(cudaStreamWaitEvent(P.s_out, P.ev_done[sl], 0));
+        CK(cudaMemcpyAsync(x[k], P.st_o[sl], bytes, cudaMemcpyDeviceToHost, P.s_out));
+        CK(cudaEventRecord(P.ev_out[sl], P.s_out));
+    }
+    CK(cudaStreamSynchronize(P.s_out));
+    CK(cudaStreamSynchronize(h->stream));
+    h->dev_problem = true;
+    return p2p_check(h);
+}
+
+}  // extern "C"
+
+namespace {
+// Conjugate gradients preconditioned with one V-cycle (ldiv!(z, H, r)); expects the initial guess in cg_x and the
+// right-hand side in level 0's rhs buffer, which becomes the residual.  The solution is left in cg_x.
+int pcg_alloc(amg1d* h) {
+    Level& l0 = h->L[0];
     if (!h->cg_x.raw) {
         RET(vec_alloc(h, h->cg_x, l0.n, l0.m));
         RET(vec_alloc(h, h->cg_p, l0.n, l0.m));
         RET(vec_alloc(h, h->cg_ap, l0.n, l0.m));
     }
+    return AMG1D_OK;
+}
+
+int pcg_run(amg1d* h, int maxiter, double tol, int nPre, int nPost, double alpha, int* iters, double* res) {
+    Level& l0 = h->L[0];
+    const int64_t N = l0.n * l0.m;
     h->norm_valid = false;
     h->dev_problem = false;                   // level 0's rhs buffer becomes the CG residual
     double* X = h->cg_x.p;
@@ -2054,8 +2508,6 @@ int amg1d_pcg(amg1d_t* h, double* x, const double* b, int maxiter, double tol, i
     double* AP = h->cg_ap.p;
     double* R = l0.b.p;                       // the residual lives in the level's rhs buffer: it IS the
                                               // right-hand side of every preconditioner application
-    RET(to_device(h, 0, b, R));
-    RET(to_device(h, 0, x, X));
     RET(op_norm(h, R, nullptr, N, CG_NB));                       // ||b||
     // r = b - A x0
     RET(op_matvec_dot(h, 0, X, AP, -1));
@@ -2073,10 +2525,8 @@ int amg1d_pcg(amg1d_t* h, double* x, const double* b, int maxiter, double tol, i
     RET(read_scalars(h, 3));
     if (!std::isfinite(h->h_scal[CG_RES]) || !std::isfinite(h->h_scal[CG_NB]))
         return fail(h, AMG1D_ERR_ARG, "amg1d_pcg: non-finite right-hand side or initial guess");
-    if (h->h_scal[CG_NB] == 0.0 || h->h_scal[CG_RES] <= tol * h->h_scal[CG_NB]) {
-        *iters = 0;
-        return to_host(h, 0, X, x);
-    }
+    *iters = 0;
+    if (h->h_scal[CG_NB] == 0.0 || h->h_scal[CG_RES] <= tol * h->h_scal[CG_NB]) return AMG1D_OK;
     for (int i = 0; i < maxiter; ++i) {
         // z = M^-1 r: one V-cycle from a zero guess with rhs r (already in place); z = level-0 iterate
         if (l0.sharded) { rc = op_halo(h, R, l0.n, l0.m); if (rc) break; }
@@ -2108,7 +2558,35 @@ int amg1d_pcg(amg1d_t* h, double* x, const double* b, int maxiter, double tol, i
     if (it > 0 && !std::isfinite(res[it - 1]))                   // never AMG1D_OK with NaNs in the caller's x
         return fail(h, AMG1D_ERR_ARG, "amg1d_pcg: breakdown at iteration %d (non-finite residual: the operator "
                     "or the V-cycle preconditioner is not symmetric positive definite)", it);
-    return to_host(h, 0, X, x);
+    return AMG1D_OK;
+}
+}  // namespace
+
+extern "C" {
+
+int amg1d_pcg(amg1d_t* h, double* x, const double* b, int maxiter, double tol, int nPre, int nPost,
+              double alpha, int* iters, double* res) {
+    RET(check_ready(h));
+    if (!x || !b || !res || !iters) return fail(h, AMG1D_ERR_ARG, "null argument");
+    if (maxiter < 0) return fail(h, AMG1D_ERR_ARG, "maxiter must be >= 0");
+    RET(pcg_alloc(h));
+    RET(to_device(h, 0, b, h->L[0].b.p));
+    RET(to_device(h, 0, x, h->cg_x.p));
+    RET(pcg_run(h, maxiter, tol, nPre, nPost, alpha, iters, res));
+    return to_host(h, 0, h->cg_x.p, x);
+}
+
+int amg1d_dev_pcg(amg1d_t* h, int maxiter, double tol, int nPre, int nPost, double alpha, int* iters, double* res) {
+    RET(check_dev_problem(h));
+    if (!res || !iters) return fail(h, AMG1D_ERR_ARG, "null argument");
+    if (maxiter < 0) return fail(h, AMG1D_ERR_ARG, "maxiter must be >= 0");
+    Level& l0 = h->L[0];
+    RET(pcg_alloc(h));
+    CK(cudaMemcpyAsync(h->cg_x.p, l0.x[l0.cur].p, (size_t)l0.x[0].len * 8, cudaMemcpyDeviceToDevice, h->stream));
+    RET(pcg_run(h, maxiter, tol, nPre, nPost, alpha, iters, res));
+    l0.cur = 0;                                                  // the solution becomes the resident iterate
+    CK(cudaMemcpyAsync(l0.x[0].p, h->cg_x.p, (size_t)l0.x[0].len * 8, cudaMemcpyDeviceToDevice, h->stream));
+    return AMG1D_OK;
 }
 
 int amg1d_apply_smoother(amg1d_t* h, int level, double* Y, const double* B, int64_t n_rhs,
@@ -2278,10 +2756,15 @@ int amg1d_set_option(amg1d_t* h, const char* key, int64_t value) {
         if (value < 0 || value > 2) return fail(h, AMG1D_ERR_ARG, "pattern_resident must be 0, 1 or 2");
         h->opt_pattern = (int)value;
     }
+    else if (!strcmp(key, "p2p_halo")) {
+        if (h->finalized) return fail(h, AMG1D_ERR_STATE, "'p2p_halo' must be set before amg1d_finalize");
+        h->opt_p2p = value != 0;
+    }
     else if (!strcmp(key, "recompute_dinv")) {
         // before the first level: whether uploaded inverses are replaced by the device's own (adopt_device_dinv);
         // afterwards: whether the fused legs recompute them or stream the stored ones (same bits either way)
-        h->opt_dvrec = value != 0;
+        if (value < 0) return fail(h, AMG1D_ERR_ARG, "recompute_dinv must be >= 0");
+        h->opt_dvrec = (int)value;
     }
     else if (!strcmp(key, "rows_per_thread")) {
         if (value != 0 && !rows_rpt_ok((int)value)) return fail(h, AMG1D_ERR_ARG, "rows_per_thread must be 0 (auto), 1, 2 or 3");
@@ -2329,9 +2812,14 @@ int64_t amg1d_get_info(amg1d_t* h, const char* key) {
         return valid_level(h, l) && h->L[l].pat ? 1 : 0;
     }
     if (!strcmp(key, "recompute_dinv")) return h->opt_dvrec;
+    if (!strcmp(key, "p2p_halo")) return h->p2p.on ? 1 : 0;     // 1: slab edges travel through peer memory, 0: NCCL
+    if (!strncmp(key, "dinv_pivots:", 12)) {        // 1: some element of the level swaps rows in its inverse
+        const int l = atoi(key + 12);
+        return valid_level(h, l) && h->L[l].set ? (h->L[l].dv_rec == 1) : -1;
+    }
     if (!strncmp(key, "dinv_recompute:", 15)) {     // 1: the fused legs of this level invert A_di in registers
         const int l = atoi(key + 15);               //    instead of streaming the stored inverse
-        if (!valid_level(h, l) || !h->L[l].set || !h->L[l].dv_rec || !h->opt_dvrec) return 0;
+        if (!valid_level(h, l) || !h->L[l].set || !leg_rec(h, h->L[l])) return 0;
         if (h->opt_pattern && h->L[l].pat) return 0;
         return (h->L[l].m <= 5 && l + 1 < h->n_levels && h->T[l].fusable) ? 1 : 0;
     }

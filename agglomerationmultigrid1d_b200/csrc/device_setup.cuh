@@ -227,7 +227,8 @@ __global__ void k_extract_dinv(const double* __restrict__ mat, MatDesc d, int64_
 // stored inverse must be THE SAME Gauss-Jordan result.  This kernel recomputes it per element with the
 // arithmetic of reg_invert (kernels_fused.cuh: partial pivoting by a compare-and-swap chain, same operation order).
 //   mode 0: dev[0] = max over the elements of  max|Dinv_stored - inv(A_di)| / max|inv(A_di)|  (as an ordered
-//           int64 bit pattern, atomicMax), flag[0] |= 1 for a singular block - nothing is written;
+//           int64 bit pattern, atomicMax), flag[0] |= 1 for a singular block, |= 2 if any element swaps rows -
+//           nothing is written;
 //   mode 1: overwrite the stored Dinv rows with the recomputed inverse.
 // Addressing: element e (e_first <= e < e_end, may be negative: left ghosts) lives at
 // base + (e >> 5) * K * tile_stride + (e & 31) with row stride tile_stride (element tiles: tile_stride = 32);
@@ -250,6 +251,7 @@ __global__ void k_dinv_recompute(double* __restrict__ base, MatDesc d, int64_t e
         for (int r = c + 1; r < m; ++r) {         // compare-and-swap chain: the largest |a(r, c)|, r >= c, ends on the diagonal
             const bool s = fabs(A[c * m + r]) > fabs(A[c * m + c]);
             sw[c][r] = s;
+            if (s && mode == 0) atomicOr(flag, 2);   // this level pivots somewhere: the legs keep the swap chain
             for (int q = 0; q < m; ++q) {
                 const double x = A[q * m + c], y = A[q * m + r];
                 A[q * m + c] = s ? y : x;
@@ -286,5 +288,90 @@ __global__ void k_dinv_recompute(double* __restrict__ base, MatDesc d, int64_t e
         atomicMax(dev, (unsigned long long)__double_as_longlong(rel >= 0.0 ? rel : INFINITY));   // NaN -> inf
     } else {
         for (int k = 0; k < m * m; ++k) T[(int64_t)(d.o_dv + k) * rs] = A[k];
+    }
+}
+
+// ---- device-side right-hand side ----------------------------------------------------------------
+// The volume part of dg_flux_rhs (src/dg_mesh.jl:342-365: f[el.mNodesInd] += J sum_q w_q phi_i(xi_q) func(x_q)) and of
+// cg_stiffness_and_rhs / cg_rhs (src/cg_mesh.jl:150-160, :205-215), with func given as a sum of terms
+//     coef * x^pow * g(w x + phi),   g = 1 | cos | sin | exp            (terms[5 t ..]: kind, coef, pow, w, phi)
+// - the manufactured right-hand sides of the reference's scripts (cos(x), exp(-x), 1) and of the BASELINE configs.
+// One thread per element: x_q = xc + (h / 2) xi_q on the element [xl, xr], xl = xin + (e / n)(xout - xin) exactly as
+// tests/mesh_generator.jl:20-32 computes the vertices (or xl, xr from an uploaded vertex array), then
+// fe[i] = (h / 2) sum_q func(x_q) W[q][i], W[q][i] = w_q phi_i(xi_q).
+//   kind 0 (DG-type level):  b[e m + i] = fe[i]
+//   kind 1 (CG level in group form, group k = [vertex k, interior nodes of element k]): vertex k += fe[0] of element
+//          k and fe[1] of element k - 1; interior slot j = fe[j + 1].  Two contributions per vertex onto a zeroed b:
+//          the sum does not depend on their order.
+// e runs over the rank's slab (global element e_off + e); b points at local element / group 0.
+#define AMG1D_RHS_MAXQ 16
+#define AMG1D_RHS_MAXM 10
+#define AMG1D_RHS_MAXT 8
+struct RhsSpec {
+    int kind, nq, m, n_terms;                 // m = local basis functions per element (p + 1)
+    double xi[AMG1D_RHS_MAXQ];
+    double W[AMG1D_RHS_MAXQ * AMG1D_RHS_MAXM];  // [q][i]
+    double terms[5 * AMG1D_RHS_MAXT];
+    double xin, xout;
+    int64_t n_glob;                           // elements of the whole mesh
+};
+
+__device__ __forceinline__ double rhs_func(const RhsSpec& sp, double x) {
+    double s = 0.0;
+    for (int t = 0; t < sp.n_terms; ++t) {
+        const double* T = sp.terms + 5 * t;
+        const int kind = (int)T[0];
+        const double arg = fma(T[3], x, T[4]);
+        double g = kind == 1 ? cos(arg) : kind == 2 ? sin(arg) : kind == 3 ? exp(arg) : 1.0;
+        const int pw = (int)T[2];
+        for (int k = 0; k < pw; ++k) g *= x;
+        s = fma(T[1], g, s);
+    }
+    return s;
+}
+
+// only_next = 1 (kind 1): add nothing but the element's fe[1] to the NEXT group's vertex - for the element left of a
+// slab's first ghost group, whose own group lies outside the slab.
+__global__ void k_assemble_rhs(const __grid_constant__ RhsSpec sp, const double* __restrict__ vertices, int64_t e_off,
+                               int64_t e_begin, int64_t e_end, int64_t slots_end, double* __restrict__ b, int only_next) {
+    const int64_t e = e_begin + (int64_t)blockIdx.x * blockDim.x + threadIdx.x;     // local element (may be a ghost)
+    if (e >= e_end) return;
+    const int64_t eg = e + e_off;
+    if (eg < 0 || eg >= sp.n_glob) return;
+    double xl, xr;
+    if (vertices) { xl = vertices[eg]; xr = vertices[eg + 1]; }
+    else {
+        const double L = __dsub_rn(sp.xout, sp.xin), nn = (double)sp.n_glob;
+        xl = __dadd_rn(sp.xin, __dmul_rn(__ddiv_rn((double)eg, nn), L));
+        xr = __dadd_rn(sp.xin, __dmul_rn(__ddiv_rn((double)(eg + 1), nn), L));
+    }
+    const double hh = __dsub_rn(xr, xl), xc = __dmul_rn(__dadd_rn(xl, xr), 0.5), hj = __dmul_rn(hh, 0.5);
+    double fe[AMG1D_RHS_MAXM];
+    for (int i = 0; i < sp.m; ++i) fe[i] = 0.0;
+    for (int q = 0; q < sp.nq; ++q) {
+        const double fx = rhs_func(sp, __dadd_rn(xc, __dmul_rn(hj, sp.xi[q])));
+        for (int i = 0; i < sp.m; ++i) fe[i] = fma(fx, sp.W[q * AMG1D_RHS_MAXM + i], fe[i]);
+    }
+    if (sp.kind == 0) {
+        for (int i = 0; i < sp.m; ++i) b[e * sp.m + i] = __dmul_rn(hj, fe[i]);
+    } else {
+        const int p = sp.m - 1;                              // group size
+        if (!only_next) {
+            atomicAdd(&b[e * p], __dmul_rn(hj, fe[0]));
+            for (int j = 1; j < p; ++j) b[e * p + j] = __dmul_rn(hj, fe[j + 1]);
+        }
+        if ((e + 1) * p < slots_end) atomicAdd(&b[(e + 1) * p], __dmul_rn(hj, fe[1]));
+    }
+}
+
+// ops[k] = 0: b[slot] += val;  1: b[slot] = val   (boundary terms; applied in order by ONE thread - a handful of entries)
+__global__ void k_apply_fixes(double* __restrict__ b, int64_t slot_off, int64_t slot_begin, int64_t slot_end, int n,
+                              const int64_t* __restrict__ slots, const double* __restrict__ vals,
+                              const int* __restrict__ ops) {
+    if (blockIdx.x || threadIdx.x) return;
+    for (int k = 0; k < n; ++k) {
+        const int64_t s = slots[k] - slot_off;               // local slot
+        if (s < slot_begin || s >= slot_end) continue;
+        b[s] = ops[k] ? vals[k] : b[s] + vals[k];
     }
 }

@@ -425,11 +425,15 @@ __device__ __forceinline__ void cp_async_commit_wait_all() {
 // is swapped up whenever |a(r, c)| exceeds the current pivot candidate, which leaves the largest entry on the
 // diagonal) recorded as booleans: every array index is a compile-time constant and the swaps are selects, so
 // the block never leaves the register file (an integer pivot index made the compiler index local memory).
-template <int M>
+// PIV = false: the level's set-up pass found that no element ever swaps (every pivot already sits on the diagonal,
+// as for the symmetric positive definite, diagonally heavy blocks of the DG operators) - the compare-and-swap
+// chain is skipped, which leaves exactly the same arithmetic at a third of the instructions.
+template <int M, bool PIV>
 __device__ __forceinline__ void reg_invert(double (&a)[M * M]) {
     bool sw[M][M];
 #pragma unroll
     for (int c = 0; c < M; ++c) {
+        if constexpr (PIV) {
 #pragma unroll
         for (int r = c + 1; r < M; ++r) {
             const bool s = fabs(a[c * M + r]) > fabs(a[c * M + c]);
@@ -440,6 +444,7 @@ __device__ __forceinline__ void reg_invert(double (&a)[M * M]) {
                 a[q * M + c] = s ? y : x;
                 a[q * M + r] = s ? x : y;
             }
+        }
         }
         const double dd = 1.0 / a[c * M + c];
         a[c * M + c] = 1.0;
@@ -454,6 +459,7 @@ __device__ __forceinline__ void reg_invert(double (&a)[M * M]) {
             for (int q = 0; q < M; ++q) a[q * M + r] = fma(-f, a[q * M + c], a[q * M + r]);
         }
     }
+    if constexpr (PIV) {
 #pragma unroll
     for (int c = M - 1; c >= 0; --c) {            // undo the row swaps as column swaps, in reverse order
 #pragma unroll
@@ -467,7 +473,28 @@ __device__ __forceinline__ void reg_invert(double (&a)[M * M]) {
             }
         }
     }
+    }
 }
+
+// Option recompute_dinv: this thread's Dinv = inv(A_di) from the registers into its shared-memory column
+// (rec = 1: with the pivot chain, 2: the level never pivots).  Called right after the operator loads, BEFORE the
+// programmatic-dependency wait and the vector loads: placing it after them (to overlap their latency) was
+// measured 40 % slower on T level 0 - the vectors' registers are then live across the inversion and it spills.
+template <int M, int B, int ST, bool DIAG>
+__device__ __forceinline__ void recompute_dinv(const RegOp<M, ST>& A, double (*ds)[B], bool active, int rec) {
+    if constexpr (!DIAG) {
+        if (rec && active) {
+            double w[M * M];
+#pragma unroll
+            for (int k = 0; k < M * M; ++k) w[k] = A.di[k];
+            if (rec == 2) reg_invert<M, false>(w); else reg_invert<M, true>(w);
+#pragma unroll
+            for (int k = 0; k < M * M; ++k) ds[k][threadIdx.x] = w[k];
+        }
+    }
+}
+template <int M, int B, int ST, bool DIAG>
+__device__ __forceinline__ void recompute_dinv(const ParamOp<M, ST, DIAG>&, double (*)[B], bool, int) {}
 
 template <int M, int ST, class OP>
 __device__ __forceinline__ void reg_residual(const OP& A, int ilo, int iup,
@@ -504,8 +531,8 @@ __device__ __forceinline__ void exchange(Exchange<M, B>& ex, int buf, int ilo, i
 
 // A_lo / A_di / A_up go to registers; Dinv (used once per sweep) is copied global -> shared with
 // cp.async, i.e. without register staging, into this thread's own column ds[k][thread].
-// rec (block smoothers, streamed tiles only): Dinv is NOT loaded - the caller inverts A.di in registers
-// (reg_invert) and puts the result into the same shared-memory column.
+// rec (block smoothers, streamed tiles only): Dinv is NOT loaded - the leg inverts A.di in registers
+// (recompute_dinv) and puts the result into the same shared-memory column.
 template <int M, int B, int ST, bool DIAG, int STRIDE>
 __device__ __forceinline__ void load_blocks_from(const double* __restrict__ T, RegOp<M, ST>& A, double (*ds)[B],
                                                  bool rec = false) {
@@ -549,16 +576,6 @@ __device__ __forceinline__ void load_blocks(const double* __restrict__ mat, cons
         } else {
             load_blocks_from<M, B, ST, DIAG, AMG1D_TILE>(mat + (e >> 5) * (int64_t)(K * AMG1D_TILE) + (e & 31), A, ds,
                                                          rec);
-            if constexpr (!DIAG) {
-                if (rec) {                 // Dinv = inv(A_di), in registers, into this thread's shared column
-                    double w[M * M];
-#pragma unroll
-                    for (int k = 0; k < M * M; ++k) w[k] = A.di[k];
-                    reg_invert<M>(w);
-#pragma unroll
-                    for (int k = 0; k < M * M; ++k) ds[k][t] = w[k];
-                }
-            }
         }
     } else {
 #pragma unroll
@@ -707,6 +724,7 @@ f_down(const double* __restrict__ mat, PatOp po, int ilo, int iup, const double*
     exch_init<M, B>(ex);
     RegOp<M, ST> A;
     load_blocks<M, B, ST, DIAG>(mat, po, e, e + sl.e_off, active, A, ds, rec != 0);   // operator: independent of earlier kernels
+    recompute_dinv<M, B, ST, DIAG>(A, ds, active, rec);          // before the dependency wait: few registers are live yet
     down_leg<M, MC, B, ST, DIAG>(A, &ds[0][t], ex, rs, e, active, ilo, iup, b, xin, xout, P0, P1, tm, rc, n, alpha,
                                  nsweep, zero_guess, wi, sl);
 }
@@ -833,6 +851,7 @@ f_up(const double* __restrict__ mat, PatOp po, int ilo, int iup, const double* _
     exch_init<M, B>(ex);
     RegOp<M, ST> A;
     load_blocks<M, B, ST, DIAG>(mat, po, e, e + sl.e_off, active, A, ds, rec != 0);   // operator: independent of earlier kernels
+    recompute_dinv<M, B, ST, DIAG>(A, ds, active, rec);          // before the dependency wait: few registers are live yet
     up_leg<M, MC, B, ST, DIAG>(A, &ds[0][t], ex, e, active, ilo, iup, b, xin, xout, P0, P1, tm, xcoarse, n, alpha,
                                nsweep, wi, partial, sl);
 }
@@ -1241,7 +1260,7 @@ enum { FUSED_NA = 0, FUSED_OK = 1, FUSED_ERR = -1 };
 inline int fused_down(const MatDesc& d, int mc, const TransferMap& tm, int nsweep, bool zero,
                        const double* mat, const PatOp& po, const double* b, const double* xin, double* xout,
                        const double* P0, const double* P1, double* rc, int64_t n, int64_t n_cover,
-                       double alpha, const Slab& sl, cudaStream_t st, bool pdl, cudaError_t* err, bool rec = false) {
+                       double alpha, const Slab& sl, cudaStream_t st, bool pdl, cudaError_t* err, int rec = 0) {
     const WinIdx w = fused_window(nsweep, tm, P1 != nullptr || tm.shift != 0 || tm.base != 0, sl);
     if (w.out < tm.ratio || w.out < FUSED_B / 2 || !fast_tier_ok(d)) return FUSED_NA;
     const unsigned grid = (unsigned)((n_cover + w.out - 1) / w.out);
@@ -1256,7 +1275,7 @@ inline int fused_down(const MatDesc& d, int mc, const TransferMap& tm, int nswee
         } else                                                                                           \
         *err = launch_fused(f_down<MM, MCC, FUSED_B, SS, DG>, grid, FUSED_B, 0, st, pdl, mat, po, d.ilo, d.iup, \
                             b, xin, xout, P0, P1, tm, rc, n, alpha, nsweep, zero ? 1 : 0, w, sl,         \
-                            (rec && !po.tab && !DG) ? 1 : 0);                                            \
+                            (!po.tab && !DG) ? rec : 0);                                                 \
         return *err == cudaSuccess ? FUSED_OK : FUSED_ERR;
         FUSED_COMBOS(X)
 #undef X
@@ -1268,7 +1287,7 @@ inline int fused_up(const MatDesc& d, int mc, const TransferMap& tm, int nsweep,
                      const PatOp& po, const double* b, const double* xin, double* xout, const double* P0,
                      const double* P1, const double* xcoarse, int64_t n, double alpha, double* partial,
                      int64_t partial_cap, int* nblocks, const Slab& sl, cudaStream_t st, bool pdl,
-                     cudaError_t* err, bool rec = false) {
+                     cudaError_t* err, int rec = 0) {
     const WinIdx w = fused_window(nsweep, tm, false, sl);
     if (w.out < tm.ratio || w.out < FUSED_B / 2 || !fast_tier_ok(d)) return FUSED_NA;
     const int64_t grid = (n + w.out - 1) / w.out;
@@ -1285,7 +1304,7 @@ inline int fused_up(const MatDesc& d, int mc, const TransferMap& tm, int nsweep,
         } else                                                                                           \
         *err = launch_fused(f_up<MM, MCC, FUSED_B, SS, DG>, (unsigned)grid, FUSED_B, 0, st, pdl, mat, po,    \
                             d.ilo, d.iup, b, xin, xout, P0, P1, tm, xcoarse, n, alpha, nsweep, w, partial, sl, \
-                            (rec && !po.tab && !DG) ? 1 : 0);                                            \
+                            (!po.tab && !DG) ? rec : 0);                                                 \
         return *err == cudaSuccess ? FUSED_OK : FUSED_ERR;
         FUSED_COMBOS(X)
 #undef X

@@ -155,6 +155,20 @@ class DeviceHierarchy:
         self._ck(self._lib.amg1d_ldiv(self._h, capi.dptr(y), capi.dptr(b), nPre, nPost, alpha))
         return y
 
+    def vcycle_batch(self, xs, bs, zero_guess=False, nPre=3, nPost=3, alpha=2.0 / 3.0):
+        """One V-cycle per (x, b) pair, pipelined over PCIe (amg1d_vcycle_batch).  xs: list of C-contiguous float64
+        arrays, overwritten with the iterates (pinned memory overlaps the copies with the compute); bs likewise."""
+        n = len(xs)
+        assert len(bs) == n
+        for v in list(xs) + list(bs):
+            self._check_len(0, v)
+            assert v.dtype == np.float64 and v.flags["C_CONTIGUOUS"]
+        PD = C.POINTER(C.c_double)
+        xa = (PD * n)(*[v.ctypes.data_as(PD) for v in xs])
+        ba = (PD * n)(*[v.ctypes.data_as(PD) for v in bs])
+        self._ck(self._lib.amg1d_vcycle_batch(self._h, n, xa, ba, int(bool(zero_guess)), nPre, nPost, alpha))
+        return xs
+
     def pcg(self, x0, b, maxiter, tol, nPre=3, nPost=3, alpha=2.0 / 3.0):
         x = np.array(x0, dtype=np.float64, order="C", copy=True)
         b = capi.f64(b)
@@ -237,6 +251,44 @@ class DeviceHierarchy:
         x0 = capi.f64(x0) if x0 is not None else None
         b = capi.f64(b) if b is not None else None
         self._ck(self._lib.amg1d_dev_set_problem(self._h, capi.dptr(x0), capi.dptr(b)))
+
+    def dev_assemble_rhs(self, kind, xi, W, terms, xin, xout, vertices=None, fixes=()):
+        """Right-hand side assembled on the device (amg1d_dev_assemble_rhs).  kind: 0 DG-type level 0, 1 CG level
+        0 in group order; xi (nq,), W (nq, p + 1) = w_q phi_i(xi_q); terms: iterable of (kind, coef, pow, w, phi)
+        with kind in {"1", "cos", "sin", "exp"} or 0..3; fixes: iterable of (global slot, value, op) with op
+        "add" / "set" (the boundary terms, computed by the host)."""
+        names = {"1": 0, "const": 0, "cos": 1, "sin": 2, "exp": 3}
+        t = np.array([[names.get(k, k) if isinstance(k, str) else k, c, pw, w, ph] for (k, c, pw, w, ph) in terms],
+                     dtype=np.float64).reshape(-1, 5)
+        xi = capi.f64(xi)
+        W = capi.f64(W)
+        fs = capi.i64([f[0] for f in fixes])
+        fv = capi.f64([f[1] for f in fixes])
+        fo = np.ascontiguousarray([1 if f[2] in (1, "set") else 0 for f in fixes], dtype=np.int32)
+        vt = capi.f64(vertices) if vertices is not None else None
+        self._ck(self._lib.amg1d_dev_assemble_rhs(
+            self._h, int(kind), len(xi), capi.dptr(xi), capi.dptr(W), W.shape[1], t.shape[0], capi.dptr(t),
+            float(xin), float(xout), capi.dptr(vt), len(fs), capi.iptr(fs) if len(fs) else None,
+            capi.dptr(fv) if len(fs) else None, fo.ctypes.data_as(C.POINTER(C.c_int)) if len(fs) else None))
+
+    def dev_get_rhs(self):
+        b = np.zeros(self.n_dof[0])
+        self._ck(self._lib.amg1d_dev_get_rhs(self._h, capi.dptr(b)))
+        return b
+
+    def dev_solve(self, maxiter, tol, nPre=3, nPost=3, alpha=2.0 / 3.0):
+        """``multigrid`` on the device-resident problem; returns (iters, res) - the solution stays on the device."""
+        res = np.zeros(max(maxiter, 1))
+        it = C.c_int(0)
+        self._ck(self._lib.amg1d_dev_solve(self._h, maxiter, tol, nPre, nPost, alpha, C.byref(it), capi.dptr(res)))
+        return it.value, res[:it.value].copy()
+
+    def dev_pcg(self, maxiter, tol, nPre=3, nPost=3, alpha=2.0 / 3.0):
+        """``pcg`` on the device-resident problem; returns (iters, res) - the solution stays on the device."""
+        res = np.zeros(max(maxiter, 1))
+        it = C.c_int(0)
+        self._ck(self._lib.amg1d_dev_pcg(self._h, maxiter, tol, nPre, nPost, alpha, C.byref(it), capi.dptr(res)))
+        return it.value, res[:it.value].copy()
 
     def dev_fill_rhs_random(self, seed=0):
         self._ck(self._lib.amg1d_dev_fill_rhs_random(self._h, seed))

@@ -268,13 +268,26 @@ class UniformDgHierarchy:
             hh, xc = xr - xl, (xl + xr) / 2.0
             xq = xc[:, None] + (hh / 2.0)[:, None] * ref.mGaussQuadNodes[None, :]
             b[(e0 - lo_e) * m:(e1 - lo_e) * m] = ((hh / 2.0)[:, None] * (eval_func(func, xq) @ W)).ravel()
+        for slot, val, _ in self.rhs_boundary_fixes(bc_values):      # (all "add")
+            if lo_e * m <= slot < hi_e * m:
+                b[slot - lo_e * m] += val
+        return b
+
+    def rhs_boundary_fixes(self, bc_values):
+        """The boundary terms of b = f - D (M \\ r) (src/dg_mesh.jl:366-457: penalty and flux terms at the two end
+        elements) as a list of (global level-0 slot, value, "add") - a handful of entries, shared by the host
+        path above and the device-side assembly."""
+        p0 = self.dg_orders[0]
+        m = p0 + 1
+        n = self.n
         lv = self.levels[0]
         Dlo, Ddi, Dup = lv.ops["D"] if lv.explicit else lv.ops["D"].expand(min(n, NV))
         Minv = np.linalg.inv(lv.mass)
         e1, e2 = 0, (1 if p0 >= 1 else 0)
-        def add(el, vec):                                   # b[el] += vec if el lies in the slab
-            if lo_e <= el < hi_e:
-                b[(el - lo_e) * m:(el - lo_e + 1) * m] += vec
+        fixes = []
+
+        def add(el, vec):
+            fixes.extend((el * m + i, float(v), "add") for i, v in enumerate(vec) if v != 0.0)
 
         for side, el, loc, sgn in ((0, 0, e1, -1.0), (1, n - 1, e2, 1.0)):
             val = bc_values[side]
@@ -289,7 +302,17 @@ class UniformDgHierarchy:
                     add(el - 1, -(Dup[w - 1] @ s))
             else:
                 add(el, sgn * val * unit)
-        return b
+        return fixes
+
+    def device_rhs(self, terms, bc_values, dev=None):
+        """The same right-hand side assembled ON THE DEVICE (amg1d_dev_assemble_rhs; every rank its own slab):
+        func(x) = sum of terms (kind, coef, pow, w, phi), e.g. [("cos", w * w, 0, w, 0.0)].  Leaves b on level 0 and
+        x = 0; nothing but the quadrature tables and the boundary entries crosses PCIe."""
+        dev = dev or self.device
+        ref = ReferenceElement(self.dg_orders[0])
+        W = ref.mGaussQuadWeights[:, None] * ref.mBasisGQFunVal
+        dev.dev_assemble_rhs(0, ref.mGaussQuadNodes, W, terms, self.xin, self.xout,
+                             fixes=self.rhs_boundary_fixes(bc_values))
 
     # ---- upload --------------------------------------------------------------------------------------
     def upload(self, device=0, stream=None, dist=None, options=None):
@@ -544,10 +567,6 @@ class UniformCgHierarchy:
         g0, g1 = (0, n + 1) if group_range is None else group_range
         b = np.zeros((g1 - g0, p))
 
-        def add(g, col, val):                                             # b[g, col] += val if g is in the slab
-            if g0 <= g < g1:
-                b[g - g0, col] += val
-
         W = ref.mGaussQuadWeights[:, None] * ref.mBasisGQFunVal            # (nq, p+1)
         for e0 in range(max(g0 - 1, 0), min(g1, n), chunk):                # elements touching the slab
             e1 = min(min(g1, n), e0 + chunk)
@@ -565,6 +584,26 @@ class UniformCgHierarchy:
             a, z = max(e0 + 1, g0), min(e1 + 1, g1)                        # right vertex: group e + 1
             if z > a:
                 b[a - g0:z - g0, 0] += fe[a - 1 - e0:z - 1 - e0, 1]
+        b = b.ravel()
+        for slot, val, op in self.rhs_boundary_fixes(bc_values):
+            if g0 * p <= slot < g1 * p:
+                if op == "set":
+                    b[slot - g0 * p] = val
+                else:
+                    b[slot - g0 * p] += val
+        return b
+
+    def rhs_boundary_fixes(self, bc_values):
+        """Neumann terms (src/cg_mesh.jl:164-174) and the strong-Dirichlet column terms and rows (:177-182) as an
+        ordered list of (global level-0 slot in group order, value, "add" | "set")."""
+        p = self.cg_orders[0]
+        ref = ReferenceElement(p)
+        n = self.n
+        fixes = []
+
+        def add(g, col, val):
+            fixes.append((g * p + col, float(val), "add"))
+
         kref = np.einsum("l,li,lj->ij", ref.mGaussQuadWeights, ref.mBasisGQDerivVal, ref.mBasisGQDerivVal)
         for side in (0, 1):                                               # Neumann terms first (:164-174)
             if self.bc_kinds[side] == "neu":
@@ -581,10 +620,18 @@ class UniformCgHierarchy:
             for q in range(2, p + 1):
                 add(el, q - 1, -col[q])
         for side in (0, 1):
-            g = 0 if side == 0 else n
-            if self.bc_kinds[side] == "dir" and g0 <= g < g1:
-                b[g - g0, 0] = bc_values[side]
-        return b.ravel()
+            if self.bc_kinds[side] == "dir":
+                fixes.append(((0 if side == 0 else n) * p, float(bc_values[side]), "set"))
+        return fixes
+
+    def device_rhs(self, terms, bc_values, dev=None):
+        """The right-hand side of cg_stiffness_and_rhs assembled ON THE DEVICE in group order
+        (amg1d_dev_assemble_rhs, kind 1); see UniformDgHierarchy.device_rhs."""
+        dev = dev or self.device
+        ref = ReferenceElement(self.cg_orders[0])
+        W = ref.mGaussQuadWeights[:, None] * ref.mBasisGQFunVal
+        dev.dev_assemble_rhs(1, ref.mGaussQuadNodes, W, terms, self.xin, self.xout,
+                             fixes=self.rhs_boundary_fixes(bc_values))
 
     # ---- upload ------------------------------------------------------------------------------------------
     def upload(self, device=0, stream=None, dist=None, options=None):

@@ -370,6 +370,52 @@ def measure(ctx, args, workload, ranks, full):
         bufs.append(p)
     xh = np.ctypeslib.as_array(C.cast(bufs[0], C.POINTER(C.c_double)), shape=(N0,))
     bh = np.ctypeslib.as_array(C.cast(bufs[1], C.POINTER(C.c_double)), shape=(N0,))
+    # the right-hand side assembled ON THE DEVICE (amg1d_dev_assemble_rhs: every rank its slab, nothing but the
+    # quadrature tables crosses PCIe) and multigrid() on the device-resident problem
+    w = 2.0 * math.pi / 64.0
+    barrier()
+    t0 = time.perf_counter()
+    U.device_rhs([("cos", w * w, 0, w, 0.0)], pr["bc_values"], dev)
+    dev.synchronize()
+    barrier()
+    t_rhs_dev = mx(time.perf_counter() - t0)
+    t0 = time.perf_counter()
+    it_dev, res_dev = dev.dev_solve(100, 1e-10)
+    barrier()
+    t_solve_dev = mx(time.perf_counter() - t0)
+    nb_dev = dev.dev_rhs_norm()
+    dev_solve = {"rhs_assembly_s": t_rhs_dev, "iters": it_dev, "seconds": t_solve_dev,
+                 "final_relative_residual": float(res_dev[-1] / nb_dev), "converged": bool(res_dev[-1] < 1e-10 * nb_dev),
+                 "call": "amg1d_dev_assemble_rhs + amg1d_dev_solve (multigrid on the device-resident problem)"}
+    if not dev_solve["converged"]:
+        # plain V-cycle iteration stalls in FP64 at this size (CG-first hierarchy at 2^26 elements: cond ~ 1 / eps; the
+        # CPU oracle shows the same history, profiles/r02_hist_*_C4_2p26.json): CG with the same V-cycle as preconditioner
+        U.device_rhs([("cos", w * w, 0, w, 0.0)], pr["bc_values"], dev)
+        barrier()
+        t0 = time.perf_counter()
+        it_p, res_p = dev.dev_pcg(100, 1e-10)
+        barrier()
+        t_p = mx(time.perf_counter() - t0)
+        dev_solve["pcg"] = {"iters": it_p, "seconds": t_p, "final_relative_residual": float(res_p[-1] / nb_dev),
+                            "converged": bool(res_p[-1] < 1e-10 * nb_dev), "call": "amg1d_dev_pcg"}
+        dev_solve["converged_via"] = "pcg" if dev_solve["pcg"]["converged"] else None
+        dev_solve["seconds_to_1e-10"] = t_p if dev_solve["pcg"]["converged"] else None
+    else:
+        dev_solve["converged_via"] = "multigrid"
+        dev_solve["seconds_to_1e-10"] = t_solve_dev
+    if not full:
+        # secondary objects: no host vectors at all; CG as the fall-back where plain cycling stalls in FP64
+        line_light = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms_step, "scaling": "strong" if strong else "weak",
+            "config": {"workload": f"{workload}: {desc}", "n_elements": n, "elements_per_gpu": nloc, "levels": len(U.levels),
+                       "gather_level": dev.info("gather_level"), "p2p_halo": dev.info("p2p_halo"),
+                       "options": args.opt + args.pre_opt, "setup_s": t_setup, "dof_updates_per_step": upd},
+            "clocks": clocks, "gpu_launches": int(launches), "time_to_1e-10": dev_solve}
+        for p in bufs:
+            lib.amg1d_host_free(p)
+        dev.close()
+        return line_light
     t_rhs = time.perf_counter()
     bh[:] = rhs_slab(U, pr, rank, world)
     t_rhs = time.perf_counter() - t_rhs
@@ -427,23 +473,18 @@ def measure(ctx, args, workload, ranks, full):
               "tile_rows": [U.tile_rows(l) for l in range(min(4, len(U.levels)))],
               "streamed_operator_doubles": [U.streamed_operator_doubles(l) for l in range(min(4, len(U.levels)))],
               "tail_start": dev.info("tail_start"), "options": args.opt + args.pre_opt,
-              "gather_level": dev.info("gather_level"),
-              "device_bytes": dev.info("device_bytes"), "setup_s": t_setup, "rhs_assembly_s": t_rhs,
+              "gather_level": dev.info("gather_level"), "p2p_halo": dev.info("p2p_halo"),
+              "device_bytes": dev.info("device_bytes"), "setup_s": t_setup, "rhs_assembly_s": t_rhs_dev,
+              "rhs_assembly_host_numpy_s": t_rhs,
               "residual_after_timed_steps": res_after}
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True,
         "scaling": "strong" if strong else "weak",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": config,
-        "clocks": clocks, "time_to_1e-10": solve, "gpu_launches": int(launches),
+        "clocks": clocks, "time_to_1e-10": solve, "time_to_1e-10_device_resident": dev_solve, "gpu_launches": int(launches),
         "fine_dof_cycles_per_s": N0_all / (ms_step * 1e-3),
     }
-    if not full:
-        for p in bufs:
-            lib.amg1d_host_free(p)
-        dev.close()
-        return line
-
     # ---- roofline of the dominant kernel, CUDA events around each launch (un-graphed pass) --------
     peak, peak_src = measured_peak()
     dev.dev_fill_rhs_random(0)
@@ -500,6 +541,39 @@ def measure(ctx, args, workload, ranks, full):
     e2e = {"value": upd / t_e2e, "unit": UNIT, "h2d_bytes_per_step": 2 * N0_all * 8,
            "d2h_bytes_per_step": N0_all * 8, "ms_per_step": t_e2e * 1e3, "steps": e2e_steps,
            "call": "amg1d_vcycle (multigrid_v_cycle(H, x0, b)) with pinned host x0, b"}
+    # ---- the same call for a stream of independent problems: amg1d_vcycle_batch pipelines upload / cycle /
+    # download over the full-duplex PCIe link.  Every step still moves its own x0 and b up and its own x down.
+    pipe_steps = max(4, 2 * e2e_steps)
+    pb = []
+    for _ in range(4):                       # two (x, b) pairs of pinned host vectors, used alternately
+        p = C.c_void_p()
+        capi.check(None, lib.amg1d_host_alloc(C.byref(p), N0 * 8))
+        pb.append(p)
+    hv = [np.ctypeslib.as_array(C.cast(p, C.POINTER(C.c_double)), shape=(N0,)) for p in pb]
+    hv[0][:] = 0.0; hv[1][:] = 0.0; hv[2][:] = bh; hv[3][:] = bh
+    PD = C.POINTER(C.c_double)
+    xa = (PD * pipe_steps)(*[hv[k % 2].ctypes.data_as(PD) for k in range(pipe_steps)])
+    ba = (PD * pipe_steps)(*[hv[2 + k % 2].ctypes.data_as(PD) for k in range(pipe_steps)])
+    capi.check(dev._h, lib.amg1d_vcycle_batch(dev._h, 2, xa, ba, 0, 3, 3, 2.0 / 3.0))            # warm (allocates staging)
+    barrier()
+    t0 = time.perf_counter()
+    capi.check(dev._h, lib.amg1d_vcycle_batch(dev._h, pipe_steps, xa, ba, 0, 3, 3, 2.0 / 3.0))
+    barrier()
+    t_pipe = mx(time.perf_counter() - t0) / pipe_steps
+    barrier()
+    t0 = time.perf_counter()
+    capi.check(dev._h, lib.amg1d_vcycle_batch(dev._h, pipe_steps, xa, ba, 1, 3, 3, 2.0 / 3.0))
+    barrier()
+    t_pipe0 = mx(time.perf_counter() - t0) / pipe_steps
+    for p in pb:
+        lib.amg1d_host_free(p)
+    e2e["single_call"] = {"value": e2e["value"], "ms_per_step": e2e["ms_per_step"], "call": e2e["call"]}
+    e2e.update(value=upd / t_pipe, ms_per_step=t_pipe * 1e3, steps=pipe_steps,
+               call="amg1d_vcycle_batch: multigrid_v_cycle(H, x0_k, b_k) for a stream of independent problems, pinned host "
+                    "vectors; upload of problem k + 1, V-cycle of k and download of k - 1 overlap; every step moves its own "
+                    "x0, b up and x down (one problem per call: see single_call)")
+    e2e["ldiv_pipelined"] = {"value": upd / t_pipe0, "ms_per_step": t_pipe0 * 1e3, "h2d_bytes_per_step": N0_all * 8,
+                             "d2h_bytes_per_step": N0_all * 8, "call": "amg1d_vcycle_batch with zero_guess = 1 (ldiv!(y_k, H, b_k))"}
     # ---- ldiv!(y, H, b): one V-cycle from zero, only b travels up ----------------------------------------
     capi.check(dev._h, lib.amg1d_ldiv(dev._h, capi.dptr(xh), capi.dptr(bh), 3, 3, 2.0 / 3.0))
     barrier()
@@ -593,8 +667,8 @@ def run_gpu(args):
     ctx = Ctx()
     world = ctx.world
     workload = args.workload or default_workload(world)
-    line = measure(ctx, args, workload, world, full=True)
-    if not args.workload and not args.no_extra:
+    line = measure(ctx, args, workload, world, full=not args.light)
+    if not args.workload and not args.no_extra and not args.light:
         # The default run also carries BASELINE's other multi-GPU configuration and the bases its scaling is
         # judged against, measured in this very process group (rank 0 alone for the single-GPU bases).
         light = argparse.Namespace(**vars(args))
@@ -641,6 +715,8 @@ def main():
                     help="default: T on one GPU, C5 (weak, 2^24 elements per GPU) on several")
     ap.add_argument("--no-cpu", action="store_true", help="skip the CPU baseline leg")
     ap.add_argument("--no-pattern", action="store_true", help="skip the pattern-resident variants")
+    ap.add_argument("--light", action="store_true",
+                    help="throughput + device-resident time-to-1e-10 only (A/B runs; not the contract line)")
     ap.add_argument("--no-extra", action="store_true",
                     help="skip the secondary objects of the default run (C5 base, C4 strong)")
     ap.add_argument("--pre-opt", action="append", default=[], metavar="KEY=VALUE",

@@ -175,6 +175,14 @@ int amg1d_solve(amg1d_t* h, double* x, const double* b, int maxiter, double tol,
  * the finest level skips the operator (x = alpha Dinv b), exactly as the levels below always do. */
 int amg1d_ldiv(amg1d_t* h, double* y, const double* b, int nPre, int nPost, double alpha);
 
+/* The same V-cycle on `count` independent problems, pipelined over PCIe: problem k + 1 is uploaded and the
+ * iterate of problem k - 1 downloaded on two copy streams while problem k runs (one amg1d_vcycle call is bound
+ * by its three serial vector transfers; PCIe is full duplex).  x[k]: in = initial guess, ignored with zero_guess
+ * = 1 (the ldiv! form: x0 = 0 is neither uploaded nor read), out = the iterate; b[k]: right-hand side.  Host
+ * vectors should be pinned (amg1d_host_alloc).  Bit-identical to `count` amg1d_vcycle / amg1d_ldiv calls. */
+int amg1d_vcycle_batch(amg1d_t* h, int count, double* const* x, const double* const* b, int zero_guess,
+                       int nPre, int nPost, double alpha);
+
 /* Conjugate gradients on the finest level, preconditioned with ldiv!(z, H, r) - what the reference's
  * ldiv! methods exist for (src/solvers.jl:63-92 make MeshHierarchy usable as `Pl` of a Krylov solver
  * such as IterativeSolvers.cg; the reference ships no driver for it).  Textbook PCG: z = M^-1 r,
@@ -221,6 +229,30 @@ int amg1d_direct_solve(amg1d_t* h, int level, double* x, const double* b);
  * amg1d_ldiv upload their own vectors and are not affected. */
 int amg1d_dev_set_problem(amg1d_t* h, const double* x0, const double* b); /* host -> device, x0 NULL = 0 */
 int amg1d_dev_fill_rhs_random(amg1d_t* h, uint64_t seed);          /* b[i] ~ U(-1,1) on the device, x = 0 */
+/* Right-hand side assembled ON THE DEVICE: the volume integrals of dg_flux_rhs
+ * (src/dg_mesh.jl:342-365) - kind 0, level 0 a DG-type level - or of cg_stiffness_and_rhs / cg_rhs
+ * (src/cg_mesh.jl:150-160, :205-215) - kind 1, level 0 a CG level uploaded in group order - for
+ *     func(x) = sum_t coef_t x^pow_t g_t(w_t x + phi_t),   g = 1 | cos | sin | exp
+ * (terms: 5 doubles per term: kind 0 / 1 / 2 / 3, coef, pow (integer 0..16), w, phi), integrated with the
+ * host's quadrature: xi (nq reference nodes) and W (nq x n_basis row-major, W[q][i] = w_q phi_i(xi_q),
+ * n_basis = p + 1).  Elements are those of the reference's mesh generator (tests/mesh_generator.jl:20-32:
+ * x_i = xin + (i / n)(xout - xin)) or, if `vertices` is not NULL, [vertices[e], vertices[e + 1]] (n + 1 doubles).
+ * The boundary terms of the reference (flux / penalty terms at the two end elements, Neumann data, strong
+ * Dirichlet rows) are a handful of entries the host computes and passes as a fix list, applied in order:
+ * fix_op[k] = 0: b[fix_slot[k]] += fix_val[k]; 1: b[fix_slot[k]] = fix_val[k]; fix_slot are GLOBAL level-0 slots.
+ * Sharded handles assemble their own slab (and its ghost elements).  x is set to 0. */
+int amg1d_dev_assemble_rhs(amg1d_t* h, int kind, int nq, const double* xi, const double* W, int n_basis,
+                           int n_terms, const double* terms, double xin, double xout, const double* vertices,
+                           int n_fix, const int64_t* fix_slot, const double* fix_val, const int* fix_op);
+int amg1d_dev_get_rhs(amg1d_t* h, double* b);                      /* device -> host (this rank's slab) */
+/* multigrid(H, x0, b, maxiter, tol) (src/solvers.jl:116-139) on the device-resident problem: no host vector
+ * moves; res[i] = ||A x - b||_2 after cycle i + 1; the solution stays on the device (amg1d_dev_get_solution). */
+int amg1d_dev_solve(amg1d_t* h, int maxiter, double tol, int nPre, int nPost, double alpha, int* iters,
+                    double* res);
+/* amg1d_pcg on the device-resident problem (initial guess = the resident iterate); the solution becomes the
+ * resident iterate, the resident right-hand side is consumed (it becomes the CG residual). */
+int amg1d_dev_pcg(amg1d_t* h, int maxiter, double tol, int nPre, int nPost, double alpha, int* iters,
+                  double* res);
 /* asynchronous on the stream; with_residual_norm = 1 also leaves ||A x - b||_2 of the new iterate on the
  * device (fused into the last kernel of the cycle), which amg1d_dev_residual_norm then just reads */
 int amg1d_dev_vcycle(amg1d_t* h, int nPre, int nPost, double alpha, int with_residual_norm);
@@ -242,11 +274,17 @@ void* amg1d_dev_ptr(amg1d_t* h, int level, int which);             /* raw device
  * set as a kernel parameter and use it as constant operands; default 0; bit-identical results in all modes),
  * "rows_window" (elements per CTA of the row-per-thread legs for 5..9-row blocks: 32, 64; 0 = off;
  * default 64), "rows_per_thread" (block rows per thread of those legs: 1, 2, 3; 0 = auto, default);
- * "recompute_dinv" (default 1.  Set before the first level: the block-Jacobi inverses of a level - when the
- * uploaded Dinv agrees with inv(A_di) to 1e-8 - are replaced by the device's own pivoted Gauss-Jordan inverse
- * of the stored diagonal blocks, so that the fused legs can invert A_di in registers instead of streaming the
- * stored inverse from HBM while every other kernel, which reads the stored inverse, produces the same bits.
- * Later: 0 makes the fused legs stream the stored inverse again - same results, more bytes);
+ * "recompute_dinv" (default 4 = levels with 4 x 4 blocks; v = blocks of v x v up to 4 x 4 - larger blocks were
+ * measured slower; 0 = never.  Where non-zero when a level is
+ * set, its block-Jacobi inverses - if the uploaded Dinv agrees with inv(A_di) to 1e-8 - are replaced by the
+ * device's own pivoted Gauss-Jordan inverse of the stored diagonal blocks, so that the fused legs can invert
+ * A_di in registers instead of streaming the stored inverse from HBM while every other kernel, which reads the
+ * stored inverse, produces the same bits.  Changing the value later only selects which levels recompute -
+ * same results, other byte counts);
+ * "p2p_halo" (before amg1d_finalize, multi-GPU handles; default 1: the slab-edge exchanges of the V-cycle go
+ * through CUDA-IPC peer memory over NVLink - two small kernels per exchange - instead of NCCL send / recv groups;
+ * falls back to NCCL, on every rank alike, if the peer mapping is refused; amg1d_get_info("p2p_halo") tells
+ * which one is active; bit-identical results);
  * before the first level is
  * set: "compress" (1 = store only the structurally non-zero column / row of the off-diagonal blocks
  * where every element of the level has that structure, default 1), "shard_min" (elements per rank

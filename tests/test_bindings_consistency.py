@@ -14,16 +14,18 @@ C_TYPES = {
     "amg1d_t*": "ptr", "const amg1d_t*": "ptr", "amg1d_t**": "ptr*", "void*": "ptr", "const void*": "ptr",
     "void**": "ptr*", "int": "i32", "int64_t": "i64", "uint64_t": "u64", "double": "f64",
     "double*": "f64*", "const double*": "f64*", "int64_t*": "i64*", "const int64_t*": "i64*",
-    "int*": "i32*", "const char*": "str",
+    "int*": "i32*", "const int*": "i32*", "const char*": "str", "double*const*": "f64**",
+    "const double*const*": "f64**",
 }
 CT_TYPES = {
     C.c_void_p: "ptr", C.POINTER(C.c_void_p): "ptr*", C.c_int: "i32", C.c_int64: "i64", C.c_uint64: "u64",
     C.c_double: "f64", C.POINTER(C.c_double): "f64*", C.POINTER(C.c_int64): "i64*",
-    C.POINTER(C.c_int): "i32*", C.c_char_p: "str",
+    C.POINTER(C.c_int): "i32*", C.c_char_p: "str", C.POINTER(C.POINTER(C.c_double)): "f64**",
 }
 JL_TYPES = {
     "Ptr{Cvoid}": "ptr", "Ref{Ptr{Cvoid}}": "ptr*", "Cint": "i32", "Int64": "i64", "UInt64": "u64",
-    "Float64": "f64", "Ptr{Float64}": "f64*", "Ptr{Int64}": "i64*", "Ref{Cint}": "i32*", "Cstring": "str",
+    "Float64": "f64", "Ptr{Float64}": "f64*", "Ptr{Int64}": "i64*", "Ref{Cint}": "i32*", "Ptr{Cint}": "i32*",
+    "Cstring": "str", "Ptr{Ptr{Float64}}": "f64**",
 }
 
 

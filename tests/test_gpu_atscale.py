@@ -81,8 +81,9 @@ def test_residual_histories_match_the_oracle_at_baseline_sizes(name, log2n, cg, 
     assert it == it_or, (it, it_or, res / nb, res_or / nb)
     assert res_or[-1] < 1e-10 * nb
     assert np.all(np.abs(res - res_or) <= np.maximum(1e-10 * res_or, floor)), (res, res_or)
-    # while the residual is far above the floor the 1e-10 bound holds with nothing else in play
-    far = res_or > 1e4 * floor
+    # while the residual is far above the floor the 1e-10 bound holds with nothing else in play (`floor` is a
+    # worst-case bound; the observed noise of the reported norm is ~1e-5 of it, so "far" = 1e-10 res > 1e-4 floor)
+    far = res_or > 1e6 * floor
     assert far.sum() >= 3 and np.all(np.abs(res - res_or)[far] <= 1e-10 * res_or[far])
     # (no bound on x itself: cond(A) ~ (2n / pi)^2 reaches 4e14 at 2^25 elements, so two iterates whose residuals
     # both sit at 1e-10 ||b|| may differ by far more than that in the smoothest modes; the difference is printed)

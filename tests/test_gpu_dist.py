@@ -16,7 +16,8 @@ def _ngpu():
 
 
 # *_pat: option pattern_resident = 1, *_pat2: = 2 (constant-bank operands in the interior CTAs)
-KINDS = ["dg", "cg", "dg8", "cg8", "dg_pat", "cg_pat", "dg8_pat", "dg_pat2", "cg_pat2"]
+# *_nccl: slab edges through NCCL send / recv groups (option p2p_halo = 0); all others through peer memory
+KINDS = ["dg", "cg", "dg8", "cg8", "dg_pat", "cg_pat", "dg8_pat", "dg_pat2", "cg_pat2", "dg_nccl", "cg_nccl"]
 
 
 @pytest.mark.parametrize("world", [2, 4, 8])
@@ -44,3 +45,4 @@ def test_sharded_solve_matches_single_gpu(world, tmp_path):
     for kind, rep in reps.items():
         assert rep["ok"], (kind, rep)
         assert rep["gather_level"] > 0, (kind, rep)
+        assert rep["p2p_halo"] == rep["p2p_requested"], (kind, rep)     # the peer mapping was not refused

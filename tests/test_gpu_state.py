@@ -103,3 +103,28 @@ def test_failed_level_upload_can_be_retried(lib):
     assert rc == capi.OK
     capi.check(h, lib.amg1d_finalize(h))
     lib.amg1d_destroy(h)
+
+
+@pytest.mark.parametrize("shape", ["C2_dg3_agg", "cg_heirarchy"])
+def test_pipelined_batch_equals_single_calls(shape):
+    """amg1d_vcycle_batch (copy-in / compute / copy-out overlapped over PCIe) gives, problem by problem, the bits
+    of amg1d_vcycle and - with zero_guess - of amg1d_ldiv; DG level 0 (plain copies) and CG level 0 (permuted)."""
+    Hp, _, b = build_package(**SHAPES[shape])
+    dev = Hp.device
+    rng = np.random.default_rng(11)
+    K = 5
+    bs = [b * (1.0 + 0.25 * k) + 1e-3 * rng.standard_normal(len(b)) for k in range(K)]
+    x0 = [rng.standard_normal(len(b)) for _ in range(K)]
+    ref = [dev.vcycle(x0[k], bs[k], nPre=2, nPost=3, alpha=0.6) for k in range(K)]
+    xs = [v.copy() for v in x0]
+    dev.vcycle_batch(xs, bs, nPre=2, nPost=3, alpha=0.6)
+    for k in range(K):
+        assert np.array_equal(xs[k], ref[k]), k
+    ref0 = [dev.ldiv(bs[k]) for k in range(K)]
+    ys = [np.full(len(b), np.nan) for _ in range(K)]            # never read in the zero-guess form
+    dev.vcycle_batch(ys, bs, zero_guess=True)
+    for k in range(K):
+        assert np.array_equal(ys[k], ref0[k]), k
+    dev.vcycle_batch([], [])                                    # an empty batch is fine
+    assert np.array_equal(dev.vcycle(x0[0], bs[0], nPre=2, nPost=3, alpha=0.6), ref[0])   # the handle is still sane
+    dev.close()
