@@ -107,6 +107,7 @@ struct Transfer {
     bool single_parent_uniform = false;  // parent[e] = e / ratio, no P1
     bool closed = false;     // parent[e] = (e + shift) / ratio + base for every e (pattern or detected)
     bool fusable = false;    // closed, and every coarse element has a first P0-child (f_down's gather rule)
+    int64_t p_first = 0;     // explicit blocks of a sharded level: global fine element of the first block kept
     int reach = 0;           // sharded two-parent transfers: fine ghost elements the restriction reads
     int64_t cover_extra = 0; // sharded: ghost elements right of the slab that own coarse elements of this rank
 };
@@ -305,6 +306,11 @@ TransferMap make_map_closed(const Transfer& t) {
     tm.cp = nullptr;
     return tm;
 }
+
+// Transfer blocks as the kernels index them: by pattern position, or - explicit blocks - by GLOBAL fine element;
+// a sharded level keeps only the blocks of its slab (p_first = first one kept), hence the bias.
+inline const double* tp0(const Transfer& t) { return t.P0 ? t.P0 - t.p_first * (int64_t)(t.mf * t.mc) : nullptr; }
+inline const double* tp1(const Transfer& t) { return t.P1 ? t.P1 - t.p_first * (int64_t)(t.mf * t.mc) : nullptr; }
 
 // slab of rank r of a level with n_glob elements split over nranks: [start, start + n)
 inline int64_t slab_start(int64_t n_glob, int nranks, int r) { return (n_glob / nranks) * r; }
@@ -628,25 +634,87 @@ int op_p2p_push(amg1d* h, int ch, int l, int vec, int l2 = -1, int vec2 = 0) {
     return AMG1D_OK;
 }
 
-int op_p2p_wait(amg1d* h, int ch) {
+// elements a channel receives per cycle and side: ghost_depth of the iterate (+ ghost_depth of the coarse rhs on a
+// down-leg channel whose coarse level is sharded too)
+unsigned long long p2p_quantum(const amg1d* h, int ch) {
+    const int l = ch / 2;
+    const bool down = (ch & 1) == 0;
+    return (unsigned long long)h->ghost_depth * ((down && l + 1 < h->n_levels && h->L[l + 1].sharded) ? 2 : 1);
+}
+
+int op_p2p_begin_cycle(amg1d* h) {
     amg1d::P2P& P = h->p2p;
-    k_halo_wait<<<1, 1, 0, h->stream>>>(p2p_my_flag(h, 0, ch), p2p_my_flag(h, 1, ch), P.epoch, 0ULL, P.err);
+    k_epoch_wait<<<1, 1, 0, h->stream>>>(P.epoch, p2p_my_flag(h, 0, 1), p2p_my_flag(h, 1, 1), p2p_quantum(h, 1),
+                                         P.err);                                                    // channel 1 = U_0
     h->launch_counter++;
     LAUNCH_CHECK();
     return AMG1D_OK;
 }
 
-int op_p2p_begin_cycle(amg1d* h) {
+// neighbour-side addresses of a level's vector: slot of MY element 0 in the left neighbour (its right ghosts) and of
+// MY element n - gd in the right neighbour (its left ghosts)
+void p2p_peer_slots(amg1d* h, int level, int vec, double** left, double** right) {
     amg1d::P2P& P = h->p2p;
-    k_epoch_wait<<<1, 1, 0, h->stream>>>(P.epoch, p2p_my_flag(h, 0, 1), p2p_my_flag(h, 1, 1), P.err);   // channel 1 = U_0
-    h->launch_counter++;
-    LAUNCH_CHECK();
+    const Level& lv = h->L[level];
+    *left = *right = nullptr;
+    if (P.peer[0]) {
+        const amg1d::P2P::Nb& nb = P.nb[0][(size_t)level];
+        *left = reinterpret_cast<double*>(P.peer[0] + nb.off[vec]) + nb.n * lv.m;
+    }
+    if (P.peer[1]) {
+        const amg1d::P2P::Nb& nb = P.nb[1][(size_t)level];
+        *right = reinterpret_cast<double*>(P.peer[1] + nb.off[vec]) - (int64_t)h->ghost_depth * lv.m;
+    }
+}
+
+// The exchange of one leg of sharded level l as the fused kernels perform it themselves (halo_p2p.cuh: HaloLeg).
+// out_vec: the x buffer the leg writes (its edges go to the neighbours) or -1: no push from inside the kernel.
+HaloLeg make_halo_leg(amg1d* h, int l, bool down, int out_vec) {
+    HaloLeg hl;
+    memset(&hl, 0, sizeof hl);
+    amg1d::P2P& P = h->p2p;
+    if (!P.on || !h->L[l].sharded) return hl;
+    hl.on = 1;
+    hl.gd = h->ghost_depth;
+    hl.epoch = P.epoch;
+    hl.err = P.err;
+    const bool coarse_sharded = l + 1 < h->n_levels && h->L[l + 1].sharded;
+    int wch[2] = {-1, -1};
+    if (down) { if (l > 0) wch[0] = 2 * (l - 1); }               // rhs ghosts: the finer level's down-leg channel
+    else { wch[0] = 2 * l; if (coarse_sharded) wch[1] = 2 * (l + 1) + 1; }   // pre-smoothed ghosts; coarse correction
+    for (int i = 0; i < 2; ++i) {
+        if (wch[i] < 0) continue;
+        hl.w_left[i] = p2p_my_flag(h, 0, wch[i]);
+        hl.w_right[i] = p2p_my_flag(h, 1, wch[i]);
+        hl.wq[i] = p2p_quantum(h, wch[i]);
+        hl.wlag[i] = 0;
+    }
+    if (out_vec >= 0) {
+        const int ch = down ? 2 * l : 2 * l + 1;
+        p2p_peer_slots(h, l, out_vec, &hl.x_left, &hl.x_right);
+        if (down && coarse_sharded) p2p_peer_slots(h, l + 1, 2, &hl.c_left, &hl.c_right);
+        if (P.peer[0]) hl.f_left = reinterpret_cast<unsigned long long*>(P.peer[0]) + 1 * P.n_ch + ch;
+        if (P.peer[1]) hl.f_right = reinterpret_cast<unsigned long long*>(P.peer[1]) + 0 * P.n_ch + ch;
+        hl.nc = make_slab(h, l).nc;
+    }
+    return hl;
+}
+
+// the same waits as stand-alone kernels (legs that are not f_down / f_up)
+int op_p2p_wait_for(amg1d* h, const HaloLeg& hl) {
+    for (int i = 0; i < 2; ++i) {
+        if (!hl.w_left[i] && !hl.w_right[i]) continue;
+        k_halo_wait<<<1, 1, 0, h->stream>>>(hl.w_left[i], hl.w_right[i], hl.epoch, hl.wlag[i], hl.wq[i], hl.err);
+        h->launch_counter++;
+        LAUNCH_CHECK();
+    }
     return AMG1D_OK;
 }
 #else
 int op_p2p_push(amg1d* h, int, int, int, int = -1, int = 0) { return fail(h, AMG1D_ERR_UNSUPPORTED, "built without NCCL"); }
-int op_p2p_wait(amg1d* h, int) { return fail(h, AMG1D_ERR_UNSUPPORTED, "built without NCCL"); }
 int op_p2p_begin_cycle(amg1d* h) { return fail(h, AMG1D_ERR_UNSUPPORTED, "built without NCCL"); }
+HaloLeg make_halo_leg(amg1d*, int, bool, int) { HaloLeg hl; memset(&hl, 0, sizeof hl); return hl; }
+int op_p2p_wait_for(amg1d* h, const HaloLeg&) { return fail(h, AMG1D_ERR_UNSUPPORTED, "built without NCCL"); }
 int op_halo(amg1d* h, double*, int64_t, int, double* = nullptr, int64_t = 0, int = 0) { return fail(h, AMG1D_ERR_UNSUPPORTED, "built without NCCL"); }
 int op_gather_rhs(amg1d* h, int) { return fail(h, AMG1D_ERR_UNSUPPORTED, "built without NCCL"); }
 int op_scatter_sol(amg1d* h, int) { return fail(h, AMG1D_ERR_UNSUPPORTED, "built without NCCL"); }
@@ -844,13 +912,22 @@ int leg_down(amg1d* h, int l, int nPre, double alpha, bool zero0) {
     if (h->opt_fused && t.fusable && !lv.smooth_tri) {
         const int ob = zero ? 0 : 1 - lv.cur;
         cudaError_t le = cudaSuccess;
+        const bool p2p = h->p2p.on && lv.sharded;
+        // peer-memory exchange done by the leg itself: wait for the rhs ghosts, push the pre-smoothed edges + coarse rhs
+        const HaloLeg hl = p2p ? make_halo_leg(h, l, true, ob) : HaloLeg();
         int fr = fused_down(lv.md, t.mc, make_map_closed(t), nPre, zero, lv.mat, make_pat(h, l), lv.b.p, lv.x[lv.cur].p,
-                            lv.x[ob].p, t.P0, t.P1, lc.b.p, lv.n, lv.n + (lv.gr ? t.cover_extra : 0),
-                            alpha, make_slab(h, l), h->stream, h->opt_pdl != 0, &le, leg_rec(h, lv));
-        if (fr == FUSED_NA && h->opt_rows)      // large blocks: one thread per block row
+                            lv.x[ob].p, tp0(t), tp1(t), lc.b.p, lv.n, lv.n + (lv.gr ? t.cover_extra : 0),
+                            alpha, make_slab(h, l), h->stream, h->opt_pdl != 0, &le, leg_rec(h, lv), hl);
+        if (fr == FUSED_NA && h->opt_rows) {    // large blocks: one thread per block row; exchange by stand-alone kernels
+            if (p2p) RET(op_p2p_wait_for(h, hl));
             fr = rows_down(lv.md, t.mc, make_map_closed(t), nPre, zero, lv.mat, make_pat(h, l), lv.b.p, lv.x[lv.cur].p,
-                           lv.x[ob].p, t.P0, t.P1, lc.b.p, lv.n, lv.n + (lv.gr ? t.cover_extra : 0), alpha,
+                           lv.x[ob].p, tp0(t), tp1(t), lc.b.p, lv.n, lv.n + (lv.gr ? t.cover_extra : 0), alpha,
                            make_slab(h, l), h->opt_rows, rows_rpt(h, l), h->stream, h->opt_pdl != 0, &le);
+            if (fr == FUSED_OK && p2p) {
+                if (lc.sharded) RET(op_p2p_push(h, 2 * l, l, ob, l + 1, 2));
+                else RET(op_p2p_push(h, 2 * l, l, ob));
+            }
+        }
         if (fr == FUSED_ERR) return fail(h, AMG1D_ERR_CUDA, "f_down launch failed on level %d: %s", l, cudaGetErrorString(le));
         if (fr == FUSED_OK) {
             lv.cur = ob;
@@ -885,7 +962,8 @@ int leg_down(amg1d* h, int l, int nPre, double alpha, bool zero0) {
 }
 
 // Up leg of level l: x += L x_c, nPost sweeps; optionally ||b - A x|| of the result (level 0).
-int leg_up(amg1d* h, int l, int nPost, double alpha, bool fuse_norm, bool* norm_done) {
+int leg_up(amg1d* h, int l, int nPost, double alpha, bool fuse_norm, bool* norm_done, bool* halo_pushed) {
+    *halo_pushed = false;
     Level& lv = h->L[l];
     Transfer& t = h->T[l];
     Level& lc = h->L[l + 1];
@@ -893,15 +971,24 @@ int leg_up(amg1d* h, int l, int nPost, double alpha, bool fuse_norm, bool* norm_
     if (h->opt_fused && t.fusable && !lv.smooth_tri) {
         int nb = 0;
         cudaError_t le = cudaSuccess;
+        const bool p2p = h->p2p.on && lv.sharded;
+        // Level 0's edges are pushed from inside the kernel only if the leg writes buffer 0, where the next cycle
+        // reads them (a zero-guess cycle ends in buffer 1 and is copied over: enqueue_vcycle pushes after that copy)
+        const int ob = 1 - lv.cur;
+        const bool push_inside = l > 0 || ob == 0;
+        const HaloLeg hl = p2p ? make_halo_leg(h, l, false, push_inside ? ob : -1) : HaloLeg();
         int fr = fused_up(lv.md, t.mc, make_map_closed(t), nPost, lv.mat, make_pat(h, l), lv.b.p, lv.x[lv.cur].p,
-                          lv.x[1 - lv.cur].p, t.P0, t.P1, lc.x[lc.cur].p, lv.n, alpha,
+                          lv.x[1 - lv.cur].p, tp0(t), tp1(t), lc.x[lc.cur].p, lv.n, alpha,
                           fuse_norm ? h->partial : nullptr, h->partial_cap, &nb, make_slab(h, l),
-                          h->stream, h->opt_pdl != 0, &le, leg_rec(h, lv));
-        if (fr == FUSED_NA && h->opt_rows)
+                          h->stream, h->opt_pdl != 0, &le, leg_rec(h, lv), hl);
+        if (fr == FUSED_OK && p2p && push_inside) *halo_pushed = true;
+        if (fr == FUSED_NA && h->opt_rows) {
+            if (p2p) RET(op_p2p_wait_for(h, hl));
             fr = rows_up(lv.md, t.mc, make_map_closed(t), nPost, lv.mat, make_pat(h, l), lv.b.p, lv.x[lv.cur].p,
-                         lv.x[1 - lv.cur].p, t.P0, t.P1, lc.x[lc.cur].p, lv.n, alpha,
+                         lv.x[1 - lv.cur].p, tp0(t), tp1(t), lc.x[lc.cur].p, lv.n, alpha,
                          fuse_norm ? h->partial : nullptr, h->partial_cap, &nb, make_slab(h, l), h->opt_rows,
                          rows_rpt(h, l), h->stream, h->opt_pdl != 0, &le);
+        }
         if (fr == FUSED_ERR) return fail(h, AMG1D_ERR_CUDA, "f_up launch failed on level %d: %s", l, cudaGetErrorString(le));
         if (fr == FUSED_OK) {
             lv.cur = 1 - lv.cur;
@@ -940,6 +1027,7 @@ int enqueue_vcycle(amg1d* h, int nPre, int nPost, double alpha, bool want_norm, 
     // levels [ts, nl) run inside the single-CTA tail kernel (rank 0 holds them; ts > gather level)
     const int ts = (h->tail_start > 0 && h->L[h->tail_start].present) ? h->tail_start : nl;
     const bool p2p = g >= 0 && h->p2p.on;       // slab edges through peer memory (halo_p2p.cuh) instead of NCCL
+    bool u0_pushed = false;
     if (p2p) RET(op_p2p_begin_cycle(h));
     // ---- down ----
     for (int l = 0; l < nl - 1 && l < ts; ++l) {
@@ -949,14 +1037,8 @@ int enqueue_vcycle(amg1d* h, int nPre, int nPost, double alpha, bool want_norm, 
         if (lv.sharded) {
             Level& lc = h->L[l + 1];
             // ghosts of the pre-smoothed iterate (for the up leg) and of the coarse rhs, in one exchange
-            if (p2p) {
-                if (lc.sharded) {
-                    RET(op_p2p_push(h, 2 * l, l, lv.cur, l + 1, 2));
-                    RET(op_p2p_wait(h, 2 * l));                       // level l + 1's down leg reads the rhs ghosts
-                } else {
-                    RET(op_p2p_push(h, 2 * l, l, lv.cur));            // (awaited just before this level's up leg)
-                    RET(op_gather_rhs(h, l + 1));                     // slabs -> rank 0
-                }
+            if (p2p) {                    // the leg exchanged its edges itself (leg_down)
+                if (!lc.sharded) RET(op_gather_rhs(h, l + 1));        // slabs -> rank 0
             } else if (lc.sharded) RET(op_halo(h, lv.x[lv.cur].p, lv.n, lv.m, lc.b.p, lc.n, lc.m));
             else {
                 RET(op_halo(h, lv.x[lv.cur].p, lv.n, lv.m));
@@ -981,13 +1063,13 @@ int enqueue_vcycle(amg1d* h, int nPre, int nPost, double alpha, bool want_norm, 
         Level& lv = h->L[l];
         Level& lc = h->L[l + 1];
         if (!lv.present) continue;
-        if (lv.sharded && !lc.sharded) {
-            RET(op_scatter_sol(h, l + 1));                              // rank 0 -> slabs (+ ghosts)
-            if (p2p) RET(op_p2p_wait(h, 2 * l));                        // this level's pre-smoothed ghosts
-        } else if (p2p && lv.sharded) RET(op_p2p_wait(h, 2 * (l + 1) + 1));   // ghosts of the coarse correction
-        RET(leg_up(h, l, nPost, alpha, want_norm && l == 0, &norm_done));
-        if (p2p && lv.sharded && l > 0) RET(op_p2p_push(h, 2 * l + 1, l, lv.cur));   // level l - 1's prolongation
-        else if (lv.sharded && l > 0) RET(op_halo(h, lv.x[lv.cur].p, lv.n, lv.m));
+        if (lv.sharded && !lc.sharded) RET(op_scatter_sol(h, l + 1));   // rank 0 -> slabs (+ ghosts)
+        bool pushed = false;
+        RET(leg_up(h, l, nPost, alpha, want_norm && l == 0, &norm_done, &pushed));
+        if (p2p && lv.sharded) {
+            if (l == 0) u0_pushed = pushed;
+            else if (!pushed) RET(op_p2p_push(h, 2 * l + 1, l, lv.cur));   // (a leg without the fused exchange)
+        } else if (lv.sharded && l > 0) RET(op_halo(h, lv.x[lv.cur].p, lv.n, lv.m));   // for level l-1's prolongation
     }
     Level& l0 = h->L[0];
     if (l0.cur != 0) {
@@ -997,7 +1079,7 @@ int enqueue_vcycle(amg1d* h, int nPre, int nPost, double alpha, bool want_norm, 
     }
     // level 0's corrected iterate: the incoming iterate of the next cycle, and the signal that this rank's up
     // leg no longer reads the ghosts which the neighbours' next down leg overwrites
-    if (p2p && l0.sharded) RET(op_p2p_push(h, 1, 0, 0));
+    if (p2p && l0.sharded && !u0_pushed) RET(op_p2p_push(h, 1, 0, 0));
     if (want_norm && !norm_done) RET(op_resnorm(h, 0, 0));
     return AMG1D_OK;
 }
@@ -1964,9 +2046,9 @@ int amg1d_set_transfer(amg1d_t* h, int level, int64_t n_fine_elem, int m_f, int 
                        const int64_t* parent, const double* P0, const double* P1) {
     RET(transfer_common(h, level, n_fine_elem, m_f, m_c));
     if (!parent || !P0) return fail(h, AMG1D_ERR_ARG, "null transfer array");
-    if (h->L[level].set && h->L[level].sharded)
-        return fail(h, AMG1D_ERR_UNSUPPORTED, "transfer %d: a sharded level needs a pattern transfer "
-                    "(amg1d_set_transfer_pattern)", level);
+    if (h->nranks > 1 && !h->L[level].set)
+        return fail(h, AMG1D_ERR_STATE, "multi-GPU: level %d must be set before its transfer", level);
+    const bool slab = h->L[level].set && h->L[level].sharded;   // keep this rank's slab of blocks only (below)
     Transfer& t = h->T[level];
     t.n_fine = n_fine_elem; t.mf = m_f; t.mc = m_c; t.period = 0;
     int64_t maxp = -1;
@@ -1997,6 +2079,26 @@ int amg1d_set_transfer(amg1d_t* h, int level, int64_t n_fine_elem, int m_f, int 
     }
     t.single_parent_uniform = t.closed && P1 == nullptr && t.shift == 0 && t.base == 0;
     const int bs = m_f * m_c;
+    if (slab) {
+        // A sharded level runs the fused legs only: they need the closed-form parent map (checked again at
+        // amg1d_finalize) and index the blocks by global fine element.  This rank keeps the blocks its legs can
+        // touch: its slab, the ghost elements and the children of the coarse elements next to them.
+        if (!t.closed)
+            return fail(h, AMG1D_ERR_UNSUPPORTED, "transfer %d: a sharded level needs parent[e] = (e + shift) / ratio + base", level);
+        const Level& lf = h->L[level];
+        const int64_t margin = h->ghost_depth + 2 * (int64_t)t.ratio + 2;
+        const int64_t lo = std::max<int64_t>(0, lf.start - margin), hi = std::min<int64_t>(n_fine_elem, lf.start + lf.n + margin);
+        t.p_first = lo;
+        t.nblk = hi - lo;
+        RET(dev_alloc(h, (void**)&t.P0, t.nblk * bs * 8));
+        CK(cudaMemcpy(t.P0, P0 + lo * bs, (size_t)t.nblk * bs * 8, cudaMemcpyHostToDevice));
+        if (P1) {
+            RET(dev_alloc(h, (void**)&t.P1, t.nblk * bs * 8));
+            CK(cudaMemcpy(t.P1, P1 + lo * bs, (size_t)t.nblk * bs * 8, cudaMemcpyHostToDevice));
+        }
+        t.set = true;
+        return AMG1D_OK;
+    }
     RET(dev_alloc(h, (void**)&t.P0, n_fine_elem * bs * 8));
     CK(cudaMemcpy(t.P0, P0, (size_t)n_fine_elem * bs * 8, cudaMemcpyHostToDevice));
     if (P1) {
@@ -2066,9 +2168,9 @@ int amg1d_finalize(amg1d_t* h) {
         t.fusable = t.closed && (-(int64_t)t.base * t.ratio - t.shift) >= 0 &&
                     ((lc.n_glob - 1 - t.base) * (int64_t)t.ratio - t.shift) < t.n_fine;
         if (lf.sharded) {
-            if (!t.fusable || t.period == 0)
-                return fail(h, AMG1D_ERR_UNSUPPORTED, "transfer %d: sharded levels need a closed-form "
-                            "pattern transfer (amg1d_set_transfer_pattern)", l);
+            if (!t.fusable)
+                return fail(h, AMG1D_ERR_UNSUPPORTED, "transfer %d: sharded levels need a closed-form parent map "
+                            "parent[e] = (e + shift) / ratio + base in which every coarse element has a first child", l);
             if (lf.n < 2 * h->ghost_depth)
                 return fail(h, AMG1D_ERR_UNSUPPORTED, "transfer %d: slab of %lld elements is too small", l,
                             (long long)lf.n);

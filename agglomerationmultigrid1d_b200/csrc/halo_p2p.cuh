@@ -20,6 +20,15 @@
 // exchanges of the levels above them - and is closed by k_epoch_wait: nobody starts cycle c before both
 // neighbours' up-leg push of cycle c - 1 on level 0 has arrived, which they issue after that up leg completed.
 //
+// FUSED FORM (the register-resident legs f_down / f_up, kernels_fused.cuh).  The stand-alone kernels above cost a
+// launch and a serialisation point per exchange.  The fused legs therefore do both halves themselves (HaloLeg):
+// the threads that own one of the ghost_depth edge elements store it to the neighbour as well, fence and add 1 to
+// the neighbour's counter - the exchange overlaps the rest of the grid - and the CTAs whose window reaches the
+// slab edge poll the counters they depend on right after the programmatic-dependency wait, while every other CTA
+// of the leg is already computing.  Counters therefore count ELEMENTS: a channel receives q = ghost_depth (+
+// ghost_depth coarse elements on a down leg whose coarse level is sharded too) per cycle and side, and "arrived"
+// means counter >= epoch * q.  Levels whose legs are not f_down / f_up (row-per-thread legs) use the kernels above.
+//
 // A neighbour that never arrives (crashed rank) must not hang the GPU: every spin gives up after
 // AMG1D_P2P_TIMEOUT_CYCLES clock ticks and raises the handle's error word, which the host reports as
 // AMG1D_ERR_NCCL at the next synchronising call.
@@ -42,6 +51,58 @@ __device__ __forceinline__ void spin_until(const unsigned long long* flag, unsig
     while (ld_acquire_sys(flag) < target) {
         if (clock64() - t0 > AMG1D_P2P_TIMEOUT_CYCLES) { atomicExch(err, 1); break; }
         __nanosleep(64);
+    }
+}
+
+// Per-launch description of the fused exchange of one leg (all pointers null / on = 0: no exchange).
+struct HaloLeg {
+    int on;
+    int gd;                                   // ghost depth
+    // consumer: counters that must reach (epoch - lag) * q before this leg reads its ghosts
+    const unsigned long long* w_left[2];
+    const unsigned long long* w_right[2];
+    unsigned long long wq[2], wlag[2];
+    const unsigned long long* epoch;
+    int* err;
+    // producer: where this leg's edge elements go
+    double* x_left;                           // left neighbour's slot for my element 0 of the output iterate
+    double* x_right;                          // right neighbour's slot for my element n - gd
+    double* c_left;                           // (down leg) the same for the coarse right-hand side
+    double* c_right;
+    unsigned long long* f_left;               // the neighbours' receive counters of this leg's channel
+    unsigned long long* f_right;
+    long long nc;                             // owned coarse elements
+};
+
+// edge CTAs: one thread polls, the CTA follows (call from all threads of the CTA; the condition is CTA-uniform)
+__device__ __forceinline__ void halo_leg_wait(const HaloLeg& hl, bool touch_left, bool touch_right) {
+    if (!hl.on || !(touch_left || touch_right)) return;
+    if (threadIdx.x == 0) {
+        const unsigned long long e = *hl.epoch;
+        for (int i = 0; i < 2; ++i) {
+            const unsigned long long target = (e - hl.wlag[i]) * hl.wq[i];
+            if (touch_left) spin_until(hl.w_left[i], target, hl.err);
+            if (touch_right) spin_until(hl.w_right[i], target, hl.err);
+        }
+    }
+    __syncthreads();
+}
+
+// the owner of edge element e (0 <= e < n) of a vector with block size M sends it on
+template <int M>
+__device__ __forceinline__ void halo_leg_push(const double (&v)[M], long long e, long long n, int gd, double* left,
+                                              double* right, unsigned long long* f_left, unsigned long long* f_right) {
+    if (left && e < gd) {
+#pragma unroll
+        for (int i = 0; i < M; ++i) left[e * M + i] = v[i];
+        __threadfence_system();
+        atomicAdd_system(f_left, 1ULL);
+    }
+    if (right && e >= n - gd) {
+#pragma unroll
+        for (int i = 0; i < M; ++i) right[(e - (n - gd)) * M + i] = v[i];
+        __threadfence_system();
+        atomicAdd_system(f_right, 1ULL);
     }
 }
 
@@ -68,16 +129,17 @@ __global__ void k_halo_push(HaloPush a) {
     }
     __threadfence_system();          // every writer orders its own stores before the signal
     __syncthreads();
-    if (t == 0) {
-        if (a.flag_left) atomicAdd_system(a.flag_left, 1ULL);
-        if (a.flag_right) atomicAdd_system(a.flag_right, 1ULL);
+    if (t == 0) {                    // counters count elements (see the fused form)
+        const unsigned long long q = (unsigned long long)a.gd * ((a.src[0] ? 1 : 0) + (a.src[1] ? 1 : 0));
+        if (a.flag_left) atomicAdd_system(a.flag_left, q);
+        if (a.flag_right) atomicAdd_system(a.flag_right, q);
     }
 }
 
 // consumer: both receive counters of a channel must have reached epoch - lag
 __global__ void k_halo_wait(const unsigned long long* flag_left, const unsigned long long* flag_right,
-                            const unsigned long long* epoch, unsigned long long lag, int* err) {
-    const unsigned long long target = *epoch - lag;
+                            const unsigned long long* epoch, unsigned long long lag, unsigned long long q, int* err) {
+    const unsigned long long target = (*epoch - lag) * q;
     spin_until(flag_left, target, err);
     spin_until(flag_right, target, err);
 }
@@ -85,9 +147,9 @@ __global__ void k_halo_wait(const unsigned long long* flag_left, const unsigned 
 // start of a V-cycle: advance the cycle number, then wait for the neighbours' level-0 up-leg push of the
 // previous cycle (see the header: iterate ghosts + the level-0 write-after-read hazard)
 __global__ void k_epoch_wait(unsigned long long* epoch, const unsigned long long* flag_left,
-                             const unsigned long long* flag_right, int* err) {
+                             const unsigned long long* flag_right, unsigned long long q, int* err) {
     const unsigned long long e = *epoch + 1;
     *epoch = e;
-    spin_until(flag_left, e - 1, err);
-    spin_until(flag_right, e - 1, err);
+    spin_until(flag_left, (e - 1) * q, err);
+    spin_until(flag_right, (e - 1) * q, err);
 }

@@ -29,6 +29,7 @@
 #include <cuda_runtime.h>
 #include "kernels_generic.cuh"
 #include "layout.cuh"
+#include "halo_p2p.cuh"
 
 // Position of a rank's slab inside its level (single GPU: gl = gr = e_off = c_off = 0).  Local element
 // index e runs over [-gl, n + gr): gl / gr ghost elements (with operator blocks, rhs and iterate) on the
@@ -633,11 +634,15 @@ down_leg(const OP& A, const double* __restrict__ dcol, Exchange<M, B>& ex, doubl
          bool active, int ilo, int iup, const double* __restrict__ b, const double* __restrict__ xin,
          double* __restrict__ xout, const double* __restrict__ P0, const double* __restrict__ P1,
          const TransferMap& tm, double* __restrict__ rc, int64_t n, double alpha, int nsweep, int zero_guess,
-         const WinIdx& wi, const Slab& sl) {
+         const WinIdx& wi, const Slab& sl, const HaloLeg& hl) {
     const int t = threadIdx.x;
     const int halo = wi.halo, out = wi.out;
     double bb[M], xc[M], xl[M], xr[M];
     pdl_wait();                                                  // b, x and everything written below are not
+    {   // peer-memory exchange: CTAs whose window reaches a slab edge wait for the neighbour's edge (halo_p2p.cuh)
+        const int64_t e0 = (int64_t)blockIdx.x * out - halo;
+        halo_leg_wait(hl, sl.gl > 0 && e0 < 0, sl.gr > 0 && e0 + B > n);
+    }
     if (active) {
         load_vec<M>(b + e * M, bb);
         if (zero_guess) {
@@ -662,7 +667,10 @@ down_leg(const OP& A, const double* __restrict__ dcol, Exchange<M, B>& ex, doubl
         reg_sweep<M, ST, DIAG, B>(A, ilo, iup, dcol, bb, xl, xc, xr, alpha, zg);
     }
     const bool mine = t >= halo && t < halo + out;              // this CTA's share of the level (e >= 0)
-    if (mine && e < n) store_vec<M>(xout + e * M, xc);
+    if (mine && e < n) {
+        store_vec<M>(xout + e * M, xc);
+        if (hl.on) halo_leg_push<M>(xc, e, n, hl.gd, hl.x_left, hl.x_right, hl.f_left, hl.f_right);
+    }
     // residual with the final iterate, then restriction
     exchange<M, B, ST>(ex, buf, ilo, iup, xc, xl, xr);
     double r[M];
@@ -703,6 +711,7 @@ down_leg(const OP& A, const double* __restrict__ dcol, Exchange<M, B>& ex, doubl
                 }
 #pragma unroll
                 for (int j = 0; j < MC; ++j) rc[Kl * MC + j] = acc[j];
+                if (hl.on) halo_leg_push<MC>(acc, Kl, hl.nc, hl.gd, hl.c_left, hl.c_right, hl.f_left, hl.f_right);
             }
         }
     }
@@ -713,7 +722,7 @@ __global__ void FUSED_BOUNDS(M)
 f_down(const double* __restrict__ mat, PatOp po, int ilo, int iup, const double* __restrict__ b,
        const double* __restrict__ xin, double* __restrict__ xout, const double* __restrict__ P0,
        const double* __restrict__ P1, TransferMap tm, double* __restrict__ rc, int64_t n, double alpha,
-       int nsweep, int zero_guess, WinIdx wi, Slab sl, int rec) {
+       int nsweep, int zero_guess, WinIdx wi, Slab sl, int rec, const __grid_constant__ HaloLeg hl) {
     __shared__ Exchange<M, B> ex;
     __shared__ double rs[M][B + 8];
     __shared__ double ds[DIAG ? M : M * M][B];
@@ -726,7 +735,7 @@ f_down(const double* __restrict__ mat, PatOp po, int ilo, int iup, const double*
     load_blocks<M, B, ST, DIAG>(mat, po, e, e + sl.e_off, active, A, ds, rec != 0);   // operator: independent of earlier kernels
     recompute_dinv<M, B, ST, DIAG>(A, ds, active, rec);          // before the dependency wait: few registers are live yet
     down_leg<M, MC, B, ST, DIAG>(A, &ds[0][t], ex, rs, e, active, ilo, iup, b, xin, xout, P0, P1, tm, rc, n, alpha,
-                                 nsweep, zero_guess, wi, sl);
+                                 nsweep, zero_guess, wi, sl, hl);
 }
 
 // CTA-uniform test of the constant-operand legs: the whole window of this CTA is active (inside the slab
@@ -747,7 +756,8 @@ __global__ void FUSED_C_BOUNDS(M)
 f_down_c(const __grid_constant__ ParamOp<M, ST, DIAG> pk, PatOp po, int ilo, int iup,
          const double* __restrict__ b, const double* __restrict__ xin, double* __restrict__ xout,
          const double* __restrict__ P0, const double* __restrict__ P1, TransferMap tm, double* __restrict__ rc,
-         int64_t n, double alpha, int nsweep, int zero_guess, WinIdx wi, Slab sl) {
+         int64_t n, double alpha, int nsweep, int zero_guess, WinIdx wi, Slab sl,
+         const __grid_constant__ HaloLeg hl) {
     __shared__ Exchange<M, B> ex;
     __shared__ double rs[M][B + 8];
     __shared__ double ds[DIAG ? M : M * M][B];
@@ -757,13 +767,13 @@ f_down_c(const __grid_constant__ ParamOp<M, ST, DIAG> pk, PatOp po, int ilo, int
     exch_init<M, B>(ex);
     if (window_is_interior(po, wi, sl, n, B)) {
         down_leg<M, MC, B, ST, DIAG>(pk, nullptr, ex, rs, e, true, ilo, iup, b, xin, xout, P0, P1, tm, rc, n, alpha,
-                                     nsweep, zero_guess, wi, sl);
+                                     nsweep, zero_guess, wi, sl, hl);
     } else {
         const bool active = e >= -(int64_t)sl.gl && e < n + sl.gr;
         RegOp<M, ST> A;
         load_blocks<M, B, ST, DIAG>(nullptr, po, e, e + sl.e_off, active, A, ds);
         down_leg<M, MC, B, ST, DIAG>(A, &ds[0][t], ex, rs, e, active, ilo, iup, b, xin, xout, P0, P1, tm, rc, n,
-                                     alpha, nsweep, zero_guess, wi, sl);
+                                     alpha, nsweep, zero_guess, wi, sl, hl);
     }
 }
 
@@ -774,11 +784,15 @@ up_leg(const OP& A, const double* __restrict__ dcol, Exchange<M, B>& ex, int64_t
        const double* __restrict__ b, const double* __restrict__ xin, double* __restrict__ xout,
        const double* __restrict__ P0, const double* __restrict__ P1, const TransferMap& tm,
        const double* __restrict__ xcoarse, int64_t n, double alpha, int nsweep, const WinIdx& wi,
-       double* __restrict__ partial, const Slab& sl) {
+       double* __restrict__ partial, const Slab& sl, const HaloLeg& hl) {
     const int t = threadIdx.x;
     const int halo = wi.halo, out = wi.out;
     double bb[M], xc[M], xl[M], xr[M];
     pdl_wait();
+    {   // peer-memory exchange: the CTAs near a slab edge read fine ghosts and / or ghosts of the coarse correction
+        const int64_t e0 = (int64_t)blockIdx.x * out - halo;
+        halo_leg_wait(hl, sl.gl > 0 && e0 < tm.ratio + 1, sl.gr > 0 && e0 + B + tm.ratio + 1 > n);
+    }
     if (active) {
         load_vec<M>(b + e * M, bb);
         load_vec<M>(xin + e * M, xc);
@@ -821,7 +835,10 @@ up_leg(const OP& A, const double* __restrict__ dcol, Exchange<M, B>& ex, int64_t
         reg_sweep<M, ST, DIAG, B>(A, ilo, iup, dcol, bb, xl, xc, xr, alpha, false);
     }
     const bool emit = e < n && t >= halo && t < halo + out;     // e >= 0 for these threads
-    if (emit) store_vec<M>(xout + e * M, xc);
+    if (emit) {
+        store_vec<M>(xout + e * M, xc);
+        if (hl.on) halo_leg_push<M>(xc, e, n, hl.gd, hl.x_left, hl.x_right, hl.f_left, hl.f_right);
+    }
     if (partial) {
         exchange<M, B, ST>(ex, buf, ilo, iup, xc, xl, xr);
         double r[M];
@@ -841,7 +858,8 @@ __global__ void FUSED_BOUNDS(M)
 f_up(const double* __restrict__ mat, PatOp po, int ilo, int iup, const double* __restrict__ b,
      const double* __restrict__ xin, double* __restrict__ xout, const double* __restrict__ P0,
      const double* __restrict__ P1, TransferMap tm, const double* __restrict__ xcoarse, int64_t n,
-     double alpha, int nsweep, WinIdx wi, double* __restrict__ partial, Slab sl, int rec) {
+     double alpha, int nsweep, WinIdx wi, double* __restrict__ partial, Slab sl, int rec,
+     const __grid_constant__ HaloLeg hl) {
     __shared__ Exchange<M, B> ex;
     __shared__ double ds[DIAG ? M : M * M][B];
     pdl_launch_dependents();
@@ -853,7 +871,7 @@ f_up(const double* __restrict__ mat, PatOp po, int ilo, int iup, const double* _
     load_blocks<M, B, ST, DIAG>(mat, po, e, e + sl.e_off, active, A, ds, rec != 0);   // operator: independent of earlier kernels
     recompute_dinv<M, B, ST, DIAG>(A, ds, active, rec);          // before the dependency wait: few registers are live yet
     up_leg<M, MC, B, ST, DIAG>(A, &ds[0][t], ex, e, active, ilo, iup, b, xin, xout, P0, P1, tm, xcoarse, n, alpha,
-                               nsweep, wi, partial, sl);
+                               nsweep, wi, partial, sl, hl);
 }
 
 // f_up with constant-bank operands for the interior CTAs of a pattern level (see f_down_c)
@@ -862,7 +880,8 @@ __global__ void FUSED_C_BOUNDS(M)
 f_up_c(const __grid_constant__ ParamOp<M, ST, DIAG> pk, PatOp po, int ilo, int iup, const double* __restrict__ b,
        const double* __restrict__ xin, double* __restrict__ xout, const double* __restrict__ P0,
        const double* __restrict__ P1, TransferMap tm, const double* __restrict__ xcoarse, int64_t n,
-       double alpha, int nsweep, WinIdx wi, double* __restrict__ partial, Slab sl) {
+       double alpha, int nsweep, WinIdx wi, double* __restrict__ partial, Slab sl,
+       const __grid_constant__ HaloLeg hl) {
     __shared__ Exchange<M, B> ex;
     __shared__ double ds[DIAG ? M : M * M][B];
     pdl_launch_dependents();
@@ -871,13 +890,13 @@ f_up_c(const __grid_constant__ ParamOp<M, ST, DIAG> pk, PatOp po, int ilo, int i
     exch_init<M, B>(ex);
     if (window_is_interior(po, wi, sl, n, B)) {
         up_leg<M, MC, B, ST, DIAG>(pk, nullptr, ex, e, true, ilo, iup, b, xin, xout, P0, P1, tm, xcoarse, n, alpha,
-                                   nsweep, wi, partial, sl);
+                                   nsweep, wi, partial, sl, hl);
     } else {
         const bool active = e >= -(int64_t)sl.gl && e < n + sl.gr;
         RegOp<M, ST> A;
         load_blocks<M, B, ST, DIAG>(nullptr, po, e, e + sl.e_off, active, A, ds);
         up_leg<M, MC, B, ST, DIAG>(A, &ds[0][t], ex, e, active, ilo, iup, b, xin, xout, P0, P1, tm, xcoarse, n, alpha,
-                                   nsweep, wi, partial, sl);
+                                   nsweep, wi, partial, sl, hl);
     }
 }
 
@@ -1260,7 +1279,8 @@ enum { FUSED_NA = 0, FUSED_OK = 1, FUSED_ERR = -1 };
 inline int fused_down(const MatDesc& d, int mc, const TransferMap& tm, int nsweep, bool zero,
                        const double* mat, const PatOp& po, const double* b, const double* xin, double* xout,
                        const double* P0, const double* P1, double* rc, int64_t n, int64_t n_cover,
-                       double alpha, const Slab& sl, cudaStream_t st, bool pdl, cudaError_t* err, int rec = 0) {
+                       double alpha, const Slab& sl, cudaStream_t st, bool pdl, cudaError_t* err, int rec = 0,
+                       const HaloLeg& hl = HaloLeg()) {
     const WinIdx w = fused_window(nsweep, tm, P1 != nullptr || tm.shift != 0 || tm.base != 0, sl);
     if (w.out < tm.ratio || w.out < FUSED_B / 2 || !fast_tier_ok(d)) return FUSED_NA;
     const unsigned grid = (unsigned)((n_cover + w.out - 1) / w.out);
@@ -1271,11 +1291,11 @@ inline int fused_down(const MatDesc& d, int mc, const TransferMap& tm, int nswee
             ParamOp<MM, SS, DG> pk;                                                                      \
             memcpy(&pk, po.host_interior, sizeof(pk));                                                   \
             *err = launch_fused(f_down_c<MM, MCC, FUSED_B, SS, DG>, grid, FUSED_B, 0, st, pdl, pk, po, d.ilo, \
-                                d.iup, b, xin, xout, P0, P1, tm, rc, n, alpha, nsweep, zero ? 1 : 0, w, sl); \
+                                d.iup, b, xin, xout, P0, P1, tm, rc, n, alpha, nsweep, zero ? 1 : 0, w, sl, hl); \
         } else                                                                                           \
         *err = launch_fused(f_down<MM, MCC, FUSED_B, SS, DG>, grid, FUSED_B, 0, st, pdl, mat, po, d.ilo, d.iup, \
                             b, xin, xout, P0, P1, tm, rc, n, alpha, nsweep, zero ? 1 : 0, w, sl,         \
-                            (!po.tab && !DG) ? rec : 0);                                                 \
+                            (!po.tab && !DG) ? rec : 0, hl);                                             \
         return *err == cudaSuccess ? FUSED_OK : FUSED_ERR;
         FUSED_COMBOS(X)
 #undef X
@@ -1287,7 +1307,7 @@ inline int fused_up(const MatDesc& d, int mc, const TransferMap& tm, int nsweep,
                      const PatOp& po, const double* b, const double* xin, double* xout, const double* P0,
                      const double* P1, const double* xcoarse, int64_t n, double alpha, double* partial,
                      int64_t partial_cap, int* nblocks, const Slab& sl, cudaStream_t st, bool pdl,
-                     cudaError_t* err, int rec = 0) {
+                     cudaError_t* err, int rec = 0, const HaloLeg& hl = HaloLeg()) {
     const WinIdx w = fused_window(nsweep, tm, false, sl);
     if (w.out < tm.ratio || w.out < FUSED_B / 2 || !fast_tier_ok(d)) return FUSED_NA;
     const int64_t grid = (n + w.out - 1) / w.out;
@@ -1300,11 +1320,11 @@ inline int fused_up(const MatDesc& d, int mc, const TransferMap& tm, int nsweep,
             ParamOp<MM, SS, DG> pk;                                                                      \
             memcpy(&pk, po.host_interior, sizeof(pk));                                                   \
             *err = launch_fused(f_up_c<MM, MCC, FUSED_B, SS, DG>, (unsigned)grid, FUSED_B, 0, st, pdl, pk, po, \
-                                d.ilo, d.iup, b, xin, xout, P0, P1, tm, xcoarse, n, alpha, nsweep, w, partial, sl); \
+                                d.ilo, d.iup, b, xin, xout, P0, P1, tm, xcoarse, n, alpha, nsweep, w, partial, sl, hl); \
         } else                                                                                           \
         *err = launch_fused(f_up<MM, MCC, FUSED_B, SS, DG>, (unsigned)grid, FUSED_B, 0, st, pdl, mat, po,    \
                             d.ilo, d.iup, b, xin, xout, P0, P1, tm, xcoarse, n, alpha, nsweep, w, partial, sl, \
-                            (!po.tab && !DG) ? rec : 0);                                                 \
+                            (!po.tab && !DG) ? rec : 0, hl);                                             \
         return *err == cudaSuccess ? FUSED_OK : FUSED_ERR;
         FUSED_COMBOS(X)
 #undef X

@@ -264,10 +264,13 @@ class MeshHierarchy:
         self.mSmoothers, self.mInterpolation, self.mBdConds = Sm, I, list(mBdConds)
 
     # ---- upload (stands in for the end of construction) ------------------------------------------
-    def upload(self, device=0, stream=None, options=None):
-        """options: dict for amg1d_set_option, applied before the first level (e.g. {"compress": 0})."""
+    def upload(self, device=0, stream=None, options=None, dist=None):
+        """options: dict for amg1d_set_option, applied before the first level (e.g. {"compress": 0}).
+        dist = (rank, nranks, nccl_id_bytes): every rank passes the same global arrays and the library keeps its
+        contiguous slab of the large levels (DG-first hierarchies; any mesh - the transfers go up as explicit
+        per-element blocks); host vectors are then the rank's slab (``device.info("local_dofs")``)."""
         nL = len(self.mMeshes)
-        dev = DeviceHierarchy(nL, device=device, stream=stream)
+        dev = DeviceHierarchy(nL, device=device, stream=stream, dist=dist)
         for k, v in (options or {}).items():
             dev.set_option(k, v)
         slots = [blk.level_slots(m) for m in self.mMeshes]
@@ -280,6 +283,8 @@ class MeshHierarchy:
             parent, P0, P1 = blk.transfer_to_blocks(self.mInterpolation[l], slots[l], slots[l + 1])
             dev.set_transfer_blocks(l, parent, P0, P1)
         dev.finalize()
+        if dist is not None and dist[1] > 1:
+            dev.n_dof[0] = dev.info("local_dofs")
         self.device = dev
         self.mSlots = slots
         return dev

@@ -36,7 +36,71 @@ def main():
     dist.destroy_process_group()
 
 
+def run_graded(world, rank, ids):
+    """DG 3 -> 1 -> ten agglomerated levels on a GRADED (non-uniform) mesh of 2^14 elements, host-built by the
+    general path (MeshHierarchy: global sparse algebra, explicit per-element operator and transfer blocks - no
+    pattern upload anywhere): every rank passes the same global arrays and keeps its slab.  Bit-identical to the
+    single-GPU handle."""
+    import agglomerationmultigrid1d_b200 as aggmg
+    n = 2 ** 14
+    rng = np.random.default_rng(0)
+    x = np.concatenate([[0.0], np.cumsum(0.5 + rng.random(n))])
+    xout = float(x[-1])
+    w = 2.0 * math.pi / 64.0
+    mesh = aggmg.Mesh(x)
+    bd = aggmg.set_boundary(mesh, 0.0, xout, [("neu", 0.0), ("dir", math.cos(w * xout))])
+    meshes = [aggmg.DgMesh(mesh, 3), aggmg.DgMesh(mesh, 1)]
+    cur = n
+    for i in range(10):
+        agg = [[2 * j, 2 * j + 1] for j in range(cur // 2)]
+        cur //= 2
+        meshes.append(aggmg.AgglomeratedDgMesh1(1, agg, mesh, meshes[1]) if i == 0
+                      else aggmg.AgglomeratedDgMeshN(1, agg, meshes[-1], meshes[1]))
+    G, D, C = aggmg.dg_flux_operators(meshes[0], mesh, bd, 1000.0)
+    A = (C - D @ meshes[0].mMassMatrixLU.solve(G)).tocsc()
+    f, r = aggmg.dg_flux_rhs(meshes[0], mesh, lambda t: w * w * np.cos(w * t), bd, 1000.0)
+    b = f - D @ meshes[0].mMassMatrixLU.solve(r)
+    H = aggmg.MeshHierarchy(meshes, [bd] * len(meshes), A, G, D, C, nDG=2, nAgg=10, upload=False)
+    dev = H.upload(device=rank, dist=(rank, world, ids[0]), options={"shard_min": 256})
+    nloc = n // world
+    lo, hi = rank * nloc * 4, (rank + 1) * nloc * 4
+    report = {"rank": rank, "gather_level": dev.info("gather_level"), "local_dofs": dev.info("local_dofs"),
+              "ghost_depth": dev.info("ghost_depth"), "p2p_halo": dev.info("p2p_halo"), "p2p_requested": 1}
+    x_loc, it, res, _ = dev.solve(np.zeros(hi - lo), b[lo:hi], 100, 1e-10)
+    rng = np.random.default_rng(5)
+    x0 = rng.standard_normal(len(b))
+    v = dev.vcycle(x0[lo:hi], b[lo:hi], nPre=2, nPost=1, alpha=0.7)
+    gathered = [None] * world
+    dist.gather_object((x_loc, it, res, v), gathered if rank == 0 else None, dst=0)
+    if rank == 0:
+        d1 = H.upload(device=0)
+        x1, it1, res1, _ = d1.solve(np.zeros(len(b)), b, 100, 1e-10)
+        v1 = d1.vcycle(x0, b, nPre=2, nPost=1, alpha=0.7)
+        ok, msgs = True, []
+        if gathered[0][1] != it1 or not np.allclose(gathered[0][2], res1, rtol=1e-12, atol=0):
+            ok = False; msgs.append(f"iters / history {gathered[0][1]} vs {it1}")
+        if not np.array_equal(np.concatenate([g[0] for g in gathered]), x1):
+            ok = False; msgs.append("solve x differs")
+        if not np.array_equal(np.concatenate([g[3] for g in gathered]), v1):
+            ok = False; msgs.append("vcycle x differs")
+        if not res1[-1] < 1e-10 * np.linalg.norm(b):
+            ok = False; msgs.append("not converged")
+        report.update(ok=ok, msgs=msgs, iters=int(it1), world=world, res_last=float(res1[-1]))
+        d1.close()
+    dev.close()
+    return report
+
+
 def run_kind(kind, log2n):
+    if kind == "dg_graded":
+        lib = capi.load()
+        ids = [None]
+        if dist.get_rank() == 0:
+            buf = C.create_string_buffer(128)
+            capi.check(None, lib.amg1d_nccl_unique_id(C.cast(buf, C.c_void_p)))
+            ids[0] = buf.raw
+        dist.broadcast_object_list(ids, src=0)
+        return run_graded(dist.get_world_size(), dist.get_rank(), ids)
     # *_pat / *_pat2: the sharded handle reads its operators from the pattern tables (option pattern_resident
     # = 1) / takes the interior block set as constant-bank kernel parameters (= 2)
     pattern_resident = 2 if kind.endswith("_pat2") else 1 if kind.endswith("_pat") else 0

@@ -17,7 +17,8 @@ def _ngpu():
 
 # *_pat: option pattern_resident = 1, *_pat2: = 2 (constant-bank operands in the interior CTAs)
 # *_nccl: slab edges through NCCL send / recv groups (option p2p_halo = 0); all others through peer memory
-KINDS = ["dg", "cg", "dg8", "cg8", "dg_pat", "cg_pat", "dg8_pat", "dg_pat2", "cg_pat2", "dg_nccl", "cg_nccl"]
+# dg_graded: non-uniform mesh, host-built general hierarchy with explicit per-element transfer blocks
+KINDS = ["dg", "cg", "dg8", "cg8", "dg_pat", "cg_pat", "dg8_pat", "dg_pat2", "cg_pat2", "dg_nccl", "cg_nccl", "dg_graded"]
 
 
 @pytest.mark.parametrize("world", [2, 4, 8])
