@@ -145,6 +145,10 @@ struct amg1d {
     int opt_rows_rpt = 0;         // block rows per thread of those legs: 1, 2, 3; 0 = auto (rows_rpt() below)
     int opt_dvrec = 4;            // block-Jacobi inverses recomputed inside the fused legs of levels with blocks of at
                                   // least this size and at most 4 x 4 (0 = never; see adopt_device_dinv, leg_rec)
+    int opt_dvreg = 0;            // 1: 4 x 4 DG legs keep the recomputed inverse in registers (f_down_dv / f_up_dv, 4 CTAs
+                                  // per SM); 2: the 2 x 2 levels too
+    int opt_pipe = 1;             // 4 x 4 DG legs run as persistent CTAs that prefetch their next window with TMA bulk
+                                  // copies (f_down_pp / f_up_pp, kernels_fused.cuh); needs recompute_dinv
     int opt_pattern = 0;          // 1: levels given as patterns read their operator from the pattern table;
                                   // 2: and the interior CTAs of f_down / f_up take it as constant-bank operands
     // single-CTA coarse tail (f_tail): levels [tail_start, n_levels)
@@ -368,10 +372,17 @@ int rows_rpt(const amg1d* h, int l) {
 }
 
 // 0: the fused legs of this level stream the stored inverse; 1 / 2: they invert A_di in registers (with / without pivots)
-int leg_rec(const amg1d* h, const Level& lv) {
+int leg_rec(const amg1d* h, const Level& lv, int mc = 0) {
     // measured on B200 (profiles/r02c_sweep_dvrec_*.jsonl): 4 x 4 DG blocks gain 4-5 % per leg (T level 0: 4.63 / 4.31
     // -> 4.43 / 4.12 ms); 5 x 5 blocks lose 10 % (the inversion's registers cost a resident CTA), 2 x 2 lose 5 %
-    return (h->opt_dvrec > 0 && lv.dv_rec && lv.m >= h->opt_dvrec && lv.m <= 4) ? lv.dv_rec : 0;
+    // bits 0-1: invert A_di in registers (1: with the pivot chain, 2: the level never pivots); bit 3: keep the inverse
+    // in registers (option dinv_registers); bit 4: pipelined persistent leg (option leg_pipeline)
+    int rec = (h->opt_dvrec > 0 && lv.dv_rec && lv.m >= h->opt_dvrec && lv.m <= 4)
+                  ? (lv.dv_rec | (h->opt_dvreg ? 8 : 0) | (h->opt_pipe ? 16 : 0)) : 0;
+    // option dinv_registers = 2: the 2 x 2 levels too, through the legs that keep the inverse in registers
+    if (!rec && h->opt_dvrec > 0 && h->opt_dvreg >= 2 && lv.dv_rec && lv.m == 2 && fused_has_dv(lv.m, mc, lv.md.st, lv.diag))
+        rec = lv.dv_rec | 8;
+    return rec;
 }
 
 // pattern-resident operator of level l (option pattern_resident = 1 and the level was given as a pattern)
@@ -482,6 +493,10 @@ int op_scatter_sol(amg1d* h, int g) {
 
 // d_scal[slot] currently holds a local SUM OF SQUARES: make it the global 2-norm
 __global__ void k_sqrt_inplace(double* v, int slot) { v[slot] = sqrt(v[slot]); }
+int op_allreduce_max(amg1d* h, double* dptr, int count) {
+    NCK(g_nccl.AllReduce(dptr, dptr, (size_t)count, ncclDouble, ncclMax, h->comm, h->stream));
+    return AMG1D_OK;
+}
 int op_allreduce_norm(amg1d* h, int slot) {
     NCK(g_nccl.AllReduce(h->d_scal + slot, h->d_scal + slot, 1, ncclDouble, ncclSum, h->comm, h->stream));
     k_sqrt_inplace<<<1, 1, 0, h->stream>>>(h->d_scal, slot);
@@ -719,6 +734,7 @@ int op_halo(amg1d* h, double*, int64_t, int, double* = nullptr, int64_t = 0, int
 int op_gather_rhs(amg1d* h, int) { return fail(h, AMG1D_ERR_UNSUPPORTED, "built without NCCL"); }
 int op_scatter_sol(amg1d* h, int) { return fail(h, AMG1D_ERR_UNSUPPORTED, "built without NCCL"); }
 int op_allreduce_norm(amg1d* h, int) { return fail(h, AMG1D_ERR_UNSUPPORTED, "built without NCCL"); }
+int op_allreduce_max(amg1d* h, double*, int) { return fail(h, AMG1D_ERR_UNSUPPORTED, "built without NCCL"); }
 #endif
 
 // ---- elementary enqueued operations ---------------------------------------------------------------
@@ -917,7 +933,7 @@ int leg_down(amg1d* h, int l, int nPre, double alpha, bool zero0) {
         const HaloLeg hl = p2p ? make_halo_leg(h, l, true, ob) : HaloLeg();
         int fr = fused_down(lv.md, t.mc, make_map_closed(t), nPre, zero, lv.mat, make_pat(h, l), lv.b.p, lv.x[lv.cur].p,
                             lv.x[ob].p, tp0(t), tp1(t), lc.b.p, lv.n, lv.n + (lv.gr ? t.cover_extra : 0),
-                            alpha, make_slab(h, l), h->stream, h->opt_pdl != 0, &le, leg_rec(h, lv), hl);
+                            alpha, make_slab(h, l), h->stream, h->opt_pdl != 0, &le, leg_rec(h, lv, t.mc), hl);
         if (fr == FUSED_NA && h->opt_rows) {    // large blocks: one thread per block row; exchange by stand-alone kernels
             if (p2p) RET(op_p2p_wait_for(h, hl));
             fr = rows_down(lv.md, t.mc, make_map_closed(t), nPre, zero, lv.mat, make_pat(h, l), lv.b.p, lv.x[lv.cur].p,
@@ -980,7 +996,7 @@ int leg_up(amg1d* h, int l, int nPost, double alpha, bool fuse_norm, bool* norm_
         int fr = fused_up(lv.md, t.mc, make_map_closed(t), nPost, lv.mat, make_pat(h, l), lv.b.p, lv.x[lv.cur].p,
                           lv.x[1 - lv.cur].p, tp0(t), tp1(t), lc.x[lc.cur].p, lv.n, alpha,
                           fuse_norm ? h->partial : nullptr, h->partial_cap, &nb, make_slab(h, l),
-                          h->stream, h->opt_pdl != 0, &le, leg_rec(h, lv), hl);
+                          h->stream, h->opt_pdl != 0, &le, leg_rec(h, lv, t.mc), hl);
         if (fr == FUSED_OK && p2p && push_inside) *halo_pushed = true;
         if (fr == FUSED_NA && h->opt_rows) {
             if (p2p) RET(op_p2p_wait_for(h, hl));
@@ -1452,38 +1468,55 @@ void free_flux(amg1d* h, Level& lv) {
 }
 
 // Option "recompute_dinv" (default on): replace the uploaded block-Jacobi inverses of a level by the device's own
-// pivoted Gauss-Jordan inverse of the stored diagonal blocks - provided the upload agrees with it to 1e-8, i.e.
+// Gauss-Jordan inverse of the stored diagonal blocks - provided the upload agrees with it to 1e-8, i.e.
 // really is inv(A_di) (src/smoother.jl:154-164) and not some other smoother block.  Afterwards every kernel that
 // reads the stored inverse and the fused legs that recompute it in registers (reg_invert; 16 of the 40 stored
 // doubles of a 4 x 4 DG element never leave HBM) produce the same bits.  Point-Jacobi levels keep their diagonal.
+// The elimination is unpivoted when the level does not need its pivots (k_dinv_recompute: no element swaps rows, or
+// every element that does gets the same inverse to 1e-12 without), else it keeps the partial-pivoting chain.  On a
+// sharded level the verdict is reduced over the ranks, so that all slabs - and the single-GPU run, whose level is
+// the union of the slabs - use the same elimination.
 int adopt_device_dinv(amg1d* h, int level) {
     Level& lv = h->L[level];
     lv.dv_rec = 0;
-    if (!h->opt_dvrec || lv.diag || !lv.present || lv.m > AMG1D_DVREC_MAXM) return AMG1D_OK;
+    if (!h->opt_dvrec || lv.diag || lv.m > AMG1D_DVREC_MAXM) return AMG1D_OK;
+    const bool collective = h->nranks > 1 && lv.sharded;
+    if (!lv.present && !collective) return AMG1D_OK;
     DevBuf sc;
-    CK(sc.alloc(2));
-    CK(cudaMemsetAsync(sc.p, 0, 16, h->stream));
+    CK(sc.alloc(4));
+    CK(cudaMemsetAsync(sc.p, 0, 32, h->stream));
     unsigned long long* d_dev = reinterpret_cast<unsigned long long*>(sc.p);
     int* d_flag = reinterpret_cast<int*>(sc.p + 1);
     const int64_t e0 = -(int64_t)lv.gl, e1 = lv.n + lv.gr;
     const unsigned grid = (unsigned)((e1 - e0 + 127) / 128);
-    k_dinv_recompute<<<grid, 128, 0, h->stream>>>(lv.mat, lv.md, e0, e1, AMG1D_TILE, 0, d_dev, d_flag);
-    double host[2] = {0.0, 0.0};
+    if (lv.present)
+        k_dinv_recompute<<<grid, 128, 0, h->stream>>>(lv.mat, lv.md, e0, e1, AMG1D_TILE, 2, d_dev, d_flag);   // one pass
+    double host[4] = {0.0, 0.0, 0.0, 0.0};
     CK(cudaMemcpyAsync(host, sc.p, 16, cudaMemcpyDeviceToHost, h->stream));
     CK(cudaStreamSynchronize(h->stream));
     CK(cudaGetLastError());
     int flag;
     memcpy(&flag, &host[1], sizeof flag);
+    if (collective) {                              // max over the ranks of (deviation, singular, swaps, needs pivots)
+        const double v[4] = {host[0], (flag & 1) ? 1.0 : 0.0, (flag & 2) ? 1.0 : 0.0, (flag & 4) ? 1.0 : 0.0};
+        CK(cudaMemcpyAsync(sc.p, v, 32, cudaMemcpyHostToDevice, h->stream));
+        RET(op_allreduce_max(h, sc.p, 4));
+        CK(cudaMemcpyAsync(host, sc.p, 32, cudaMemcpyDeviceToHost, h->stream));
+        CK(cudaStreamSynchronize(h->stream));
+        flag = (host[1] != 0.0 ? 1 : 0) | (host[2] != 0.0 ? 2 : 0) | (host[3] != 0.0 ? 4 : 0);
+    }
     if ((flag & 1) || !(host[0] <= 1e-8)) return AMG1D_OK;    // not the inverse of A_di: keep what was uploaded
-    k_dinv_recompute<<<grid, 128, 0, h->stream>>>(lv.mat, lv.md, e0, e1, AMG1D_TILE, 1, d_dev, d_flag);
+    const bool unpivot = (flag & 2) && !(flag & 4);           // rows swap somewhere, but no element needs it
+    if (unpivot && lv.present)
+        k_dinv_recompute<<<grid, 128, 0, h->stream>>>(lv.mat, lv.md, e0, e1, AMG1D_TILE, 3, d_dev, d_flag);
     if (lv.pat) {                                             // the pattern table's Dinv rows as well
         const int ns = lv.pat_head + 1 + lv.pat_tail;
-        k_dinv_recompute<<<1, 128, 0, h->stream>>>(lv.pat, lv.md, 0, ns, 1, 1, d_dev, d_flag);
+        k_dinv_recompute<<<1, 128, 0, h->stream>>>(lv.pat, lv.md, 0, ns, 1, unpivot ? 3 : 1, d_dev, d_flag);
         CK(cudaMemcpyAsync(lv.pat_host.data(), lv.pat, lv.pat_host.size() * 8, cudaMemcpyDeviceToHost, h->stream));
     }
     CK(cudaStreamSynchronize(h->stream));
     CK(cudaGetLastError());
-    lv.dv_rec = (flag & 2) ? 1 : 2;
+    lv.dv_rec = (flag & 4) ? 1 : 2;
     return AMG1D_OK;
 }
 
@@ -2251,6 +2284,10 @@ int amg1d_finalize(amg1d_t* h) {
     CK(cudaMallocHost(&h->h_scal, 64 * 8));
     if (h->L[h->n_levels - 1].present) RET(factor_coarsest(h));
     RET(build_tail(h));
+    {
+        const cudaError_t pe = pipe_configure_all();          // shared-memory limit of the pipelined legs (f_*_pp)
+        if (pe != cudaSuccess) return fail(h, AMG1D_ERR_CUDA, "pipelined leg configuration failed: %s", cudaGetErrorString(pe));
+    }
     // the row-per-thread legs of the large-block levels use > 48 KB of dynamic shared memory
     for (int l = 0; l + 1 < h->n_levels; ++l) {
         const Level& lv = h->L[l];
@@ -2862,6 +2899,8 @@ int amg1d_set_option(amg1d_t* h, const char* key, int64_t value) {
         if (h->finalized) return fail(h, AMG1D_ERR_STATE, "'p2p_halo' must be set before amg1d_finalize");
         h->opt_p2p = value != 0;
     }
+    else if (!strcmp(key, "dinv_registers")) h->opt_dvreg = (int)value;
+    else if (!strcmp(key, "leg_pipeline")) h->opt_pipe = value != 0;
     else if (!strcmp(key, "recompute_dinv")) {
         // before the first level: whether uploaded inverses are replaced by the device's own (adopt_device_dinv);
         // afterwards: whether the fused legs recompute them or stream the stored ones (same bits either way)
@@ -2914,16 +2953,40 @@ int64_t amg1d_get_info(amg1d_t* h, const char* key) {
         return valid_level(h, l) && h->L[l].pat ? 1 : 0;
     }
     if (!strcmp(key, "recompute_dinv")) return h->opt_dvrec;
+    if (!strcmp(key, "dinv_registers")) return h->opt_dvreg;
+    if (!strcmp(key, "leg_pipeline")) return h->opt_pipe;
+    if (!strncmp(key, "leg_pipeline:", 13)) {       // 1: the fused legs of this level are the pipelined persistent kernels
+        const int l = atoi(key + 13);
+        if (!valid_level(h, l) || !h->L[l].set || l + 1 >= h->n_levels || !h->T[l].fusable) return 0;
+        if (h->opt_pattern && h->L[l].pat) return 0;
+        const int rec = leg_rec(h, h->L[l], h->T[l].mc);
+        return ((rec & 16) && (rec & 3) && fused_has_pp(h->L[l].m, h->T[l].mc, h->L[l].md.st, h->L[l].diag)) ? 1 : 0;
+    }
     if (!strcmp(key, "p2p_halo")) return h->p2p.on ? 1 : 0;     // 1: slab edges travel through peer memory, 0: NCCL
+    if (!strcmp(key, "halo_bytes_per_cycle")) {                  // algorithmic bytes this rank SENDS to its slab neighbours
+        int64_t bytes = 0;                                       // per V-cycle: per sharded level the pre-smoothed edges, the
+        const int sides = (h->rank > 0) + (h->rank < h->nranks - 1);   // coarse rhs edges and the corrected edges
+        for (int l = 0; l < h->n_levels; ++l) {
+            if (!h->L[l].sharded) continue;
+            bytes += 2LL * h->ghost_depth * h->L[l].m * 8 * sides;
+            if (l + 1 < h->n_levels && h->L[l + 1].sharded) bytes += (int64_t)h->ghost_depth * h->L[l + 1].m * 8 * sides;
+        }
+        return bytes;
+    }
+    if (!strcmp(key, "sharded_levels")) {
+        int c = 0;
+        for (const auto& lv : h->L) c += lv.sharded ? 1 : 0;
+        return c;
+    }
     if (!strncmp(key, "dinv_pivots:", 12)) {        // 1: some element of the level swaps rows in its inverse
         const int l = atoi(key + 12);
         return valid_level(h, l) && h->L[l].set ? (h->L[l].dv_rec == 1) : -1;
     }
     if (!strncmp(key, "dinv_recompute:", 15)) {     // 1: the fused legs of this level invert A_di in registers
         const int l = atoi(key + 15);               //    instead of streaming the stored inverse
-        if (!valid_level(h, l) || !h->L[l].set || !leg_rec(h, h->L[l])) return 0;
+        if (!valid_level(h, l) || !h->L[l].set || l + 1 >= h->n_levels || !(leg_rec(h, h->L[l], h->T[l].mc) & 3)) return 0;
         if (h->opt_pattern && h->L[l].pat) return 0;
-        return (h->L[l].m <= 5 && l + 1 < h->n_levels && h->T[l].fusable) ? 1 : 0;
+        return (h->L[l].m <= 5 && h->T[l].fusable) ? 1 : 0;
     }
     if (!strncmp(key, "structure:", 10)) {          // "structure:<level>" -> structure class (layout.cuh)
         const int l = atoi(key + 10);

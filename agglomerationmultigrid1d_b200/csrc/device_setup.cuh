@@ -227,13 +227,42 @@ __global__ void k_extract_dinv(const double* __restrict__ mat, MatDesc d, int64_
 // stored inverse must be THE SAME Gauss-Jordan result.  This kernel recomputes it per element with the
 // arithmetic of reg_invert (kernels_fused.cuh: partial pivoting by a compare-and-swap chain, same operation order).
 //   mode 0: dev[0] = max over the elements of  max|Dinv_stored - inv(A_di)| / max|inv(A_di)|  (as an ordered
-//           int64 bit pattern, atomicMax), flag[0] |= 1 for a singular block, |= 2 if any element swaps rows -
-//           nothing is written;
-//   mode 1: overwrite the stored Dinv rows with the recomputed inverse.
+//           int64 bit pattern, atomicMax), flag[0] |= 1 for a singular block, |= 2 if any element swaps rows,
+//           |= 4 if some element that swaps rows NEEDS to (below) - nothing is written;
+//   mode 1: overwrite the stored Dinv rows with the recomputed (pivoted) inverse;
+//   mode 2: modes 0 and 1 in one pass over the level - an element is overwritten iff ITS upload agrees to 1e-8 (if
+//           some element of the level fails, the level is not marked for recomputation and keeps a stored inverse
+//           that is valid element by element);
+//   mode 3: overwrite the stored Dinv rows with the UNPIVOTED Gauss-Jordan inverse (reg_invert<M, false>).
+// Pivoting is a property of the node numbering more than of the numbers: the DG blocks of the reference (end nodes
+// first, src/dg_mesh.jl:41-46) swap rows in every element although they are symmetric positive definite, for which
+// elimination without pivoting is just as stable - and the swap chain is a third of the instructions of a fused leg
+// that inverts in registers (192 selects per 4 x 4 element).  So for every element that swaps, modes 0 / 2 also run
+// the elimination WITHOUT pivoting and compare: if the two inverses agree to 1e-12 (relative to the largest entry) in
+// every such element, the level adopts the unpivoted inverse (host: a second pass in mode 3) and its legs skip the
+// chain; one element that disagrees, or hits a zero pivot, keeps the whole level on the pivoted path (flag 4).
 // Addressing: element e (e_first <= e < e_end, may be negative: left ghosts) lives at
 // base + (e >> 5) * K * tile_stride + (e & 31) with row stride tile_stride (element tiles: tile_stride = 32);
 // a pattern table tab[set][k] is addressed with tile_stride = 1 and "elements" = its rows: base + e * K.
 #define AMG1D_DVREC_MAXM 9
+#define AMG1D_NOPIVOT_TOL 1e-12
+// in-place Gauss-Jordan inverse without pivoting (column-major m x m), statement for statement reg_invert<M, false>
+__device__ inline bool gj_invert_nopivot(double* A, int m) {
+    for (int c = 0; c < m; ++c) {
+        if (A[c * m + c] == 0.0) return false;
+        const double dd = 1.0 / A[c * m + c];
+        A[c * m + c] = 1.0;
+        for (int q = 0; q < m; ++q) A[q * m + c] *= dd;
+        for (int r = 0; r < m; ++r) {
+            if (r == c) continue;
+            const double f = A[c * m + r];
+            A[c * m + r] = 0.0;
+            for (int q = 0; q < m; ++q) A[q * m + r] = fma(-f, A[q * m + c], A[q * m + r]);
+        }
+    }
+    return true;
+}
+
 __global__ void k_dinv_recompute(double* __restrict__ base, MatDesc d, int64_t e_first, int64_t e_end, int tile_stride,
                                  int mode, unsigned long long* __restrict__ dev, int* __restrict__ flag) {
     const int64_t e = e_first + (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -247,11 +276,17 @@ __global__ void k_dinv_recompute(double* __restrict__ base, MatDesc d, int64_t e
     bool allzero = true;
     for (int k = 0; k < m * m; ++k) { A[k] = T[(int64_t)(d.o_di + k) * rs]; allzero = allzero && A[k] == 0.0; }
     if (allzero) return;                          // zero-filled slots outside the level (slab padding)
+    if (mode == 3) {
+        if (!gj_invert_nopivot(A, m)) { atomicOr(flag, 1); return; }
+        for (int k = 0; k < m * m; ++k) T[(int64_t)(d.o_dv + k) * rs] = A[k];
+        return;
+    }
+    bool swapped = false;
     for (int c = 0; c < m; ++c) {
         for (int r = c + 1; r < m; ++r) {         // compare-and-swap chain: the largest |a(r, c)|, r >= c, ends on the diagonal
             const bool s = fabs(A[c * m + r]) > fabs(A[c * m + c]);
             sw[c][r] = s;
-            if (s && mode == 0) atomicOr(flag, 2);   // this level pivots somewhere: the legs keep the swap chain
+            swapped = swapped || s;
             for (int q = 0; q < m; ++q) {
                 const double x = A[q * m + c], y = A[q * m + r];
                 A[q * m + c] = s ? y : x;
@@ -278,7 +313,7 @@ __global__ void k_dinv_recompute(double* __restrict__ base, MatDesc d, int64_t e
                 A[r2 * m + r] = s ? x : y;
             }
         }
-    if (mode == 0) {
+    if (mode != 1) {
         double mx = 0.0, df = 0.0;
         for (int k = 0; k < m * m; ++k) {
             mx = fmax(mx, fabs(A[k]));
@@ -286,9 +321,20 @@ __global__ void k_dinv_recompute(double* __restrict__ base, MatDesc d, int64_t e
         }
         const double rel = mx > 0.0 ? df / mx : 0.0;
         atomicMax(dev, (unsigned long long)__double_as_longlong(rel >= 0.0 ? rel : INFINITY));   // NaN -> inf
-    } else {
-        for (int k = 0; k < m * m; ++k) T[(int64_t)(d.o_dv + k) * rs] = A[k];
+        if (swapped) {                            // does this element need its pivots?
+            atomicOr(flag, 2);
+            double U[AMG1D_DVREC_MAXM * AMG1D_DVREC_MAXM];
+            for (int k = 0; k < m * m; ++k) U[k] = T[(int64_t)(d.o_di + k) * rs];
+            bool same = gj_invert_nopivot(U, m);
+            double du = 0.0;
+            for (int k = 0; k < m * m; ++k) du = fmax(du, fabs(U[k] - A[k]));
+            same = same && (du <= AMG1D_NOPIVOT_TOL * mx);                                    // false for NaN
+            if (!same) atomicOr(flag, 4);
+        }
+        if (mode == 2 && !(rel <= 1e-8)) return;      // this element's upload is not inv(A_di): leave it alone
     }
+    if (mode != 0)
+        for (int k = 0; k < m * m; ++k) T[(int64_t)(d.o_dv + k) * rs] = A[k];
 }
 
 // ---- device-side right-hand side ----------------------------------------------------------------

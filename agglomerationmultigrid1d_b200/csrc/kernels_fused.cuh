@@ -27,6 +27,8 @@
 // against S * 8 (4 M^2 + 3 M) + 8 (3 M^2 + 2 M + ...) for the unfused dense sequence (SURVEY 8d B_ref).
 #pragma once
 #include <cuda_runtime.h>
+#include <algorithm>
+#include <cstdint>
 #include "kernels_generic.cuh"
 #include "layout.cuh"
 #include "halo_p2p.cuh"
@@ -87,9 +89,18 @@ __device__ __forceinline__ int64_t win_blk(const TransferMap& tm, const WinIdx& 
 __device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 
+// true while the most recent fused launch was one of the persistent pipelined legs (f_down_pp / f_up_pp): the kernel
+// after such a leg is launched as an ordinary stream successor (see the comment above those kernels)
+inline bool& fused_prev_persistent() {
+    static bool v = false;
+    return v;
+}
+
 template <typename... KArgs, typename... Args>
 inline cudaError_t launch_fused(void (*kern)(KArgs...), unsigned grid, unsigned block, size_t smem,
                                 cudaStream_t st, bool pdl, Args... args) {
+    if (fused_prev_persistent()) pdl = false;
+    fused_prev_persistent() = false;
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(grid, 1, 1);
     cfg.blockDim = dim3(block, 1, 1);
@@ -330,6 +341,14 @@ struct ParamOp {
     double lo[OpShape<M, ST>::NO], di[M * M], up[OpShape<M, ST>::NO], dv[DIAG ? M : M * M];
 };
 
+// The element's blocks AND its block-Jacobi inverse in registers (f_down_dv / f_up_dv: the inverse is computed
+// in registers and never goes through shared memory).
+template <int M, int ST>
+struct RegOpDv {
+    static constexpr bool has_dv = true;
+    double lo[OpShape<M, ST>::NO], di[M * M], up[OpShape<M, ST>::NO], dv[M * M];
+};
+
 template <int M, int ST, class OP>
 __device__ __forceinline__ void reg_Ax(const OP& A, int ilo, int iup, const double (&xl)[M],
                                        const double (&xc)[M], const double (&xr)[M], double (&y)[M]) {
@@ -497,6 +516,8 @@ __device__ __forceinline__ void recompute_dinv(const RegOp<M, ST>& A, double (*d
 template <int M, int B, int ST, bool DIAG>
 __device__ __forceinline__ void recompute_dinv(const ParamOp<M, ST, DIAG>&, double (*)[B], bool, int) {}
 
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+
 template <int M, int ST, class OP>
 __device__ __forceinline__ void reg_residual(const OP& A, int ilo, int iup,
                                              const double (&bb)[M], const double (&xl)[M],
@@ -626,47 +647,42 @@ constexpr int fused_c_min_blocks(int m, int st) {
 //   out = elements emitted per CTA (a multiple of the agglomeration ratio).
 //   Coarse element Kc is gathered by the thread of its first P0-child, in the order of g_restrict:
 //   the P1 blocks of the children of Kc - 1, then the P0 blocks of its own children.
-// The leg after the operator has been placed (A: RegOp in registers + Dinv column dcol in shared memory, or
-// ParamOp in the constant bank); everything from the dependency wait on.
-template <int M, int MC, int B, int ST, bool DIAG, class OP>
+// down_body: the leg of window `win` (elements [win * out - halo, win * out - halo + B) of the slab) once the
+// operator (A: RegOp in registers + Dinv column dcol in shared memory, RegOpDv, or ParamOp in the constant bank) and
+// the thread's right-hand side bb / incoming iterate xc are in registers.  One CTA per window (f_down, f_down_dv,
+// f_down_c: win = blockIdx.x) or a persistent CTA walking over windows (f_down_pp).
+template <int M, int MC, int B, int ST, bool DIAG, class OP, int NSW = 0>   // NSW > 0: nsweep known at compile time
 __device__ __forceinline__ void
-down_leg(const OP& A, const double* __restrict__ dcol, Exchange<M, B>& ex, double (*rs)[B + 8], int64_t e,
-         bool active, int ilo, int iup, const double* __restrict__ b, const double* __restrict__ xin,
-         double* __restrict__ xout, const double* __restrict__ P0, const double* __restrict__ P1,
-         const TransferMap& tm, double* __restrict__ rc, int64_t n, double alpha, int nsweep, int zero_guess,
-         const WinIdx& wi, const Slab& sl, const HaloLeg& hl) {
+down_body(const OP& A, const double* __restrict__ dcol, Exchange<M, B>& ex, double (*rs)[B + 8], int64_t e, int64_t win,
+          const double (&bb)[M], double (&xc)[M], int ilo, int iup, double* __restrict__ xout,
+          const double* __restrict__ P0, const double* __restrict__ P1, const TransferMap& tm,
+          double* __restrict__ rc, int64_t n, double alpha, int nsweep, int zero_guess, const WinIdx& wi,
+          const Slab& sl, const HaloLeg& hl) {
     const int t = threadIdx.x;
     const int halo = wi.halo, out = wi.out;
-    double bb[M], xc[M], xl[M], xr[M];
-    pdl_wait();                                                  // b, x and everything written below are not
-    {   // peer-memory exchange: CTAs whose window reaches a slab edge wait for the neighbour's edge (halo_p2p.cuh)
-        const int64_t e0 = (int64_t)blockIdx.x * out - halo;
-        halo_leg_wait(hl, sl.gl > 0 && e0 < 0, sl.gr > 0 && e0 + B > n);
-    }
-    if (active) {
-        load_vec<M>(b + e * M, bb);
-        if (zero_guess) {
+    double xl[M], xr[M];
+    int buf = 0;
+    if constexpr (NSW > 0) {
 #pragma unroll
-            for (int i = 0; i < M; ++i) xc[i] = 0.0;
-        } else {
-            load_vec<M>(xin + e * M, xc);
+        for (int s = 0; s < NSW; ++s) {
+            const bool zg = zero_guess && s == 0;
+            if (!zg) {
+                exchange<M, B, ST>(ex, buf, ilo, iup, xc, xl, xr);
+                buf ^= 1;
+            }
+            reg_sweep<M, ST, DIAG, B>(A, ilo, iup, dcol, bb, xl, xc, xr, alpha, zg);
         }
     } else {
-#pragma unroll
-        for (int i = 0; i < M; ++i) { bb[i] = 0.0; xc[i] = 0.0; }
-    }
-    cp_async_commit_wait_all();  // this thread's Dinv column has landed (only this thread reads it)
-    __syncthreads();             // exch_init visible
-    int buf = 0;
-    for (int s = 0; s < nsweep; ++s) {
-        const bool zg = zero_guess && s == 0;
-        if (!zg) {
-            exchange<M, B, ST>(ex, buf, ilo, iup, xc, xl, xr);
-            buf ^= 1;
+        for (int s = 0; s < nsweep; ++s) {
+            const bool zg = zero_guess && s == 0;
+            if (!zg) {
+                exchange<M, B, ST>(ex, buf, ilo, iup, xc, xl, xr);
+                buf ^= 1;
+            }
+            reg_sweep<M, ST, DIAG, B>(A, ilo, iup, dcol, bb, xl, xc, xr, alpha, zg);
         }
-        reg_sweep<M, ST, DIAG, B>(A, ilo, iup, dcol, bb, xl, xc, xr, alpha, zg);
     }
-    const bool mine = t >= halo && t < halo + out;              // this CTA's share of the level (e >= 0)
+    const bool mine = t >= halo && t < halo + out;              // this window's share of the level (e >= 0)
     if (mine && e < n) {
         store_vec<M>(xout + e * M, xc);
         if (hl.on) halo_leg_push<M>(xc, e, n, hl.gd, hl.x_left, hl.x_right, hl.f_left, hl.f_right);
@@ -683,7 +699,7 @@ down_leg(const OP& A, const double* __restrict__ dcol, Exchange<M, B>& ex, doubl
         int kdiv, kmod;                                         // (eg + shift) = ratio * (.. + kdiv) + kmod
         small_divmod(wi.qmod0 + t, tm.ratio, &kdiv, &kmod);
         if (kmod == 0) {
-            const int64_t Kc = (int64_t)blockIdx.x * wi.opr + wi.qdiv0 + kdiv + tm.base;   // eg == tm.first(Kc)
+            const int64_t Kc = win * wi.opr + wi.qdiv0 + kdiv + tm.base;   // eg == tm.first(Kc)
             const int64_t Kl = Kc - sl.c_off;                   // local coarse element index
             if (Kc >= 0 && Kc < tm.n_coarse && Kl >= 0 && Kl < sl.nc) {
                 double acc[MC];
@@ -715,6 +731,38 @@ down_leg(const OP& A, const double* __restrict__ dcol, Exchange<M, B>& ex, doubl
             }
         }
     }
+}
+
+// The one-window-per-CTA leg after the operator has been placed: everything from the dependency wait on.
+template <int M, int MC, int B, int ST, bool DIAG, class OP>
+__device__ __forceinline__ void
+down_leg(const OP& A, const double* __restrict__ dcol, Exchange<M, B>& ex, double (*rs)[B + 8], int64_t e,
+         bool active, int ilo, int iup, const double* __restrict__ b, const double* __restrict__ xin,
+         double* __restrict__ xout, const double* __restrict__ P0, const double* __restrict__ P1,
+         const TransferMap& tm, double* __restrict__ rc, int64_t n, double alpha, int nsweep, int zero_guess,
+         const WinIdx& wi, const Slab& sl, const HaloLeg& hl) {
+    double bb[M], xc[M];
+    pdl_wait();                                                  // b, x and everything written below are not
+    {   // peer-memory exchange: CTAs whose window reaches a slab edge wait for the neighbour's edge (halo_p2p.cuh)
+        const int64_t e0 = (int64_t)blockIdx.x * wi.out - wi.halo;
+        halo_leg_wait(hl, sl.gl > 0 && e0 < 0, sl.gr > 0 && e0 + B > n);
+    }
+    if (active) {
+        load_vec<M>(b + e * M, bb);
+        if (zero_guess) {
+#pragma unroll
+            for (int i = 0; i < M; ++i) xc[i] = 0.0;
+        } else {
+            load_vec<M>(xin + e * M, xc);
+        }
+    } else {
+#pragma unroll
+        for (int i = 0; i < M; ++i) { bb[i] = 0.0; xc[i] = 0.0; }
+    }
+    cp_async_commit_wait_all();  // this thread's Dinv column has landed (only this thread reads it)
+    __syncthreads();             // exch_init visible
+    down_body<M, MC, B, ST, DIAG>(A, dcol, ex, rs, e, (int64_t)blockIdx.x, bb, xc, ilo, iup, xout, P0, P1, tm, rc, n,
+                                  alpha, nsweep, zero_guess, wi, sl, hl);
 }
 
 template <int M, int MC, int B, int ST, bool DIAG>
@@ -777,6 +825,72 @@ f_down_c(const __grid_constant__ ParamOp<M, ST, DIAG> pk, PatOp po, int ilo, int
     }
 }
 
+// x += P0 x_c[parent] (+ P1 x_c[parent + 1]) for window thread t of window `win`; c0 / c1 = the MC values of the
+// parent(s) (same operation order as g_prolong)
+template <int M, int MC>
+__device__ __forceinline__ void up_correct(double (&xc)[M], const double* __restrict__ P0, const double* __restrict__ P1,
+                                           int64_t pb, const double (&c0)[MC], const double (&c1)[MC]) {
+    double y[M];
+#pragma unroll
+    for (int i = 0; i < M; ++i) y[i] = 0.0;
+#pragma unroll
+    for (int j = 0; j < MC; ++j)
+#pragma unroll
+        for (int i = 0; i < M; ++i) y[i] = fma(P0[pb + j * M + i], c0[j], y[i]);
+    if (P1) {
+#pragma unroll
+        for (int j = 0; j < MC; ++j)
+#pragma unroll
+            for (int i = 0; i < M; ++i) y[i] = fma(P1[pb + j * M + i], c1[j], y[i]);
+    }
+#pragma unroll
+    for (int i = 0; i < M; ++i) xc[i] = xc[i] + y[i];
+}
+
+// up_body: nsweep post-smoothing sweeps of window `win` on the corrected iterate xc, emission, optional
+// || b - A x ||^2 partial sum of the window (partial[win]).
+template <int M, int MC, int B, int ST, bool DIAG, class OP, int NSW = 0>
+__device__ __forceinline__ void
+up_body(const OP& A, const double* __restrict__ dcol, Exchange<M, B>& ex, int64_t e, int64_t win,
+        const double (&bb)[M], double (&xc)[M], int ilo, int iup, double* __restrict__ xout, int64_t n, double alpha,
+        int nsweep, const WinIdx& wi, double* __restrict__ partial, const HaloLeg& hl) {
+    const int t = threadIdx.x;
+    const int halo = wi.halo, out = wi.out;
+    double xl[M], xr[M];
+    int buf = 0;
+    if constexpr (NSW > 0) {
+#pragma unroll
+        for (int s = 0; s < NSW; ++s) {
+            exchange<M, B, ST>(ex, buf, ilo, iup, xc, xl, xr);
+            buf ^= 1;
+            reg_sweep<M, ST, DIAG, B>(A, ilo, iup, dcol, bb, xl, xc, xr, alpha, false);
+        }
+    } else {
+        for (int s = 0; s < nsweep; ++s) {
+            exchange<M, B, ST>(ex, buf, ilo, iup, xc, xl, xr);
+            buf ^= 1;
+            reg_sweep<M, ST, DIAG, B>(A, ilo, iup, dcol, bb, xl, xc, xr, alpha, false);
+        }
+    }
+    const bool emit = e < n && t >= halo && t < halo + out;     // e >= 0 for these threads
+    if (emit) {
+        store_vec<M>(xout + e * M, xc);
+        if (hl.on) halo_leg_push<M>(xc, e, n, hl.gd, hl.x_left, hl.x_right, hl.f_left, hl.f_right);
+    }
+    if (partial) {
+        exchange<M, B, ST>(ex, buf, ilo, iup, xc, xl, xr);
+        double r[M];
+        reg_residual<M, ST>(A, ilo, iup, bb, xl, xc, xr, r);
+        double s2 = 0.0;
+        if (emit) {
+#pragma unroll
+            for (int i = 0; i < M; ++i) s2 = fma(r[i], r[i], s2);
+        }
+        s2 = block_sum(s2);
+        if (t == 0) partial[win] = s2;
+    }
+}
+
 // prolongation + correction, nsweep post-smoothing sweeps, optional || b - A x ||^2 partial sums.
 template <int M, int MC, int B, int ST, bool DIAG, class OP>
 __device__ __forceinline__ void
@@ -786,11 +900,10 @@ up_leg(const OP& A, const double* __restrict__ dcol, Exchange<M, B>& ex, int64_t
        const double* __restrict__ xcoarse, int64_t n, double alpha, int nsweep, const WinIdx& wi,
        double* __restrict__ partial, const Slab& sl, const HaloLeg& hl) {
     const int t = threadIdx.x;
-    const int halo = wi.halo, out = wi.out;
-    double bb[M], xc[M], xl[M], xr[M];
+    double bb[M], xc[M];
     pdl_wait();
     {   // peer-memory exchange: the CTAs near a slab edge read fine ghosts and / or ghosts of the coarse correction
-        const int64_t e0 = (int64_t)blockIdx.x * out - halo;
+        const int64_t e0 = (int64_t)blockIdx.x * wi.out - wi.halo;
         halo_leg_wait(hl, sl.gl > 0 && e0 < tm.ratio + 1, sl.gr > 0 && e0 + B + tm.ratio + 1 > n);
     }
     if (active) {
@@ -828,29 +941,8 @@ up_leg(const OP& A, const double* __restrict__ dcol, Exchange<M, B>& ex, int64_t
     }
     cp_async_commit_wait_all();
     __syncthreads();
-    int buf = 0;
-    for (int s = 0; s < nsweep; ++s) {
-        exchange<M, B, ST>(ex, buf, ilo, iup, xc, xl, xr);
-        buf ^= 1;
-        reg_sweep<M, ST, DIAG, B>(A, ilo, iup, dcol, bb, xl, xc, xr, alpha, false);
-    }
-    const bool emit = e < n && t >= halo && t < halo + out;     // e >= 0 for these threads
-    if (emit) {
-        store_vec<M>(xout + e * M, xc);
-        if (hl.on) halo_leg_push<M>(xc, e, n, hl.gd, hl.x_left, hl.x_right, hl.f_left, hl.f_right);
-    }
-    if (partial) {
-        exchange<M, B, ST>(ex, buf, ilo, iup, xc, xl, xr);
-        double r[M];
-        reg_residual<M, ST>(A, ilo, iup, bb, xl, xc, xr, r);
-        double s2 = 0.0;
-        if (emit) {
-#pragma unroll
-            for (int i = 0; i < M; ++i) s2 = fma(r[i], r[i], s2);
-        }
-        s2 = block_sum(s2);
-        if (t == 0) partial[blockIdx.x] = s2;
-    }
+    up_body<M, MC, B, ST, DIAG>(A, dcol, ex, e, (int64_t)blockIdx.x, bb, xc, ilo, iup, xout, n, alpha, nsweep, wi,
+                                partial, hl);
 }
 
 template <int M, int MC, int B, int ST, bool DIAG>
@@ -872,6 +964,431 @@ f_up(const double* __restrict__ mat, PatOp po, int ilo, int iup, const double* _
     recompute_dinv<M, B, ST, DIAG>(A, ds, active, rec);          // before the dependency wait: few registers are live yet
     up_leg<M, MC, B, ST, DIAG>(A, &ds[0][t], ex, e, active, ilo, iup, b, xin, xout, P0, P1, tm, xcoarse, n, alpha,
                                nsweep, wi, partial, sl, hl);
+}
+
+// ---- the legs with the inverse in REGISTERS (option dinv_registers) ---------------------------------------------
+// ncu of f_down / f_up with the recomputed inverse (profiles/r02_summary.md): DRAM traffic = algorithmic bytes, but
+// the L1 / shared-memory pipe is the busiest unit at 82-85 % - operator loads, iterate exchange, and the inverse
+// written to and read back from shared memory once per sweep (64 of ~165 LSU instructions per element).  These
+// variants keep the inverse where reg_invert leaves it: 16 more live doubles (4 x 4), hence 4 instead of 5 resident
+// CTAs per SM, no shared memory for it at all.  Block smoothers, streamed tiles only; same arithmetic, same bits.
+template <int M, int ST>
+__device__ __forceinline__ void load_blocks_dv(const double* __restrict__ mat, int64_t e, bool active, int rec,
+                                               RegOpDv<M, ST>& A) {
+    using S = OpShape<M, ST>;
+    constexpr int K = S::O_DV + M * M;
+    if (active) {
+        const double* T = mat + (e >> 5) * (int64_t)(K * AMG1D_TILE) + (e & 31);
+#pragma unroll
+        for (int k = 0; k < S::NO; ++k) A.lo[k] = T[k * AMG1D_TILE];
+#pragma unroll
+        for (int k = 0; k < M * M; ++k) A.di[k] = T[(S::O_DI + k) * AMG1D_TILE];
+#pragma unroll
+        for (int k = 0; k < S::NO; ++k) A.up[k] = T[(S::O_UP + k) * AMG1D_TILE];
+#pragma unroll
+        for (int k = 0; k < M * M; ++k) A.dv[k] = A.di[k];
+        if ((rec & 3) == 2) reg_invert<M, false>(A.dv); else reg_invert<M, true>(A.dv);
+    } else {
+#pragma unroll
+        for (int k = 0; k < S::NO; ++k) { A.lo[k] = 0.0; A.up[k] = 0.0; }
+#pragma unroll
+        for (int k = 0; k < M * M; ++k) { A.di[k] = 0.0; A.dv[k] = 0.0; }
+    }
+}
+
+constexpr int fused_dv_min_blocks(int m) { return m >= 4 ? 4 : 8; }
+inline bool fused_has_dv(int m, int mc, int st, int diag) {
+    return !diag && ((m == 4 && st == AMG1D_ST_COLROW && (mc == 2 || mc == 3)) || (m == 2 && mc == 2 && st != AMG1D_ST_ROWCOL));
+}
+
+template <int M, int MC, int B, int ST>
+__global__ void __launch_bounds__(B, fused_dv_min_blocks(M))
+f_down_dv(const double* __restrict__ mat, int ilo, int iup, const double* __restrict__ b,
+          const double* __restrict__ xin, double* __restrict__ xout, const double* __restrict__ P0,
+          const double* __restrict__ P1, TransferMap tm, double* __restrict__ rc, int64_t n, double alpha,
+          int nsweep, int zero_guess, WinIdx wi, Slab sl, int rec, const __grid_constant__ HaloLeg hl) {
+    __shared__ Exchange<M, B> ex;
+    __shared__ double rs[M][B + 8];
+    pdl_launch_dependents();
+    const int t = threadIdx.x;
+    const int64_t e = (int64_t)blockIdx.x * wi.out - wi.halo + t;
+    const bool active = e >= -(int64_t)sl.gl && e < n + sl.gr;
+    exch_init<M, B>(ex);
+    RegOpDv<M, ST> A;
+    load_blocks_dv<M, ST>(mat, e, active, rec, A);               // operator + inversion: independent of earlier kernels
+    down_leg<M, MC, B, ST, false>(A, nullptr, ex, rs, e, active, ilo, iup, b, xin, xout, P0, P1, tm, rc, n, alpha,
+                                  nsweep, zero_guess, wi, sl, hl);
+}
+
+template <int M, int MC, int B, int ST>
+__global__ void __launch_bounds__(B, fused_dv_min_blocks(M))
+f_up_dv(const double* __restrict__ mat, int ilo, int iup, const double* __restrict__ b,
+        const double* __restrict__ xin, double* __restrict__ xout, const double* __restrict__ P0,
+        const double* __restrict__ P1, TransferMap tm, const double* __restrict__ xcoarse, int64_t n,
+        double alpha, int nsweep, WinIdx wi, double* __restrict__ partial, Slab sl, int rec,
+        const __grid_constant__ HaloLeg hl) {
+    __shared__ Exchange<M, B> ex;
+    pdl_launch_dependents();
+    const int t = threadIdx.x;
+    const int64_t e = (int64_t)blockIdx.x * wi.out - wi.halo + t;
+    const bool active = e >= -(int64_t)sl.gl && e < n + sl.gr;
+    exch_init<M, B>(ex);
+    RegOpDv<M, ST> A;
+    load_blocks_dv<M, ST>(mat, e, active, rec, A);
+    up_leg<M, MC, B, ST, false>(A, nullptr, ex, e, active, ilo, iup, b, xin, xout, P0, P1, tm, xcoarse, n, alpha,
+                                nsweep, wi, partial, sl, hl);
+}
+
+// ---- pipelined persistent legs (option leg_pipeline): TMA bulk copies + mbarrier, one window ahead -----------------
+// What still separates f_down_dv / f_up_dv from the HBM roofline is not a saturated unit but the life of a CTA: load
+// the operator (one memory latency), invert, wait for the predecessor, load the vectors (a second latency), sweep,
+// store - with 4 resident CTAs per SM the bytes in flight per SM average ~45 KB, about what 6.5 TB/s needs at the
+// loaded latency, and nothing hides the gaps.  f_down_pp / f_up_pp are the same legs as PERSISTENT CTAs (4 per SM):
+// CTA c walks over the windows c, c + grid, c + 2 grid ...; while it computes window w out of registers, the
+// operator tiles and the b / x slices of its NEXT window are already in flight into shared memory - 1-D bulk copies
+// (cp.async.bulk.shared::cluster.global, the TMA engine: no registers, no LSU instructions) issued by one thread
+// and signalled through one mbarrier per CTA (expect_tx = bytes issued; parity flips per window).  A window of
+// B = 128 elements starts at w * out - halo, which is never tile aligned, so the stage holds the B / 32 + 1 element
+// tiles it touches - only their A_lo / A_di / A_up rows, which are contiguous at the start of a tile; the inverse
+// is recomputed in registers (reg_invert) as in f_*_dv - the neighbouring windows' copies of the shared tiles are
+// served by L2.  The coarse values of the up leg (a few doubles per thread at a thread-dependent address) follow
+// through per-thread cp.async into the thread's own shared-memory slots.  ~52 KB of shared memory per CTA: one
+// operator stage suffices because the operator moves to registers at the start of a window and the stage is
+// refilled right after.  Arithmetic, order and emitted values are those of f_down / f_up (down_body / up_body):
+// bit-identical.  Slab edges: thread 0 waits for the neighbour's flags before the first copy of a window that
+// touches an edge (the spin of halo_leg_wait), the edge owners push as in f_down / f_up.
+// The persistent legs are launched as ordinary stream successors, not as programmatic dependents: an early
+// launch places their CTAs on SMs that still run the predecessor's last wave under ITS shared-memory carve-out,
+// fewer than PIPE_MINB fit, the SM can never be reconfigured while a persistent CTA lives on it, and the
+// CTAs that found no place run as a second wave; and a programmatic successor of a persistent leg starts on SMs
+// that still hold persistent CTAs, inherits their maximal shared-memory carve-out (no L1 to speak of) and hands it
+// down the whole PDL chain, because no SM ever drains (measured on T: 17.0 instead of 15.6 ms per cycle).  So the
+// legs before and after a persistent leg are separated by ordinary stream dependencies (fused_prev_persistent).
+__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned long long* bar, unsigned count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async;" ::: "memory"); }
+__device__ __forceinline__ void mbar_arrive_expect_tx(unsigned long long* bar, unsigned bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void* smem_dst, const void* gmem_src, unsigned bytes, unsigned long long* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smem_u32(smem_dst)), "l"(gmem_src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(unsigned long long* bar, unsigned parity) {
+    unsigned ok;
+    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.b32 %0, 1, 0, p;\n\t}"
+                 : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+    return ok != 0;
+}
+// A bulk copy that never completes (a bad address would fault instead) must not hang the GPU: give up after ~2 s.
+__device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned parity) {
+    if (mbar_try_wait(bar, parity)) return;
+    const long long t0 = clock64();
+    while (!mbar_try_wait(bar, parity))
+        if (clock64() - t0 > 4000000000LL) __trap();
+}
+
+template <int M, int B, int ST>
+struct PipeStage {
+    static constexpr int NT = B / AMG1D_TILE + 1;      // element tiles a window of B elements can touch
+    static constexpr int NR = OpShape<M, ST>::O_DV;    // tile rows of A_lo, A_di, A_up (contiguous at the tile's start)
+    alignas(128) double op[NT][NR][AMG1D_TILE];
+    alignas(16) double bv[B * M];
+    alignas(16) double xv[B * M];
+    alignas(8) unsigned long long bar;
+};
+
+// thread 0: the operator tiles of the window starting at local element e0; returns the bytes issued
+template <int M, int B, int ST>
+__device__ __forceinline__ unsigned pipe_issue_op(PipeStage<M, B, ST>& st, const double* __restrict__ mat, int64_t e0,
+                                                  int64_t lo, int64_t hi) {
+    using PS = PipeStage<M, B, ST>;
+    constexpr int K = OpShape<M, ST>::O_DV + M * M;
+    constexpr unsigned TB = PS::NR * AMG1D_TILE * 8;
+    const int64_t t0 = e0 >> 5, t1 = (e0 + B - 1) >> 5, tlo = lo >> 5, thi = (hi - 1) >> 5;
+    unsigned bytes = 0;
+#pragma unroll
+    for (int j = 0; j < PS::NT; ++j) {
+        const int64_t tj = t0 + j;
+        if (tj <= t1 && tj >= tlo && tj <= thi) {
+            bulk_g2s(&st.op[j][0][0], mat + tj * (int64_t)(K * AMG1D_TILE), TB, &st.bar);
+            bytes += TB;
+        }
+    }
+    return bytes;
+}
+
+// thread 0: the slice [e0, e0 + B) of a vector with M doubles per element, clipped to the slab [lo, hi)
+template <int M, int B>
+__device__ __forceinline__ unsigned pipe_issue_vec(double* dst, const double* __restrict__ src, int64_t e0, int64_t lo,
+                                                   int64_t hi, unsigned long long* bar) {
+    const int64_t a = e0 > lo ? e0 : lo, z = e0 + B < hi ? e0 + B : hi;
+    if (z <= a) return 0;
+    const unsigned bytes = (unsigned)(z - a) * (M * 8);
+    bulk_g2s(dst + (a - e0) * M, src + a * M, bytes, bar);
+    return bytes;
+}
+
+// The window's operator from the stage into registers; the diagonal block is read twice - once as A.di and once as
+// the start of the in-place inversion A.dv (16 shared-memory loads instead of 32 register moves).  GUARD = false: the
+// whole window lies inside the slab (CTA-uniform test by the caller), no thread needs the zero fill.
+template <int M, int B, int ST, bool GUARD>
+__device__ __forceinline__ void pipe_take_op(const PipeStage<M, B, ST>& st, int64_t e0, int64_t e, bool active,
+                                             RegOpDv<M, ST>& A) {
+    using S = OpShape<M, ST>;
+    if (!GUARD || active) {
+        const double* T = &st.op[(int)((e >> 5) - (e0 >> 5))][0][(int)(e & 31)];
+#pragma unroll
+        for (int k = 0; k < S::NO; ++k) A.lo[k] = T[k * AMG1D_TILE];
+#pragma unroll
+        for (int k = 0; k < M * M; ++k) A.di[k] = T[(S::O_DI + k) * AMG1D_TILE];
+#pragma unroll
+        for (int k = 0; k < S::NO; ++k) A.up[k] = T[(S::O_UP + k) * AMG1D_TILE];
+#pragma unroll
+        for (int k = 0; k < M * M; ++k) A.dv[k] = T[(S::O_DI + k) * AMG1D_TILE];
+    } else {
+#pragma unroll
+        for (int k = 0; k < S::NO; ++k) { A.lo[k] = 0.0; A.up[k] = 0.0; }
+#pragma unroll
+        for (int k = 0; k < M * M; ++k) { A.di[k] = 0.0; A.dv[k] = 0.0; }
+    }
+}
+
+template <int M, int ST>
+__device__ __forceinline__ void pipe_invert(RegOpDv<M, ST>& A, bool active, int rec) {
+    if (active) {
+        if ((rec & 3) == 2) reg_invert<M, false>(A.dv); else reg_invert<M, true>(A.dv);
+    }
+}
+
+#ifndef PIPE_MINB
+#define PIPE_MINB 4      // persistent CTAs per SM (128 registers)
+#endif
+
+template <int M, int MC, int B, int ST>
+struct PipeDownSmem {
+    PipeStage<M, B, ST> st;
+    Exchange<M, B> ex;
+    double rs[M][B + 8];
+};
+
+template <int M, int MC, int B, int ST, int NSW>
+__global__ void __launch_bounds__(B, PIPE_MINB)
+f_down_pp(const double* __restrict__ mat, int ilo, int iup, const double* __restrict__ b,
+          const double* __restrict__ xin, double* __restrict__ xout, const double* __restrict__ P0,
+          const double* __restrict__ P1, TransferMap tm, double* __restrict__ rc, int64_t n, double alpha,
+          int nsweep, int zero_guess, WinIdx wi, Slab sl, int rec, const __grid_constant__ HaloLeg hl, int64_t n_win) {
+    extern __shared__ __align__(128) unsigned char pipe_smem[];
+    PipeDownSmem<M, MC, B, ST>& S = *reinterpret_cast<PipeDownSmem<M, MC, B, ST>*>(pipe_smem);
+    pdl_launch_dependents();
+    const int t = threadIdx.x;
+    const int64_t lo = -(int64_t)sl.gl, hi = n + sl.gr;
+    if (t == 0) mbar_init(&S.st.bar, 1);
+    exch_init<M, B>(S.ex);
+    __syncthreads();
+    int64_t win = blockIdx.x;
+    unsigned tx = 0;
+    if (t == 0) tx = pipe_issue_op<M, B, ST>(S.st, mat, win * wi.out - wi.halo, lo, hi);   // independent of earlier kernels
+    pdl_wait();
+    {
+        const int64_t e0 = win * wi.out - wi.halo;
+        halo_leg_wait(hl, sl.gl > 0 && e0 < 0, sl.gr > 0 && e0 + B > n);
+        if (t == 0) {
+            if (hl.on) fence_proxy_async();
+            tx += pipe_issue_vec<M, B>(S.st.bv, b, e0, lo, hi, &S.st.bar);
+            if (!zero_guess) tx += pipe_issue_vec<M, B>(S.st.xv, xin, e0, lo, hi, &S.st.bar);
+            mbar_arrive_expect_tx(&S.st.bar, tx);
+        }
+    }
+    unsigned parity = 0;
+    for (; win < n_win; win += gridDim.x) {
+        const int64_t e0 = win * wi.out - wi.halo, e = e0 + t;
+        const bool active = e >= lo && e < hi;
+        RegOpDv<M, ST> A;
+        double bb[M], xc[M];
+        mbar_wait(&S.st.bar, parity);
+        parity ^= 1;
+        if (e0 >= lo && e0 + B <= hi) {                          // CTA-uniform: the whole window is inside the slab
+            pipe_take_op<M, B, ST, false>(S.st, e0, e, true, A);
+            load_vec<M>(&S.st.bv[t * M], bb);
+            if (zero_guess) {
+#pragma unroll
+                for (int i = 0; i < M; ++i) xc[i] = 0.0;
+            } else {
+                load_vec<M>(&S.st.xv[t * M], xc);
+            }
+        } else {
+            pipe_take_op<M, B, ST, true>(S.st, e0, e, active, A);
+            if (active) {
+                load_vec<M>(&S.st.bv[t * M], bb);
+                if (zero_guess) {
+#pragma unroll
+                    for (int i = 0; i < M; ++i) xc[i] = 0.0;
+                } else {
+                    load_vec<M>(&S.st.xv[t * M], xc);
+                }
+            } else {
+#pragma unroll
+                for (int i = 0; i < M; ++i) { bb[i] = 0.0; xc[i] = 0.0; }
+            }
+        }
+        const int64_t wn = win + gridDim.x;
+        if (wn < n_win) {                                        // CTA-uniform
+            const int64_t en = wn * wi.out - wi.halo;
+            halo_leg_wait(hl, sl.gl > 0 && en < 0, sl.gr > 0 && en + B > n);
+            __syncthreads();                                     // the stage has been consumed by every thread
+            if (t == 0) {
+                fence_proxy_async();
+                tx = pipe_issue_op<M, B, ST>(S.st, mat, en, lo, hi);
+                tx += pipe_issue_vec<M, B>(S.st.bv, b, en, lo, hi, &S.st.bar);
+                if (!zero_guess) tx += pipe_issue_vec<M, B>(S.st.xv, xin, en, lo, hi, &S.st.bar);
+                mbar_arrive_expect_tx(&S.st.bar, tx);
+            }
+        } else {
+            __syncthreads();
+        }
+        pipe_invert<M, ST>(A, active, rec);
+        down_body<M, MC, B, ST, false, RegOpDv<M, ST>, NSW>(A, nullptr, S.ex, S.rs, e, win, bb, xc, ilo, iup, xout, P0, P1,
+                                                             tm, rc, n, alpha, nsweep, zero_guess, wi, sl, hl);
+    }
+}
+
+template <int M, int MC, int B, int ST>
+struct PipeUpSmem {
+    PipeStage<M, B, ST> st;
+    Exchange<M, B> ex;
+    double cs[2 * MC][B];        // coarse values of the thread's parent(s), filled by the thread's own cp.async
+};
+
+// all threads: the coarse values window thread t of window `win` needs, into its own slots cs[.][t]
+template <int M, int MC, int B>
+__device__ __forceinline__ void pipe_issue_coarse(double (*cs)[B], const double* __restrict__ xcoarse, bool two,
+                                                  const TransferMap& tm, const WinIdx& wi, const Slab& sl, int64_t win,
+                                                  bool active) {
+    const int t = threadIdx.x;
+    if (active) {
+        int kdiv, kmod;
+        small_divmod(wi.qmod0 + t, tm.ratio, &kdiv, &kmod);
+        const int64_t par = win * wi.opr + wi.qdiv0 + kdiv + tm.base;     // == tm.par(global element)
+        const double* c0 = xcoarse + (par - sl.c_off) * MC;
+#pragma unroll
+        for (int j = 0; j < MC; ++j) cp_async8(&cs[j][t], c0 + j);
+        if (two) {
+#pragma unroll
+            for (int j = 0; j < MC; ++j) cp_async8(&cs[MC + j][t], c0 + MC + j);
+        }
+    }
+    cp_async_commit();
+}
+
+template <int M, int MC, int B, int ST, int NSW>
+__global__ void __launch_bounds__(B, PIPE_MINB)
+f_up_pp(const double* __restrict__ mat, int ilo, int iup, const double* __restrict__ b,
+        const double* __restrict__ xin, double* __restrict__ xout, const double* __restrict__ P0,
+        const double* __restrict__ P1, TransferMap tm, const double* __restrict__ xcoarse, int64_t n,
+        double alpha, int nsweep, WinIdx wi, double* __restrict__ partial, Slab sl, int rec,
+        const __grid_constant__ HaloLeg hl, int64_t n_win) {
+    extern __shared__ __align__(128) unsigned char pipe_smem[];
+    PipeUpSmem<M, MC, B, ST>& S = *reinterpret_cast<PipeUpSmem<M, MC, B, ST>*>(pipe_smem);
+    pdl_launch_dependents();
+    const int t = threadIdx.x;
+    const int64_t lo = -(int64_t)sl.gl, hi = n + sl.gr;
+    if (t == 0) mbar_init(&S.st.bar, 1);
+    exch_init<M, B>(S.ex);
+    __syncthreads();
+    int64_t win = blockIdx.x;
+    unsigned tx = 0;
+    if (t == 0) tx = pipe_issue_op<M, B, ST>(S.st, mat, win * wi.out - wi.halo, lo, hi);   // independent of earlier kernels
+    pdl_wait();
+    {
+        const int64_t e0 = win * wi.out - wi.halo;
+        halo_leg_wait(hl, sl.gl > 0 && e0 < tm.ratio + 1, sl.gr > 0 && e0 + B + tm.ratio + 1 > n);
+        if (t == 0) {
+            if (hl.on) fence_proxy_async();
+            tx += pipe_issue_vec<M, B>(S.st.bv, b, e0, lo, hi, &S.st.bar);
+            tx += pipe_issue_vec<M, B>(S.st.xv, xin, e0, lo, hi, &S.st.bar);
+            mbar_arrive_expect_tx(&S.st.bar, tx);
+        }
+        pipe_issue_coarse<M, MC, B>(S.cs, xcoarse, P1 != nullptr, tm, wi, sl, win, e0 + t >= lo && e0 + t < hi);
+    }
+    unsigned parity = 0;
+    for (; win < n_win; win += gridDim.x) {
+        const int64_t e0 = win * wi.out - wi.halo, e = e0 + t;
+        const bool active = e >= lo && e < hi;
+        RegOpDv<M, ST> A;
+        double bb[M], xc[M];
+        mbar_wait(&S.st.bar, parity);
+        parity ^= 1;
+        if (e0 >= lo && e0 + B <= hi) pipe_take_op<M, B, ST, false>(S.st, e0, e, true, A);     // CTA-uniform
+        else pipe_take_op<M, B, ST, true>(S.st, e0, e, active, A);
+        asm volatile("cp.async.wait_group 0;" ::: "memory");
+        if (active) {
+            load_vec<M>(&S.st.bv[t * M], bb);
+            load_vec<M>(&S.st.xv[t * M], xc);
+            double c0[MC], c1[MC];
+#pragma unroll
+            for (int j = 0; j < MC; ++j) { c0[j] = S.cs[j][t]; c1[j] = P1 ? S.cs[MC + j][t] : 0.0; }
+            const int64_t pb = win_blk(tm, wi, e + sl.e_off, t) * (M * MC);
+            up_correct<M, MC>(xc, P0, P1, pb, c0, c1);
+        } else {
+#pragma unroll
+            for (int i = 0; i < M; ++i) { bb[i] = 0.0; xc[i] = 0.0; }
+        }
+        const int64_t wn = win + gridDim.x;
+        if (wn < n_win) {                                        // CTA-uniform
+            const int64_t en = wn * wi.out - wi.halo;
+            halo_leg_wait(hl, sl.gl > 0 && en < tm.ratio + 1, sl.gr > 0 && en + B + tm.ratio + 1 > n);
+            __syncthreads();                                     // the stage has been consumed by every thread
+            if (t == 0) {
+                fence_proxy_async();
+                tx = pipe_issue_op<M, B, ST>(S.st, mat, en, lo, hi);
+                tx += pipe_issue_vec<M, B>(S.st.bv, b, en, lo, hi, &S.st.bar);
+                tx += pipe_issue_vec<M, B>(S.st.xv, xin, en, lo, hi, &S.st.bar);
+                mbar_arrive_expect_tx(&S.st.bar, tx);
+            }
+            pipe_issue_coarse<M, MC, B>(S.cs, xcoarse, P1 != nullptr, tm, wi, sl, wn, en + t >= lo && en + t < hi);
+        } else {
+            __syncthreads();
+        }
+        pipe_invert<M, ST>(A, active, rec);
+        up_body<M, MC, B, ST, false, RegOpDv<M, ST>, NSW>(A, nullptr, S.ex, e, win, bb, xc, ilo, iup, xout, n, alpha, nsweep,
+                                                           wi, partial, hl);
+    }
+}
+
+inline bool fused_has_pp(int m, int mc, int st, int diag) {
+    return !diag && m == 4 && st == AMG1D_ST_COLROW && (mc == 2 || mc == 3);
+}
+
+// persistent grid of the pipelined legs: PIPE_MINB CTAs per SM of the current device; the first launch of an
+// dynamic shared-memory limit of the kernels is raised once (pipe_configure_all)
+inline int pipe_sm_count() {
+    static int sms = 0;
+    if (!sms) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sms <= 0) sms = 148;
+    }
+    return sms;
+}
+template <class KERN>
+inline cudaError_t pipe_configure(KERN kern, size_t smem) {
+    return cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+}
+// once per device context, outside stream capture (amg1d_finalize): the pipelined legs need > 48 KB per CTA
+inline cudaError_t pipe_configure_all() {
+    cudaError_t e = cudaSuccess;
+#define PP(MM, MCC, SS)                                                                                            \
+    if (e == cudaSuccess) e = pipe_configure(f_down_pp<MM, MCC, FUSED_B, SS, 0>, sizeof(PipeDownSmem<MM, MCC, FUSED_B, SS>)); \
+    if (e == cudaSuccess) e = pipe_configure(f_down_pp<MM, MCC, FUSED_B, SS, 3>, sizeof(PipeDownSmem<MM, MCC, FUSED_B, SS>)); \
+    if (e == cudaSuccess) e = pipe_configure(f_up_pp<MM, MCC, FUSED_B, SS, 0>, sizeof(PipeUpSmem<MM, MCC, FUSED_B, SS>)); \
+    if (e == cudaSuccess) e = pipe_configure(f_up_pp<MM, MCC, FUSED_B, SS, 3>, sizeof(PipeUpSmem<MM, MCC, FUSED_B, SS>));
+    PP(4, 2, 1) PP(4, 3, 1)
+#undef PP
+    return e;
 }
 
 // f_up with constant-bank operands for the interior CTAs of a pattern level (see f_down_c)
@@ -1284,6 +1801,32 @@ inline int fused_down(const MatDesc& d, int mc, const TransferMap& tm, int nswee
     const WinIdx w = fused_window(nsweep, tm, P1 != nullptr || tm.shift != 0 || tm.base != 0, sl);
     if (w.out < tm.ratio || w.out < FUSED_B / 2 || !fast_tier_ok(d)) return FUSED_NA;
     const unsigned grid = (unsigned)((n_cover + w.out - 1) / w.out);
+    if ((rec & 16) && (rec & 3) && !po.tab && fused_has_pp(d.m, mc, d.st, d.diag) &&
+        (((uintptr_t)b | (uintptr_t)xin | (uintptr_t)mat) & 15) == 0) {               // pipelined persistent leg
+#define PP(MM, MCC, SS)                                                                                   \
+        if (d.m == MM && mc == MCC && d.st == SS) {                                                       \
+            const size_t smem = sizeof(PipeDownSmem<MM, MCC, FUSED_B, SS>);                               \
+            const int64_t pg = std::min<int64_t>((int64_t)grid, (int64_t)pipe_sm_count() * PIPE_MINB);    \
+            *err = launch_fused(nsweep == 3 ? f_down_pp<MM, MCC, FUSED_B, SS, 3> : f_down_pp<MM, MCC, FUSED_B, SS, 0>, \
+                                (unsigned)pg, FUSED_B, smem, st, false, mat, d.ilo,                       \
+                                d.iup, b, xin, xout, P0, P1, tm, rc, n, alpha, nsweep, zero ? 1 : 0, w, sl, rec, hl, \
+                                (int64_t)grid);                                                           \
+            fused_prev_persistent() = true;                                                               \
+            return *err == cudaSuccess ? FUSED_OK : FUSED_ERR;                                            \
+        }
+        PP(4, 2, 1) PP(4, 3, 1)
+#undef PP
+    }
+    if ((rec & 8) && (rec & 3) && !po.tab && fused_has_dv(d.m, mc, d.st, d.diag)) {   // inverse in registers
+#define DV(MM, MCC, SS)                                                                                   \
+        if (d.m == MM && mc == MCC && d.st == SS) {                                                       \
+            *err = launch_fused(f_down_dv<MM, MCC, FUSED_B, SS>, grid, FUSED_B, 0, st, pdl, mat, d.ilo, d.iup, b, xin, \
+                                xout, P0, P1, tm, rc, n, alpha, nsweep, zero ? 1 : 0, w, sl, rec, hl);     \
+            return *err == cudaSuccess ? FUSED_OK : FUSED_ERR;                                            \
+        }
+        DV(4, 2, 1) DV(4, 3, 1) DV(2, 2, 0) DV(2, 2, 1)
+#undef DV
+    }
     switch (fused_key(d.m, mc, d.st, d.diag)) {
 #define X(MM, MCC, SS, DG)                                                                               \
     case ((MM * 16 + MCC) * 4 + SS) * 2 + (DG ? 1 : 0):                                                  \
@@ -1295,7 +1838,7 @@ inline int fused_down(const MatDesc& d, int mc, const TransferMap& tm, int nswee
         } else                                                                                           \
         *err = launch_fused(f_down<MM, MCC, FUSED_B, SS, DG>, grid, FUSED_B, 0, st, pdl, mat, po, d.ilo, d.iup, \
                             b, xin, xout, P0, P1, tm, rc, n, alpha, nsweep, zero ? 1 : 0, w, sl,         \
-                            (!po.tab && !DG) ? rec : 0, hl);                                             \
+                            ((!po.tab && !DG) ? (rec & 3) : 0), hl);                                  \
         return *err == cudaSuccess ? FUSED_OK : FUSED_ERR;
         FUSED_COMBOS(X)
 #undef X
@@ -1313,6 +1856,32 @@ inline int fused_up(const MatDesc& d, int mc, const TransferMap& tm, int nsweep,
     const int64_t grid = (n + w.out - 1) / w.out;
     if (partial && grid > partial_cap) return FUSED_NA;
     if (nblocks) *nblocks = (int)grid;
+    if ((rec & 16) && (rec & 3) && !po.tab && fused_has_pp(d.m, mc, d.st, d.diag) &&
+        (((uintptr_t)b | (uintptr_t)xin | (uintptr_t)mat) & 15) == 0) {               // pipelined persistent leg
+#define PP(MM, MCC, SS)                                                                                   \
+        if (d.m == MM && mc == MCC && d.st == SS) {                                                       \
+            const size_t smem = sizeof(PipeUpSmem<MM, MCC, FUSED_B, SS>);                                 \
+            const int64_t pg = std::min<int64_t>(grid, (int64_t)pipe_sm_count() * PIPE_MINB);             \
+            *err = launch_fused(nsweep == 3 ? f_up_pp<MM, MCC, FUSED_B, SS, 3> : f_up_pp<MM, MCC, FUSED_B, SS, 0>, \
+                                (unsigned)pg, FUSED_B, smem, st, false, mat, d.ilo,                       \
+                                d.iup, b, xin, xout, P0, P1, tm, xcoarse, n, alpha, nsweep, w, partial, sl, rec, hl, \
+                                grid);                                                                    \
+            fused_prev_persistent() = true;                                                               \
+            return *err == cudaSuccess ? FUSED_OK : FUSED_ERR;                                            \
+        }
+        PP(4, 2, 1) PP(4, 3, 1)
+#undef PP
+    }
+    if ((rec & 8) && (rec & 3) && !po.tab && fused_has_dv(d.m, mc, d.st, d.diag)) {
+#define DV(MM, MCC, SS)                                                                                   \
+        if (d.m == MM && mc == MCC && d.st == SS) {                                                       \
+            *err = launch_fused(f_up_dv<MM, MCC, FUSED_B, SS>, (unsigned)grid, FUSED_B, 0, st, pdl, mat, d.ilo, d.iup, b, \
+                                xin, xout, P0, P1, tm, xcoarse, n, alpha, nsweep, w, partial, sl, rec, hl); \
+            return *err == cudaSuccess ? FUSED_OK : FUSED_ERR;                                            \
+        }
+        DV(4, 2, 1) DV(4, 3, 1) DV(2, 2, 0) DV(2, 2, 1)
+#undef DV
+    }
     switch (fused_key(d.m, mc, d.st, d.diag)) {
 #define X(MM, MCC, SS, DG)                                                                               \
     case ((MM * 16 + MCC) * 4 + SS) * 2 + (DG ? 1 : 0):                                                  \
@@ -1324,7 +1893,7 @@ inline int fused_up(const MatDesc& d, int mc, const TransferMap& tm, int nsweep,
         } else                                                                                           \
         *err = launch_fused(f_up<MM, MCC, FUSED_B, SS, DG>, (unsigned)grid, FUSED_B, 0, st, pdl, mat, po,    \
                             d.ilo, d.iup, b, xin, xout, P0, P1, tm, xcoarse, n, alpha, nsweep, w, partial, sl, \
-                            (!po.tab && !DG) ? rec : 0, hl);                                             \
+                            ((!po.tab && !DG) ? (rec & 3) : 0), hl);                                  \
         return *err == cudaSuccess ? FUSED_OK : FUSED_ERR;
         FUSED_COMBOS(X)
 #undef X

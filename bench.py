@@ -410,6 +410,8 @@ def measure(ctx, args, workload, ranks, full):
             "ms_per_step": ms_step, "scaling": "strong" if strong else "weak",
             "config": {"workload": f"{workload}: {desc}", "n_elements": n, "elements_per_gpu": nloc, "levels": len(U.levels),
                        "gather_level": dev.info("gather_level"), "p2p_halo": dev.info("p2p_halo"),
+                       "sharded_levels": dev.info("sharded_levels"),
+                       "halo_bytes_per_cycle_per_rank": dev.info("halo_bytes_per_cycle"),
                        "options": args.opt + args.pre_opt, "setup_s": t_setup, "dof_updates_per_step": upd},
             "clocks": clocks, "gpu_launches": int(launches), "time_to_1e-10": dev_solve}
         for p in bufs:
@@ -474,6 +476,8 @@ def measure(ctx, args, workload, ranks, full):
               "streamed_operator_doubles": [U.streamed_operator_doubles(l) for l in range(min(4, len(U.levels)))],
               "tail_start": dev.info("tail_start"), "options": args.opt + args.pre_opt,
               "gather_level": dev.info("gather_level"), "p2p_halo": dev.info("p2p_halo"),
+              "sharded_levels": dev.info("sharded_levels"),
+              "halo_bytes_per_cycle_per_rank": dev.info("halo_bytes_per_cycle"),
               "device_bytes": dev.info("device_bytes"), "setup_s": t_setup, "rhs_assembly_s": t_rhs_dev,
               "rhs_assembly_host_numpy_s": t_rhs,
               "residual_after_timed_steps": res_after}
@@ -527,6 +531,37 @@ def measure(ctx, args, workload, ranks, full):
                         "B_ref_equiv_GBps": U.bytes_per_cycle_reference_model() / (ms_step * 1e-3) / 1e9},
         "leg_ms": legs,
     }
+
+    # ---- the same legs with the smoother inverse STREAMED from HBM instead of recomputed in registers (option
+    # recompute_dinv = 0; same bits): the byte count of round 1, reported beside the default for comparison
+    if dev.info("dinv_recompute:0") == 1:
+        rec_default = dev.info("recompute_dinv")
+        dev.set_option("recompute_dinv", 0)
+        dev.dev_fill_rhs_random(0)
+        for _ in range(args.warmup):
+            dev.dev_vcycle(with_residual_norm=True)
+        barrier()
+        ev0.record()
+        for _ in range(args.steps):
+            dev.dev_vcycle(with_residual_norm=True)
+        ev1.record()
+        barrier()
+        ms_s = mx(ev0.elapsed_time(ev1)) / args.steps
+        dev.set_option("profile", 1)
+        for _ in range(args.steps):
+            dev.dev_vcycle(with_residual_norm=True)
+        dev.synchronize()
+        t_s, c_s = dev.profile(0, 1)
+        t_sd, c_sd = dev.profile(0, 0)
+        dev.set_option("profile", 0)
+        b_s = U.bytes_per_leg_fused(0, down=False) // world
+        roofline["streamed_inverse"] = {
+            "what": "option recompute_dinv = 0: level 0 streams the stored block-Jacobi inverses (bit-identical results)",
+            "algorithmic_bytes_per_launch": b_s, "avg_launch_ms": t_s / max(c_s, 1),
+            "achieved": b_s / (t_s / max(c_s, 1) * 1e-3) / 1e9, "frac": b_s / (t_s / max(c_s, 1) * 1e-3) / 1e9 / peak,
+            "L0_down_ms": t_sd / max(c_sd, 1), "ms_per_step": ms_s, "value": upd / (ms_s * 1e-3),
+            "whole_cycle_bytes": U.bytes_per_cycle_fused()}
+        dev.set_option("recompute_dinv", rec_default)
 
     # ---- e2e: the reference-facing call with pinned host vectors, copies inside the timed region ---
     xh[:] = 0.0

@@ -177,6 +177,30 @@ function pcg(D::DeviceHierarchy, x0::AbstractVector, b::AbstractVector, maxiter:
     return x, Int(it[]), res[1:it[]]
 end
 
+# One V-cycle per (x0, b) pair of a stream of independent problems, pipelined over PCIe inside the library (upload
+# of problem k + 1, cycle of k, download of k - 1 overlap).  zeroGuess = true is the ldiv! form.  X is overwritten.
+function multigrid_v_cycle!(D::DeviceHierarchy, X::Vector{Vector{Float64}}, B::Vector{Vector{Float64}};
+                            zeroGuess::Bool = false, nPre::Integer = 3, nPost::Integer = 3,
+                            alpha::AbstractFloat = 2.0 / 3.0)
+    xp = [pointer(x) for x in X]; bp = [pointer(b) for b in B]
+    GC.@preserve X B amg1d_check(D.handle, ccall((:amg1d_vcycle_batch, libamg1d), Cint,
+        (Ptr{Cvoid}, Cint, Ptr{Ptr{Float64}}, Ptr{Ptr{Float64}}, Cint, Cint, Cint, Float64),
+        D.handle, length(X), xp, bp, zeroGuess ? 1 : 0, nPre, nPost, alpha))
+    return X
+end
+
+# multigrid(H, x0, b, maxiter, tol) on a problem that already lives on the device (amg1d_dev_set_problem or
+# amg1d_dev_assemble_rhs): no vector crosses PCIe; fetch the solution with dev_solution.
+function multigrid_resident(D::DeviceHierarchy, maxiter::Integer, tol::AbstractFloat)
+    res = zeros(maxiter); it = Ref{Cint}(0)
+    amg1d_check(D.handle, ccall((:amg1d_dev_solve, libamg1d), Cint,
+        (Ptr{Cvoid}, Cint, Float64, Cint, Cint, Float64, Ref{Cint}, Ptr{Float64}),
+        D.handle, maxiter, tol, 3, 3, 2.0 / 3.0, it, res))
+    return Int(it[]), res[1:it[]]
+end
+dev_solution(D::DeviceHierarchy) = (x = Vector{Float64}(undef, D.nDof[1]);
+    amg1d_check(D.handle, ccall((:amg1d_dev_get_solution, libamg1d), Cint, (Ptr{Cvoid}, Ptr{Float64}), D.handle, x)); x)
+
 function apply_smoother(D::DeviceHierarchy, level::Integer, B::AbstractVecOrMat; alpha::Float64 = 1.0)
     Bd = Matrix{Float64}(reshape(Array(B), size(B, 1), :)); Y = similar(Bd)
     amg1d_check(D.handle, ccall((:amg1d_apply_smoother, libamg1d), Cint,

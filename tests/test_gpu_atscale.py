@@ -8,7 +8,8 @@ rounding to the independent literal Python oracle.  Both sides consume the IDENT
 blocks of agglomerationmultigrid1d_b200/uniform.py that `upload` hands to amg1d_set_level_pattern /
 amg1d_set_transfer_pattern, and the same right-hand side.
 
-Cases: C2 at its own 2^20 elements; the T / C5 shape at 2^22 and (C5's own size) 2^24; C3 (DG p=4) at 2^22;
+Cases: C2 at its own 2^20 elements; the T / C5 shape at 2^22 and (C5's own size) 2^24; C3 (DG p=4) at 2^22 and at its
+own 2^24 (T at its own 2^26: histories of both sides under profiles/r02_hist_*_T_2p26.json, tools/history.py);
 C4 (CG 3 -> 1 -> DG 1 -> agglomerated) at 2^22 and 2^25, the largest size at which FP64 still converges for
 that hierarchy (the 2^26 histories of both sides are committed under profiles/).
 
@@ -35,6 +36,7 @@ CASES = [
     ("T_C5_dg3_2p22", 22, [], [3, 1], False),
     ("C5_dg3_2p24", 24, [], [3, 1], True),
     ("C3_dg4_2p22", 22, [], [4, 2, 1], False),
+    ("C3_dg4_2p24", 24, [], [4, 2, 1], True),
     ("C4_cg3_2p22", 22, [3, 1], [1], False),
     ("C4_cg3_2p25", 25, [3, 1], [1], True),
 ]

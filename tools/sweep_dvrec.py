@@ -13,7 +13,10 @@ import bench  # noqa: E402
 def main():
     import torch
     workload = sys.argv[1] if len(sys.argv) > 1 else "T"
-    values = [int(v) for v in (sys.argv[2] if len(sys.argv) > 2 else "0,2,3,4").split(",")]
+    # a value is  <recompute_dinv>[:key=val[:key=val]]  (extra options for that variant, e.g. 4:leg_pipeline=0:dinv_registers=1)
+    specs = (sys.argv[2] if len(sys.argv) > 2 else "0,2,3,4").split(",")
+    values = [int(v.split(":")[0]) for v in specs]
+    extras = [dict(kv.split("=") for kv in v.split(":")[1:]) for v in specs]
     log2n = bench.WORKLOADS[workload][0]
     U = bench.build_hierarchy(workload, 2 ** log2n)
     ts = torch.cuda.Stream()
@@ -21,7 +24,11 @@ def main():
     dev = U.upload(stream=ts.cuda_stream)
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     ref = None
-    for v in values:
+    for v, extra in zip(values, extras):
+        dev.set_option("dinv_registers", 0)
+        dev.set_option("leg_pipeline", 1)
+        for k, val in extra.items():
+            dev.set_option(k, int(val))
         dev.set_option("recompute_dinv", v)
         dev.dev_fill_rhs_random(0)
         for _ in range(3):
@@ -45,9 +52,10 @@ def main():
                 t, c = dev.profile(l, leg)
                 legs[f"L{l}_{nm}"] = round(t / max(c, 1), 4)
         dev.set_option("profile", 0)
-        print(json.dumps({"workload": workload, "recompute_dinv": v, "ms_per_cycle": ms, "legs": legs,
+        print(json.dumps({"workload": workload, "recompute_dinv": v, "extra": extra, "ms_per_cycle": ms, "legs": legs,
                           "recomputing_levels": [l for l in range(len(U.levels) - 1) if dev.info(f"dinv_recompute:{l}") == 1][:8],
                           "pivots": [dev.info(f"dinv_pivots:{l}") for l in range(4)],
+                          "pipelined_levels": [l for l in range(len(U.levels) - 1) if dev.info(f"leg_pipeline:{l}") == 1][:8],
                           "bytes_per_cycle": U.bytes_per_cycle_fused(), "residual_bit_identical": res == ref}), flush=True)
     dev.close()
 
