@@ -147,8 +147,9 @@ struct amg1d {
                                   // least this size and at most 4 x 4 (0 = never; see adopt_device_dinv, leg_rec)
     int opt_dvreg = 0;            // 1: 4 x 4 DG legs keep the recomputed inverse in registers (f_down_dv / f_up_dv, 4 CTAs
                                   // per SM); 2: the 2 x 2 levels too
-    int opt_pipe = 1;             // 4 x 4 DG legs run as persistent CTAs that prefetch their next window with TMA bulk
-                                  // copies (f_down_pp / f_up_pp, kernels_fused.cuh); needs recompute_dinv
+    int opt_pipe = 1;             // 1: 4 x 4 DG legs run as persistent CTAs that prefetch their next window with TMA bulk
+                                  // copies (f_down_pp / f_up_pp, kernels_fused.cuh); 2: the 2 x 2 levels too; needs
+                                  // recompute_dinv > 0
     int opt_pattern = 0;          // 1: levels given as patterns read their operator from the pattern table;
                                   // 2: and the interior CTAs of f_down / f_up take it as constant-bank operands
     // single-CTA coarse tail (f_tail): levels [tail_start, n_levels)
@@ -382,6 +383,9 @@ int leg_rec(const amg1d* h, const Level& lv, int mc = 0) {
     // option dinv_registers = 2: the 2 x 2 levels too, through the legs that keep the inverse in registers
     if (!rec && h->opt_dvrec > 0 && h->opt_dvreg >= 2 && lv.dv_rec && lv.m == 2 && fused_has_dv(lv.m, mc, lv.md.st, lv.diag))
         rec = lv.dv_rec | 8;
+    // option leg_pipeline = 2: the 2 x 2 levels through the pipelined legs (which invert in registers as well)
+    if (h->opt_dvrec > 0 && h->opt_pipe >= 2 && lv.dv_rec && lv.m == 2 && fused_has_pp(lv.m, mc, lv.md.st, lv.diag))
+        rec = (rec & 8) | lv.dv_rec | 16;
     return rec;
 }
 
@@ -2900,7 +2904,10 @@ int amg1d_set_option(amg1d_t* h, const char* key, int64_t value) {
         h->opt_p2p = value != 0;
     }
     else if (!strcmp(key, "dinv_registers")) h->opt_dvreg = (int)value;
-    else if (!strcmp(key, "leg_pipeline")) h->opt_pipe = value != 0;
+    else if (!strcmp(key, "leg_pipeline")) {
+        if (value < 0 || value > 2) return fail(h, AMG1D_ERR_ARG, "leg_pipeline must be 0, 1 or 2");
+        h->opt_pipe = (int)value;
+    }
     else if (!strcmp(key, "recompute_dinv")) {
         // before the first level: whether uploaded inverses are replaced by the device's own (adopt_device_dinv);
         // afterwards: whether the fused legs recompute them or stream the stored ones (same bits either way)

@@ -28,6 +28,7 @@
 #pragma once
 #include <cuda_runtime.h>
 #include <algorithm>
+#include <type_traits>
 #include <cstdint>
 #include "kernels_generic.cuh"
 #include "layout.cuh"
@@ -879,7 +880,7 @@ up_body(const OP& A, const double* __restrict__ dcol, Exchange<M, B>& ex, int64_
     }
     if (partial) {
         exchange<M, B, ST>(ex, buf, ilo, iup, xc, xl, xr);
-        double r[M];
+            double r[M];
         reg_residual<M, ST>(A, ilo, iup, bb, xl, xc, xr, r);
         double s2 = 0.0;
         if (emit) {
@@ -1054,12 +1055,13 @@ f_up_dv(const double* __restrict__ mat, int ilo, int iup, const double* __restri
 // served by L2.  The coarse values of the up leg (a few doubles per thread at a thread-dependent address) follow
 // through per-thread cp.async into the thread's own shared-memory slots.  ~52 KB of shared memory per CTA: one
 // operator stage suffices because the operator moves to registers at the start of a window and the stage is
-// refilled right after.  Arithmetic, order and emitted values are those of f_down / f_up (down_body / up_body):
+// refilled right after (one block-wide barrier; folding the refill into the leg's first exchange barrier was
+// measured slower - the longer live ranges spill).  Arithmetic, order and emitted values are those of f_down / f_up (down_body / up_body):
 // bit-identical.  Slab edges: thread 0 waits for the neighbour's flags before the first copy of a window that
 // touches an edge (the spin of halo_leg_wait), the edge owners push as in f_down / f_up.
 // The persistent legs are launched as ordinary stream successors, not as programmatic dependents: an early
 // launch places their CTAs on SMs that still run the predecessor's last wave under ITS shared-memory carve-out,
-// fewer than PIPE_MINB fit, the SM can never be reconfigured while a persistent CTA lives on it, and the
+// fewer than pipe_min_blocks fit, the SM can never be reconfigured while a persistent CTA lives on it, and the
 // CTAs that found no place run as a second wave; and a programmatic successor of a persistent leg starts on SMs
 // that still hold persistent CTAs, inherits their maximal shared-memory carve-out (no L1 to speak of) and hands it
 // down the whole PDL chain, because no SM ever drains (measured on T: 17.0 instead of 15.6 ms per cycle).  So the
@@ -1101,35 +1103,55 @@ struct PipeStage {
     alignas(8) unsigned long long bar;
 };
 
-// thread 0: the operator tiles of the window starting at local element e0; returns the bytes issued
+// Warp 0 (all 32 lanes call this): the bulk copies of the window that starts at local element e0 - parts & 1: its
+// operator tiles, parts & 2: its b / x slices followed by the ONE arrival that arms the barrier with the bytes of
+// both parts (the prologue issues the operator before the dependency wait and the vectors after it).  A window that
+// lies inside the slab needs every tile and both slices whole: lanes 0 .. NT + 1 issue one copy each, side by side,
+// and lane 0 arrives with the constant byte count - the common case costs the warp one copy's worth of
+// instructions.  Windows at the ends of the slab are clipped by lane 0 alone.
 template <int M, int B, int ST>
-__device__ __forceinline__ unsigned pipe_issue_op(PipeStage<M, B, ST>& st, const double* __restrict__ mat, int64_t e0,
-                                                  int64_t lo, int64_t hi) {
+__device__ __forceinline__ void pipe_issue_window(PipeStage<M, B, ST>& st, const double* __restrict__ mat,
+                                                  const double* __restrict__ b, const double* __restrict__ xin,
+                                                  int64_t e0, int64_t lo, int64_t hi, int parts) {
     using PS = PipeStage<M, B, ST>;
     constexpr int K = OpShape<M, ST>::O_DV + M * M;
-    constexpr unsigned TB = PS::NR * AMG1D_TILE * 8;
-    const int64_t t0 = e0 >> 5, t1 = (e0 + B - 1) >> 5, tlo = lo >> 5, thi = (hi - 1) >> 5;
+    constexpr unsigned TB = PS::NR * AMG1D_TILE * 8, VB = B * M * 8;
+    const int lane = threadIdx.x;
+    const int64_t t0 = e0 >> 5, t1 = (e0 + B - 1) >> 5;
+    if (e0 >= lo && e0 + B <= hi && t1 - t0 == PS::NT - 1) {        // warp-uniform
+        if (lane < PS::NT) {
+            if (parts & 1) bulk_g2s(&st.op[lane][0][0], mat + (t0 + lane) * (int64_t)(K * AMG1D_TILE), TB, &st.bar);
+        } else if (lane == PS::NT) {
+            if (parts & 2) bulk_g2s(st.bv, b + e0 * M, VB, &st.bar);
+        } else if (lane == PS::NT + 1) {
+            if ((parts & 2) && xin) bulk_g2s(st.xv, xin + e0 * M, VB, &st.bar);
+        }
+        if (lane == 0 && (parts & 2)) mbar_arrive_expect_tx(&st.bar, PS::NT * TB + (xin ? 2 * VB : VB));
+        return;
+    }
+    if (lane != 0) return;
+    const int64_t tlo = lo >> 5, thi = (hi - 1) >> 5;
     unsigned bytes = 0;
 #pragma unroll
     for (int j = 0; j < PS::NT; ++j) {
         const int64_t tj = t0 + j;
         if (tj <= t1 && tj >= tlo && tj <= thi) {
-            bulk_g2s(&st.op[j][0][0], mat + tj * (int64_t)(K * AMG1D_TILE), TB, &st.bar);
+            if (parts & 1) bulk_g2s(&st.op[j][0][0], mat + tj * (int64_t)(K * AMG1D_TILE), TB, &st.bar);
             bytes += TB;
         }
     }
-    return bytes;
-}
-
-// thread 0: the slice [e0, e0 + B) of a vector with M doubles per element, clipped to the slab [lo, hi)
-template <int M, int B>
-__device__ __forceinline__ unsigned pipe_issue_vec(double* dst, const double* __restrict__ src, int64_t e0, int64_t lo,
-                                                   int64_t hi, unsigned long long* bar) {
+    if (!(parts & 2)) return;
     const int64_t a = e0 > lo ? e0 : lo, z = e0 + B < hi ? e0 + B : hi;
-    if (z <= a) return 0;
-    const unsigned bytes = (unsigned)(z - a) * (M * 8);
-    bulk_g2s(dst + (a - e0) * M, src + a * M, bytes, bar);
-    return bytes;
+    if (z > a) {
+        const unsigned vb = (unsigned)(z - a) * (M * 8);
+        bulk_g2s(st.bv + (a - e0) * M, b + a * M, vb, &st.bar);
+        bytes += vb;
+        if (xin) {
+            bulk_g2s(st.xv + (a - e0) * M, xin + a * M, vb, &st.bar);
+            bytes += vb;
+        }
+    }
+    mbar_arrive_expect_tx(&st.bar, bytes);
 }
 
 // The window's operator from the stage into registers; the diagonal block is read twice - once as A.di and once as
@@ -1164,9 +1186,10 @@ __device__ __forceinline__ void pipe_invert(RegOpDv<M, ST>& A, bool active, int 
     }
 }
 
-#ifndef PIPE_MINB
-#define PIPE_MINB 4      // persistent CTAs per SM (128 registers)
-#endif
+// persistent CTAs per SM: 4 x 4 blocks keep 40 operator doubles per thread (128 registers, 4 CTAs of ~52 KB), 2 x 2
+// blocks 12 - 16 (64 registers, 8 CTAs of ~26 KB)
+constexpr int pipe_min_blocks(int m) { return m >= 4 ? 4 : 8; }
+#define PIPE_MINB(M) pipe_min_blocks(M)
 
 template <int M, int MC, int B, int ST>
 struct PipeDownSmem {
@@ -1176,7 +1199,7 @@ struct PipeDownSmem {
 };
 
 template <int M, int MC, int B, int ST, int NSW>
-__global__ void __launch_bounds__(B, PIPE_MINB)
+__global__ void __launch_bounds__(B, PIPE_MINB(M))
 f_down_pp(const double* __restrict__ mat, int ilo, int iup, const double* __restrict__ b,
           const double* __restrict__ xin, double* __restrict__ xout, const double* __restrict__ P0,
           const double* __restrict__ P1, TransferMap tm, double* __restrict__ rc, int64_t n, double alpha,
@@ -1186,21 +1209,19 @@ f_down_pp(const double* __restrict__ mat, int ilo, int iup, const double* __rest
     pdl_launch_dependents();
     const int t = threadIdx.x;
     const int64_t lo = -(int64_t)sl.gl, hi = n + sl.gr;
+    const double* xsrc = zero_guess ? nullptr : xin;
     if (t == 0) mbar_init(&S.st.bar, 1);
     exch_init<M, B>(S.ex);
     __syncthreads();
     int64_t win = blockIdx.x;
-    unsigned tx = 0;
-    if (t == 0) tx = pipe_issue_op<M, B, ST>(S.st, mat, win * wi.out - wi.halo, lo, hi);   // independent of earlier kernels
-    pdl_wait();
     {
         const int64_t e0 = win * wi.out - wi.halo;
+        if (t < 32) pipe_issue_window<M, B, ST>(S.st, mat, b, xsrc, e0, lo, hi, 1);    // operator: independent of earlier kernels
+        pdl_wait();
         halo_leg_wait(hl, sl.gl > 0 && e0 < 0, sl.gr > 0 && e0 + B > n);
-        if (t == 0) {
-            if (hl.on) fence_proxy_async();
-            tx += pipe_issue_vec<M, B>(S.st.bv, b, e0, lo, hi, &S.st.bar);
-            if (!zero_guess) tx += pipe_issue_vec<M, B>(S.st.xv, xin, e0, lo, hi, &S.st.bar);
-            mbar_arrive_expect_tx(&S.st.bar, tx);
+        if (t < 32) {
+            fence_proxy_async();
+            pipe_issue_window<M, B, ST>(S.st, mat, b, xsrc, e0, lo, hi, 2);
         }
     }
     unsigned parity = 0;
@@ -1235,24 +1256,23 @@ f_down_pp(const double* __restrict__ mat, int ilo, int iup, const double* __rest
                 for (int i = 0; i < M; ++i) { bb[i] = 0.0; xc[i] = 0.0; }
             }
         }
+        // once every thread has taken its share of the stage: refill it for the next window
         const int64_t wn = win + gridDim.x;
-        if (wn < n_win) {                                        // CTA-uniform
-            const int64_t en = wn * wi.out - wi.halo;
-            halo_leg_wait(hl, sl.gl > 0 && en < 0, sl.gr > 0 && en + B > n);
-            __syncthreads();                                     // the stage has been consumed by every thread
-            if (t == 0) {
-                fence_proxy_async();
-                tx = pipe_issue_op<M, B, ST>(S.st, mat, en, lo, hi);
-                tx += pipe_issue_vec<M, B>(S.st.bv, b, en, lo, hi, &S.st.bar);
-                if (!zero_guess) tx += pipe_issue_vec<M, B>(S.st.xv, xin, en, lo, hi, &S.st.bar);
-                mbar_arrive_expect_tx(&S.st.bar, tx);
+        auto refill = [&]() {
+            if (wn < n_win) {                                    // CTA-uniform
+                const int64_t en = wn * wi.out - wi.halo;
+                halo_leg_wait(hl, sl.gl > 0 && en < 0, sl.gr > 0 && en + B > n);
+                if (t < 32) {
+                    fence_proxy_async();
+                    pipe_issue_window<M, B, ST>(S.st, mat, b, xsrc, en, lo, hi, 3);
+                }
             }
-        } else {
-            __syncthreads();
-        }
+        };
+        __syncthreads();
+        refill();
         pipe_invert<M, ST>(A, active, rec);
-        down_body<M, MC, B, ST, false, RegOpDv<M, ST>, NSW>(A, nullptr, S.ex, S.rs, e, win, bb, xc, ilo, iup, xout, P0, P1,
-                                                             tm, rc, n, alpha, nsweep, zero_guess, wi, sl, hl);
+        down_body<M, MC, B, ST, false, RegOpDv<M, ST>, NSW>(A, nullptr, S.ex, S.rs, e, win, bb, xc, ilo, iup, xout, P0, P1, tm,
+                                                             rc, n, alpha, nsweep, zero_guess, wi, sl, hl);
     }
 }
 
@@ -1285,7 +1305,7 @@ __device__ __forceinline__ void pipe_issue_coarse(double (*cs)[B], const double*
 }
 
 template <int M, int MC, int B, int ST, int NSW>
-__global__ void __launch_bounds__(B, PIPE_MINB)
+__global__ void __launch_bounds__(B, PIPE_MINB(M))
 f_up_pp(const double* __restrict__ mat, int ilo, int iup, const double* __restrict__ b,
         const double* __restrict__ xin, double* __restrict__ xout, const double* __restrict__ P0,
         const double* __restrict__ P1, TransferMap tm, const double* __restrict__ xcoarse, int64_t n,
@@ -1300,17 +1320,14 @@ f_up_pp(const double* __restrict__ mat, int ilo, int iup, const double* __restri
     exch_init<M, B>(S.ex);
     __syncthreads();
     int64_t win = blockIdx.x;
-    unsigned tx = 0;
-    if (t == 0) tx = pipe_issue_op<M, B, ST>(S.st, mat, win * wi.out - wi.halo, lo, hi);   // independent of earlier kernels
-    pdl_wait();
     {
         const int64_t e0 = win * wi.out - wi.halo;
+        if (t < 32) pipe_issue_window<M, B, ST>(S.st, mat, b, xin, e0, lo, hi, 1);     // operator: independent of earlier kernels
+        pdl_wait();
         halo_leg_wait(hl, sl.gl > 0 && e0 < tm.ratio + 1, sl.gr > 0 && e0 + B + tm.ratio + 1 > n);
-        if (t == 0) {
-            if (hl.on) fence_proxy_async();
-            tx += pipe_issue_vec<M, B>(S.st.bv, b, e0, lo, hi, &S.st.bar);
-            tx += pipe_issue_vec<M, B>(S.st.xv, xin, e0, lo, hi, &S.st.bar);
-            mbar_arrive_expect_tx(&S.st.bar, tx);
+        if (t < 32) {
+            fence_proxy_async();
+            pipe_issue_window<M, B, ST>(S.st, mat, b, xin, e0, lo, hi, 2);
         }
         pipe_issue_coarse<M, MC, B>(S.cs, xcoarse, P1 != nullptr, tm, wi, sl, win, e0 + t >= lo && e0 + t < hi);
     }
@@ -1337,22 +1354,21 @@ f_up_pp(const double* __restrict__ mat, int ilo, int iup, const double* __restri
 #pragma unroll
             for (int i = 0; i < M; ++i) { bb[i] = 0.0; xc[i] = 0.0; }
         }
+        // once every thread has taken its share of the stage: refill it for the next window
         const int64_t wn = win + gridDim.x;
-        if (wn < n_win) {                                        // CTA-uniform
-            const int64_t en = wn * wi.out - wi.halo;
-            halo_leg_wait(hl, sl.gl > 0 && en < tm.ratio + 1, sl.gr > 0 && en + B + tm.ratio + 1 > n);
-            __syncthreads();                                     // the stage has been consumed by every thread
-            if (t == 0) {
-                fence_proxy_async();
-                tx = pipe_issue_op<M, B, ST>(S.st, mat, en, lo, hi);
-                tx += pipe_issue_vec<M, B>(S.st.bv, b, en, lo, hi, &S.st.bar);
-                tx += pipe_issue_vec<M, B>(S.st.xv, xin, en, lo, hi, &S.st.bar);
-                mbar_arrive_expect_tx(&S.st.bar, tx);
+        auto refill = [&]() {
+            if (wn < n_win) {                                    // CTA-uniform
+                const int64_t en = wn * wi.out - wi.halo;
+                halo_leg_wait(hl, sl.gl > 0 && en < tm.ratio + 1, sl.gr > 0 && en + B + tm.ratio + 1 > n);
+                if (t < 32) {
+                    fence_proxy_async();
+                    pipe_issue_window<M, B, ST>(S.st, mat, b, xin, en, lo, hi, 3);
+                }
+                pipe_issue_coarse<M, MC, B>(S.cs, xcoarse, P1 != nullptr, tm, wi, sl, wn, en + t >= lo && en + t < hi);
             }
-            pipe_issue_coarse<M, MC, B>(S.cs, xcoarse, P1 != nullptr, tm, wi, sl, wn, en + t >= lo && en + t < hi);
-        } else {
-            __syncthreads();
-        }
+        };
+        __syncthreads();
+        refill();
         pipe_invert<M, ST>(A, active, rec);
         up_body<M, MC, B, ST, false, RegOpDv<M, ST>, NSW>(A, nullptr, S.ex, e, win, bb, xc, ilo, iup, xout, n, alpha, nsweep,
                                                            wi, partial, hl);
@@ -1360,10 +1376,10 @@ f_up_pp(const double* __restrict__ mat, int ilo, int iup, const double* __restri
 }
 
 inline bool fused_has_pp(int m, int mc, int st, int diag) {
-    return !diag && m == 4 && st == AMG1D_ST_COLROW && (mc == 2 || mc == 3);
+    return !diag && ((m == 4 && st == AMG1D_ST_COLROW && (mc == 2 || mc == 3)) || (m == 2 && mc == 2 && st != AMG1D_ST_ROWCOL));
 }
 
-// persistent grid of the pipelined legs: PIPE_MINB CTAs per SM of the current device; the first launch of an
+// persistent grid of the pipelined legs: pipe_min_blocks(m) CTAs per SM of the current device; the first launch of an
 // dynamic shared-memory limit of the kernels is raised once (pipe_configure_all)
 inline int pipe_sm_count() {
     static int sms = 0;
@@ -1386,7 +1402,7 @@ inline cudaError_t pipe_configure_all() {
     if (e == cudaSuccess) e = pipe_configure(f_down_pp<MM, MCC, FUSED_B, SS, 3>, sizeof(PipeDownSmem<MM, MCC, FUSED_B, SS>)); \
     if (e == cudaSuccess) e = pipe_configure(f_up_pp<MM, MCC, FUSED_B, SS, 0>, sizeof(PipeUpSmem<MM, MCC, FUSED_B, SS>)); \
     if (e == cudaSuccess) e = pipe_configure(f_up_pp<MM, MCC, FUSED_B, SS, 3>, sizeof(PipeUpSmem<MM, MCC, FUSED_B, SS>));
-    PP(4, 2, 1) PP(4, 3, 1)
+    PP(4, 2, 1) PP(4, 3, 1) PP(2, 2, 0) PP(2, 2, 1)
 #undef PP
     return e;
 }
@@ -1806,7 +1822,7 @@ inline int fused_down(const MatDesc& d, int mc, const TransferMap& tm, int nswee
 #define PP(MM, MCC, SS)                                                                                   \
         if (d.m == MM && mc == MCC && d.st == SS) {                                                       \
             const size_t smem = sizeof(PipeDownSmem<MM, MCC, FUSED_B, SS>);                               \
-            const int64_t pg = std::min<int64_t>((int64_t)grid, (int64_t)pipe_sm_count() * PIPE_MINB);    \
+            const int64_t pg = std::min<int64_t>((int64_t)grid, (int64_t)pipe_sm_count() * PIPE_MINB(MM));    \
             *err = launch_fused(nsweep == 3 ? f_down_pp<MM, MCC, FUSED_B, SS, 3> : f_down_pp<MM, MCC, FUSED_B, SS, 0>, \
                                 (unsigned)pg, FUSED_B, smem, st, false, mat, d.ilo,                       \
                                 d.iup, b, xin, xout, P0, P1, tm, rc, n, alpha, nsweep, zero ? 1 : 0, w, sl, rec, hl, \
@@ -1814,7 +1830,7 @@ inline int fused_down(const MatDesc& d, int mc, const TransferMap& tm, int nswee
             fused_prev_persistent() = true;                                                               \
             return *err == cudaSuccess ? FUSED_OK : FUSED_ERR;                                            \
         }
-        PP(4, 2, 1) PP(4, 3, 1)
+        PP(4, 2, 1) PP(4, 3, 1) PP(2, 2, 0) PP(2, 2, 1)
 #undef PP
     }
     if ((rec & 8) && (rec & 3) && !po.tab && fused_has_dv(d.m, mc, d.st, d.diag)) {   // inverse in registers
@@ -1861,7 +1877,7 @@ inline int fused_up(const MatDesc& d, int mc, const TransferMap& tm, int nsweep,
 #define PP(MM, MCC, SS)                                                                                   \
         if (d.m == MM && mc == MCC && d.st == SS) {                                                       \
             const size_t smem = sizeof(PipeUpSmem<MM, MCC, FUSED_B, SS>);                                 \
-            const int64_t pg = std::min<int64_t>(grid, (int64_t)pipe_sm_count() * PIPE_MINB);             \
+            const int64_t pg = std::min<int64_t>(grid, (int64_t)pipe_sm_count() * PIPE_MINB(MM));             \
             *err = launch_fused(nsweep == 3 ? f_up_pp<MM, MCC, FUSED_B, SS, 3> : f_up_pp<MM, MCC, FUSED_B, SS, 0>, \
                                 (unsigned)pg, FUSED_B, smem, st, false, mat, d.ilo,                       \
                                 d.iup, b, xin, xout, P0, P1, tm, xcoarse, n, alpha, nsweep, w, partial, sl, rec, hl, \
@@ -1869,7 +1885,7 @@ inline int fused_up(const MatDesc& d, int mc, const TransferMap& tm, int nsweep,
             fused_prev_persistent() = true;                                                               \
             return *err == cudaSuccess ? FUSED_OK : FUSED_ERR;                                            \
         }
-        PP(4, 2, 1) PP(4, 3, 1)
+        PP(4, 2, 1) PP(4, 3, 1) PP(2, 2, 0) PP(2, 2, 1)
 #undef PP
     }
     if ((rec & 8) && (rec & 3) && !po.tab && fused_has_dv(d.m, mc, d.st, d.diag)) {

@@ -508,10 +508,12 @@ def measure(ctx, args, workload, ranks, full):
     # f_up at level 0 (prolongation + 3 sweeps + ||b - A x||^2), this rank's slab: the level's stored
     # operator once (tile_rows doubles per element for its structure class), b, x in, x out, coarse x
     bytes_up = U.bytes_per_leg_fused(0, down=False) // world
-    kname = "f_up<%d,%d,128" % (m, mc) if m <= 5 else "r_up<%d,%d,%d" % (m, mc, dev.info("rows_window"))
+    kname = ("f_up_pp<%d,%d,128" if dev.info("leg_pipeline:0") == 1 else "f_up<%d,%d,128") % (m, mc) if m <= 5 \
+        else "r_up<%d,%d,%d" % (m, mc, dev.info("rows_window"))
     kern = (f"{kname},st={st0},{'point' if getattr(lv0, 'is_cg', False) else 'block'}-Jacobi> level 0 "
             f"(prolong + 3 sweeps + ||b-Ax||^2; {U.streamed_operator_doubles(0)} operator + {3 * m} vector doubles per "
-            f"element streamed; {U.tile_rows(0)} stored" + (", Dinv recomputed in registers" if dev.info("dinv_recompute:0") == 1 else "") + ")")
+            f"element streamed; {U.tile_rows(0)} stored" + (", Dinv recomputed in registers" if dev.info("dinv_recompute:0") == 1 else "")
+            + ("; persistent CTAs, next window prefetched by TMA bulk copies" if dev.info("leg_pipeline:0") == 1 else "") + ")")
     t_k = legs["L0_up"]
     achieved = bytes_up / (t_k * 1e-3) / 1e9
     cyc_bytes = U.bytes_per_cycle_fused()

@@ -5,6 +5,8 @@
   ... + dinv_registers = 1                f_down_dv / f_up_dv: the inverse stays in registers
   recompute_dinv = 4, leg_pipeline = 1    f_down_pp / f_up_pp: persistent CTAs, next window prefetched with TMA bulk
                                           copies + mbarrier (the default)
+  leg_pipeline = 2 / dinv_registers = 2   the same two forms on the 2 x 2 levels below as well (measured slower, kept
+                                          as options)
 
 They perform the same arithmetic in the same order, so iterates, residual norms (same window partition of the
 two-stage reduction) and whole solves must be BIT-IDENTICAL - on sizes that are not a multiple of the window, with
@@ -26,6 +28,8 @@ VARIANTS = (
     ("recompute_smem", dict(recompute_dinv=4, leg_pipeline=0, dinv_registers=0)),
     ("recompute_regs", dict(recompute_dinv=4, leg_pipeline=0, dinv_registers=1)),
     ("pipelined", dict(recompute_dinv=4, leg_pipeline=1, dinv_registers=0)),
+    ("pipelined_2x2_too", dict(recompute_dinv=4, leg_pipeline=2, dinv_registers=0)),
+    ("registers_2x2_too", dict(recompute_dinv=4, leg_pipeline=0, dinv_registers=2)),
 )
 
 
@@ -61,7 +65,7 @@ def test_leg_variants_bit_identical(orders, n):
         ref = None
         for name, opts in VARIANTS:
             _set(dev, opts)
-            assert dev.info("leg_pipeline:0") == (1 if name == "pipelined" else 0)
+            assert dev.info("leg_pipeline:0") == (1 if name.startswith("pipelined") else 0)
             assert dev.info("dinv_recompute:0") == (0 if name == "streamed" else 1)
             got = _run(dev, x0, b)
             if ref is None:

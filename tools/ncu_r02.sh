@@ -11,8 +11,10 @@ timeout 200 ncu --metrics gpu__time_duration.sum --clock-control none --kernel-n
     --log-file gpurun_out/${tag}_launches_T.csv python bench.py --steps 2 --warmup 3 --no-cpu --no-extra --no-pattern > gpurun_out/ncu_launches.log 2>&1
 echo "launch list exit $?"
 timeout 200 ncu --set full --clock-control none --import-source on --kernel-name-base demangled \
-    -k 'regex:f_(up|down)<\(int\)4' -s 6 -c 2 -f -o gpurun_out/${tag}_full_L0 \
+    -k 'regex:f_(up|down)(_pp|_dv)?<\(int\)4' -s 6 -c 2 -f -o gpurun_out/${tag}_full_L0 \
     python bench.py --steps 2 --warmup 3 --no-cpu --no-extra --no-pattern > gpurun_out/ncu_full.log 2>&1
 echo "full capture exit $?"
 ncu -i gpurun_out/${tag}_full_L0.ncu-rep --page raw --csv > gpurun_out/${tag}_ncu_full_L0_raw.csv 2>/dev/null
-ls -la gpurun_out/*.ncu-rep 2>/dev/null
+ncu -i gpurun_out/${tag}_full_L0.ncu-rep --page source --csv --print-source sass > gpurun_out/${tag}_ncu_source_sass.csv 2>/dev/null
+[ "${KEEP_REP:-0}" = 1 ] || rm -f gpurun_out/${tag}_full_L0.ncu-rep    # 48 MB each; gpurun_out travels back only up to 64 MiB
+ls -la gpurun_out/${tag}_*
