@@ -145,6 +145,7 @@ struct amg1d {
     int opt_rows_rpt = 0;         // block rows per thread of those legs: 1, 2, 3; 0 = auto (rows_rpt() below)
     int opt_dvrec = 4;            // block-Jacobi inverses recomputed inside the fused legs of levels with blocks of at
                                   // least this size and at most 4 x 4 (0 = never; see adopt_device_dinv, leg_rec)
+    int opt_dvrec_max = 4;        // ... and at most this size (option recompute_dinv_max, <= 5)
     int opt_dvreg = 0;            // 1: 4 x 4 DG legs keep the recomputed inverse in registers (f_down_dv / f_up_dv, 4 CTAs
                                   // per SM); 2: the 2 x 2 levels too
     int opt_pipe = 1;             // 1: 4 x 4 DG legs run as persistent CTAs that prefetch their next window with TMA bulk
@@ -378,7 +379,7 @@ int leg_rec(const amg1d* h, const Level& lv, int mc = 0) {
     // -> 4.43 / 4.12 ms); 5 x 5 blocks lose 10 % (the inversion's registers cost a resident CTA), 2 x 2 lose 5 %
     // bits 0-1: invert A_di in registers (1: with the pivot chain, 2: the level never pivots); bit 3: keep the inverse
     // in registers (option dinv_registers); bit 4: pipelined persistent leg (option leg_pipeline)
-    int rec = (h->opt_dvrec > 0 && lv.dv_rec && lv.m >= h->opt_dvrec && lv.m <= 4)
+    int rec = (h->opt_dvrec > 0 && lv.dv_rec && lv.m >= h->opt_dvrec && lv.m <= h->opt_dvrec_max)
                   ? (lv.dv_rec | (h->opt_dvreg ? 8 : 0) | (h->opt_pipe ? 16 : 0)) : 0;
     // option dinv_registers = 2: the 2 x 2 levels too, through the legs that keep the inverse in registers
     if (!rec && h->opt_dvrec > 0 && h->opt_dvreg >= 2 && lv.dv_rec && lv.m == 2 && fused_has_dv(lv.m, mc, lv.md.st, lv.diag))
@@ -2904,6 +2905,10 @@ int amg1d_set_option(amg1d_t* h, const char* key, int64_t value) {
         h->opt_p2p = value != 0;
     }
     else if (!strcmp(key, "dinv_registers")) h->opt_dvreg = (int)value;
+    else if (!strcmp(key, "recompute_dinv_max")) {
+        if (value < 1 || value > 5) return fail(h, AMG1D_ERR_ARG, "recompute_dinv_max must be in [1, 5]");
+        h->opt_dvrec_max = (int)value;
+    }
     else if (!strcmp(key, "leg_pipeline")) {
         if (value < 0 || value > 2) return fail(h, AMG1D_ERR_ARG, "leg_pipeline must be 0, 1 or 2");
         h->opt_pipe = (int)value;

@@ -256,6 +256,37 @@ def run_reference(args):
 
 
 # ---- GPU arm ----------------------------------------------------------------------------------------
+def bind_to_gpu_numa_node(torch, local):
+    """Run this rank on the CPUs of the NUMA node its GPU hangs off, so that the pinned host vectors it allocates
+    afterwards (cudaMallocHost, first touch) and its PCIe copies stay node-local - with all ranks of a box on node 0
+    the end-to-end numbers at 4 / 8 GPUs were bound by one node's memory controllers (round 1: e2e weak efficiency
+    0.32 at 8 GPUs).  Returns what was done, for the JSON line; never fails the run."""
+    info = {"gpu_numa_node": None, "bound": False}
+    try:
+        pr = torch.cuda.get_device_properties(local)
+        bdf = "%04x:%02x:%02x.0" % (getattr(pr, "pci_domain_id", 0), pr.pci_bus_id, pr.pci_device_id)
+        info["pci"] = bdf
+        with open(f"/sys/bus/pci/devices/{bdf}/numa_node") as f:
+            node = int(f.read().strip())
+        info["gpu_numa_node"] = node
+        if node < 0:
+            return info
+        cpus = set()
+        with open(f"/sys/devices/system/node/node{node}/cpulist") as f:
+            for part in f.read().strip().split(","):
+                a, _, b = part.partition("-")
+                cpus.update(range(int(a), int(b or a) + 1))
+        allowed = os.sched_getaffinity(0)
+        use = cpus & allowed
+        info["node_cpus_allowed"] = len(use)
+        if use and use != allowed:
+            os.sched_setaffinity(0, use)
+            info["bound"] = True
+    except Exception as e:                                   # no sysfs, no such attribute, cpuset forbids it ...
+        info["note"] = f"{type(e).__name__}: {e}"[:120]
+    return info
+
+
 class Ctx:
     """Process-wide plumbing of the GPU arm: torch stream / events, torch.distributed group, libamg1d."""
 
@@ -270,6 +301,8 @@ class Ctx:
         if self.world & (self.world - 1):
             raise SystemExit("the slab-sharded workloads need a power-of-two rank count")
         torch.cuda.set_device(self.local)
+        # before any pinned allocation (first touch); a single rank keeps all host cores (its CPU-baseline leg uses them)
+        self.numa = bind_to_gpu_numa_node(torch, self.local) if self.world > 1 else {"bound": False, "note": "single rank"}
         self.tdist = None
         if self.world > 1:
             import torch.distributed as tdist
@@ -409,7 +442,7 @@ def measure(ctx, args, workload, ranks, full):
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_step, "scaling": "strong" if strong else "weak",
             "config": {"workload": f"{workload}: {desc}", "n_elements": n, "elements_per_gpu": nloc, "levels": len(U.levels),
-                       "gather_level": dev.info("gather_level"), "p2p_halo": dev.info("p2p_halo"),
+                       "gather_level": dev.info("gather_level"), "p2p_halo": dev.info("p2p_halo"), "numa": ctx.numa, "numa": ctx.numa,
                        "sharded_levels": dev.info("sharded_levels"),
                        "halo_bytes_per_cycle_per_rank": dev.info("halo_bytes_per_cycle"),
                        "options": args.opt + args.pre_opt, "setup_s": t_setup, "dof_updates_per_step": upd},
@@ -475,7 +508,7 @@ def measure(ctx, args, workload, ranks, full):
               "tile_rows": [U.tile_rows(l) for l in range(min(4, len(U.levels)))],
               "streamed_operator_doubles": [U.streamed_operator_doubles(l) for l in range(min(4, len(U.levels)))],
               "tail_start": dev.info("tail_start"), "options": args.opt + args.pre_opt,
-              "gather_level": dev.info("gather_level"), "p2p_halo": dev.info("p2p_halo"),
+              "gather_level": dev.info("gather_level"), "p2p_halo": dev.info("p2p_halo"), "numa": ctx.numa,
               "sharded_levels": dev.info("sharded_levels"),
               "halo_bytes_per_cycle_per_rank": dev.info("halo_bytes_per_cycle"),
               "device_bytes": dev.info("device_bytes"), "setup_s": t_setup, "rhs_assembly_s": t_rhs_dev,

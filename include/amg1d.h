@@ -274,13 +274,19 @@ void* amg1d_dev_ptr(amg1d_t* h, int level, int which);             /* raw device
  * set as a kernel parameter and use it as constant operands; default 0; bit-identical results in all modes),
  * "rows_window" (elements per CTA of the row-per-thread legs for 5..9-row blocks: 32, 64; 0 = off;
  * default 64), "rows_per_thread" (block rows per thread of those legs: 1, 2, 3; 0 = auto, default);
- * "recompute_dinv" (default 4 = levels with 4 x 4 blocks; v = blocks of v x v up to 4 x 4 - larger blocks were
- * measured slower; 0 = never.  Where non-zero when a level is
+ * "recompute_dinv" (default 4 = levels with 4 x 4 blocks; v = blocks of v x v up to "recompute_dinv_max" (default
+ * 4, at most 5 - larger and smaller blocks were measured slower); 0 = never.  Where non-zero when a level is
  * set, its block-Jacobi inverses - if the uploaded Dinv agrees with inv(A_di) to 1e-8 - are replaced by the
- * device's own pivoted Gauss-Jordan inverse of the stored diagonal blocks, so that the fused legs can invert
- * A_di in registers instead of streaming the stored inverse from HBM while every other kernel, which reads the
- * stored inverse, produces the same bits.  Changing the value later only selects which levels recompute -
- * same results, other byte counts);
+ * device's own Gauss-Jordan inverse of the stored diagonal blocks (without pivoting when every element of the level
+ * that would swap rows gets the same inverse to 1e-12 without - the DG blocks of the reference; else with partial
+ * pivoting), so that the fused legs can invert A_di in registers instead of streaming the stored inverse from HBM
+ * while every other kernel, which reads the stored inverse, produces the same bits.  Changing the value later only
+ * selects which levels recompute - same results, other byte counts);
+ * "leg_pipeline" (default 1: the recomputing legs of 4 x 4 levels run as persistent CTAs that fetch their next
+ * window with TMA bulk copies while they compute the current one - f_down_pp / f_up_pp; 2: the 2 x 2 levels too;
+ * 0: one window per CTA), "dinv_registers" (with "leg_pipeline" = 0: 1 = the recomputed inverse of 4 x 4 levels
+ * stays in registers - f_down_dv / f_up_dv; 2 = of 2 x 2 levels too; 0 = it goes through shared memory) - every
+ * combination gives the same bits;
  * "p2p_halo" (before amg1d_finalize, multi-GPU handles; default 1: the slab-edge exchanges of the V-cycle go
  * through CUDA-IPC peer memory over NVLink - two small kernels per exchange - instead of NCCL send / recv groups;
  * falls back to NCCL, on every rank alike, if the peer mapping is refused; amg1d_get_info("p2p_halo") tells
@@ -297,6 +303,9 @@ int64_t amg1d_get_info(amg1d_t* h, const char* key); /* "kernel_launches", "laun
                                                         "ghost_depth", "structure:<level>",
                                                         "tile_rows:<level>", "dinv_recompute:<level>" (1 = the fused
                                                         legs of the level invert A_di in registers),
+                                                        "leg_pipeline:<level>" (1 = they are the persistent
+                                                        pipelined legs), "dinv_pivots:<level>" (1 = that
+                                                        inversion keeps the partial-pivoting chain),
                                                         "pattern:<level>" (1 = the
                                                         level has a pattern table), the option keys,
                                                         ... (-1: unknown key) */
