@@ -151,6 +151,10 @@ struct amg1d {
     int opt_pipe = 1;             // 1: 4 x 4 DG legs run as persistent CTAs that prefetch their next window with TMA bulk
                                   // copies (f_down_pp / f_up_pp, kernels_fused.cuh); 2: the 2 x 2 levels too; needs
                                   // recompute_dinv > 0
+    int64_t opt_pipe_min = 500000;   // ... on levels with at least this many elements on this rank (option leg_pipeline_min;
+                                  // measured, profiles/r03a_sweep_sizes.jsonl: 3 - 12 % per cycle from 2^20 elements up,
+                                  // -2 % at 2^18, where the two ordinary stream dependencies around a persistent leg
+                                  // cost more than the pipeline gains)
     int opt_pattern = 0;          // 1: levels given as patterns read their operator from the pattern table;
                                   // 2: and the interior CTAs of f_down / f_up take it as constant-bank operands
     // single-CTA coarse tail (f_tail): levels [tail_start, n_levels)
@@ -380,12 +384,13 @@ int leg_rec(const amg1d* h, const Level& lv, int mc = 0) {
     // bits 0-1: invert A_di in registers (1: with the pivot chain, 2: the level never pivots); bit 3: keep the inverse
     // in registers (option dinv_registers); bit 4: pipelined persistent leg (option leg_pipeline)
     int rec = (h->opt_dvrec > 0 && lv.dv_rec && lv.m >= h->opt_dvrec && lv.m <= h->opt_dvrec_max)
-                  ? (lv.dv_rec | (h->opt_dvreg ? 8 : 0) | (h->opt_pipe ? 16 : 0)) : 0;
+                  ? (lv.dv_rec | (h->opt_dvreg ? 8 : 0) | ((h->opt_pipe && lv.n >= h->opt_pipe_min) ? 16 : 0)) : 0;
     // option dinv_registers = 2: the 2 x 2 levels too, through the legs that keep the inverse in registers
     if (!rec && h->opt_dvrec > 0 && h->opt_dvreg >= 2 && lv.dv_rec && lv.m == 2 && fused_has_dv(lv.m, mc, lv.md.st, lv.diag))
         rec = lv.dv_rec | 8;
     // option leg_pipeline = 2: the 2 x 2 levels through the pipelined legs (which invert in registers as well)
-    if (h->opt_dvrec > 0 && h->opt_pipe >= 2 && lv.dv_rec && lv.m == 2 && fused_has_pp(lv.m, mc, lv.md.st, lv.diag))
+    if (h->opt_dvrec > 0 && h->opt_pipe >= 2 && lv.n >= h->opt_pipe_min && lv.dv_rec && lv.m == 2 &&
+        fused_has_pp(lv.m, mc, lv.md.st, lv.diag))
         rec = (rec & 8) | lv.dv_rec | 16;
     return rec;
 }
@@ -1495,7 +1500,7 @@ int adopt_device_dinv(amg1d* h, int level) {
     const int64_t e0 = -(int64_t)lv.gl, e1 = lv.n + lv.gr;
     const unsigned grid = (unsigned)((e1 - e0 + 127) / 128);
     if (lv.present)
-        k_dinv_recompute<<<grid, 128, 0, h->stream>>>(lv.mat, lv.md, e0, e1, AMG1D_TILE, 2, d_dev, d_flag);   // one pass
+        launch_dinv_recompute(grid, h->stream, lv.mat, lv.md, e0, e1, AMG1D_TILE, 2, d_dev, d_flag);   // one pass
     double host[4] = {0.0, 0.0, 0.0, 0.0};
     CK(cudaMemcpyAsync(host, sc.p, 16, cudaMemcpyDeviceToHost, h->stream));
     CK(cudaStreamSynchronize(h->stream));
@@ -1513,10 +1518,10 @@ int adopt_device_dinv(amg1d* h, int level) {
     if ((flag & 1) || !(host[0] <= 1e-8)) return AMG1D_OK;    // not the inverse of A_di: keep what was uploaded
     const bool unpivot = (flag & 2) && !(flag & 4);           // rows swap somewhere, but no element needs it
     if (unpivot && lv.present)
-        k_dinv_recompute<<<grid, 128, 0, h->stream>>>(lv.mat, lv.md, e0, e1, AMG1D_TILE, 3, d_dev, d_flag);
+        launch_dinv_recompute(grid, h->stream, lv.mat, lv.md, e0, e1, AMG1D_TILE, 3, d_dev, d_flag);
     if (lv.pat) {                                             // the pattern table's Dinv rows as well
         const int ns = lv.pat_head + 1 + lv.pat_tail;
-        k_dinv_recompute<<<1, 128, 0, h->stream>>>(lv.pat, lv.md, 0, ns, 1, unpivot ? 3 : 1, d_dev, d_flag);
+        launch_dinv_recompute(1, h->stream, lv.pat, lv.md, 0, ns, 1, unpivot ? 3 : 1, d_dev, d_flag);
         CK(cudaMemcpyAsync(lv.pat_host.data(), lv.pat, lv.pat_host.size() * 8, cudaMemcpyDeviceToHost, h->stream));
     }
     CK(cudaStreamSynchronize(h->stream));
@@ -2905,6 +2910,10 @@ int amg1d_set_option(amg1d_t* h, const char* key, int64_t value) {
         h->opt_p2p = value != 0;
     }
     else if (!strcmp(key, "dinv_registers")) h->opt_dvreg = (int)value;
+    else if (!strcmp(key, "leg_pipeline_min")) {
+        if (value < 0) return fail(h, AMG1D_ERR_ARG, "leg_pipeline_min must be >= 0");
+        h->opt_pipe_min = value;
+    }
     else if (!strcmp(key, "recompute_dinv_max")) {
         if (value < 1 || value > 5) return fail(h, AMG1D_ERR_ARG, "recompute_dinv_max must be in [1, 5]");
         h->opt_dvrec_max = (int)value;
@@ -2967,6 +2976,7 @@ int64_t amg1d_get_info(amg1d_t* h, const char* key) {
     if (!strcmp(key, "recompute_dinv")) return h->opt_dvrec;
     if (!strcmp(key, "dinv_registers")) return h->opt_dvreg;
     if (!strcmp(key, "leg_pipeline")) return h->opt_pipe;
+    if (!strcmp(key, "leg_pipeline_min")) return h->opt_pipe_min;
     if (!strncmp(key, "leg_pipeline:", 13)) {       // 1: the fused legs of this level are the pipelined persistent kernels
         const int l = atoi(key + 13);
         if (!valid_level(h, l) || !h->L[l].set || l + 1 >= h->n_levels || !h->T[l].fusable) return 0;

@@ -226,6 +226,7 @@ __global__ void k_extract_dinv(const double* __restrict__ mat, MatDesc d, int64_
 // stored inverse (generic tier, streaming kernels, single-CTA tail, pattern tables) to stay bit-identical, the
 // stored inverse must be THE SAME Gauss-Jordan result.  This kernel recomputes it per element with the
 // arithmetic of reg_invert (kernels_fused.cuh: partial pivoting by a compare-and-swap chain, same operation order).
+// (k_dinv_recompute below = the kernel template k_dinv_recompute_t behind launch_dinv_recompute.)
 //   mode 0: dev[0] = max over the elements of  max|Dinv_stored - inv(A_di)| / max|inv(A_di)|  (as an ordered
 //           int64 bit pattern, atomicMax), flag[0] |= 1 for a singular block, |= 2 if any element swaps rows,
 //           |= 4 if some element that swaps rows NEEDS to (below) - nothing is written;
@@ -246,47 +247,63 @@ __global__ void k_extract_dinv(const double* __restrict__ mat, MatDesc d, int64_
 // a pattern table tab[set][k] is addressed with tile_stride = 1 and "elements" = its rows: base + e * K.
 #define AMG1D_DVREC_MAXM 9
 #define AMG1D_NOPIVOT_TOL 1e-12
+// The kernel is instantiated for the block sizes 1 .. 5 (MT = m: every loop unrolls, the block lives in registers) and
+// once for any size up to AMG1D_DVREC_MAXM (MT = 0: run-time loops over per-thread arrays, i.e. local memory - 160 ms
+// of T's set-up before the instantiations existed); the statements, and with them the bits, are the same.
 // in-place Gauss-Jordan inverse without pivoting (column-major m x m), statement for statement reg_invert<M, false>
-__device__ inline bool gj_invert_nopivot(double* A, int m) {
+template <int MT>
+__device__ __forceinline__ bool gj_invert_nopivot(double* A, int m_rt) {
+    const int m = MT > 0 ? MT : m_rt;
+#pragma unroll
     for (int c = 0; c < m; ++c) {
         if (A[c * m + c] == 0.0) return false;
         const double dd = 1.0 / A[c * m + c];
         A[c * m + c] = 1.0;
+#pragma unroll
         for (int q = 0; q < m; ++q) A[q * m + c] *= dd;
+#pragma unroll
         for (int r = 0; r < m; ++r) {
             if (r == c) continue;
             const double f = A[c * m + r];
             A[c * m + r] = 0.0;
+#pragma unroll
             for (int q = 0; q < m; ++q) A[q * m + r] = fma(-f, A[q * m + c], A[q * m + r]);
         }
     }
     return true;
 }
 
-__global__ void k_dinv_recompute(double* __restrict__ base, MatDesc d, int64_t e_first, int64_t e_end, int tile_stride,
-                                 int mode, unsigned long long* __restrict__ dev, int* __restrict__ flag) {
+template <int MT>
+__global__ void k_dinv_recompute_t(double* __restrict__ base, MatDesc d, int64_t e_first, int64_t e_end, int tile_stride,
+                                   int mode, unsigned long long* __restrict__ dev, int* __restrict__ flag) {
+    constexpr int MM = MT > 0 ? MT : AMG1D_DVREC_MAXM;
     const int64_t e = e_first + (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (e >= e_end) return;
-    const int m = d.m;
+    const int m = MT > 0 ? MT : d.m;
     double* T = tile_stride == 1 ? base + e * (int64_t)d.K
                                  : base + (e >> 5) * (int64_t)d.K * AMG1D_TILE + (e & 31);    // e >> 5 floors
     const int rs = tile_stride == 1 ? 1 : AMG1D_TILE;
-    double A[AMG1D_DVREC_MAXM * AMG1D_DVREC_MAXM];
-    bool sw[AMG1D_DVREC_MAXM][AMG1D_DVREC_MAXM];
+    double A[MM * MM];
+    bool sw[MM][MM];
     bool allzero = true;
+#pragma unroll
     for (int k = 0; k < m * m; ++k) { A[k] = T[(int64_t)(d.o_di + k) * rs]; allzero = allzero && A[k] == 0.0; }
     if (allzero) return;                          // zero-filled slots outside the level (slab padding)
     if (mode == 3) {
-        if (!gj_invert_nopivot(A, m)) { atomicOr(flag, 1); return; }
+        if (!gj_invert_nopivot<MT>(A, m)) { atomicOr(flag, 1); return; }
+#pragma unroll
         for (int k = 0; k < m * m; ++k) T[(int64_t)(d.o_dv + k) * rs] = A[k];
         return;
     }
     bool swapped = false;
+#pragma unroll
     for (int c = 0; c < m; ++c) {
+#pragma unroll
         for (int r = c + 1; r < m; ++r) {         // compare-and-swap chain: the largest |a(r, c)|, r >= c, ends on the diagonal
             const bool s = fabs(A[c * m + r]) > fabs(A[c * m + c]);
             sw[c][r] = s;
             swapped = swapped || s;
+#pragma unroll
             for (int q = 0; q < m; ++q) {
                 const double x = A[q * m + c], y = A[q * m + r];
                 A[q * m + c] = s ? y : x;
@@ -296,25 +313,33 @@ __global__ void k_dinv_recompute(double* __restrict__ base, MatDesc d, int64_t e
         if (A[c * m + c] == 0.0) { atomicOr(flag, 1); return; }
         const double dd = 1.0 / A[c * m + c];
         A[c * m + c] = 1.0;
+#pragma unroll
         for (int q = 0; q < m; ++q) A[q * m + c] *= dd;
+#pragma unroll
         for (int r = 0; r < m; ++r) {
             if (r == c) continue;
             const double f = A[c * m + r];
             A[c * m + r] = 0.0;
+#pragma unroll
             for (int q = 0; q < m; ++q) A[q * m + r] = fma(-f, A[q * m + c], A[q * m + r]);
         }
     }
-    for (int c = m - 1; c >= 0; --c)              // undo the row swaps as column swaps, in reverse order
+#pragma unroll
+    for (int c = m - 1; c >= 0; --c) {            // undo the row swaps as column swaps, in reverse order
+#pragma unroll
         for (int r2 = m - 1; r2 > c; --r2) {
             const bool s = sw[c][r2];
+#pragma unroll
             for (int r = 0; r < m; ++r) {
                 const double x = A[c * m + r], y = A[r2 * m + r];
                 A[c * m + r] = s ? y : x;
                 A[r2 * m + r] = s ? x : y;
             }
         }
+    }
     if (mode != 1) {
         double mx = 0.0, df = 0.0;
+#pragma unroll
         for (int k = 0; k < m * m; ++k) {
             mx = fmax(mx, fabs(A[k]));
             df = fmax(df, fabs(A[k] - T[(int64_t)(d.o_dv + k) * rs]));
@@ -323,18 +348,34 @@ __global__ void k_dinv_recompute(double* __restrict__ base, MatDesc d, int64_t e
         atomicMax(dev, (unsigned long long)__double_as_longlong(rel >= 0.0 ? rel : INFINITY));   // NaN -> inf
         if (swapped) {                            // does this element need its pivots?
             atomicOr(flag, 2);
-            double U[AMG1D_DVREC_MAXM * AMG1D_DVREC_MAXM];
+            double U[MM * MM];
+#pragma unroll
             for (int k = 0; k < m * m; ++k) U[k] = T[(int64_t)(d.o_di + k) * rs];
-            bool same = gj_invert_nopivot(U, m);
+            bool same = gj_invert_nopivot<MT>(U, m);
             double du = 0.0;
+#pragma unroll
             for (int k = 0; k < m * m; ++k) du = fmax(du, fabs(U[k] - A[k]));
             same = same && (du <= AMG1D_NOPIVOT_TOL * mx);                                    // false for NaN
             if (!same) atomicOr(flag, 4);
         }
         if (mode == 2 && !(rel <= 1e-8)) return;      // this element's upload is not inv(A_di): leave it alone
     }
-    if (mode != 0)
+    if (mode != 0) {
+#pragma unroll
         for (int k = 0; k < m * m; ++k) T[(int64_t)(d.o_dv + k) * rs] = A[k];
+    }
+}
+
+inline void launch_dinv_recompute(unsigned grid, cudaStream_t st, double* base, const MatDesc& d, int64_t e_first,
+                                  int64_t e_end, int tile_stride, int mode, unsigned long long* dev, int* flag) {
+    switch (d.m) {
+        case 1: k_dinv_recompute_t<1><<<grid, 128, 0, st>>>(base, d, e_first, e_end, tile_stride, mode, dev, flag); break;
+        case 2: k_dinv_recompute_t<2><<<grid, 128, 0, st>>>(base, d, e_first, e_end, tile_stride, mode, dev, flag); break;
+        case 3: k_dinv_recompute_t<3><<<grid, 128, 0, st>>>(base, d, e_first, e_end, tile_stride, mode, dev, flag); break;
+        case 4: k_dinv_recompute_t<4><<<grid, 128, 0, st>>>(base, d, e_first, e_end, tile_stride, mode, dev, flag); break;
+        case 5: k_dinv_recompute_t<5><<<grid, 128, 0, st>>>(base, d, e_first, e_end, tile_stride, mode, dev, flag); break;
+        default: k_dinv_recompute_t<0><<<grid, 128, 0, st>>>(base, d, e_first, e_end, tile_stride, mode, dev, flag); break;
+    }
 }
 
 // ---- device-side right-hand side ----------------------------------------------------------------

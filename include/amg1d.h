@@ -283,8 +283,8 @@ void* amg1d_dev_ptr(amg1d_t* h, int level, int which);             /* raw device
  * while every other kernel, which reads the stored inverse, produces the same bits.  Changing the value later only
  * selects which levels recompute - same results, other byte counts);
  * "leg_pipeline" (default 1: the recomputing legs of 4 x 4 levels run as persistent CTAs that fetch their next
- * window with TMA bulk copies while they compute the current one - f_down_pp / f_up_pp; 2: the 2 x 2 levels too;
- * 0: one window per CTA), "dinv_registers" (with "leg_pipeline" = 0: 1 = the recomputed inverse of 4 x 4 levels
+ * window with TMA bulk copies while they compute the current one - f_down_pp / f_up_pp - on levels of at least
+ * "leg_pipeline_min" elements per rank (default 500000); 2: the 2 x 2 levels too; 0: one window per CTA), "dinv_registers" (with "leg_pipeline" = 0: 1 = the recomputed inverse of 4 x 4 levels
  * stays in registers - f_down_dv / f_up_dv; 2 = of 2 x 2 levels too; 0 = it goes through shared memory) - every
  * combination gives the same bits;
  * "p2p_halo" (before amg1d_finalize, multi-GPU handles; default 1: the slab-edge exchanges of the V-cycle go

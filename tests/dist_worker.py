@@ -61,7 +61,7 @@ def run_graded(world, rank, ids):
     f, r = aggmg.dg_flux_rhs(meshes[0], mesh, lambda t: w * w * np.cos(w * t), bd, 1000.0)
     b = f - D @ meshes[0].mMassMatrixLU.solve(r)
     H = aggmg.MeshHierarchy(meshes, [bd] * len(meshes), A, G, D, C, nDG=2, nAgg=10, upload=False)
-    dev = H.upload(device=rank, dist=(rank, world, ids[0]), options={"shard_min": 256})
+    dev = H.upload(device=rank, dist=(rank, world, ids[0]), options={"shard_min": 256, "leg_pipeline_min": 0})   # pipelined legs on the slabs
     nloc = n // world
     lo, hi = rank * nloc * 4, (rank + 1) * nloc * 4
     report = {"rank": rank, "gather_level": dev.info("gather_level"), "local_dofs": dev.info("local_dofs"),
@@ -131,7 +131,9 @@ def run_kind(kind, log2n):
         return uniform.UniformDgHierarchy(n, [3, 1], [2] * log2n, xin=0.0, xout=float(n), CDir=1000.0)
 
     U = build()
-    dev = U.upload(device=rank, dist=(rank, world, ids[0]), options={"shard_min": 512, "p2p_halo": p2p})
+    dev = U.upload(device=rank, dist=(rank, world, ids[0]), options={"shard_min": 512, "p2p_halo": p2p,
+                                                                     "leg_pipeline_min": 0})   # persistent pipelined legs
+    # on the sharded 4 x 4 levels even at this size (the single-GPU reference below keeps the default: one window per CTA)
     if pattern_resident:                          # the single-GPU reference below keeps streaming its operators
         dev.set_option("pattern_resident", pattern_resident)
     nloc = n // world

@@ -61,7 +61,10 @@ def test_leg_variants_bit_identical(orders, n):
         w = 2.0 * math.pi / 64.0
         b = U.rhs(lambda x: w * w * np.cos(w * x), [0.0, math.cos(w * n)])
         x0 = np.random.default_rng(5).standard_normal(len(b))
-        assert dev.info("leg_pipeline") == 1 and dev.info("leg_pipeline:0") == 1      # the default
+        # the default: pipelined from leg_pipeline_min elements up (smaller levels keep the one-window-per-CTA legs)
+        assert dev.info("leg_pipeline") == 1
+        assert dev.info("leg_pipeline:0") == (1 if n >= dev.info("leg_pipeline_min") else 0)
+        dev.set_option("leg_pipeline_min", 0)                      # here: every size through every form
         ref = None
         for name, opts in VARIANTS:
             _set(dev, opts)
@@ -106,6 +109,7 @@ def test_pipelined_legs_on_a_graded_mesh():
     H = aggmg.MeshHierarchy(meshes, [bd] * len(meshes), A, G, D, C, nDG=2, nAgg=10, upload=False)
     dev = H.upload()
     try:
+        dev.set_option("leg_pipeline_min", 0)
         assert dev.info("pattern:0") == 0 and dev.info("leg_pipeline:0") == 1
         x0 = np.random.default_rng(7).standard_normal(len(b))
         ref = None

@@ -17,7 +17,7 @@ def main():
     specs = (sys.argv[2] if len(sys.argv) > 2 else "0,2,3,4").split(",")
     values = [int(v.split(":")[0]) for v in specs]
     extras = [dict(kv.split("=") for kv in v.split(":")[1:]) for v in specs]
-    log2n = bench.WORKLOADS[workload][0]
+    log2n = int(sys.argv[3]) if len(sys.argv) > 3 else bench.WORKLOADS[workload][0]    # optional size override
     U = bench.build_hierarchy(workload, 2 ** log2n)
     ts = torch.cuda.Stream()
     torch.cuda.set_stream(ts)
@@ -27,6 +27,8 @@ def main():
     for v, extra in zip(values, extras):
         dev.set_option("dinv_registers", 0)
         dev.set_option("leg_pipeline", 1)
+        dev.set_option("leg_pipeline_min", 500000)                # the library default
+        dev.set_option("recompute_dinv_max", 4)
         for k, val in extra.items():
             dev.set_option(k, int(val))
         dev.set_option("recompute_dinv", v)
@@ -52,7 +54,7 @@ def main():
                 t, c = dev.profile(l, leg)
                 legs[f"L{l}_{nm}"] = round(t / max(c, 1), 4)
         dev.set_option("profile", 0)
-        print(json.dumps({"workload": workload, "recompute_dinv": v, "extra": extra, "ms_per_cycle": ms, "legs": legs,
+        print(json.dumps({"workload": workload, "log2n": log2n, "recompute_dinv": v, "extra": extra, "ms_per_cycle": ms, "legs": legs,
                           "recomputing_levels": [l for l in range(len(U.levels) - 1) if dev.info(f"dinv_recompute:{l}") == 1][:8],
                           "pivots": [dev.info(f"dinv_pivots:{l}") for l in range(4)],
                           "pipelined_levels": [l for l in range(len(U.levels) - 1) if dev.info(f"leg_pipeline:{l}") == 1][:8],
