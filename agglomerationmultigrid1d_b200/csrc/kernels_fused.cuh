@@ -1047,8 +1047,8 @@ f_up_dv(const double* __restrict__ mat, int ilo, int iup, const double* __restri
 // loaded latency, and nothing hides the gaps.  f_down_pp / f_up_pp are the same legs as PERSISTENT CTAs (4 per SM):
 // CTA c walks over the windows c, c + grid, c + 2 grid ...; while it computes window w out of registers, the
 // operator tiles and the b / x slices of its NEXT window are already in flight into shared memory - 1-D bulk copies
-// (cp.async.bulk.shared::cluster.global, the TMA engine: no registers, no LSU instructions) issued by one thread
-// and signalled through one mbarrier per CTA (expect_tx = bytes issued; parity flips per window).  A window of
+// (cp.async.bulk.shared::cluster.global, the TMA engine: no registers, no LSU instructions) issued by the lanes of
+// warp 0 and signalled through one mbarrier per CTA (expect_tx = bytes issued; parity flips per window).  A window of
 // B = 128 elements starts at w * out - halo, which is never tile aligned, so the stage holds the B / 32 + 1 element
 // tiles it touches - only their A_lo / A_di / A_up rows, which are contiguous at the start of a tile; the inverse
 // is recomputed in registers (reg_invert) as in f_*_dv - the neighbouring windows' copies of the shared tiles are
@@ -1056,8 +1056,9 @@ f_up_dv(const double* __restrict__ mat, int ilo, int iup, const double* __restri
 // through per-thread cp.async into the thread's own shared-memory slots.  ~52 KB of shared memory per CTA: one
 // operator stage suffices because the operator moves to registers at the start of a window and the stage is
 // refilled right after (one block-wide barrier; folding the refill into the leg's first exchange barrier was
-// measured slower - the longer live ranges spill).  Arithmetic, order and emitted values are those of f_down / f_up (down_body / up_body):
-// bit-identical.  Slab edges: thread 0 waits for the neighbour's flags before the first copy of a window that
+// measured slower - the longer live ranges spill).  Arithmetic, order and emitted values are those of f_down / f_up
+// (down_body / up_body): bit-identical.  Used on levels of at least leg_pipeline_min elements per rank: below ~2^19
+// the two ordinary stream dependencies around a persistent leg (next paragraph) cost more than the pipeline gains.  Slab edges: thread 0 waits for the neighbour's flags before the first copy of a window that
 // touches an edge (the spin of halo_leg_wait), the edge owners push as in f_down / f_up.
 // The persistent legs are launched as ordinary stream successors, not as programmatic dependents: an early
 // launch places their CTAs on SMs that still run the predecessor's last wave under ITS shared-memory carve-out,
@@ -1379,8 +1380,8 @@ inline bool fused_has_pp(int m, int mc, int st, int diag) {
     return !diag && ((m == 4 && st == AMG1D_ST_COLROW && (mc == 2 || mc == 3)) || (m == 2 && mc == 2 && st != AMG1D_ST_ROWCOL));
 }
 
-// persistent grid of the pipelined legs: pipe_min_blocks(m) CTAs per SM of the current device; the first launch of an
-// dynamic shared-memory limit of the kernels is raised once (pipe_configure_all)
+// persistent grid of the pipelined legs: pipe_min_blocks(m) CTAs per SM of the current device; the dynamic
+// shared-memory limit of the kernels is raised once per device context (pipe_configure_all, at amg1d_finalize)
 inline int pipe_sm_count() {
     static int sms = 0;
     if (!sms) {
