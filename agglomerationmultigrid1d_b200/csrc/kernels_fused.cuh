@@ -93,7 +93,7 @@ __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;"
 // true while the most recent fused launch was one of the persistent pipelined legs (f_down_pp / f_up_pp): the kernel
 // after such a leg is launched as an ordinary stream successor (see the comment above those kernels)
 inline bool& fused_prev_persistent() {
-    static bool v = false;
+    static thread_local bool v = false;      // per host thread: launches of one handle come from one thread at a time
     return v;
 }
 
@@ -1383,13 +1383,16 @@ inline bool fused_has_pp(int m, int mc, int st, int diag) {
 // persistent grid of the pipelined legs: pipe_min_blocks(m) CTAs per SM of the current device; the dynamic
 // shared-memory limit of the kernels is raised once per device context (pipe_configure_all, at amg1d_finalize)
 inline int pipe_sm_count() {
-    static int sms = 0;
-    if (!sms) {
-        int dev = 0;
-        cudaGetDevice(&dev);
-        if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sms <= 0) sms = 148;
+    static int sms[64] = {0};                // per device ordinal
+    int dev = 0;
+    cudaGetDevice(&dev);
+    const int slot = (dev >= 0 && dev < 64) ? dev : 0;
+    if (!sms[slot]) {
+        int v = 0;
+        if (cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || v <= 0) v = 148;
+        sms[slot] = v;
     }
-    return sms;
+    return sms[slot];
 }
 template <class KERN>
 inline cudaError_t pipe_configure(KERN kern, size_t smem) {

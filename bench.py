@@ -279,7 +279,7 @@ def bind_to_gpu_numa_node(torch, local):
         allowed = os.sched_getaffinity(0)
         use = cpus & allowed
         info["node_cpus_allowed"] = len(use)
-        if use and use != allowed:
+        if len(use) >= 2 and use != allowed:                 # never squeeze a rank (and its NCCL threads) onto one CPU
             os.sched_setaffinity(0, use)
             info["bound"] = True
     except Exception as e:                                   # no sysfs, no such attribute, cpuset forbids it ...
