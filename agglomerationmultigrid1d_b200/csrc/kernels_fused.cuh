@@ -652,7 +652,10 @@ constexpr int fused_c_min_blocks(int m, int st) {
 // operator (A: RegOp in registers + Dinv column dcol in shared memory, RegOpDv, or ParamOp in the constant bank) and
 // the thread's right-hand side bb / incoming iterate xc are in registers.  One CTA per window (f_down, f_down_dv,
 // f_down_c: win = blockIdx.x) or a persistent CTA walking over windows (f_down_pp).
-template <int M, int MC, int B, int ST, bool DIAG, class OP, int NSW = 0>   // NSW > 0: nsweep known at compile time
+// SINGLE: the launcher knows that every coarse element has exactly one child and one parent transfer (ratio == 1, no
+// P1 - the p-coarsening transfers dg_dg): the thread restricts its own residual straight from registers, the trip
+// through shared memory and its barrier are not needed (same products in the same order).
+template <int M, int MC, int B, int ST, bool DIAG, class OP, int NSW = 0, bool SINGLE = false>   // NSW > 0: nsweep known at compile time
 __device__ __forceinline__ void
 down_body(const OP& A, const double* __restrict__ dcol, Exchange<M, B>& ex, double (*rs)[B + 8], int64_t e, int64_t win,
           const double (&bb)[M], double (&xc)[M], int ilo, int iup, double* __restrict__ xout,
@@ -692,10 +695,30 @@ down_body(const OP& A, const double* __restrict__ dcol, Exchange<M, B>& ex, doub
     exchange<M, B, ST>(ex, buf, ilo, iup, xc, xl, xr);
     double r[M];
     reg_residual<M, ST>(A, ilo, iup, bb, xl, xc, xr, r);
+    const int64_t eg = e + sl.e_off;                            // global element index
+    if constexpr (SINGLE) {
+        if (mine && eg < tm.n_fine) {
+            const int64_t Kc = win * wi.opr + wi.qdiv0 + (wi.qmod0 + t) + tm.base;     // ratio == 1: kdiv = qmod0 + t, kmod = 0
+            const int64_t Kl = Kc - sl.c_off;                   // local coarse element index
+            if (Kc >= 0 && Kc < tm.n_coarse && Kl >= 0 && Kl < sl.nc) {
+                const double* P = P0 + win_blk(tm, wi, eg, t) * (M * MC);
+                double acc[MC];
+#pragma unroll
+                for (int j = 0; j < MC; ++j) acc[j] = 0.0;
+#pragma unroll
+                for (int j = 0; j < MC; ++j)
+#pragma unroll
+                    for (int i = 0; i < M; ++i) acc[j] = fma(P[j * M + i], r[i], acc[j]);
+#pragma unroll
+                for (int j = 0; j < MC; ++j) rc[Kl * MC + j] = acc[j];
+                if (hl.on) halo_leg_push<MC>(acc, Kl, hl.nc, hl.gd, hl.c_left, hl.c_right, hl.f_left, hl.f_right);
+            }
+        }
+        return;
+    }
 #pragma unroll
     for (int i = 0; i < M; ++i) rs[i][t] = r[i];
     __syncthreads();
-    const int64_t eg = e + sl.e_off;                            // global element index
     if (mine && eg < tm.n_fine) {
         int kdiv, kmod;                                         // (eg + shift) = ratio * (.. + kdiv) + kmod
         small_divmod(wi.qmod0 + t, tm.ratio, &kdiv, &kmod);
@@ -1199,7 +1222,7 @@ struct PipeDownSmem {
     double rs[M][B + 8];
 };
 
-template <int M, int MC, int B, int ST, int NSW>
+template <int M, int MC, int B, int ST, int NSW, bool SINGLE>
 __global__ void __launch_bounds__(B, PIPE_MINB(M))
 f_down_pp(const double* __restrict__ mat, int ilo, int iup, const double* __restrict__ b,
           const double* __restrict__ xin, double* __restrict__ xout, const double* __restrict__ P0,
@@ -1272,8 +1295,8 @@ f_down_pp(const double* __restrict__ mat, int ilo, int iup, const double* __rest
         __syncthreads();
         refill();
         pipe_invert<M, ST>(A, active, rec);
-        down_body<M, MC, B, ST, false, RegOpDv<M, ST>, NSW>(A, nullptr, S.ex, S.rs, e, win, bb, xc, ilo, iup, xout, P0, P1, tm,
-                                                             rc, n, alpha, nsweep, zero_guess, wi, sl, hl);
+        down_body<M, MC, B, ST, false, RegOpDv<M, ST>, NSW, SINGLE>(A, nullptr, S.ex, S.rs, e, win, bb, xc, ilo, iup, xout, P0,
+                                                                     P1, tm, rc, n, alpha, nsweep, zero_guess, wi, sl, hl);
     }
 }
 
@@ -1402,8 +1425,10 @@ inline cudaError_t pipe_configure(KERN kern, size_t smem) {
 inline cudaError_t pipe_configure_all() {
     cudaError_t e = cudaSuccess;
 #define PP(MM, MCC, SS)                                                                                            \
-    if (e == cudaSuccess) e = pipe_configure(f_down_pp<MM, MCC, FUSED_B, SS, 0>, sizeof(PipeDownSmem<MM, MCC, FUSED_B, SS>)); \
-    if (e == cudaSuccess) e = pipe_configure(f_down_pp<MM, MCC, FUSED_B, SS, 3>, sizeof(PipeDownSmem<MM, MCC, FUSED_B, SS>)); \
+    if (e == cudaSuccess) e = pipe_configure(f_down_pp<MM, MCC, FUSED_B, SS, 0, false>, sizeof(PipeDownSmem<MM, MCC, FUSED_B, SS>)); \
+    if (e == cudaSuccess) e = pipe_configure(f_down_pp<MM, MCC, FUSED_B, SS, 3, false>, sizeof(PipeDownSmem<MM, MCC, FUSED_B, SS>)); \
+    if (e == cudaSuccess) e = pipe_configure(f_down_pp<MM, MCC, FUSED_B, SS, 0, true>, sizeof(PipeDownSmem<MM, MCC, FUSED_B, SS>)); \
+    if (e == cudaSuccess) e = pipe_configure(f_down_pp<MM, MCC, FUSED_B, SS, 3, true>, sizeof(PipeDownSmem<MM, MCC, FUSED_B, SS>)); \
     if (e == cudaSuccess) e = pipe_configure(f_up_pp<MM, MCC, FUSED_B, SS, 0>, sizeof(PipeUpSmem<MM, MCC, FUSED_B, SS>)); \
     if (e == cudaSuccess) e = pipe_configure(f_up_pp<MM, MCC, FUSED_B, SS, 3>, sizeof(PipeUpSmem<MM, MCC, FUSED_B, SS>));
     PP(4, 2, 1) PP(4, 3, 1) PP(2, 2, 0) PP(2, 2, 1)
@@ -1827,7 +1852,11 @@ inline int fused_down(const MatDesc& d, int mc, const TransferMap& tm, int nswee
         if (d.m == MM && mc == MCC && d.st == SS) {                                                       \
             const size_t smem = sizeof(PipeDownSmem<MM, MCC, FUSED_B, SS>);                               \
             const int64_t pg = std::min<int64_t>((int64_t)grid, (int64_t)pipe_sm_count() * PIPE_MINB(MM));    \
-            *err = launch_fused(nsweep == 3 ? f_down_pp<MM, MCC, FUSED_B, SS, 3> : f_down_pp<MM, MCC, FUSED_B, SS, 0>, \
+            const bool single = tm.ratio == 1 && P1 == nullptr;      /* one child per coarse element */ \
+            *err = launch_fused(single ? (nsweep == 3 ? f_down_pp<MM, MCC, FUSED_B, SS, 3, true>                   \
+                                                      : f_down_pp<MM, MCC, FUSED_B, SS, 0, true>)                  \
+                                       : (nsweep == 3 ? f_down_pp<MM, MCC, FUSED_B, SS, 3, false>                  \
+                                                      : f_down_pp<MM, MCC, FUSED_B, SS, 0, false>),                \
                                 (unsigned)pg, FUSED_B, smem, st, false, mat, d.ilo,                       \
                                 d.iup, b, xin, xout, P0, P1, tm, rc, n, alpha, nsweep, zero ? 1 : 0, w, sl, rec, hl, \
                                 (int64_t)grid);                                                           \
